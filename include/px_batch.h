@@ -1,0 +1,242 @@
+/*
+ * px_batch.h -- the C-ABI batch layer: N independent pdphyzx worlds stepped on one B200.
+ *
+ * This is the drop-in boundary.  The reference has no FFI; its only entry into the hot path
+ * is `bool (*step)(PxWorld *)` (reference src/includes/px_world_api.h:34 -> pxWorldStep,
+ * src/px_world.c:422-445), whose body is 5 x pxWorldStepWithDt per fired fixed step
+ * (src/px_world.c:410-420, 435-437).  pxBatchStep(b, K) is K x pxWorldStepWithDt for every
+ * world of the batch, executed by the sm_100a kernel in pdphyzx_b200/csrc/px_step.cu.
+ * Everything in this header is plain C: pointers, sizes, ints.  No CUDA or torch types.
+ *
+ * Each function below names the reference interface it replaces or batches.
+ *
+ * Error convention: int rc; 0 = ok, < 0 = CUDA/driver/argument error (text in
+ * pxBatchLastError()), > 0 = number of worlds whose last step overflowed a capacity (their
+ * PxContactStats.overflow / PxWorldHeader.statOverflow says which).  Nothing aborts.
+ * Threading: one host thread per PxBatch at a time.
+ */
+#ifndef PX_BATCH_H
+#define PX_BATCH_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define PX_API __attribute__((visibility("default")))
+#else
+#define PX_API
+#endif
+
+typedef struct PxBatch PxBatch;
+struct PxWorld; /* include/pdphyzx.h */
+
+/* PxBatchDesc.flags */
+#define PX_BATCH_FLAG_TRACE 1u        /* keep the last substep's ordered pair + manifold lists */
+#define PX_BATCH_FLAG_SERIAL_SOLVER 2u /* debug: one thread walks the manifolds in pool order */
+
+/* PxWorldHeader.statOverflow bits */
+#define PX_BATCH_OVERFLOW_PAIRS 1u     /* more AABB-pass pairs than maxPairs: extra pairs dropped */
+#define PX_BATCH_OVERFLOW_MANIFOLDS 2u /* more manifolds than maxManifolds: extra manifolds dropped */
+/* (the reference dereferences NULL when its 64-manifold pool runs out, src/px_world.c:333-336;
+ *  there is no behaviour to match, so the device drops the excess and raises the flag) */
+
+/* pxBatchReadback flags */
+#define PX_READBACK_STATS_ONLY 1u
+
+typedef struct PxBatchDesc {
+  uint32_t structSize;   /* sizeof(PxBatchDesc), for forward compatibility */
+  float unit;            /* PDPHYZX_UNIT of the host code: 1, 100 or 1000 (px_unit.h:18-20) */
+  uint32_t maxDynamic;   /* per-world capacities; 0 = take from the worlds given to pxBatchNew */
+  uint32_t maxStatic;
+  uint32_t maxVertices;  /* polygon vertices per world (sum over bodies) */
+  uint32_t maxManifolds; /* 0 = 3 * maxDynamic + 64 */
+  uint32_t maxPairs;     /* 0 = 8 * maxDynamic + 64 */
+  int32_t device;        /* CUDA device ordinal, -1 = current device */
+  void *stream;          /* cudaStream_t to launch on; NULL = a stream owned by the batch */
+  uint32_t flags;        /* PX_BATCH_FLAG_* */
+  uint32_t threads;      /* threads per world-CTA: 0 = default */
+  const float *sinTable; /* the host's pxSinTable (256 floats, px_math.h:206-218); NULL = the
+                            library fills one with sinf exactly as pxInitSinTable does */
+} PxBatchDesc;
+
+static inline PxBatchDesc pxBatchDescDefault(float unit) {
+  PxBatchDesc d = {0};
+  d.structSize = (uint32_t)sizeof(PxBatchDesc);
+  d.unit = unit;
+  d.device = -1;
+  return d;
+}
+
+/*
+ * Per-world header at the start of every world's mutable block (64 bytes).  The first ten
+ * fields are the world-level inputs pxWorldStepWithDt reads every substep (PxWorld fields,
+ * src/includes/px_world.h:36-41, and the clock-derived dt, src/px_world.c:432); the stat*
+ * fields are written by the device after every pxBatchStep.
+ */
+typedef struct PxWorldHeader {
+  float gravityX, gravityY;     /* already unit-scaled, as px->world->setGravity stores it */
+  float dt;                     /* substep dt */
+  float linearSleepThresholdSq;
+  float angularSleepThreshold;
+  float timeToSleep;
+  uint32_t iterations;
+  uint32_t nDynamic, nStatic;   /* active lengths (PxBodyArray.length) */
+  uint32_t nVertices;
+  uint32_t statManifolds;       /* manifolds kept by the last substep (= contacts.length) */
+  uint32_t statSleeping;        /* sleeping dynamic bodies after the last substep */
+  uint32_t statOverflow;        /* PX_BATCH_OVERFLOW_* accumulated since upload */
+  uint32_t statPairs;           /* AABB-pass pairs of the last substep */
+  uint32_t substeps;            /* substeps executed since upload */
+  uint32_t reserved;
+} PxWorldHeader;
+
+/* rows of the per-world dynamic-body float matrix f32[PX_DYN_ROWS][maxDynamic], indexed by
+ * SLOT (PxBody.worldIndex); mutable state in the order of px_body.h:82-120 */
+enum {
+  PX_DYN_PX = 0, PX_DYN_PY, PX_DYN_VX, PX_DYN_VY, PX_DYN_AV, PX_DYN_ANGLE, PX_DYN_FX, PX_DYN_FY,
+  PX_DYN_TORQUE, PX_DYN_SLEEP, PX_DYN_M00, PX_DYN_M01, PX_DYN_M10, PX_DYN_M11, PX_DYN_ROWS
+};
+/* rows of the immutable dynamic matrix f32[PX_DYNC_ROWS][maxDynamic] */
+enum { PX_DYNC_IMASS = 0, PX_DYNC_IINERTIA, PX_DYNC_E, PX_DYNC_SF, PX_DYNC_DF, PX_DYNC_RADIUS, PX_DYNC_ROWS };
+/* rows of the static matrix f32[PX_STAT_ROWS][maxStatic], indexed by POSITION in the static
+ * iteration order (staticBodies.activeIndices), not by slot */
+enum {
+  PX_STAT_PX = 0, PX_STAT_PY, PX_STAT_M00, PX_STAT_M01, PX_STAT_M10, PX_STAT_M11, PX_STAT_E, PX_STAT_SF,
+  PX_STAT_DF, PX_STAT_RADIUS, PX_STAT_ROWS
+};
+
+/*
+ * Where things are inside the two per-world blocks (all offsets in bytes from the start of
+ * the world's block, all 16-byte aligned).  World w lives at mut + w * mutStride and
+ * imm + w * immStride.  The same layout is used in pinned host staging and in HBM.
+ */
+typedef struct PxBatchLayout {
+  uint32_t nWorlds;
+  uint32_t maxDynamic, maxStatic, maxVertices, maxManifolds, maxPairs; /* maxDynamic/maxStatic padded to x4 */
+  uint32_t mutStride, immStride;
+  /* mutable block */
+  uint32_t offHeader;    /* PxWorldHeader */
+  uint32_t offDyn;       /* f32[PX_DYN_ROWS][maxDynamic] */
+  uint32_t offDynFlags;  /* u8[maxDynamic]   PxBody.flags by slot */
+  uint32_t offDynOrder;  /* u8[maxDynamic]   dynamicBodies.activeIndices */
+  /* immutable block */
+  uint32_t offDynConst;  /* f32[PX_DYNC_ROWS][maxDynamic] */
+  uint32_t offDynShape;  /* u32[maxDynamic]  (vertexOffset << 8) | vertexCount, count 0 = circle; see PX_SHAPE_* */
+  uint32_t offStat;      /* f32[PX_STAT_ROWS][maxStatic] */
+  uint32_t offStatShape; /* u32[maxStatic] */
+  uint32_t offStatSlot;  /* u8[maxStatic]    slot (worldIndex) of the static at each position */
+  uint32_t offVerts;     /* float4[maxVertices] = {vertex.x, vertex.y, normal.x, normal.y} */
+  /* trace block (PX_BATCH_FLAG_TRACE), per world at trace + w * traceStride */
+  uint32_t traceStride;
+  uint32_t offTracePairs;     /* u16[2][maxPairs]: slotA, then (bIsDynamic << 15) | slotB */
+  uint32_t offTraceManifolds; /* f32[PX_TRACE_M_F32][maxManifolds] then u32 ids[maxManifolds] */
+  /* unit-derived constants, computed on the host with the reference's expressions */
+  float unit;
+  float epsilon;          /* 0.0001f * U                   px_math.h:23 */
+  float epsilonSq;        /* ((0.0001f * U) * 0.0001f) * U  as PX_EPSILON * PX_EPSILON expands */
+  float allowedPenetration; /* 0.0001f * U                 px_manifold.h:15 */
+} PxBatchLayout;
+
+#define PX_SHAPE_COUNT(s) ((uint32_t)(s) & 255u)
+#define PX_SHAPE_OFFSET(s) ((uint32_t)(s) >> 8)
+#define PX_SHAPE_PACK(offset, count) ((uint32_t)(((uint32_t)(offset) << 8) | (uint32_t)(count)))
+#define PX_MAX_DEVICE_VERTS 32 /* per polygon, as PX_MAX_POLY_VERTEX_COUNT */
+
+/* trace manifold rows: normal.x normal.y penetration staticFriction dynamicFriction
+ * mixedRestitution c0.x c0.y c1.x c1.y; ids = slotA | slotB << 8 | bIsDynamic << 16 | count << 24 */
+#define PX_TRACE_M_F32 10
+
+/* ------------------------------------------------------------------------------ lifecycle */
+
+/* Pack `nWorlds` host worlds (AoS PxWorld, include/pdphyzx.h) into device SoA and return the
+ * batch.  Capacities left 0 in `desc` are derived from the worlds.  Copies, among the rest,
+ * the iteration orders, sleep state, clock-derived dt, iterations, gravity, thresholds and
+ * the host's pxSinTable.  Does not take ownership of the worlds.  NULL on error.
+ * Batches: PxWorld construction state consumed by pxWorldStepWithDt (src/px_world.c:410). */
+PX_API PxBatch *pxBatchNew(struct PxWorld *const *worlds, uint32_t nWorlds, const PxBatchDesc *desc);
+
+/* Empty batch of `nWorlds` worlds with explicit capacities (all desc.max* must be non-zero);
+ * fill it with pxBatchUpload in chunks -- for batches whose AoS form would not fit host RAM. */
+PX_API PxBatch *pxBatchCreate(uint32_t nWorlds, const PxBatchDesc *desc);
+
+/* (Re)pack host worlds into batch worlds [first, first + n): the host -> device direction of
+ * every field the step reads.  Used by px->world->step to carry host-side edits over. */
+PX_API int pxBatchUpload(PxBatch *b, struct PxWorld *const *worlds, uint32_t first, uint32_t n);
+
+PX_API void pxBatchFree(PxBatch *b);
+
+/* -------------------------------------------------------------------------------- stepping */
+
+/* K x pxWorldStepWithDt (src/px_world.c:410-420) for every world, one kernel launch, state
+ * resident in shared memory across the K substeps.  Asynchronous on the batch's stream. */
+PX_API int pxBatchStep(PxBatch *b, uint32_t kSubsteps);
+
+/* Same, bracketed by CUDA events on the launching stream; blocks; *ms = device time. */
+PX_API int pxBatchStepTimed(PxBatch *b, uint32_t kSubsteps, float *ms);
+
+/* Wait for the stream; returns the number of worlds with statOverflow != 0 (or < 0). */
+PX_API int pxBatchSync(PxBatch *b);
+
+/* Sync, then write position, velocity, angularVelocity, orientationAngle, orientation, aabb,
+ * force, torque, sleepTime, flags and the dynamic activeIndices back into host worlds
+ * [first, first + n), plus PxWorld.contacts statistics.  Device -> host direction of
+ * everything pxWorldStepWithDt mutates (PxBody fields, src/includes/px_body.h:82-120). */
+PX_API int pxBatchReadback(PxBatch *b, struct PxWorld *const *worlds, uint32_t first, uint32_t n, uint32_t flags);
+
+/* ------------------------------------------------------------- control path (queued, K=1..) */
+/* Applied in call order at the start of the next pxBatchStep, before its first substep.
+ * body = slot (PxBody.worldIndex) of a dynamic body; world = index in the batch or
+ * PX_ALL_WORLDS for the setters. */
+#define PX_ALL_WORLDS 0xffffffffu
+/* px->body->applyImpulse: scales by the unit, v += J*iM, w += cross(c, J)*iI, wakes the body
+ * (src/px_body_api.c:37-42, src/px_body.c:147-156, 195-202) */
+PX_API int pxBatchApplyImpulse(PxBatch *b, uint32_t world, uint32_t body, float ix, float iy, float cx, float cy);
+/* px->body->applyForce (src/px_body_api.c:20-26, src/px_body.c:158-165) */
+PX_API int pxBatchApplyForce(PxBatch *b, uint32_t world, uint32_t body, float fx, float fy, float cx, float cy);
+/* px->world->setGravity: stores (x, y) * unit (src/px_world.c:57-63) */
+PX_API int pxBatchSetGravity(PxBatch *b, uint32_t world, float x, float y);
+/* px->world->setIterations (src/px_world.c:65-71) */
+PX_API int pxBatchSetIterations(PxBatch *b, uint32_t world, uint32_t iterations);
+
+/* ------------------------------------------------------------------ raw blocks (SoA level) */
+
+PX_API int pxBatchGetLayout(const PxBatch *b, PxBatchLayout *out);
+/* Pinned host staging of the two blocks (layout above); valid until pxBatchFree. */
+PX_API void *pxBatchHostMutable(PxBatch *b);
+PX_API void *pxBatchHostImmutable(PxBatch *b);
+/* Async copies of worlds [first, first + n) between host staging (or `host` if non-NULL,
+ * same layout, ideally pinned) and HBM on the batch's stream. */
+PX_API int pxBatchMutableH2D(PxBatch *b, const void *host, uint32_t first, uint32_t n);
+PX_API int pxBatchMutableD2H(PxBatch *b, void *host, uint32_t first, uint32_t n);
+PX_API int pxBatchImmutableH2D(PxBatch *b, const void *host, uint32_t first, uint32_t n);
+/* Copy the trace block of worlds [first, first + n) into `host` (n * traceStride bytes). */
+PX_API int pxBatchTraceD2H(PxBatch *b, void *host, uint32_t first, uint32_t n);
+/* Device pointers (for zero-copy consumers on the same GPU), as integers */
+PX_API uint64_t pxBatchDeviceMutable(PxBatch *b);
+PX_API uint64_t pxBatchDeviceImmutable(PxBatch *b);
+/* kernels launched by this batch since creation (bench.py's gpu_launches) */
+PX_API uint64_t pxBatchLaunchCount(const PxBatch *b);
+/* occupancy facts of the step kernel for this layout: CTAs per SM, dynamic smem bytes, threads */
+PX_API int pxBatchKernelInfo(const PxBatch *b, int *ctasPerSm, int *smemBytes, int *threads, int *numSms);
+
+/* Compute a layout from capacities without touching a GPU (host-only; used by the packer,
+ * the oracle and tests). */
+PX_API int pxBatchComputeLayout(uint32_t nWorlds, const PxBatchDesc *desc, PxBatchLayout *out);
+
+/* Host-only AoS <-> SoA conversion against an arbitrary buffer pair (no GPU needed). */
+PX_API int pxPackWorlds(const PxBatchLayout *layout, struct PxWorld *const *worlds, uint32_t n, void *mut, void *imm);
+PX_API int pxUnpackWorlds(const PxBatchLayout *layout, struct PxWorld *const *worlds, uint32_t n, const void *mut, uint32_t flags);
+/* Capacities the given worlds need (fills desc.max* that are 0). */
+PX_API int pxBatchFitDesc(struct PxWorld *const *worlds, uint32_t n, PxBatchDesc *desc);
+
+PX_API const char *pxBatchLastError(void);
+PX_API const char *pxBatchVersion(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PX_BATCH_H */

@@ -1,0 +1,397 @@
+/*
+ * px_batch.cu -- the C-ABI batch layer (include/px_batch.h): device memory, pinned staging,
+ * stream, command queue and launches for one batch of worlds on one B200.
+ *
+ * There is no CPU path here.  Every stepping entry point launches the sm_100a kernel in
+ * px_step.cu or fails with an error; the AoS<->SoA conversion (px_pack.c) is the only host
+ * arithmetic and it only moves values.
+ */
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "px_batch.h"
+#include "px_internal.h"
+#include "px_step.cuh"
+
+struct PxBatch {
+  PxBatchLayout L;
+  PxSmemPlan plan;
+  uint32_t flags;
+  int device;
+  cudaStream_t stream;
+  bool ownStream;
+  uint32_t threads;
+  uint8_t *dMut, *dImm, *dTrace;
+  float *dSin;
+  uint8_t *hMut, *hImm; /* pinned staging, same layout */
+  float sinTable[256];
+  /* control path */
+  std::vector<PxCommand> cmds, globalCmds;
+  uint32_t cmdSeq;
+  PxCommand *dCmds, *dGlobal;
+  uint32_t *dWorldStart;
+  size_t dCmdCap, dGlobalCap;
+  PxCommand *hCmds;
+  uint32_t *hWorldStart;
+  size_t hCmdCap;
+  uint64_t launches;
+  int ctasPerSm, numSms;
+};
+
+#define CU(call)                                                                                        \
+  do {                                                                                                  \
+    cudaError_t _e = (call);                                                                            \
+    if (_e != cudaSuccess) return pxSetError(-(int)_e - 1000, "%s: %s", #call, cudaGetErrorString(_e)); \
+  } while (0)
+
+static int useDevice(const PxBatch *b) {
+  CU(cudaSetDevice(b->device));
+  return 0;
+}
+
+extern "C" PxBatch *pxBatchCreate(uint32_t nWorlds, const PxBatchDesc *desc) {
+  if (!desc || nWorlds == 0) {
+    pxSetError(-1, "pxBatchCreate: need a descriptor and at least one world");
+    return nullptr;
+  }
+  PxBatch *b = new PxBatch();
+  memset(&b->L, 0, sizeof(b->L));
+  b->dMut = b->dImm = b->dTrace = nullptr;
+  b->dSin = nullptr;
+  b->hMut = b->hImm = nullptr;
+  b->dCmds = b->dGlobal = nullptr;
+  b->dWorldStart = nullptr;
+  b->hCmds = nullptr;
+  b->hWorldStart = nullptr;
+  b->dCmdCap = b->dGlobalCap = b->hCmdCap = 0;
+  b->cmdSeq = 0;
+  b->launches = 0;
+  b->stream = nullptr;
+  b->ownStream = false;
+  b->flags = desc->flags;
+  if (pxBatchComputeLayout(nWorlds, desc, &b->L) != 0) {
+    delete b;
+    return nullptr;
+  }
+  pxPlanSmem(&b->L, &b->plan);
+
+  auto fail = [&](const char *what, cudaError_t e) -> PxBatch * {
+    pxSetError(-(int)e - 1000, "pxBatchCreate: %s: %s", what, cudaGetErrorString(e));
+    pxBatchFree(b);
+    return nullptr;
+  };
+  cudaError_t e;
+  int dev = desc->device;
+  if (dev < 0) {
+    if ((e = cudaGetDevice(&dev)) != cudaSuccess) return fail("cudaGetDevice (is a CUDA device present?)", e);
+  }
+  b->device = dev;
+  if ((e = cudaSetDevice(dev)) != cudaSuccess) return fail("cudaSetDevice", e);
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, dev)) != cudaSuccess) return fail("cudaGetDeviceProperties", e);
+  b->numSms = prop.multiProcessorCount;
+  if (b->plan.total > (uint32_t)prop.sharedMemPerBlockOptin) {
+    pxSetError(-2, "pxBatchCreate: a world needs %u bytes of shared memory, the device offers %zu per CTA; lower the capacities",
+               b->plan.total, (size_t)prop.sharedMemPerBlockOptin);
+    pxBatchFree(b);
+    return nullptr;
+  }
+  if (desc->stream) {
+    b->stream = (cudaStream_t)desc->stream;
+  } else {
+    if ((e = cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
+    b->ownStream = true;
+  }
+  b->threads = desc->threads ? desc->threads : 256;
+  if (b->threads != 64 && b->threads != 128 && b->threads != 256) {
+    pxSetError(-1, "PxBatchDesc.threads must be 64, 128 or 256");
+    pxBatchFree(b);
+    return nullptr;
+  }
+
+  const size_t mutBytes = (size_t)nWorlds * b->L.mutStride, immBytes = (size_t)nWorlds * b->L.immStride;
+  if ((e = cudaMalloc(&b->dMut, mutBytes)) != cudaSuccess) return fail("cudaMalloc(mutable)", e);
+  if ((e = cudaMalloc(&b->dImm, immBytes)) != cudaSuccess) return fail("cudaMalloc(immutable)", e);
+  if ((e = cudaMemsetAsync(b->dMut, 0, mutBytes, b->stream)) != cudaSuccess) return fail("cudaMemset", e);
+  if ((e = cudaMemsetAsync(b->dImm, 0, immBytes, b->stream)) != cudaSuccess) return fail("cudaMemset", e);
+  if (b->flags & PX_BATCH_FLAG_TRACE) {
+    const size_t traceBytes = (size_t)nWorlds * b->L.traceStride;
+    if ((e = cudaMalloc(&b->dTrace, traceBytes)) != cudaSuccess) return fail("cudaMalloc(trace)", e);
+    if ((e = cudaMemsetAsync(b->dTrace, 0, traceBytes, b->stream)) != cudaSuccess) return fail("cudaMemset", e);
+  }
+  if ((e = cudaMallocHost(&b->hMut, mutBytes)) != cudaSuccess) return fail("cudaMallocHost(mutable)", e);
+  if ((e = cudaMallocHost(&b->hImm, immBytes)) != cudaSuccess) return fail("cudaMallocHost(immutable)", e);
+  memset(b->hMut, 0, mutBytes);
+  memset(b->hImm, 0, immBytes);
+
+  /* the sine table is the host's: pxInitSinTable, reference px_math.h:213-218 */
+  if (desc->sinTable) {
+    memcpy(b->sinTable, desc->sinTable, sizeof(b->sinTable));
+  } else {
+    for (int i = 0; i < 256; i++) b->sinTable[i] = sinf((i * 3.141592741f * 2.0f) / 256);
+  }
+  if ((e = cudaMalloc(&b->dSin, sizeof(b->sinTable))) != cudaSuccess) return fail("cudaMalloc(sin)", e);
+  if ((e = cudaMemcpyAsync(b->dSin, b->sinTable, sizeof(b->sinTable), cudaMemcpyHostToDevice, b->stream)) != cudaSuccess)
+    return fail("cudaMemcpy(sin)", e);
+
+  PxStepParams P;
+  memset(&P, 0, sizeof(P));
+  P.L = b->L;
+  P.S = b->plan;
+  b->ctasPerSm = 0;
+  int occ = 0;
+  if (pxStepOccupancy(&P, b->threads, &occ) == 0) b->ctasPerSm = occ;
+  if ((e = cudaStreamSynchronize(b->stream)) != cudaSuccess) return fail("cudaStreamSynchronize", e);
+  return b;
+}
+
+extern "C" PxBatch *pxBatchNew(struct PxWorld *const *worlds, uint32_t nWorlds, const PxBatchDesc *desc) {
+  if (!worlds || !desc || nWorlds == 0) {
+    pxSetError(-1, "pxBatchNew: need worlds and a descriptor");
+    return nullptr;
+  }
+  PxBatchDesc d = *desc;
+  if (pxBatchFitDesc(worlds, nWorlds, &d) != 0) return nullptr;
+  PxBatch *b = pxBatchCreate(nWorlds, &d);
+  if (!b) return nullptr;
+  if (pxBatchUpload(b, worlds, 0, nWorlds) != 0) {
+    pxBatchFree(b);
+    return nullptr;
+  }
+  return b;
+}
+
+extern "C" void pxBatchFree(PxBatch *b) {
+  if (!b) return;
+  cudaSetDevice(b->device);
+  if (b->stream) cudaStreamSynchronize(b->stream);
+  cudaFree(b->dMut);
+  cudaFree(b->dImm);
+  cudaFree(b->dTrace);
+  cudaFree(b->dSin);
+  cudaFree(b->dCmds);
+  cudaFree(b->dGlobal);
+  cudaFree(b->dWorldStart);
+  cudaFreeHost(b->hMut);
+  cudaFreeHost(b->hImm);
+  cudaFreeHost(b->hCmds);
+  cudaFreeHost(b->hWorldStart);
+  if (b->ownStream && b->stream) cudaStreamDestroy(b->stream);
+  delete b;
+}
+
+static int checkRange(const PxBatch *b, uint32_t first, uint32_t n, const char *who) {
+  if (!b) return pxSetError(-1, "%s: NULL batch", who);
+  if (first > b->L.nWorlds || n > b->L.nWorlds - first) return pxSetError(-1, "%s: worlds [%u, %u) out of range (%u)", who, first, first + n, b->L.nWorlds);
+  return 0;
+}
+
+extern "C" int pxBatchMutableH2D(PxBatch *b, const void *host, uint32_t first, uint32_t n) {
+  if (checkRange(b, first, n, "pxBatchMutableH2D")) return -1;
+  if (useDevice(b)) return -1;
+  const uint8_t *src = host ? (const uint8_t *)host : b->hMut + (size_t)first * b->L.mutStride;
+  CU(cudaMemcpyAsync(b->dMut + (size_t)first * b->L.mutStride, src, (size_t)n * b->L.mutStride, cudaMemcpyHostToDevice, b->stream));
+  return 0;
+}
+
+extern "C" int pxBatchMutableD2H(PxBatch *b, void *host, uint32_t first, uint32_t n) {
+  if (checkRange(b, first, n, "pxBatchMutableD2H")) return -1;
+  if (useDevice(b)) return -1;
+  uint8_t *dst = host ? (uint8_t *)host : b->hMut + (size_t)first * b->L.mutStride;
+  CU(cudaMemcpyAsync(dst, b->dMut + (size_t)first * b->L.mutStride, (size_t)n * b->L.mutStride, cudaMemcpyDeviceToHost, b->stream));
+  return 0;
+}
+
+extern "C" int pxBatchImmutableH2D(PxBatch *b, const void *host, uint32_t first, uint32_t n) {
+  if (checkRange(b, first, n, "pxBatchImmutableH2D")) return -1;
+  if (useDevice(b)) return -1;
+  const uint8_t *src = host ? (const uint8_t *)host : b->hImm + (size_t)first * b->L.immStride;
+  CU(cudaMemcpyAsync(b->dImm + (size_t)first * b->L.immStride, src, (size_t)n * b->L.immStride, cudaMemcpyHostToDevice, b->stream));
+  return 0;
+}
+
+extern "C" int pxBatchTraceD2H(PxBatch *b, void *host, uint32_t first, uint32_t n) {
+  if (checkRange(b, first, n, "pxBatchTraceD2H")) return -1;
+  if (!b->dTrace) return pxSetError(-1, "pxBatchTraceD2H: the batch was created without PX_BATCH_FLAG_TRACE");
+  if (useDevice(b)) return -1;
+  CU(cudaMemcpyAsync(host, b->dTrace + (size_t)first * b->L.traceStride, (size_t)n * b->L.traceStride, cudaMemcpyDeviceToHost, b->stream));
+  CU(cudaStreamSynchronize(b->stream));
+  return 0;
+}
+
+extern "C" int pxBatchUpload(PxBatch *b, struct PxWorld *const *worlds, uint32_t first, uint32_t n) {
+  if (checkRange(b, first, n, "pxBatchUpload")) return -1;
+  if (useDevice(b)) return -1;
+  CU(cudaStreamSynchronize(b->stream)); /* staging may still be the source of an earlier copy */
+  int rc = pxPackWorlds(&b->L, worlds, n, b->hMut + (size_t)first * b->L.mutStride, b->hImm + (size_t)first * b->L.immStride);
+  if (rc != 0) return rc;
+  if (pxBatchMutableH2D(b, nullptr, first, n)) return -1;
+  if (pxBatchImmutableH2D(b, nullptr, first, n)) return -1;
+  return 0;
+}
+
+extern "C" int pxBatchSync(PxBatch *b) {
+  if (!b) return pxSetError(-1, "pxBatchSync: NULL batch");
+  if (useDevice(b)) return -1;
+  CU(cudaStreamSynchronize(b->stream));
+  return 0;
+}
+
+extern "C" int pxBatchReadback(PxBatch *b, struct PxWorld *const *worlds, uint32_t first, uint32_t n, uint32_t flags) {
+  if (checkRange(b, first, n, "pxBatchReadback")) return -1;
+  if (pxBatchMutableD2H(b, nullptr, first, n)) return -1;
+  CU(cudaStreamSynchronize(b->stream));
+  return pxUnpackWorlds(&b->L, worlds, n, b->hMut + (size_t)first * b->L.mutStride, flags);
+}
+
+/* ------------------------------------------------------------------------- commands */
+static int pushCommand(PxBatch *b, uint32_t world, uint32_t op, uint32_t body, float a, float c0, float c1, float c2, const char *who) {
+  if (!b) return pxSetError(-1, "%s: NULL batch", who);
+  if (world != PX_ALL_WORLDS && world >= b->L.nWorlds) return pxSetError(-1, "%s: world %u out of range", who, world);
+  if (body >= b->L.maxDynamic) return pxSetError(-1, "%s: body slot %u out of range", who, body);
+  PxCommand c;
+  c.world = world;
+  c.op = op | (body << 8);
+  c.seq = b->cmdSeq++;
+  c.a = a;
+  c.b = c0;
+  c.c = c1;
+  c.d = c2;
+  if (world == PX_ALL_WORLDS) {
+    b->globalCmds.push_back(c);
+  } else {
+    b->cmds.push_back(c);
+  }
+  return 0;
+}
+
+extern "C" int pxBatchApplyImpulse(PxBatch *b, uint32_t world, uint32_t body, float ix, float iy, float cx, float cy) {
+  if (world == PX_ALL_WORLDS) return pxSetError(-1, "pxBatchApplyImpulse: needs a world index");
+  return pushCommand(b, world, PX_CMD_IMPULSE, body, ix, iy, cx, cy, "pxBatchApplyImpulse");
+}
+extern "C" int pxBatchApplyForce(PxBatch *b, uint32_t world, uint32_t body, float fx, float fy, float cx, float cy) {
+  if (world == PX_ALL_WORLDS) return pxSetError(-1, "pxBatchApplyForce: needs a world index");
+  return pushCommand(b, world, PX_CMD_FORCE, body, fx, fy, cx, cy, "pxBatchApplyForce");
+}
+extern "C" int pxBatchSetGravity(PxBatch *b, uint32_t world, float x, float y) {
+  return pushCommand(b, world, PX_CMD_GRAVITY, 0, x, y, 0, 0, "pxBatchSetGravity");
+}
+extern "C" int pxBatchSetIterations(PxBatch *b, uint32_t world, uint32_t iterations) {
+  return pushCommand(b, world, PX_CMD_ITERATIONS, 0, (float)(iterations & 255u), 0, 0, 0, "pxBatchSetIterations");
+}
+
+static int flushCommands(PxBatch *b) {
+  const size_t n = b->cmds.size(), ng = b->globalCmds.size();
+  if (n == 0 && ng == 0) return 0;
+  const uint32_t W = b->L.nWorlds;
+  if (n > 0) {
+    /* counting sort by world keeps submission order inside a world */
+    if (b->hCmdCap < n) {
+      cudaFreeHost(b->hCmds);
+      b->hCmds = nullptr;
+      b->hCmdCap = std::max(n, b->hCmdCap * 2);
+      CU(cudaMallocHost(&b->hCmds, b->hCmdCap * sizeof(PxCommand)));
+    }
+    if (!b->hWorldStart) CU(cudaMallocHost(&b->hWorldStart, (size_t)(W + 1) * sizeof(uint32_t)));
+    CU(cudaStreamSynchronize(b->stream)); /* pinned buffers may be in flight */
+    memset(b->hWorldStart, 0, (size_t)(W + 1) * sizeof(uint32_t));
+    for (const PxCommand &c : b->cmds) b->hWorldStart[c.world + 1]++;
+    for (uint32_t w = 0; w < W; w++) b->hWorldStart[w + 1] += b->hWorldStart[w];
+    std::vector<uint32_t> at(b->hWorldStart, b->hWorldStart + W);
+    for (const PxCommand &c : b->cmds) b->hCmds[at[c.world]++] = c;
+    if (b->dCmdCap < n) {
+      cudaFree(b->dCmds);
+      b->dCmds = nullptr;
+      b->dCmdCap = b->hCmdCap;
+      CU(cudaMalloc(&b->dCmds, b->dCmdCap * sizeof(PxCommand)));
+    }
+    if (!b->dWorldStart) CU(cudaMalloc(&b->dWorldStart, (size_t)(W + 1) * sizeof(uint32_t)));
+    CU(cudaMemcpyAsync(b->dCmds, b->hCmds, n * sizeof(PxCommand), cudaMemcpyHostToDevice, b->stream));
+    CU(cudaMemcpyAsync(b->dWorldStart, b->hWorldStart, (size_t)(W + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, b->stream));
+  }
+  if (ng > 0) {
+    if (b->dGlobalCap < ng) {
+      cudaFree(b->dGlobal);
+      b->dGlobal = nullptr;
+      b->dGlobalCap = std::max(ng, b->dGlobalCap * 2);
+      CU(cudaMalloc(&b->dGlobal, b->dGlobalCap * sizeof(PxCommand)));
+    }
+    /* pageable source: the copy is staged by the runtime before the call returns */
+    CU(cudaMemcpyAsync(b->dGlobal, b->globalCmds.data(), ng * sizeof(PxCommand), cudaMemcpyHostToDevice, b->stream));
+  }
+  int rc = pxLaunchCommands(&b->L, b->dMut, b->dImm, n ? b->dCmds : nullptr, n ? b->dWorldStart : nullptr,
+                            ng ? b->dGlobal : nullptr, (uint32_t)ng, b->stream);
+  if (rc != 0) return pxSetError(-rc - 1000, "command kernel: %s", cudaGetErrorString((cudaError_t)rc));
+  b->launches++;
+  b->cmds.clear();
+  b->globalCmds.clear();
+  return 0;
+}
+
+/* --------------------------------------------------------------------------- stepping */
+extern "C" int pxBatchStep(PxBatch *b, uint32_t kSubsteps) {
+  if (!b) return pxSetError(-1, "pxBatchStep: NULL batch");
+  if (useDevice(b)) return -1;
+  if (flushCommands(b)) return -1;
+  if (kSubsteps == 0) return 0;
+  PxStepParams P;
+  P.L = b->L;
+  P.S = b->plan;
+  P.mut = b->dMut;
+  P.imm = b->dImm;
+  P.trace = b->dTrace;
+  P.sinTable = b->dSin;
+  P.kSubsteps = kSubsteps;
+  P.flags = b->flags;
+  int rc = pxLaunchStep(&P, b->threads, b->stream);
+  if (rc != 0) return pxSetError(-rc - 1000, "step kernel launch: %s", cudaGetErrorString((cudaError_t)rc));
+  b->launches++;
+  return 0;
+}
+
+extern "C" int pxBatchStepTimed(PxBatch *b, uint32_t kSubsteps, float *ms) {
+  if (!b) return pxSetError(-1, "pxBatchStepTimed: NULL batch");
+  if (useDevice(b)) return -1;
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0));
+  CU(cudaEventCreate(&e1));
+  CU(cudaStreamSynchronize(b->stream));
+  CU(cudaEventRecord(e0, b->stream));
+  int rc = pxBatchStep(b, kSubsteps);
+  CU(cudaEventRecord(e1, b->stream));
+  cudaError_t err = cudaEventSynchronize(e1);
+  float t = 0;
+  if (err == cudaSuccess) err = cudaEventElapsedTime(&t, e0, e1);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  if (rc != 0) return rc;
+  if (err != cudaSuccess) return pxSetError(-(int)err - 1000, "pxBatchStepTimed: %s", cudaGetErrorString(err));
+  if (ms) *ms = t;
+  return 0;
+}
+
+/* ------------------------------------------------------------------------------ queries */
+extern "C" int pxBatchGetLayout(const PxBatch *b, PxBatchLayout *out) {
+  if (!b || !out) return pxSetError(-1, "pxBatchGetLayout: NULL argument");
+  *out = b->L;
+  return 0;
+}
+extern "C" void *pxBatchHostMutable(PxBatch *b) { return b ? b->hMut : nullptr; }
+extern "C" void *pxBatchHostImmutable(PxBatch *b) { return b ? b->hImm : nullptr; }
+extern "C" uint64_t pxBatchDeviceMutable(PxBatch *b) { return b ? (uint64_t)(uintptr_t)b->dMut : 0; }
+extern "C" uint64_t pxBatchDeviceImmutable(PxBatch *b) { return b ? (uint64_t)(uintptr_t)b->dImm : 0; }
+extern "C" uint64_t pxBatchLaunchCount(const PxBatch *b) { return b ? b->launches : 0; }
+extern "C" int pxBatchKernelInfo(const PxBatch *b, int *ctasPerSm, int *smemBytes, int *threads, int *numSms) {
+  if (!b) return pxSetError(-1, "pxBatchKernelInfo: NULL batch");
+  if (ctasPerSm) *ctasPerSm = b->ctasPerSm;
+  if (smemBytes) *smemBytes = (int)b->plan.total;
+  if (threads) *threads = (int)b->threads;
+  if (numSms) *numSms = b->numSms;
+  return 0;
+}

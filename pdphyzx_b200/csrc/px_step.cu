@@ -1,0 +1,1305 @@
+/*
+ * px_step.cu -- the pdphyzx world substep as one fused sm_100a kernel.
+ *
+ * One CTA per world.  The CTA loads its world's SoA block from HBM with coalesced 16-byte
+ * accesses, keeps all body and manifold state in shared memory across K fused substeps
+ * (K x pxWorldStepWithDt, reference src/px_world.c:410-420) and stores the mutable rows back.
+ * No tensor cores: nothing here is a dense contraction.  Compile with -fmad=false: every
+ * multiply-add must round twice, exactly like the scalar CPU build.
+ *
+ * Phases of a substep and the reference code each one restates
+ *   A  AABBs, stable order by aabb.min.x           px_body_array.c:81-102, px_circle.c:43-48
+ *   B  sweep: ordered AABB-pass pair list, binned   px_world.c:355-392, px_body.c:126-145,
+ *      by shape pair                                px_body_array.c:104-131
+ *   C  narrowphase + manifold init + resting        px_collision.c:15-465, px_manifold.c:12-92
+ *      contact + sleep flags from manifolds         px_world.c:147-177
+ *   D  per-body ordered manifold lists (CSR),       (order = manifold pool order,
+ *      integrate forces                             px_world.c:327-345), px_body.c:167-179
+ *   E  sequential impulses, `iterations` sweeps     px_world.c:249-260, px_manifold.c:98-215
+ *   F  integrate velocities, positional             px_body.c:181-188, px_manifold.c:217-255,
+ *      correction, sleep update, clear forces       px_world.c:179-219, 302-311
+ *
+ * Order preservation.  The solver is Gauss-Seidel over the manifold pool; two manifold
+ * visits commute bit-exactly iff they share no dynamic body (statics are never written,
+ * px_body.c:148).  Phase D builds, for every dynamic body, the list of manifolds touching it
+ * in pool order; phase E is a dataflow execution of the visit DAG those lists define: a
+ * visit runs when it is at the head of the lists of both its bodies.  One warp pops up to 32
+ * ready visits per round, so lanes stay dense, and iterations pipeline into each other
+ * exactly as far as the dependencies allow.  Any such schedule produces the same bits as the
+ * sequential loop.  Positional correction (px_manifold.c:217-255) depends only on the
+ * manifold's normal/penetration and inverse masses, so each body sums its terms in list
+ * order on its own thread.
+ */
+#include <cuda_runtime.h>
+#include <float.h>
+#include <stdint.h>
+
+#include "px_step.cuh"
+
+#define PX_FLAG_SLEEPING 8u /* PX_BODY_FLAG_SLEEPING, px_body.h:67 */
+#define PX_OVERFLOW_INTERNAL 0x80000000u
+
+/* ------------------------------------------------------------------ arithmetic contract */
+/* px_math.h:50-114 -- bit hack + one Newton step; rcp = rsqrt^2; div = a*rcp(b) */
+__device__ __forceinline__ float fRsqrt(float x) {
+  float y = __uint_as_float(0x5f3759dfu - (__float_as_uint(x) >> 1));
+  return y * (1.5f - (x * 0.5f * y * y));
+}
+__device__ __forceinline__ float fRcp(float x) {
+  float r = fRsqrt(x);
+  return r * r;
+}
+__device__ __forceinline__ float fDiv(float a, float b) { return a * fRcp(b); }
+__device__ __forceinline__ float fSqrt(float x) { return x * fRsqrt(x); }
+
+#define D_PI 3.141592741f
+#define D_2PI (D_PI * 2.0f)
+
+/* px_math.h:226-241; the table is the host's (glibc sinf), never recomputed on the device */
+__device__ __forceinline__ float fSin(const float *table, float radians) {
+  radians = fmodf(radians, D_2PI);
+  if (radians < 0) radians += D_2PI;
+  float position = fDiv(radians, D_2PI / 256);
+  int ip = (int)position;
+  int i1 = ip & 255;
+  int i2 = (i1 + 1) & 255;
+  float fraction = position - (float)ip;
+  return table[i1] * (1.0f - fraction) + table[i2] * fraction;
+}
+
+struct V2 {
+  float x, y;
+};
+__device__ __forceinline__ V2 v2(float x, float y) { return V2{x, y}; }
+__device__ __forceinline__ V2 operator+(V2 a, V2 b) { return v2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ V2 operator-(V2 a, V2 b) { return v2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ V2 operator*(V2 a, float s) { return v2(a.x * s, a.y * s); }
+__device__ __forceinline__ V2 operator-(V2 a) { return v2(-a.x, -a.y); }
+__device__ __forceinline__ float dot(V2 a, V2 b) { return a.x * b.x + a.y * b.y; }
+__device__ __forceinline__ float cross(V2 a, V2 b) { return a.x * b.y - a.y * b.x; }
+__device__ __forceinline__ float lensq(V2 a) { return a.x * a.x + a.y * a.y; }
+
+struct M2 {
+  float m00, m01, m10, m11;
+};
+__device__ __forceinline__ V2 mul(M2 m, V2 v) { return v2(m.m00 * v.x + m.m01 * v.y, m.m10 * v.x + m.m11 * v.y); }
+__device__ __forceinline__ V2 mulT(M2 m, V2 v) { return v2(m.m00 * v.x + m.m10 * v.y, m.m01 * v.x + m.m11 * v.y); }
+
+/* pxVec2Normalize, px_vec2.h:459-472 */
+__device__ __forceinline__ V2 normalize(V2 v, float eps) {
+  float len = fSqrt(lensq(v));
+  if (len <= eps) return v;
+  float inv = fRcp(len);
+  return v2(v.x * inv, v.y * inv);
+}
+
+/* ----------------------------------------------------------------------- shared views */
+struct Sm {
+  float *px, *py, *m00, *m01, *m10, *m11, *rad, *e, *sf, *df;
+  uint32_t *shape;
+  float *vx, *vy, *av, *iM, *iI, *angle, *fx, *fy, *tq, *slp;
+  uint8_t *flags, *order, *order2, *posOf, *restFlag, *wakeFlag;
+  float4 *verts;
+  float *sinT;
+  PxWorldHeader *hdr;
+  uint32_t *misc;
+  unsigned long long *scan;
+  float *mnx, *mny, *mpen, *mc0x, *mc0y, *mc1x, *mc1y, *msf, *mdf, *me;
+  uint32_t *mids;
+  float *sMinX, *sMaxX, *sMinY, *sMaxY;
+  uint8_t *sSlot, *sSleep;
+  float *stMinX, *stMaxX, *stMinY, *stMaxY;
+  uint16_t *list;
+  uint8_t *arr;
+  uint16_t *queue;
+  uint32_t *bins;
+  uint16_t *cnt, *cntB, *listStart, *cursor;
+  uint32_t *remaining;
+  unsigned long long *stash;
+  uint16_t *validSlot;
+  uint32_t *maskB;
+  uint16_t *base;
+};
+
+/* misc[] slots */
+enum { MI_MCOUNT = 0, MI_QTAIL, MI_OVERFLOW, MI_UNSORTED, MI_SLEEPING, MI_NPAIRS, MI_BIN0, MI_BIN1, MI_BIN2, MI_BIN3 };
+
+/* manifold ids word: slotA | bodyIdB << 8 | bIsDynamic << 17 | contactCount << 18 */
+#define MID_A(w) ((w) & 0xffu)
+#define MID_B(w) (((w) >> 8) & 0x1ffu)
+#define MID_BDYN(w) (((w) >> 17) & 1u)
+#define MID_COUNT(w) (((w) >> 18) & 3u)
+
+/* bins word: pairSeq << 17 | slotA << 9 | bodyIdB */
+#define BIN_SEQ(w) ((w) >> 17)
+#define BIN_A(w) (((w) >> 9) & 0xffu)
+#define BIN_B(w) ((w) & 0x1ffu)
+
+struct DBody {
+  V2 pos;
+  M2 rot;
+  float radius;
+  uint32_t nverts;
+  const float4 *v; /* {vertex.x, vertex.y, normal.x, normal.y} */
+};
+
+__device__ __forceinline__ DBody loadBody(const Sm &s, uint32_t id) {
+  DBody b;
+  b.pos = v2(s.px[id], s.py[id]);
+  b.rot = M2{s.m00[id], s.m01[id], s.m10[id], s.m11[id]};
+  b.radius = s.rad[id];
+  uint32_t sh = s.shape[id];
+  b.nverts = PX_SHAPE_COUNT(sh);
+  b.v = s.verts + PX_SHAPE_OFFSET(sh);
+  return b;
+}
+
+struct Contact {
+  V2 normal;
+  float pen;
+  V2 c0, c1;
+  uint32_t count;
+};
+
+/* pxCollideCircles, px_collision.c:15-52 */
+__device__ __forceinline__ void collideCircles(const DBody &A, const DBody &B, float eps, Contact &m) {
+  V2 n = B.pos - A.pos;
+  float ra = A.radius, rb = B.radius;
+  float combined = ra + rb;
+  float d2 = lensq(n);
+  m.count = 0;
+  if (d2 >= combined * combined) return;
+  float dist = fSqrt(d2);
+  if (dist < eps) {
+    m.pen = ra;
+    m.normal = v2(1.0f, 0.0f);
+    m.c0 = A.pos;
+    m.count = 1;
+    return;
+  }
+  m.pen = combined - dist;
+  float inv = fRcp(dist); /* pxVec2Divf: each component times pxFastRcp(dist) */
+  m.normal = v2(n.x * inv, n.y * inv);
+  m.c0 = A.pos + m.normal * ra;
+  m.count = 1;
+}
+
+/* pxCollideCirclePolygon, px_collision.c:61-178.  C is the circle, P the polygon; the normal
+ * points from the circle to the polygon. */
+__device__ void collideCirclePolygon(const DBody &C, const DBody &P, float eps, Contact &m) {
+  m.count = 0;
+  const float radius = C.radius;
+  const M2 rot = P.rot;
+  V2 center = mulT(rot, C.pos - P.pos);
+
+  float separation = -FLT_MAX;
+  uint32_t face = 0;
+  for (uint32_t i = 0; i < P.nverts; i++) {
+    float4 vn = P.v[i];
+    float sdist = dot(v2(vn.z, vn.w), center - v2(vn.x, vn.y));
+    if (sdist > radius) return;
+    if (sdist > separation) {
+      separation = sdist;
+      face = i;
+    }
+  }
+  float4 f1 = P.v[face];
+  if (separation < eps) { /* centre inside */
+    V2 n = -mul(rot, v2(f1.z, f1.w));
+    m.normal = n;
+    m.pen = radius;
+    m.c0 = C.pos + n * radius;
+    m.count = 1;
+    return;
+  }
+  float4 f2 = P.v[face + 1 < P.nverts ? face + 1 : 0];
+  V2 v1 = v2(f1.x, f1.y), v2_ = v2(f2.x, f2.y);
+  float radiusSq = radius * radius;
+  m.pen = radius - separation;
+
+  float dot1 = dot(center - v1, v2_ - v1);
+  if (dot1 <= 0) {
+    V2 d = center - v1;
+    if (dot(d, d) > radiusSq) return;
+    m.normal = normalize(mul(rot, v1 - center), eps);
+    m.c0 = mul(rot, v1) + P.pos;
+    m.count = 1;
+    return;
+  }
+  float dot2 = dot(center - v2_, v1 - v2_);
+  if (dot2 <= 0) {
+    V2 d = center - v2_;
+    if (dot(d, d) > radiusSq) return;
+    m.normal = normalize(mul(rot, v2_ - center), eps);
+    m.c0 = mul(rot, v2_) + P.pos;
+    m.count = 1;
+    return;
+  }
+  V2 n = v2(f1.z, f1.w);
+  if (dot(center - v1, n) > radius) return;
+  n = -mul(rot, n);
+  m.normal = n;
+  m.c0 = C.pos + n * radius;
+  m.count = 1;
+}
+
+/* pxFindAxisLeastPenetration (px_collision.c:180-218) with pxPolygonGetSupport
+ * (px_polygon.c:326-347) inlined */
+__device__ float leastPenetration(uint32_t &faceIndex, const DBody &A, const DBody &B, float epsSq) {
+  float bestD = -FLT_MAX;
+  uint32_t bestI = 0;
+  for (uint32_t i = 0; i < A.nverts; i++) {
+    float4 an = A.v[i];
+    V2 nw = mul(A.rot, v2(an.z, an.w));
+    V2 n = mulT(B.rot, nw);
+    V2 dir = -n;
+    V2 sup = v2(0.0f, 0.0f);
+    if (!(lensq(dir) < epsSq)) {
+      float best = -FLT_MAX;
+      float4 b0 = B.v[0];
+      sup = v2(b0.x, b0.y);
+      for (uint32_t k = 0; k < B.nverts; k++) {
+        float4 bv = B.v[k];
+        float proj = bv.x * dir.x + bv.y * dir.y;
+        if (proj > best) {
+          best = proj;
+          sup = v2(bv.x, bv.y);
+        }
+      }
+    }
+    V2 v = mul(A.rot, v2(an.x, an.y)) + A.pos;
+    v = v - B.pos;
+    v = mulT(B.rot, v);
+    float d = dot(n, sup - v);
+    if (d > bestD) {
+      bestD = d;
+      bestI = i;
+    }
+  }
+  faceIndex = bestI;
+  return bestD;
+}
+
+/* pxClipSegmentToLine, px_collision.c:261-290 (IEEE division) */
+__device__ __forceinline__ int clipSegment(V2 out[2], const V2 in0, const V2 in1, V2 normal, float offset) {
+  /* at most two points come out: opposite signs give the intersection plus one endpoint,
+   * equal signs give both endpoints or none */
+  int sp = 0;
+  float d1 = dot(normal, in0) - offset;
+  float d2 = dot(normal, in1) - offset;
+  if (d1 * d2 < 0.0f) {
+    float alpha = d1 / (d1 - d2);
+    out[sp] = in0 + (in1 - in0) * alpha;
+    sp++;
+  }
+  if (d2 <= 0.0f) out[sp++] = in1;
+  if (d1 <= 0.0f && sp < 2) out[sp++] = in0;
+  return sp;
+}
+
+/* pxCollidePolygons, px_collision.c:299-435 (pxFindIncidentFace :220-259 inlined) */
+__device__ void collidePolygons(const DBody &A, const DBody &B, float eps, float epsSq, Contact &m) {
+  m.count = 0;
+  uint32_t faceA, faceB;
+  float penA = leastPenetration(faceA, A, B, epsSq);
+  if (penA >= 0.0f) return;
+  float penB = leastPenetration(faceB, B, A, epsSq);
+  if (penB >= 0.0f) return;
+
+  const bool flip = !(penA >= penB * 0.95f + penA * 0.01f); /* pxBiasGt */
+  const DBody &ref = flip ? B : A;
+  const DBody &inc = flip ? A : B;
+  uint32_t refIndex = flip ? faceB : faceA;
+
+  /* incident face: most anti-parallel normal */
+  float4 rf = ref.v[refIndex];
+  V2 refNormalW = mul(ref.rot, v2(rf.z, rf.w));
+  V2 nInc = mulT(inc.rot, refNormalW);
+  uint32_t incFace = 0;
+  float minDot = FLT_MAX;
+  for (uint32_t i = 0; i < inc.nverts; i++) {
+    float4 iv = inc.v[i];
+    float d = nInc.x * iv.z + nInc.y * iv.w;
+    if (d < minDot) {
+      minDot = d;
+      incFace = i;
+    }
+  }
+  float4 i0 = inc.v[incFace];
+  float4 i1 = inc.v[(incFace + 1) % inc.nverts];
+  V2 inc0 = inc.pos + mul(inc.rot, v2(i0.x, i0.y));
+  V2 inc1 = inc.pos + mul(inc.rot, v2(i1.x, i1.y));
+
+  V2 ref0 = ref.pos + mul(ref.rot, v2(rf.x, rf.y));
+  float4 rf1 = ref.v[(refIndex + 1) % ref.nverts];
+  V2 ref1 = ref.pos + mul(ref.rot, v2(rf1.x, rf1.y));
+
+  V2 side = normalize(ref1 - ref0, eps);
+  V2 refNormal = v2(-side.y, side.x);
+  if (flip) refNormal = -refNormal;
+
+  float refC = dot(refNormal, ref0);
+  float negSide = -dot(side, ref0);
+  V2 clip1[2], clip2[2];
+  int cp = clipSegment(clip1, inc0, inc1, -side, negSide);
+  if (cp < 2) return;
+  float posSide = dot(side, ref1);
+  cp = clipSegment(clip2, clip1[0], clip1[1], side, posSide);
+  if (cp < 2) return;
+
+  m.normal = flip ? -refNormal : refNormal;
+  uint32_t n = 0;
+  float pen = 0.0f;
+  V2 c[2];
+  c[0] = c[1] = v2(0.0f, 0.0f);
+#pragma unroll
+  for (int i = 0; i < 2; i++) {
+    float separation = dot(refNormal, clip2[i]) - refC;
+    if (separation <= 0.0f) {
+      c[n] = clip2[i];
+      if (n == 0) {
+        pen = -separation;
+      } else {
+        pen += -separation;
+      }
+      n++;
+    }
+  }
+  if (n > 1) pen = fDiv(pen, (float)n);
+  m.pen = pen;
+  m.c0 = c[0];
+  m.c1 = c[1];
+  m.count = n;
+}
+
+/* ------------------------------------------------------------------------- block scan */
+/* exclusive prefix sum of a packed 4 x 16-bit counter word over the CTA, in thread order */
+template <int NT>
+__device__ __forceinline__ unsigned long long blockExclusiveScan(unsigned long long v, unsigned long long *scratch,
+                                                                 unsigned long long &total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned long long inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    unsigned long long t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) scratch[warp] = inc;
+  __syncthreads();
+  unsigned long long warpBase = 0, tot = 0;
+#pragma unroll
+  for (int w = 0; w < NT / 32; w++) {
+    unsigned long long t = scratch[w];
+    if (w < warp) warpBase += t;
+    tot += t;
+  }
+  __syncthreads();
+  total = tot;
+  return warpBase + inc - v;
+}
+
+/* pxBodyAABBsOverlap, px_body.c:126-145: strict comparisons, touching boxes overlap */
+__device__ __forceinline__ bool boxesOverlap(float aMinX, float aMinY, float aMaxX, float aMaxY, float bMinX, float bMinY,
+                                             float bMaxX, float bMaxY) {
+  if (aMaxX < bMinX || aMinX > bMaxX) return false;
+  if (aMaxY < bMinY || aMinY > bMaxY) return false;
+  return true;
+}
+
+/* pxBodyArrayFindFirstIndexAfterX, px_body_array.c:104-131: predicate on max.x over a list
+ * sorted by min.x, replicated literally */
+__device__ __forceinline__ uint32_t firstStaticAfterX(const float *stMaxX, uint32_t n, float minX) {
+  uint32_t low = 0, high = n;
+  while (low < high) {
+    uint32_t mid = low + (high - low) / 2;
+    if (stMaxX[mid] < minX) {
+      low = mid + 1;
+    } else {
+      high = mid;
+    }
+  }
+  return low;
+}
+
+/* pxManifoldApplyImpulse, px_manifold.c:98-215, for one manifold slot.  The caller
+ * guarantees nobody else touches the two bodies' velocities while this runs. */
+__device__ __forceinline__ void applyManifoldImpulse(const Sm &s, uint32_t ms, float eps) {
+  const uint32_t ids = s.mids[ms];
+  const uint32_t a = MID_A(ids), b = MID_B(ids), bdyn = MID_BDYN(ids), count = MID_COUNT(ids);
+  /* px_world.c:252-255: skip when both bodies sleep (statics never sleep) */
+  if (bdyn && (s.flags[a] & PX_FLAG_SLEEPING) && (s.flags[b] & PX_FLAG_SLEEPING)) return;
+
+  const V2 n = v2(s.mnx[ms], s.mny[ms]);
+  const float e = s.me[ms], sf = s.msf[ms], df = s.mdf[ms];
+  const V2 pa = v2(s.px[a], s.py[a]), pb = v2(s.px[b], s.py[b]);
+  const float iMA = s.iM[a], iIA = s.iI[a];
+  float iMB = 0.0f, iIB = 0.0f;
+  V2 va = v2(s.vx[a], s.vy[a]);
+  float wa = s.av[a];
+  V2 vb = v2(0.0f, 0.0f);
+  float wb = 0.0f;
+  if (bdyn) {
+    iMB = s.iM[b];
+    iIB = s.iI[b];
+    vb = v2(s.vx[b], s.vy[b]);
+    wb = s.av[b];
+  }
+  const float fcount = (float)count;
+
+  for (uint32_t i = 0; i < count; i++) {
+    V2 c = i == 0 ? v2(s.mc0x[ms], s.mc0y[ms]) : v2(s.mc1x[ms], s.mc1y[ms]);
+    V2 ra = c - pa, rb = c - pb;
+    V2 raPerp = v2(-ra.y, ra.x), rbPerp = v2(-rb.y, rb.x);
+    V2 rv = (vb + rbPerp * wb) - (va + raPerp * wa);
+    float vn = dot(rv, n);
+    if (vn > 0) continue;
+
+    float raCrossN = cross(ra, n), rbCrossN = cross(rb, n);
+    float invMassSum = iMA + iMB + raCrossN * raCrossN * iIA + rbCrossN * rbCrossN * iIB;
+    float normalMag = -(1.0f + e) * vn;
+    float denom = invMassSum * fcount;
+    float rcpDenom = fRcp(denom);
+    float j = normalMag * rcpDenom;
+    V2 impulse = n * j;
+    { /* pxBodyApplyImpulse(bodyA, -impulse, ra), px_body.c:147-156 */
+      V2 ni = -impulse;
+      va = v2(va.x + ni.x * iMA, va.y + ni.y * iMA);
+      wa = wa + cross(ra, ni) * iIA;
+    }
+    if (bdyn) {
+      vb = v2(vb.x + impulse.x * iMB, vb.y + impulse.y * iMB);
+      wb = wb + cross(rb, impulse) * iIB;
+    }
+
+    rv = (vb + rbPerp * wb) - (va + raPerp * wa);
+    V2 tangent = rv - n * dot(rv, n);
+    float tlen = fSqrt(lensq(tangent));
+    if (!(tlen > eps)) continue;
+    tangent = tangent * fRcp(tlen);
+    float tmag = -dot(rv, tangent);
+    float jt = tmag * rcpDenom; /* same denominator, same pxFastRcp value */
+    V2 friction;
+    if (fabsf(jt) < j * sf) {
+      friction = tangent * jt;
+    } else {
+      friction = tangent * (-j * df);
+    }
+    {
+      V2 nf = -friction;
+      va = v2(va.x + nf.x * iMA, va.y + nf.y * iMA);
+      wa = wa + cross(ra, nf) * iIA;
+    }
+    if (bdyn) {
+      vb = v2(vb.x + friction.x * iMB, vb.y + friction.y * iMB);
+      wb = wb + cross(rb, friction) * iIB;
+    }
+  }
+  s.vx[a] = va.x;
+  s.vy[a] = va.y;
+  s.av[a] = wa;
+  if (bdyn) {
+    s.vx[b] = vb.x;
+    s.vy[b] = vb.y;
+    s.av[b] = wb;
+  }
+}
+
+__device__ __forceinline__ void bindSmem(Sm &s, uint8_t *base, const PxSmemPlan &S) {
+#define BIND(field, type) s.field = (type *)(base + S.field)
+  BIND(px, float); BIND(py, float); BIND(m00, float); BIND(m01, float); BIND(m10, float); BIND(m11, float);
+  BIND(rad, float); BIND(e, float); BIND(sf, float); BIND(df, float); BIND(shape, uint32_t);
+  BIND(vx, float); BIND(vy, float); BIND(av, float); BIND(iM, float); BIND(iI, float);
+  BIND(angle, float); BIND(fx, float); BIND(fy, float); BIND(tq, float); BIND(slp, float);
+  BIND(flags, uint8_t); BIND(order, uint8_t); BIND(order2, uint8_t); BIND(posOf, uint8_t);
+  BIND(restFlag, uint8_t); BIND(wakeFlag, uint8_t);
+  BIND(verts, float4); BIND(sinT, float); BIND(hdr, PxWorldHeader); BIND(misc, uint32_t);
+  BIND(scan, unsigned long long);
+  BIND(mnx, float); BIND(mny, float); BIND(mpen, float); BIND(mc0x, float); BIND(mc0y, float);
+  BIND(mc1x, float); BIND(mc1y, float); BIND(msf, float); BIND(mdf, float); BIND(me, float); BIND(mids, uint32_t);
+  BIND(sMinX, float); BIND(sMaxX, float); BIND(sMinY, float); BIND(sMaxY, float);
+  BIND(sSlot, uint8_t); BIND(sSleep, uint8_t);
+  BIND(stMinX, float); BIND(stMaxX, float); BIND(stMinY, float); BIND(stMaxY, float);
+  BIND(list, uint16_t); BIND(arr, uint8_t); BIND(queue, uint16_t);
+  BIND(bins, uint32_t);
+  BIND(cnt, uint16_t); BIND(cntB, uint16_t); BIND(listStart, uint16_t); BIND(cursor, uint16_t); BIND(remaining, uint32_t);
+  BIND(stash, unsigned long long);
+  BIND(validSlot, uint16_t); BIND(maskB, uint32_t); BIND(base, uint16_t);
+#undef BIND
+}
+
+template <int NT>
+__device__ __forceinline__ void copyRows(float *dst, const float *src, uint32_t nFloats) {
+  /* 16-byte coalesced copy; nFloats is a multiple of 4 and both sides are 16-byte aligned */
+  const float4 *s4 = reinterpret_cast<const float4 *>(src);
+  float4 *d4 = reinterpret_cast<float4 *>(dst);
+  for (uint32_t i = threadIdx.x; i < nFloats / 4; i += NT) d4[i] = s4[i];
+}
+
+/* ============================================================================ kernel ==== */
+template <int NT>
+__global__ void __launch_bounds__(NT) pxStepKernel(const PxStepParams P) {
+  extern __shared__ __align__(16) uint8_t smemRaw[];
+  Sm s;
+  bindSmem(s, smemRaw, P.S);
+
+  const PxBatchLayout &L = P.L;
+  const uint32_t D = L.maxDynamic, S = L.maxStatic, MM = L.maxManifolds, MP = L.maxPairs;
+  const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  const uint32_t world = blockIdx.x;
+  uint8_t *gmut = P.mut + (size_t)world * L.mutStride;
+  const uint8_t *gimm = P.imm + (size_t)world * L.immStride;
+  const float eps = L.epsilon, epsSq = L.epsilonSq, allowedPen = L.allowedPenetration;
+  const uint32_t QMASK = P.S.qcap - 1;
+
+  /* ---------------------------------------------------------------- load (HBM -> smem) */
+  {
+    const float *gdyn = (const float *)(gmut + L.offDyn);
+    copyRows<NT>(s.px, gdyn + PX_DYN_PX * D, D);
+    copyRows<NT>(s.py, gdyn + PX_DYN_PY * D, D);
+    copyRows<NT>(s.vx, gdyn + PX_DYN_VX * D, D);
+    copyRows<NT>(s.vy, gdyn + PX_DYN_VY * D, D);
+    copyRows<NT>(s.av, gdyn + PX_DYN_AV * D, D);
+    copyRows<NT>(s.angle, gdyn + PX_DYN_ANGLE * D, D);
+    copyRows<NT>(s.fx, gdyn + PX_DYN_FX * D, D);
+    copyRows<NT>(s.fy, gdyn + PX_DYN_FY * D, D);
+    copyRows<NT>(s.tq, gdyn + PX_DYN_TORQUE * D, D);
+    copyRows<NT>(s.slp, gdyn + PX_DYN_SLEEP * D, D);
+    copyRows<NT>(s.m00, gdyn + PX_DYN_M00 * D, D);
+    copyRows<NT>(s.m01, gdyn + PX_DYN_M01 * D, D);
+    copyRows<NT>(s.m10, gdyn + PX_DYN_M10 * D, D);
+    copyRows<NT>(s.m11, gdyn + PX_DYN_M11 * D, D);
+    const float *gc = (const float *)(gimm + L.offDynConst);
+    copyRows<NT>(s.iM, gc + PX_DYNC_IMASS * D, D);
+    copyRows<NT>(s.iI, gc + PX_DYNC_IINERTIA * D, D);
+    copyRows<NT>(s.e, gc + PX_DYNC_E * D, D);
+    copyRows<NT>(s.sf, gc + PX_DYNC_SF * D, D);
+    copyRows<NT>(s.df, gc + PX_DYNC_DF * D, D);
+    copyRows<NT>(s.rad, gc + PX_DYNC_RADIUS * D, D);
+    copyRows<NT>((float *)s.shape, (const float *)(gimm + L.offDynShape), D);
+    const float *gs = (const float *)(gimm + L.offStat);
+    copyRows<NT>(s.px + D, gs + PX_STAT_PX * S, S);
+    copyRows<NT>(s.py + D, gs + PX_STAT_PY * S, S);
+    copyRows<NT>(s.m00 + D, gs + PX_STAT_M00 * S, S);
+    copyRows<NT>(s.m01 + D, gs + PX_STAT_M01 * S, S);
+    copyRows<NT>(s.m10 + D, gs + PX_STAT_M10 * S, S);
+    copyRows<NT>(s.m11 + D, gs + PX_STAT_M11 * S, S);
+    copyRows<NT>(s.e + D, gs + PX_STAT_E * S, S);
+    copyRows<NT>(s.sf + D, gs + PX_STAT_SF * S, S);
+    copyRows<NT>(s.df + D, gs + PX_STAT_DF * S, S);
+    copyRows<NT>(s.rad + D, gs + PX_STAT_RADIUS * S, S);
+    copyRows<NT>((float *)(s.shape + D), (const float *)(gimm + L.offStatShape), S);
+    copyRows<NT>((float *)s.flags, (const float *)(gmut + L.offDynFlags), D / 4);
+    copyRows<NT>((float *)s.order, (const float *)(gmut + L.offDynOrder), D / 4);
+    copyRows<NT>((float *)s.verts, (const float *)(gimm + L.offVerts), L.maxVertices * 4);
+    copyRows<NT>(s.sinT, P.sinTable, 256);
+    copyRows<NT>((float *)s.hdr, (const float *)(gmut + L.offHeader), sizeof(PxWorldHeader) / 4);
+    if (tid < 16) s.misc[tid] = 0;
+  }
+  __syncthreads();
+
+  const uint32_t nDyn = min(s.hdr->nDynamic, D), nStat = min(s.hdr->nStatic, S);
+  const float dt = s.hdr->dt;
+  const V2 g = v2(s.hdr->gravityX, s.hdr->gravityY);
+  const uint32_t iterations = s.hdr->iterations & 255u;
+  const float linSleepSq = s.hdr->linearSleepThresholdSq, angSleep = s.hdr->angularSleepThreshold;
+  const float timeToSleep = s.hdr->timeToSleep;
+  const uint32_t nRounds = (nDyn + NT - 1) / NT; /* sorted positions handled per thread */
+  uint32_t overflow = 0;                         /* thread 0 accumulates the world's flags */
+  uint32_t statPairs = 0, statManifolds = 0;
+
+  for (uint32_t step = 0; step < P.kSubsteps; step++) {
+    const bool traceNow = P.trace != nullptr && step + 1 == P.kSubsteps;
+    uint8_t *gtrace = traceNow ? P.trace + (size_t)world * L.traceStride : nullptr;
+
+    /* ====================== phase A: AABB keys, stable order by aabb.min.x ============ */
+    /* the order persists across substeps, so it is almost always already sorted */
+    if (tid < 16 && tid != MI_OVERFLOW) s.misc[tid] = 0;
+    for (uint32_t i = tid; i < D; i += NT) {
+      s.restFlag[i] = 0;
+      s.wakeFlag[i] = 0;
+    }
+    for (uint32_t i = tid; i < D * 8; i += NT) s.maskB[i] = 0;
+    __syncthreads();
+    for (uint32_t p = tid; p < nDyn; p += NT) {
+      uint32_t slot = s.order[p];
+      float key = s.px[slot] - s.rad[slot];
+      s.sMinX[p] = key;
+    }
+    __syncthreads();
+    {
+      bool unsorted = false;
+      for (uint32_t p = tid; p + 1 < nDyn; p += NT) unsorted |= s.sMinX[p] > s.sMinX[p + 1];
+      if (unsorted) s.misc[MI_UNSORTED] = 1;
+    }
+    __syncthreads();
+    if (s.misc[MI_UNSORTED]) {
+      /* rank by counting = the permutation a stable insertion sort produces
+       * (px_body_array.c:81-102 moves an element left only past strictly greater keys) */
+      for (uint32_t p = tid; p < nDyn; p += NT) {
+        float key = s.sMinX[p];
+        uint32_t rank = 0;
+        for (uint32_t q = 0; q < nDyn; q++) {
+          float kq = s.sMinX[q];
+          rank += (kq < key || (kq == key && q < p)) ? 1u : 0u;
+        }
+        s.order2[rank] = s.order[p];
+      }
+      __syncthreads();
+      for (uint32_t p = tid; p < nDyn; p += NT) s.order[p] = s.order2[p];
+      __syncthreads();
+    }
+    /* sorted-position arrays for the sweep */
+    for (uint32_t p = tid; p < nDyn; p += NT) {
+      uint32_t slot = s.order[p];
+      float x = s.px[slot], y = s.py[slot], r = s.rad[slot];
+      s.sMinX[p] = x - r;
+      s.sMaxX[p] = x + r;
+      s.sMinY[p] = y - r;
+      s.sMaxY[p] = y + r;
+      s.sSlot[p] = (uint8_t)slot;
+      s.sSleep[p] = (s.flags[slot] & PX_FLAG_SLEEPING) ? 1 : 0;
+      s.posOf[slot] = (uint8_t)p;
+    }
+    for (uint32_t q = tid; q < nStat; q += NT) {
+      float x = s.px[D + q], y = s.py[D + q], r = s.rad[D + q];
+      s.stMinX[q] = x - r;
+      s.stMaxX[q] = x + r;
+      s.stMinY[q] = y - r;
+      s.stMaxY[q] = y + r;
+    }
+    __syncthreads();
+
+    /* ====================== phase B: sweep -> ordered pair list, binned by shape pair == */
+    /* pass 1 counts, a packed 4x16-bit block scan gives every body its first sequence
+     * number and its first index in each of the three type bins, pass 2 writes.  The
+     * reference's early-exit `break` acts as `continue`; over a sorted list
+     * both give the same pairs, so the dynamic scan stops at the first min.x > A.max.x. */
+    unsigned long long carry = 0; /* running totals of earlier rounds */
+    for (uint32_t r = 0; r < nRounds; r++) {
+      const uint32_t p = r * NT + tid;
+      unsigned long long counts = 0; /* all | cc << 16 | cp << 32 | pp << 48 */
+      float aMinX = 0, aMaxX = 0, aMinY = 0, aMaxY = 0;
+      uint32_t aSlot = 0, aSleep = 0, aPoly = 0, startStat = 0;
+      if (p < nDyn) {
+        aMinX = s.sMinX[p];
+        aMaxX = s.sMaxX[p];
+        aMinY = s.sMinY[p];
+        aMaxY = s.sMaxY[p];
+        aSlot = s.sSlot[p];
+        aSleep = s.sSleep[p];
+        aPoly = PX_SHAPE_COUNT(s.shape[aSlot]) != 0;
+        for (uint32_t q = p + 1; q < nDyn; q++) {
+          float bMinX = s.sMinX[q];
+          if (bMinX > aMaxX) break;
+          if (aSleep && s.sSleep[q]) continue;
+          if (!boxesOverlap(aMinX, aMinY, aMaxX, aMaxY, bMinX, s.sMinY[q], s.sMaxX[q], s.sMaxY[q])) continue;
+          uint32_t bPoly = PX_SHAPE_COUNT(s.shape[s.sSlot[q]]) != 0;
+          counts += 1ull + (1ull << (16 * (1 + aPoly + bPoly)));
+        }
+        startStat = firstStaticAfterX(s.stMaxX, nStat, aMinX);
+        for (uint32_t q = startStat; q < nStat; q++) {
+          float bMinX = s.stMinX[q];
+          if (bMinX > aMaxX) continue;
+          if (!boxesOverlap(aMinX, aMinY, aMaxX, aMaxY, bMinX, s.stMinY[q], s.stMaxX[q], s.stMaxY[q])) continue;
+          uint32_t bPoly = PX_SHAPE_COUNT(s.shape[D + q]) != 0;
+          counts += 1ull + (1ull << (16 * (1 + aPoly + bPoly)));
+        }
+      }
+      unsigned long long total;
+      unsigned long long ex = blockExclusiveScan<NT>(counts, s.scan, total) + carry;
+      carry += total;
+      if (p < nDyn) {
+        s.base[p] = (uint16_t)min((uint32_t)(ex & 0xffffu), MP);
+        s.stash[p] = ex; /* per-type first indices for pass 2 */
+        s.order2[p] = (uint8_t)startStat;
+      }
+    }
+    const uint32_t totalPairsRaw = (uint32_t)(carry & 0xffffu);
+    const uint32_t nPairs = min(totalPairsRaw, MP);
+    const uint32_t nCC = (uint32_t)((carry >> 16) & 0xffffu), nCP = (uint32_t)((carry >> 32) & 0xffffu);
+    const uint32_t nPP = (uint32_t)((carry >> 48) & 0xffffu);
+    if (tid == 0) {
+      s.base[nDyn] = (uint16_t)nPairs;
+      if (totalPairsRaw > MP) overflow |= PX_BATCH_OVERFLOW_PAIRS;
+    }
+    /* bin regions inside bins[]: [0,nCC) circle-circle, [nCC, nCC+nCP) circle-polygon (either
+     * order), then polygon-polygon; entries whose sequence number is >= MP are dropped */
+    __syncthreads();
+    for (uint32_t p = tid; p < nDyn; p += NT) {
+      const float aMinX = s.sMinX[p], aMaxX = s.sMaxX[p], aMinY = s.sMinY[p], aMaxY = s.sMaxY[p];
+      const uint32_t aSlot = s.sSlot[p], aSleep = s.sSleep[p];
+      const uint32_t aPoly = PX_SHAPE_COUNT(s.shape[aSlot]) != 0;
+      uint32_t seq = s.base[p];
+      const unsigned long long ex = s.stash[p];
+      uint32_t binAt[3] = {(uint32_t)((ex >> 16) & 0xffffu), nCC + (uint32_t)((ex >> 32) & 0xffffu),
+                           nCC + nCP + (uint32_t)((ex >> 48) & 0xffffu)};
+      uint16_t *tpA = gtrace ? (uint16_t *)(gtrace + L.offTracePairs) : nullptr;
+      for (uint32_t q = p + 1; q < nDyn; q++) {
+        float bMinX = s.sMinX[q];
+        if (bMinX > aMaxX) break;
+        if (aSleep && s.sSleep[q]) continue;
+        if (!boxesOverlap(aMinX, aMinY, aMaxX, aMaxY, bMinX, s.sMinY[q], s.sMaxX[q], s.sMaxY[q])) continue;
+        uint32_t bSlot = s.sSlot[q];
+        uint32_t t = aPoly + (PX_SHAPE_COUNT(s.shape[bSlot]) != 0);
+        uint32_t at = binAt[t]++;
+        if (at >= MP) {
+          /* pair overflow (flagged): the world's results are unspecified from here on */
+        } else if (seq < MP) {
+          s.bins[at] = (seq << 17) | (aSlot << 9) | bSlot;
+          s.validSlot[seq] = 0;
+          if (tpA) {
+            tpA[seq] = (uint16_t)aSlot;
+            tpA[MP + seq] = (uint16_t)(0x8000u | bSlot);
+          }
+        } else {
+          s.bins[at] = 0xffffffffu;
+        }
+        seq++;
+      }
+      for (uint32_t q = s.order2[p]; q < nStat; q++) {
+        float bMinX = s.stMinX[q];
+        if (bMinX > aMaxX) continue;
+        if (!boxesOverlap(aMinX, aMinY, aMaxX, aMaxY, bMinX, s.stMinY[q], s.stMaxX[q], s.stMaxY[q])) continue;
+        uint32_t t = aPoly + (PX_SHAPE_COUNT(s.shape[D + q]) != 0);
+        uint32_t at = binAt[t]++;
+        if (at >= MP) {
+        } else if (seq < MP) {
+          s.bins[at] = (seq << 17) | (aSlot << 9) | (D + q);
+          s.validSlot[seq] = 0;
+          if (tpA) {
+            tpA[seq] = (uint16_t)aSlot;
+            tpA[MP + seq] = (uint16_t)(gimm + L.offStatSlot)[q];
+          }
+        } else {
+          s.bins[at] = 0xffffffffu;
+        }
+        seq++;
+      }
+    }
+    __syncthreads();
+
+    /* ====================== phase C: narrowphase, one pair per thread per bin ========= */
+    {
+      const uint32_t nAll = min(nCC + nCP + nPP, MP);
+      for (uint32_t idx = tid; idx < ((nAll + NT - 1) / NT) * NT; idx += NT) {
+        Contact m;
+        m.count = 0;
+        m.c1 = v2(0.0f, 0.0f);
+        uint32_t word = 0xffffffffu, a = 0, b = 0;
+        if (idx < nAll) word = s.bins[idx];
+        if (word != 0xffffffffu) {
+          a = BIN_A(word);
+          b = BIN_B(word);
+          DBody A = loadBody(s, a), B = loadBody(s, b);
+          if (idx < nCC) {
+            collideCircles(A, B, eps, m);
+          } else if (idx < nCC + nCP) {
+            /* pxCollide, px_collision.c:445-459: the polygon-circle order swaps the arguments
+             * and flips the normal */
+            if (A.nverts == 0) {
+              collideCirclePolygon(A, B, eps, m);
+            } else {
+              collideCirclePolygon(B, A, eps, m);
+              m.normal = -m.normal;
+            }
+          } else {
+            collidePolygons(A, B, eps, epsSq, m);
+          }
+        }
+        if (m.count) {
+          const uint32_t bdyn = b < D;
+          const uint32_t ms = atomicAdd(&s.misc[MI_MCOUNT], 1u);
+          if (ms < MM) {
+            /* pxManifoldInit, px_manifold.c:12-31: geometric-mean friction via pxFastSqrt */
+            s.msf[ms] = fSqrt(s.sf[a] * s.sf[b]);
+            s.mdf[ms] = fSqrt(s.df[a] * s.df[b]);
+            /* pxManifoldDetectRestingContact, px_manifold.c:46-92, on the velocities as they
+             * are before force integration */
+            float ea = s.e[a], eb = s.e[b];
+            float minE = ea < eb ? ea : eb;
+            V2 gstep = g * dt;
+            float gsq = lensq(gstep);
+            V2 pa = v2(s.px[a], s.py[a]), pb = v2(s.px[b], s.py[b]);
+            V2 va = v2(s.vx[a], s.vy[a]);
+            float wa = s.av[a];
+            V2 vb = v2(0.0f, 0.0f);
+            float wb = 0.0f;
+            if (bdyn) {
+              vb = v2(s.vx[b], s.vy[b]);
+              wb = s.av[b];
+            }
+            for (uint32_t i = 0; i < m.count; i++) {
+              V2 c = i == 0 ? m.c0 : m.c1;
+              V2 ra = c - pa, rb = c - pb;
+              V2 rv = (vb + v2(-rb.y, rb.x) * wb) - (va + v2(-ra.y, ra.x) * wa);
+              if (lensq(rv) < gsq + eps) {
+                minE = 0.0f;
+                break;
+              }
+            }
+            s.mnx[ms] = m.normal.x;
+            s.mny[ms] = m.normal.y;
+            s.mpen[ms] = m.pen;
+            s.mc0x[ms] = m.c0.x;
+            s.mc0y[ms] = m.c0.y;
+            s.mc1x[ms] = m.c1.x;
+            s.mc1y[ms] = m.c1.y;
+            s.me[ms] = minE;
+            s.mids[ms] = a | (b << 8) | (bdyn << 17) | (m.count << 18);
+            s.validSlot[BIN_SEQ(word)] = (uint16_t)(ms + 1);
+            /* manifold pass of pxUpdateSleepStates, px_world.c:147-177: flags set by SLOT */
+            const bool resting = (minE == 0.0f);
+            if (!bdyn && resting) {
+              s.restFlag[a] = 1;
+            } else if (bdyn && !resting) {
+              if (s.flags[a] & PX_FLAG_SLEEPING) s.wakeFlag[b] = 1;
+              if (s.flags[b] & PX_FLAG_SLEEPING) s.wakeFlag[a] = 1;
+            }
+            if (bdyn) { /* remember A's sorted position in B's partner mask */
+              uint32_t pa_ = s.posOf[a];
+              atomicOr(&s.maskB[b * 8 + (pa_ >> 5)], 1u << (pa_ & 31u));
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();
+    const uint32_t mRaw = s.misc[MI_MCOUNT];
+    const uint32_t M = min(mRaw, MM);
+    if (tid == 0 && mRaw > MM) overflow |= PX_BATCH_OVERFLOW_MANIFOLDS;
+
+    /* ====================== phase D: per-body manifold lists, integrate forces ======== */
+    /* Body x (sorted position p) meets its manifolds in pool order: first the ones where it
+     * is bodyB (their A-bodies come earlier in the sweep, ordered by A's sorted position),
+     * then its own block where it is bodyA, in sequence order. */
+    carry = 0;
+    for (uint32_t r = 0; r < nRounds; r++) {
+      const uint32_t p = r * NT + tid;
+      uint32_t nA = 0, nB = 0, x = 0;
+      if (p < nDyn) {
+        x = s.sSlot[p];
+        for (uint32_t seq = s.base[p]; seq < s.base[p + 1]; seq++) nA += s.validSlot[seq] != 0;
+#pragma unroll
+        for (int w = 0; w < 8; w++) nB += __popc(s.maskB[x * 8 + w]);
+      }
+      unsigned long long total;
+      unsigned long long ex = blockExclusiveScan<NT>((unsigned long long)(nA + nB) | ((unsigned long long)nA << 32), s.scan, total) + carry;
+      carry += total;
+      if (p < nDyn) {
+        s.listStart[x] = (uint16_t)(ex & 0xffffffffu);
+        s.cnt[x] = (uint16_t)(nA + nB);
+        s.cntB[x] = (uint16_t)nB;
+        s.cursor[x] = 0;
+        s.remaining[x] = (nA + nB) * iterations;
+        s.stash[p] = ex >> 32; /* manifold rank of the block's first manifold (trace output) */
+      }
+    }
+    __syncthreads();
+    for (uint32_t p = tid; p < nDyn; p += NT) {
+      const uint32_t x = s.sSlot[p];
+      const uint32_t startX = s.listStart[x], nBx = s.cntB[x];
+      uint32_t k = 0;
+      for (uint32_t seq = s.base[p]; seq < s.base[p + 1]; seq++) {
+        uint32_t vs = s.validSlot[seq];
+        if (!vs) continue;
+        const uint32_t ms = vs - 1;
+        const uint32_t ids = s.mids[ms];
+        s.list[startX + nBx + k] = (uint16_t)ms;
+        uint32_t arrivals = (nBx == 0 && k == 0) ? 1u : 0u, need = 1;
+        if (MID_BDYN(ids)) {
+          const uint32_t y = MID_B(ids);
+          /* position of this manifold among y's B-role manifolds = partners of y that sit
+           * before p in the sorted order */
+          uint32_t ordB = 0;
+          const uint32_t wq = p >> 5;
+          for (uint32_t w = 0; w < wq; w++) ordB += __popc(s.maskB[y * 8 + w]);
+          ordB += __popc(s.maskB[y * 8 + wq] & ((1u << (p & 31u)) - 1u));
+          s.list[s.listStart[y] + ordB] = (uint16_t)ms;
+          arrivals += ordB == 0 ? 1u : 0u;
+          need = 2;
+        }
+        if (arrivals == need) {
+          s.arr[ms] = 0;
+          if (iterations) s.queue[atomicAdd(&s.misc[MI_QTAIL], 1u) & QMASK] = (uint16_t)ms;
+        } else {
+          s.arr[ms] = (uint8_t)arrivals;
+        }
+        if (gtrace) { /* ordered manifold dump */
+          const uint32_t rank = (uint32_t)s.stash[p] + k;
+          float *mf = (float *)(gtrace + L.offTraceManifolds);
+          mf[0 * MM + rank] = s.mnx[ms];
+          mf[1 * MM + rank] = s.mny[ms];
+          mf[2 * MM + rank] = s.mpen[ms];
+          mf[3 * MM + rank] = s.msf[ms];
+          mf[4 * MM + rank] = s.mdf[ms];
+          mf[5 * MM + rank] = s.me[ms];
+          mf[6 * MM + rank] = s.mc0x[ms];
+          mf[7 * MM + rank] = s.mc0y[ms];
+          mf[8 * MM + rank] = s.mc1x[ms];
+          mf[9 * MM + rank] = s.mc1y[ms];
+          uint32_t bId = MID_B(ids);
+          uint32_t slotB = MID_BDYN(ids) ? bId : (uint32_t)(gimm + L.offStatSlot)[bId - D];
+          ((uint32_t *)(mf + (size_t)PX_TRACE_M_F32 * MM))[rank] = MID_A(ids) | (slotB << 8) | (MID_BDYN(ids) << 16) | (MID_COUNT(ids) << 24);
+        }
+        k++;
+      }
+      /* pxIntegrateForces, px_world.c:231-239 / px_body.c:167-179 (resting-contact detection
+       * above already consumed the pre-integration velocities) */
+      if (!(s.flags[x] & PX_FLAG_SLEEPING)) {
+        float halfDt = fDiv(dt, 2.0f);
+        float iM = s.iM[x], iI = s.iI[x];
+        V2 dv = (v2(s.fx[x], s.fy[x]) * iM + g) * halfDt;
+        s.vx[x] = s.vx[x] + dv.x;
+        s.vy[x] = s.vy[x] + dv.y;
+        s.av[x] = s.av[x] + s.tq[x] * iI * halfDt;
+      }
+    }
+    __syncthreads();
+
+    /* ====================== phase E: sequential impulses, dataflow order ============== */
+    if (P.flags & PX_BATCH_FLAG_SERIAL_SOLVER) {
+      /* debug: literal pool-order walk by one thread (needs the ordered list: rebuild it
+       * from the blocks) */
+      if (tid == 0) {
+        for (uint32_t it = 0; it < iterations; it++) {
+          for (uint32_t p = 0; p < nDyn; p++) {
+            for (uint32_t seq = s.base[p]; seq < s.base[p + 1]; seq++) {
+              uint32_t vs = s.validSlot[seq];
+              if (vs) applyManifoldImpulse(s, vs - 1, eps);
+            }
+          }
+        }
+      }
+    } else if (warp == 0) {
+      const uint32_t totalVisits = M * iterations;
+      uint32_t head = 0, tail = s.misc[MI_QTAIL], done = 0;
+      while (done < totalVisits) {
+        const uint32_t n = min(tail - head, 32u);
+        if (n == 0) { /* cannot happen for a consistent list structure */
+          if (lane == 0) overflow |= PX_OVERFLOW_INTERNAL;
+          break;
+        }
+        uint32_t ms = 0, ids = 0;
+        const bool active = lane < n;
+        if (active) {
+          ms = s.queue[(head + lane) & QMASK];
+          ids = s.mids[ms];
+          applyManifoldImpulse(s, ms, eps);
+        }
+        __syncwarp();
+        /* release: advance each touched body's cursor, signal the next visit in its list */
+        uint32_t ready0 = 0xffffffffu, ready1 = 0xffffffffu;
+        if (active) {
+#pragma unroll
+          for (int side = 0; side < 2; side++) {
+            if (side == 1 && !MID_BDYN(ids)) break;
+            const uint32_t body = side == 0 ? MID_A(ids) : MID_B(ids);
+            uint32_t left = s.remaining[body] - 1u;
+            s.remaining[body] = left;
+            uint32_t c = s.cursor[body] + 1u;
+            if (c == s.cnt[body]) c = 0;
+            s.cursor[body] = (uint16_t)c;
+            if (left) {
+              const uint32_t nxt = s.list[s.listStart[body] + c];
+              const uint32_t need = 1u + MID_BDYN(s.mids[nxt]);
+              uint32_t got = 1;
+              if (need == 2) {
+                /* two arrivals per visit, possibly from two lanes of this round */
+                got = (uint32_t)atomicAdd((unsigned int *)(s.arr + (nxt & ~3u)), 1u << (8 * (nxt & 3u)));
+                got = ((got >> (8 * (nxt & 3u))) & 0xffu) + 1u;
+              }
+              if (got == need) {
+                if (need == 2) atomicAnd((unsigned int *)(s.arr + (nxt & ~3u)), ~(0xffu << (8 * (nxt & 3u))));
+                if (side == 0) ready0 = nxt; else ready1 = nxt;
+              }
+            }
+          }
+        }
+        __syncwarp();
+        const uint32_t b0 = __ballot_sync(0xffffffffu, ready0 != 0xffffffffu);
+        const uint32_t b1 = __ballot_sync(0xffffffffu, ready1 != 0xffffffffu);
+        const uint32_t lt = (1u << lane) - 1u;
+        if (ready0 != 0xffffffffu) s.queue[(tail + __popc(b0 & lt)) & QMASK] = (uint16_t)ready0;
+        if (ready1 != 0xffffffffu) s.queue[(tail + __popc(b0) + __popc(b1 & lt)) & QMASK] = (uint16_t)ready1;
+        tail += __popc(b0) + __popc(b1);
+        head += n;
+        done += n;
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+
+    /* ====================== phase F: integrate velocities, correct positions, sleep ==== */
+    uint32_t sleepingLocal = 0;
+    for (uint32_t p = tid; p < nDyn; p += NT) {
+      const uint32_t x = s.sSlot[p];
+      uint32_t fl = s.flags[x];
+      float posx = s.px[x], posy = s.py[x];
+      /* pxBodyIntegrateVelocity, px_body.c:181-188 */
+      if (!(fl & PX_FLAG_SLEEPING)) {
+        posx = posx + s.vx[x] * dt;
+        posy = posy + s.vy[x] * dt;
+        float radians = s.angle[x] + s.av[x] * dt;
+        radians = fmodf(radians, D_2PI);
+        if (radians < 0) radians += D_2PI;
+        s.angle[x] = radians;
+        float c = fSin(s.sinT, radians + D_PI * 0.5f), sn = fSin(s.sinT, radians);
+        s.m00[x] = c;
+        s.m01[x] = -sn;
+        s.m10[x] = sn;
+        s.m11[x] = c;
+      }
+      /* pxCorrectPositions, px_world.c:288-292: this body's terms, in pool order */
+      {
+        const uint32_t start = s.listStart[x], n = s.cnt[x], nBx = s.cntB[x];
+        for (uint32_t i = 0; i < n; i++) {
+          const uint32_t ms = s.list[start + i];
+          const float pen = s.mpen[ms];
+          if (pen <= allowedPen) continue;
+          const uint32_t ids = s.mids[ms];
+          const float iMA = s.iM[MID_A(ids)];
+          const float iMB = MID_BDYN(ids) ? s.iM[MID_B(ids)] : 0.0f;
+          const float excess = pen - allowedPen;
+          const float mag = fDiv(excess * 0.2f, iMA + iMB);
+          const V2 corr = v2(s.mnx[ms], s.mny[ms]) * mag;
+          if (i >= nBx) { /* bodyA: moveBy(-(corr * iMA)) */
+            V2 d = -(corr * iMA);
+            posx = posx + d.x;
+            posy = posy + d.y;
+          } else {
+            V2 d = corr * iMB;
+            posx = posx + d.x;
+            posy = posy + d.y;
+          }
+        }
+      }
+      s.px[x] = posx;
+      s.py[x] = posy;
+
+      /* body pass of pxUpdateSleepStates, px_world.c:179-219: the flags are TESTED by sorted
+       * position p although they were set by slot -- the reference's behaviour */
+      float slp = s.slp[x];
+      if (s.wakeFlag[p]) {
+        slp = 0.0f;
+        fl &= ~PX_FLAG_SLEEPING;
+      } else {
+        const float vx = s.vx[x], vy = s.vy[x];
+        const bool below = (vx * vx + vy * vy <= linSleepSq) && (fabsf(s.av[x]) <= angSleep);
+        if (!below) {
+          slp = 0.0f;
+          fl &= ~PX_FLAG_SLEEPING;
+        } else if (!(fl & PX_FLAG_SLEEPING)) {
+          slp = slp + dt;
+          if (s.restFlag[p]) slp = slp + dt;
+          if (slp >= timeToSleep) {
+            s.vx[x] = 0.0f;
+            s.vy[x] = 0.0f;
+            s.av[x] = 0.0f;
+            s.fx[x] = 0.0f;
+            s.fy[x] = 0.0f;
+            s.tq[x] = 0.0f;
+            fl |= PX_FLAG_SLEEPING;
+          }
+        }
+      }
+      s.slp[x] = slp;
+      s.flags[x] = (uint8_t)fl;
+      /* pxClearForces, px_world.c:302-311 */
+      if (!(slp >= timeToSleep)) {
+        s.fx[x] = 0.0f;
+        s.fy[x] = 0.0f;
+        s.tq[x] = 0.0f;
+      }
+      sleepingLocal += (fl & PX_FLAG_SLEEPING) ? 1u : 0u;
+    }
+    if (step + 1 == P.kSubsteps) {
+      if (sleepingLocal) atomicAdd(&s.misc[MI_SLEEPING], sleepingLocal);
+      statPairs = nPairs;
+      statManifolds = M;
+    }
+    __syncthreads();
+  }
+
+  /* --------------------------------------------------------------- store (smem -> HBM) */
+  {
+    float *gdyn = (float *)(gmut + L.offDyn);
+    copyRows<NT>(gdyn + PX_DYN_PX * D, s.px, D);
+    copyRows<NT>(gdyn + PX_DYN_PY * D, s.py, D);
+    copyRows<NT>(gdyn + PX_DYN_VX * D, s.vx, D);
+    copyRows<NT>(gdyn + PX_DYN_VY * D, s.vy, D);
+    copyRows<NT>(gdyn + PX_DYN_AV * D, s.av, D);
+    copyRows<NT>(gdyn + PX_DYN_ANGLE * D, s.angle, D);
+    copyRows<NT>(gdyn + PX_DYN_FX * D, s.fx, D);
+    copyRows<NT>(gdyn + PX_DYN_FY * D, s.fy, D);
+    copyRows<NT>(gdyn + PX_DYN_TORQUE * D, s.tq, D);
+    copyRows<NT>(gdyn + PX_DYN_SLEEP * D, s.slp, D);
+    copyRows<NT>(gdyn + PX_DYN_M00 * D, s.m00, D);
+    copyRows<NT>(gdyn + PX_DYN_M01 * D, s.m01, D);
+    copyRows<NT>(gdyn + PX_DYN_M10 * D, s.m10, D);
+    copyRows<NT>(gdyn + PX_DYN_M11 * D, s.m11, D);
+    copyRows<NT>((float *)(gmut + L.offDynFlags), (const float *)s.flags, D / 4);
+    copyRows<NT>((float *)(gmut + L.offDynOrder), (const float *)s.order, D / 4);
+    if (tid == 0) {
+      PxWorldHeader *gh = (PxWorldHeader *)(gmut + L.offHeader);
+      gh->statManifolds = statManifolds;
+      gh->statPairs = statPairs;
+      gh->statSleeping = s.misc[MI_SLEEPING];
+      gh->statOverflow = s.hdr->statOverflow | overflow | s.misc[MI_OVERFLOW];
+      gh->substeps = s.hdr->substeps + P.kSubsteps;
+    }
+  }
+}
+
+/* ------------------------------------------------------------------- control commands */
+/* One thread per world applies that world's queued API calls in submission order, merged
+ * with the batch-wide (PX_ALL_WORLDS) calls by sequence number. */
+__global__ void pxCommandKernel(const PxBatchLayout L, uint8_t *mut, const uint8_t *imm, const PxCommand *cmds,
+                                const uint32_t *worldStart, const PxCommand *global, uint32_t nGlobal) {
+  const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= L.nWorlds) return;
+  uint8_t *gmut = mut + (size_t)w * L.mutStride;
+  const uint8_t *gimm = imm + (size_t)w * L.immStride;
+  PxWorldHeader *h = (PxWorldHeader *)(gmut + L.offHeader);
+  float *dyn = (float *)(gmut + L.offDyn);
+  uint8_t *flags = gmut + L.offDynFlags;
+  const float *dc = (const float *)(gimm + L.offDynConst);
+  const uint32_t D = L.maxDynamic;
+  uint32_t i = worldStart ? worldStart[w] : 0, iEnd = worldStart ? worldStart[w + 1] : 0, gi = 0;
+  while (i < iEnd || gi < nGlobal) {
+    const PxCommand *c;
+    if (gi < nGlobal && (i >= iEnd || global[gi].seq < cmds[i].seq)) {
+      c = &global[gi++];
+    } else {
+      c = &cmds[i++];
+    }
+    const uint32_t op = c->op & 0xffu, body = c->op >> 8;
+    if (op == PX_CMD_GRAVITY) { /* pxWorldSetGravity, px_world.c:57-63 */
+      h->gravityX = c->a * L.unit;
+      h->gravityY = c->b * L.unit;
+    } else if (op == PX_CMD_ITERATIONS) {
+      h->iterations = (uint32_t)c->a & 255u;
+    } else if (body < D) {
+      /* pxBodyApiApplyImpulse / pxBodyApiApplyForce, px_body_api.c:20-42: scale by the unit,
+       * accumulate, wake */
+      const float sx = c->a * L.unit, sy = c->b * L.unit;
+      if (op == PX_CMD_IMPULSE) {
+        dyn[PX_DYN_VX * D + body] += sx * dc[PX_DYNC_IMASS * D + body];
+        dyn[PX_DYN_VY * D + body] += sy * dc[PX_DYNC_IMASS * D + body];
+        dyn[PX_DYN_AV * D + body] += (c->c * sy - c->d * sx) * dc[PX_DYNC_IINERTIA * D + body];
+      } else if (op == PX_CMD_FORCE) {
+        dyn[PX_DYN_FX * D + body] += sx;
+        dyn[PX_DYN_FY * D + body] += sy;
+        dyn[PX_DYN_TORQUE * D + body] += c->c * sy - c->d * sx;
+      }
+      dyn[PX_DYN_SLEEP * D + body] = 0.0f; /* pxBodyWakeUp, px_body.c:195-202 */
+      flags[body] &= (uint8_t)~PX_FLAG_SLEEPING;
+    }
+  }
+}
+
+/* ---------------------------------------------------------------------- host launchers */
+static uint32_t alignUp(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
+
+extern "C" void pxPlanSmem(const PxBatchLayout *L, PxSmemPlan *S) {
+  const uint32_t D = L->maxDynamic, St = L->maxStatic, NB = D + St, V = L->maxVertices;
+  const uint32_t MM = L->maxManifolds, MP = L->maxPairs;
+  uint32_t o = 0;
+  auto take = [&](uint32_t bytes) {
+    uint32_t at = o;
+    o += alignUp(bytes, 16);
+    return at;
+  };
+  S->px = take(NB * 4); S->py = take(NB * 4); S->m00 = take(NB * 4); S->m01 = take(NB * 4);
+  S->m10 = take(NB * 4); S->m11 = take(NB * 4); S->rad = take(NB * 4); S->e = take(NB * 4);
+  S->sf = take(NB * 4); S->df = take(NB * 4); S->shape = take(NB * 4);
+  S->vx = take(D * 4); S->vy = take(D * 4); S->av = take(D * 4); S->iM = take(D * 4); S->iI = take(D * 4);
+  S->angle = take(D * 4); S->fx = take(D * 4); S->fy = take(D * 4); S->tq = take(D * 4); S->slp = take(D * 4);
+  S->flags = take(D); S->order = take(D); S->order2 = take(D); S->posOf = take(D);
+  S->restFlag = take(D); S->wakeFlag = take(D);
+  S->verts = take(V * 16);
+  S->sinT = take(256 * 4);
+  S->hdr = take(sizeof(PxWorldHeader));
+  S->misc = take(16 * 4);
+  S->scan = take(32 * 8);
+  S->mnx = take(MM * 4); S->mny = take(MM * 4); S->mpen = take(MM * 4); S->mc0x = take(MM * 4);
+  S->mc0y = take(MM * 4); S->mc1x = take(MM * 4); S->mc1y = take(MM * 4); S->msf = take(MM * 4);
+  S->mdf = take(MM * 4); S->me = take(MM * 4); S->mids = take(MM * 4);
+  uint32_t qcap = 32;
+  while (qcap < MM) qcap <<= 1;
+  S->qcap = qcap;
+  /* R1: sweep arrays | solver lists */
+  const uint32_t r1 = o;
+  S->sMinX = take(D * 4); S->sMaxX = take(D * 4); S->sMinY = take(D * 4); S->sMaxY = take(D * 4);
+  S->sSleep = take(D);
+  S->stMinX = take(St * 4); S->stMaxX = take(St * 4); S->stMinY = take(St * 4); S->stMaxY = take(St * 4);
+  const uint32_t r1a = o;
+  o = r1;
+  S->list = take(2 * MM * 2); S->arr = take(MM); S->queue = take(qcap * 2);
+  o = o > r1a ? o : r1a;
+  /* sSlot is read in phases D and F as well: keep it out of the aliased region */
+  S->sSlot = take(D);
+  /* R2: bins | per-body solver bookkeeping */
+  const uint32_t r2 = o;
+  S->bins = take(MP * 4);
+  const uint32_t r2a = o;
+  o = r2;
+  S->cnt = take(D * 2); S->cntB = take(D * 2); S->listStart = take((D + 1) * 2); S->cursor = take(D * 2);
+  S->remaining = take(D * 4);
+  o = o > r2a ? o : r2a;
+  S->stash = take(D * 8);
+  /* R3 */
+  S->validSlot = take(MP * 2);
+  S->maskB = take(D * 8 * 4);
+  S->base = take((D + 1) * 2);
+  S->total = o;
+}
+
+template <int NT>
+static cudaError_t launchT(const PxStepParams *P, cudaStream_t stream) {
+  static int configured = -1;
+  cudaError_t err = cudaSuccess;
+  if (configured < (int)P->S.total) {
+    err = cudaFuncSetAttribute(pxStepKernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->S.total);
+    if (err != cudaSuccess) return err;
+    configured = (int)P->S.total;
+  }
+  pxStepKernel<NT><<<P->L.nWorlds, NT, P->S.total, stream>>>(*P);
+  return cudaGetLastError();
+}
+
+extern "C" int pxLaunchStep(const PxStepParams *P, uint32_t threads, void *stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (threads) {
+  case 64: return (int)launchT<64>(P, st);
+  case 128: return (int)launchT<128>(P, st);
+  case 256: return (int)launchT<256>(P, st);
+  default: return (int)cudaErrorInvalidValue;
+  }
+}
+
+extern "C" int pxStepOccupancy(const PxStepParams *P, uint32_t threads, int *ctasPerSm) {
+  cudaError_t err;
+  switch (threads) {
+  case 64:
+    cudaFuncSetAttribute(pxStepKernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->S.total);
+    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctasPerSm, pxStepKernel<64>, 64, P->S.total);
+    break;
+  case 128:
+    cudaFuncSetAttribute(pxStepKernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->S.total);
+    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctasPerSm, pxStepKernel<128>, 128, P->S.total);
+    break;
+  case 256:
+    cudaFuncSetAttribute(pxStepKernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->S.total);
+    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctasPerSm, pxStepKernel<256>, 256, P->S.total);
+    break;
+  default: return (int)cudaErrorInvalidValue;
+  }
+  return (int)err;
+}
+
+extern "C" int pxLaunchCommands(const PxBatchLayout *L, uint8_t *mut, const uint8_t *imm, const PxCommand *cmds,
+                                const uint32_t *worldStart, const PxCommand *global, uint32_t nGlobal, void *stream) {
+  const uint32_t threads = 128, blocks = (L->nWorlds + threads - 1) / threads;
+  pxCommandKernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(*L, mut, imm, cmds, worldStart, global, nGlobal);
+  return (int)cudaGetLastError();
+}

@@ -1,0 +1,88 @@
+/*
+ * px_step.cuh -- parameter block and shared-memory plan of the world-step kernel
+ * (px_step.cu), shared with the C-ABI layer (px_batch.cu).
+ */
+#ifndef PX_STEP_CUH
+#define PX_STEP_CUH
+
+#include <stdint.h>
+
+#include "px_batch.h"
+
+/* Byte offsets of every shared-memory array of one world-CTA.  Computed once on the host
+ * (pxPlanSmem) from the batch layout and handed to the kernel by value. */
+struct PxSmemPlan {
+  /* persistent across the K fused substeps -------------------------------------------- */
+  /* body-id space: dynamic slot s -> id s, static position q -> id D + q (NB = D + S) */
+  uint32_t px, py, m00, m01, m10, m11, rad, e, sf, df; /* f32[NB] */
+  uint32_t shape;                                       /* u32[NB] */
+  uint32_t vx, vy, av, iM, iI;                          /* f32[D] */
+  uint32_t angle, fx, fy, tq, slp;                      /* f32[D] */
+  uint32_t flags, order, order2, posOf, restFlag, wakeFlag; /* u8[D] */
+  uint32_t verts;                                       /* float4[V] */
+  uint32_t sinT;                                        /* f32[256] */
+  uint32_t hdr;                                         /* PxWorldHeader */
+  uint32_t misc;                                        /* u32[16] counters / scan scratch */
+  uint32_t scan;                                        /* u64[32] block-scan scratch */
+  /* manifolds of the current substep, SoA by (unordered) manifold slot ------------------ */
+  uint32_t mnx, mny, mpen, mc0x, mc0y, mc1x, mc1y, msf, mdf, me; /* f32[MM] */
+  uint32_t mids;                                                 /* u32[MM] */
+  /* phase-local, aliased ------------------------------------------------------------- */
+  /* R1: broadphase sorted arrays  |  solver lists */
+  uint32_t sMinX, sMaxX, sMinY, sMaxY; /* f32[D] by sorted position */
+  uint32_t sSlot;                      /* u8[D]  slot | sleeping << ... kept separate: */
+  uint32_t sSleep;                     /* u8[D] */
+  uint32_t stMinX, stMaxX, stMinY, stMaxY; /* f32[S] static boxes by static position */
+  uint32_t list;                       /* u16[2*MM] per-body manifold lists (CSR payload) */
+  uint32_t arr;                        /* u8[MM]   arrival counters */
+  uint32_t queue;                      /* u16[QCAP] ready ring */
+  /* R2: type bins | per-body solver bookkeeping */
+  uint32_t bins;                       /* u32[MP] */
+  uint32_t cnt, cntB, listStart, cursor; /* u16[D] (listStart u16[D+1]) */
+  uint32_t remaining;                    /* u32[D] visits left per body */
+  uint32_t stash;                        /* u64[D] per-position scan results carried between passes */
+  /* R3: narrowphase -> list build */
+  uint32_t validSlot;                  /* u16[MP] manifold slot + 1 by pair sequence number */
+  uint32_t maskB;                      /* u32[D][8] sorted positions of A-partners per body */
+  uint32_t base;                       /* u16[D+1] first pair sequence number by sorted position */
+  uint32_t total;                      /* bytes */
+  uint32_t qcap;                       /* ring capacity (power of two >= MM) */
+};
+
+struct PxStepParams {
+  PxBatchLayout L;
+  PxSmemPlan S;
+  uint8_t *mut;
+  const uint8_t *imm;
+  uint8_t *trace; /* NULL unless PX_BATCH_FLAG_TRACE */
+  const float *sinTable;
+  uint32_t kSubsteps;
+  uint32_t flags;
+};
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+void pxPlanSmem(const PxBatchLayout *L, PxSmemPlan *S);
+/* launches the step kernel for all worlds of the layout; returns cudaError_t as int */
+int pxLaunchStep(const PxStepParams *P, uint32_t threads, void *stream);
+/* occupancy query: resident CTAs per SM for this plan */
+int pxStepOccupancy(const PxStepParams *P, uint32_t threads, int *ctasPerSm);
+
+/* control path: one command = one API call (px_batch.h "control path") */
+struct PxCommand {
+  uint32_t world; /* index or PX_ALL_WORLDS */
+  uint32_t op;    /* PX_CMD_* | body << 8 */
+  uint32_t seq;   /* submission order */
+  float a, b, c, d;
+};
+enum { PX_CMD_IMPULSE = 1, PX_CMD_FORCE = 2, PX_CMD_GRAVITY = 3, PX_CMD_ITERATIONS = 4 };
+/* cmds sorted by (world, seq); worldStart[w]..worldStart[w+1] is world w's range; the
+ * `global` list (PX_ALL_WORLDS, in seq order) is merged in by sequence number */
+int pxLaunchCommands(const PxBatchLayout *L, uint8_t *mut, const uint8_t *imm, const struct PxCommand *cmds,
+                     const uint32_t *worldStart, const struct PxCommand *global, uint32_t nGlobal, void *stream);
+#ifdef __cplusplus
+}
+#endif
+
+#endif

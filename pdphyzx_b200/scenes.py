@@ -1,0 +1,225 @@
+"""Synthetic scene generators for batches of independent pdphyzx worlds.
+
+A scene is plain numpy data (no physics): per body the arguments one would hand to the
+reference's ``px->world->newDynamicBody / newStaticBody`` (reference src/px_world.c:94-109)
+plus the material fields callers poke afterwards (examples/draw/circle.c:43-45).  The same
+arrays are fed to the host C API of this repo and, in tests, to the compiled reference, so
+both sides construct identical worlds through their own constructors.
+
+Randomness is counter-based -- a 64-bit mix of (seed, world, body, stream) -- so any world
+of any batch can be regenerated independently (SURVEY 8d "Seeds").
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import numpy as np
+
+KIND_CIRCLE, KIND_BOX, KIND_POLYGON = 0, 1, 2
+MAX_SCENE_VERTS = 8
+
+UNIT_M, UNIT_CM, UNIT_MM = 1.0, 100.0, 1000.0
+UNIT_NAMES = {1.0: "m", 100.0: "cm", 1000.0: "mm"}
+
+
+def _mix64(x: np.ndarray) -> np.ndarray:
+    """splitmix64 finaliser on uint64 arrays (wrap-around arithmetic)."""
+    x = x.astype(np.uint64, copy=True)
+    with np.errstate(over="ignore"):
+        x += np.uint64(0x9E3779B97F4A7C15)
+        x ^= x >> np.uint64(30)
+        x *= np.uint64(0xBF58476D1CE4E5B9)
+        x ^= x >> np.uint64(27)
+        x *= np.uint64(0x94D049BB133111EB)
+        x ^= x >> np.uint64(31)
+    return x
+
+
+def rand01(seed: int, world, body, stream: int) -> np.ndarray:
+    """float32 uniform in [0, 1) keyed by (seed, world, body, stream); vectorised."""
+    world = np.asarray(world, dtype=np.uint64)
+    body = np.asarray(body, dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        k = _mix64(np.uint64(seed) * np.uint64(0x100000001B3) + np.uint64(stream))
+        k = _mix64(k ^ (world * np.uint64(0xD6E8FEB86659FD93)))
+        k = _mix64(k ^ (body * np.uint64(0xCA5A826395121157)))
+    return ((k >> np.uint64(40)).astype(np.float32) * np.float32(1.0 / (1 << 24))).astype(np.float32)
+
+
+@dataclass
+class Scene:
+    """One world's construction arguments.  Body arrays are in creation order; static and
+    dynamic bodies are created in the order they appear (statics first by convention)."""
+
+    unit: float = UNIT_M
+    fps: int = 50
+    iterations: int = 10
+    gravity: tuple = (0.0, 9.8)
+    dynamic: np.ndarray = field(default_factory=lambda: np.zeros(0, np.uint8))
+    kind: np.ndarray = field(default_factory=lambda: np.zeros(0, np.uint8))
+    p0: np.ndarray = field(default_factory=lambda: np.zeros(0, np.float32))  # radius | width
+    p1: np.ndarray = field(default_factory=lambda: np.zeros(0, np.float32))  # height
+    nverts: np.ndarray = field(default_factory=lambda: np.zeros(0, np.uint8))
+    verts: np.ndarray = field(default_factory=lambda: np.zeros((0, MAX_SCENE_VERTS, 2), np.float32))
+    density: np.ndarray = field(default_factory=lambda: np.zeros(0, np.float32))
+    x: np.ndarray = field(default_factory=lambda: np.zeros(0, np.float32))
+    y: np.ndarray = field(default_factory=lambda: np.zeros(0, np.float32))
+    restitution: np.ndarray = field(default_factory=lambda: np.zeros(0, np.float32))
+    static_friction: np.ndarray = field(default_factory=lambda: np.zeros(0, np.float32))
+    dynamic_friction: np.ndarray = field(default_factory=lambda: np.zeros(0, np.float32))
+    # optional initial motion (applied after construction; angle via setOrientation)
+    vx: np.ndarray | None = None
+    vy: np.ndarray | None = None
+    av: np.ndarray | None = None
+    angle: np.ndarray | None = None
+
+    @property
+    def n_bodies(self) -> int:
+        return int(self.kind.shape[0])
+
+    @property
+    def n_dynamic(self) -> int:
+        return int(self.dynamic.sum())
+
+    @property
+    def n_static(self) -> int:
+        return self.n_bodies - self.n_dynamic
+
+
+class _Builder:
+    def __init__(self):
+        self.rows = []
+
+    def add(self, dynamic, kind, p0=0.0, p1=0.0, verts=None, density=0.0, x=0.0, y=0.0, e=0.2, sf=0.5,
+            df=0.3, vx=0.0, vy=0.0, av=0.0, angle=0.0):
+        v = np.zeros((MAX_SCENE_VERTS, 2), np.float32)
+        n = 0
+        if verts is not None:
+            n = len(verts)
+            v[:n] = np.asarray(verts, np.float32)
+        self.rows.append((dynamic, kind, p0, p1, n, v, density, x, y, e, sf, df, vx, vy, av, angle))
+
+    def scene(self, **kw) -> Scene:
+        r = self.rows
+        col = lambda i, dt: np.array([row[i] for row in r], dtype=dt)
+        s = Scene(
+            dynamic=col(0, np.uint8), kind=col(1, np.uint8), p0=col(2, np.float32), p1=col(3, np.float32),
+            nverts=col(4, np.uint8),
+            verts=np.stack([row[5] for row in r]).astype(np.float32) if r else np.zeros((0, MAX_SCENE_VERTS, 2), np.float32),
+            density=col(6, np.float32), x=col(7, np.float32), y=col(8, np.float32),
+            restitution=col(9, np.float32), static_friction=col(10, np.float32),
+            dynamic_friction=col(11, np.float32), vx=col(12, np.float32), vy=col(13, np.float32),
+            av=col(14, np.float32), angle=col(15, np.float32), **kw)
+        return s
+
+
+def _pen(b: _Builder, cell: float, cols: int, rows_tall: int, e=0.5, sf=0.5, df=0.3, peg=True):
+    """Static pen: ground box, two wall boxes and (peg=True) a ledge box on the right wall
+    -> 3 or 4 statics.  y grows downward (Playdate screen convention; gravity is +y).
+
+    The reference finds the first static to test with a binary search on aabb.max.x over a
+    list sorted by aabb.min.x (src/px_body_array.c:104-131) and its static AABBs are
+    radius-based (src/px_polygon.c:261-266), so a small static in the middle of the ground's
+    x-range hides the ground from every body to its right.  The ledge sits against the right
+    wall so that max.x stays monotone along the sorted list and the pile actually forms."""
+    width = cell * (cols + 1.5)
+    height = cell * (rows_tall + 6)
+    thick = cell * 1.0
+    floor_y = height
+    b.add(0, KIND_BOX, p0=width + 2 * thick, p1=thick, x=width * 0.5, y=floor_y + thick * 0.5, e=e, sf=sf, df=df)
+    b.add(0, KIND_BOX, p0=thick, p1=height, x=-thick * 0.5, y=height * 0.5, e=e, sf=sf, df=df)
+    b.add(0, KIND_BOX, p0=thick, p1=height, x=width + thick * 0.5, y=height * 0.5, e=e, sf=sf, df=df)
+    if peg:
+        b.add(0, KIND_BOX, p0=cell * 3.0, p1=cell * 0.5, x=width - cell * 1.5, y=floor_y - cell * 5.0, e=e, sf=sf, df=df)
+    return width, floor_y
+
+
+def _regular_polygon(n: int, radius: float, seed, world, body) -> np.ndarray:
+    """n points at jittered angles / radii in [0.8, 1.0]*radius: convex with all points on the
+    hull for n <= 8 (the reference's gift-wrap hull drops any that are not)."""
+    i = np.arange(n)
+    ja = rand01(seed, world, body * 16 + i, 11) - np.float32(0.5)
+    jr = rand01(seed, world, body * 16 + i, 12)
+    ang = (i + np.float32(0.35) * ja) * np.float32(2.0 * np.pi / n)
+    rad = radius * (np.float32(0.8) + np.float32(0.2) * jr)
+    return np.stack([rad * np.cos(ang), rad * np.sin(ang)], axis=1).astype(np.float32)
+
+
+def pile_scene(world: int, seed: int = 1, n_dynamic: int = 252, mix: str = "circles", unit: float = UNIT_M,
+               iterations: int = 10, cell: float | None = None, gravity=None, cols: int = 18,
+               peg: bool = True, fps: int = 50) -> Scene:
+    """Penned pile: `n_dynamic` bodies dropped on a jittered grid `cols` wide into a pen of
+    3 static boxes (+1 static circle peg) -- BASELINE configs 1-4.
+
+    mix = "circles": all circles.  mix = "mixed": 1/3 circles, 1/3 boxes, 1/3 convex polygons
+    with 3-8 vertices, interleaved by body index.  `cell` is the grid pitch in world length
+    units (default 0.6 for UNIT_M, 12 for UNIT_MM/UNIT_CM pixel-like scenes); body radius is
+    ~0.42 * cell.  Gravity defaults to (0, 9.8) m/s^2 (scaled by the unit inside setGravity).
+    """
+    if cell is None:
+        cell = 0.6 if unit == UNIT_M else 12.0
+    if gravity is None:
+        gravity = (0.0, 9.8) if unit == UNIT_M else (0.0, 1.025)
+    rows_tall = (n_dynamic + cols - 1) // cols
+    b = _Builder()
+    width, floor_y = _pen(b, cell, cols, rows_tall, peg=peg)
+    idx = np.arange(n_dynamic)
+    jx = rand01(seed, world, idx, 1) - np.float32(0.5)
+    jy = rand01(seed, world, idx, 2) - np.float32(0.5)
+    jr = rand01(seed, world, idx, 3)
+    jk = rand01(seed, world, idx, 4)
+    ja = rand01(seed, world, idx, 5)
+    for i in range(n_dynamic):
+        cx = np.float32(cell) * np.float32(0.75 + (i % cols) + 0.2 * jx[i])
+        cy = np.float32(floor_y) - np.float32(cell) * np.float32(1.0 + (i // cols) * 1.05 + 0.2 * jy[i]) - np.float32(cell)
+        r = np.float32(cell) * np.float32(0.36 + 0.06 * jr[i])
+        kind = KIND_CIRCLE
+        if mix == "mixed":
+            kind = (KIND_CIRCLE, KIND_BOX, KIND_POLYGON)[i % 3]
+        elif mix == "polygons":
+            kind = (KIND_BOX, KIND_POLYGON)[i % 2]
+        if kind == KIND_CIRCLE:
+            b.add(1, KIND_CIRCLE, p0=float(r), density=1.0, x=float(cx), y=float(cy))
+        elif kind == KIND_BOX:
+            w = np.float32(2.0) * r * np.float32(0.75 + 0.2 * jk[i])
+            h = np.float32(2.0) * r * np.float32(0.95 - 0.2 * jk[i])
+            b.add(1, KIND_BOX, p0=float(w), p1=float(h), density=1.0, x=float(cx), y=float(cy),
+                  angle=float(np.float32(0.3) * (ja[i] - np.float32(0.5))))
+        else:
+            n = 3 + int(jk[i] * 6.0) % 6  # 3..8
+            v = _regular_polygon(n, float(r) * 1.1, seed, world, i)
+            b.add(1, KIND_POLYGON, verts=v, density=1.0, x=float(cx), y=float(cy),
+                  angle=float(np.float32(6.28) * ja[i]))
+    return b.scene(unit=unit, fps=fps, iterations=iterations, gravity=tuple(gravity))
+
+
+def stack_scene(world: int, seed: int = 1, n_dynamic: int = 60, unit: float = UNIT_MM, iterations: int = 10,
+                cols: int = 6, cell: float = 20.0) -> Scene:
+    """Polygon stacking (BASELINE config 5): columns of boxes / polygons resting on a ground
+    box, UNIT_MM pixel-like lengths, gravity 9.8 m/s^2."""
+    b = _Builder()
+    rows_tall = (n_dynamic + cols - 1) // cols
+    width = cell * (cols * 1.5 + 1)
+    floor_y = cell * (rows_tall + 4)
+    b.add(0, KIND_BOX, p0=width * 1.5, p1=cell, x=width * 0.5, y=floor_y + cell * 0.5, e=0.1, sf=0.6, df=0.4)
+    idx = np.arange(n_dynamic)
+    jk = rand01(seed, world, idx, 4)
+    jx = rand01(seed, world, idx, 1) - np.float32(0.5)
+    for i in range(n_dynamic):
+        col, row = i % cols, i // cols
+        cx = cell * (1.0 + 1.5 * col) + float(np.float32(0.04) * np.float32(cell) * jx[i])
+        cy = floor_y - cell * (0.5 + row * 1.01)
+        if (i + world) % 4 == 3:
+            v = _regular_polygon(6 + 2 * (i % 2), cell * 0.5, seed, world, i)
+            b.add(1, KIND_POLYGON, verts=v, density=1.0, x=cx, y=cy, e=0.1, sf=0.6, df=0.4)
+        else:
+            w = cell * float(np.float32(0.9) + np.float32(0.1) * jk[i])
+            b.add(1, KIND_BOX, p0=w, p1=cell, density=1.0, x=cx, y=cy, e=0.1, sf=0.6, df=0.4)
+    return b.scene(unit=unit, fps=50, iterations=iterations, gravity=(0.0, 9.8))
+
+
+def drop_scene(world: int, seed: int = 1, n_dynamic: int = 20, mix: str = "mixed", unit: float = UNIT_M,
+               iterations: int = 8) -> Scene:
+    """Small pile that fits the UNMODIFIED reference (<=64 bodies, <=64 manifolds)."""
+    return pile_scene(world, seed=seed, n_dynamic=n_dynamic, mix=mix, unit=unit, iterations=iterations,
+                      cols=5, peg=False)
