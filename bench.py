@@ -1,0 +1,367 @@
+#!/usr/bin/env python
+"""bench.py -- body-steps/sec of the pdphyzx world step on B200 (BASELINE.json metric).
+
+A "step" is one pxBatchStep(b, FUSED) over every world of the batch: FUSED substeps of
+pxWorldStepWithDt (reference src/px_world.c:410-420) fused into one kernel launch; FUSED
+defaults to 5, one fired px->world->step frame (px_world.c:427-437).  The workload is the
+north_star's target scene: WORLDS worlds per GPU (weak scaling: 8192/GPU = 65,536 on 8 GPUs)
+of 256 mixed-shape bodies (252 dynamic: 1/3 circles, 1/3 boxes, 1/3 3-8-gons; 4 static),
+10 solver iterations, PDPHYZX_UNIT_M, penned piles pre-settled on the device before timing.
+
+value   = body-substeps/s, device-timed with CUDA events on the launching stream, state
+          resident in HBM, whole job (all ranks), max over ranks.
+e2e     = same metric through the C ABI with HOST buffers: every step copies the mutable
+          blocks pinned-host -> HBM, steps, and copies them back (pxBatchMutableH2D /
+          pxBatchStep / pxBatchMutableD2H).
+--impl reference = the reference's own CPU step (oracle/_ref, the unmodified sources compiled
+          under the PlaydateAPI host stub) on all host threads, bounded sample of the workload.
+
+One JSON line on stdout (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BODIES_PER_WORLD = 256
+N_DYNAMIC = 252
+# algorithmic HBM bytes per body-substep at K=1: mutable state read+written
+# (44 B x 2) + immutable (28 B) + shape (circle 0, box 64, polygon 16 B/vertex avg 5.5 verts)
+ALG_BYTES = {"circles": 116.0, "mixed": (116.0 + 180.0 + (116.0 + 16 * 5.5)) / 3.0}
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--worlds", type=int, default=8192, help="worlds per GPU")
+    ap.add_argument("--mix", default="mixed", choices=["mixed", "circles"])
+    ap.add_argument("--iterations", type=int, default=10)
+    ap.add_argument("--fused", type=int, default=5, help="substeps per launch (K)")
+    ap.add_argument("--settle", type=int, default=1000, help="untimed substeps to let the piles form")
+    ap.add_argument("--threads", type=int, default=0, help="threads per world-CTA (0 = library default)")
+    ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--max-manifolds", type=int, default=0, help="per-world manifold capacity (0 = library default)")
+    ap.add_argument("--max-pairs", type=int, default=0, help="per-world AABB-pass pair capacity (0 = library default)")
+    ap.add_argument("--cpu-worlds", type=int, default=0, help="worlds in the CPU baseline sample (0 = 2 per core)")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--profile", action="store_true", help="per-phase SM-cycle breakdown (adds clock reads)")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled during the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        for ln in self.lines:
+            p = [x.strip() for x in ln.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1]))
+                smax.append(float(p[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak_hbm():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def build_scenes(args, rank: int, n_worlds: int):
+    from pdphyzx_b200 import scenes
+    base = rank * args.worlds
+    return [scenes.pile_scene(base + w, seed=args.seed, mix=args.mix, iterations=args.iterations, n_dynamic=N_DYNAMIC)
+            for w in range(n_worlds)]
+
+
+def workload_name(args, n_gpus):
+    return (f"{args.worlds} worlds/GPU x {BODIES_PER_WORLD} {args.mix} bodies ({N_DYNAMIC} dynamic + 4 static), "
+            f"{args.iterations} iterations, PDPHYZX_UNIT_M, penned pile settled {args.settle} substeps "
+            f"(north_star target scene: 65,536 worlds on 8 GPUs)")
+
+
+# ------------------------------------------------------------------------ reference arm
+def run_reference(args):
+    """The unmodified reference (oracle/_ref) on the host cores: --impl reference."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from oracle import refbind
+    cores = os.cpu_count() or 1
+    n_worlds = args.cpu_worlds or cores
+    variant = "wide"
+    if not refbind.available(variant, 1.0):
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libpxref_wide_m.so was not built"}))
+        return 0
+    scenes = build_scenes(args, 0, n_worlds)
+    worlds = [refbind.RefWorld(s, variant) for s in scenes]
+    settle = min(args.settle, 400)  # bounded: settling is untimed but costs CPU seconds
+    refbind.time_substeps(worlds, settle, cores)
+    for _ in range(args.warmup):
+        refbind.time_substeps(worlds, args.fused, cores)
+    t = 0.0
+    for _ in range(args.steps):
+        t += refbind.time_substeps(worlds, args.fused, cores)
+    body_substeps = n_worlds * BODIES_PER_WORLD * args.fused * args.steps
+    value = body_substeps / t
+    sample = f"{n_worlds} worlds x {args.fused * args.steps} substeps after {settle} settle substeps, {cores} pthreads"
+    out = {
+        "impl": "reference", "metric": "body_steps_per_sec", "value": value, "unit": "body-substeps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args, args.gpus), "substeps_per_step": args.fused,
+                   "body_frame_steps_per_sec": value / 5.0},
+        "cpu_baseline": {"value": value, "unit": "body-substeps/s", "cores": cores, "kind": "reference", "sample": sample},
+        "e2e": {"value": value, "unit": "body-substeps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(out))
+    return 0
+
+
+# ------------------------------------------------------------------------------ our arm
+def cpu_baseline(args, batch, blocks):
+    """Reference CPU step timed on the host cores from the device's settled state."""
+    from oracle import refbind
+    cores = os.cpu_count() or 1
+    n_worlds = min(args.cpu_worlds or 2 * cores, batch.n)
+    if not refbind.available("wide", 1.0):
+        return None
+    scenes = build_scenes(args, 0, n_worlds)
+    worlds = [refbind.RefWorld(s, "wide") for s in scenes]
+    ncol = worlds[0].lib.ref_body_row_floats()
+    L = batch.L
+    for w, rw in enumerate(worlds):
+        nd = int(blocks.header[w]["nDynamic"])
+        order = blocks.order[w, :nd].copy()
+        rows = np.zeros((255, ncol), np.float32)
+        dyn = blocks.dyn[w]
+        rows[:, :14][: min(255, L.maxDynamic)] = dyn.T[:255]
+        # the reference keeps an AABB per body: pos -/+ radius (px_body.c:95-102)
+        rad = blocks.dync[w][5][:255]
+        rows[:, 14] = rows[:, 0] - rad
+        rows[:, 15] = rows[:, 1] - rad
+        rows[:, 16] = rows[:, 0] + rad
+        rows[:, 17] = rows[:, 1] + rad
+        rw.set_bodies(rows, blocks.flags[w, :255].copy(), order, True)
+    substeps = max(5, min(50, int(2.0e6 * cores / (n_worlds * BODIES_PER_WORLD * 10))))
+    refbind.time_substeps(worlds, 2, cores)
+    best = None
+    for _ in range(3):
+        t = refbind.time_substeps(worlds, substeps, cores)
+        best = t if best is None else min(best, t)
+    value = n_worlds * BODIES_PER_WORLD * substeps / best
+    return {"value": value, "unit": "body-substeps/s", "cores": cores, "kind": "reference",
+            "sample": f"first {n_worlds} worlds of the batch from the device's settled state, {substeps} substeps, "
+                      f"best of 3, {cores} pthreads over disjoint worlds"}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from pdphyzx_b200 import batch as pxb
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world_size = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world_size > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    scenes = build_scenes(args, rank, args.worlds)
+    worlds = pxb.HostWorlds(scenes)
+    # a real (non-default) torch stream, made current, so torch.cuda.Event times the stream
+    # the kernels are launched on
+    tstream = torch.cuda.Stream()
+    torch.cuda.set_stream(tstream)
+    b = pxb.Batch(worlds, device=local_rank, stream=tstream.cuda_stream, threads=args.threads,
+                  flags=pxb.FLAG_PROFILE if args.profile else 0, max_manifolds=args.max_manifolds,
+                  max_pairs=args.max_pairs)
+    del scenes
+    info = b.kernel_info()
+
+    # settle the piles (untimed), in chunks so a hung kernel cannot run for minutes
+    done = 0
+    while done < args.settle:
+        k = min(50, args.settle - done)
+        b.step(k)
+        done += k
+    b.sync()
+    for _ in range(max(args.warmup, 3)):
+        b.step(args.fused)
+    b.sync()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world_size > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing: CUDA events on the launching stream ------------------
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = b.launches
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        b.step(args.fused)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    gpu_launches = b.launches - launches0
+    clocks = sampler.stop()
+
+    # ---- end to end through the C ABI with host buffers -------------------------------
+    e2e_ms = None
+    mut_bytes = b.n * b.L.mutStride
+    if not args.no_e2e:
+        b.mutable_d2h()
+        b.sync()
+        for _ in range(2):
+            b.mutable_h2d()
+            b.step(args.fused)
+            b.mutable_d2h()
+        barrier()
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(args.steps):
+            b.mutable_h2d()
+            b.step(args.fused)
+            b.mutable_d2h()
+            b.sync()  # the host reads the result of every step
+        e1.record()
+        barrier()
+        e2e_ms = max(e0.elapsed_time(e1), 1e3 * (time.perf_counter() - t0))
+
+    if world_size > 1:
+        t = torch.tensor([ms, e2e_ms or 0.0], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_max = float(t[0]), float(t[1])
+        e2e_ms = e2e_max if e2e_ms is not None else None
+
+    blocks = b.download_blocks()
+    stats = np.array([blocks.header["statManifolds"].mean(), blocks.header["statPairs"].mean(),
+                      blocks.header["statSleeping"].mean(), float((blocks.header["statOverflow"] != 0).sum())])
+    if world_size > 1:
+        # the only collective of the whole run: an end-of-run statistics reduction over NCCL
+        t = torch.tensor(stats, device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        stats = t.cpu().numpy()
+        stats[:3] /= world_size
+
+    if rank == 0:
+        total_worlds = args.worlds * world_size
+        body_substeps = total_worlds * BODIES_PER_WORLD * args.fused * args.steps
+        value = body_substeps / (ms * 1e-3)
+        peak, peak_src = measured_peak_hbm()
+        alg = ALG_BYTES[args.mix]
+        # dominant (only) kernel: algorithmic bytes of one launch = bodies x B_alg (state is
+        # streamed once per launch whatever K is) / average launch duration
+        launch_ms = ms / max(gpu_launches, 1)
+        achieved = args.worlds * BODIES_PER_WORLD * alg / (launch_ms * 1e-3) / 1e9
+        out = {
+            "metric": "body_steps_per_sec", "value": value, "unit": "body-substeps/s", "n_gpus": world_size,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {
+                "workload": workload_name(args, world_size), "substeps_per_step": args.fused,
+                "body_frame_steps_per_sec": value / 5.0, "l2": "inputs larger than L2 (state > 126 MB per GPU)"
+                if args.worlds * (b.L.mutStride + b.L.immStride) > 126e6 else "inputs smaller than L2",
+                "threads_per_world_cta": info["threads"], "ctas_per_sm": info["ctas_per_sm"],
+                "smem_bytes_per_cta": info["smem_bytes"], "seed": args.seed,
+                "avg_manifolds_per_world": stats[0], "avg_pairs_per_world": stats[1],
+                "avg_sleeping_per_world": stats[2], "worlds_overflowed": int(stats[3]),
+            },
+            "clocks": clocks, "gpu_launches": int(gpu_launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src,
+                         "note": "HBM is not what binds this path: the solver's dependency chain and fp32 issue do "
+                                 "(SURVEY 8d); see DESIGN.md and profiles/"},
+        }
+        if args.profile:
+            pr = b.profile().astype(np.float64)
+            tot = pr.sum()
+            out["phase_share"] = {n: float(pr[:, i].sum() / tot) for i, n in enumerate(
+                ("A_sort", "B_sweep", "C_narrowphase", "D_lists", "E_solver", "F_integrate"))}
+            out["cycles_per_world_substep"] = float(pr.sum(axis=1).mean() / float(blocks.header["substeps"].mean()))
+        if e2e_ms is not None:
+            out["e2e"] = {"value": body_substeps / (e2e_ms * 1e-3), "unit": "body-substeps/s",
+                          "h2d_bytes_per_step": int(mut_bytes), "d2h_bytes_per_step": int(mut_bytes),
+                          "ms_per_step": e2e_ms / args.steps}
+        if world_size == 1 and not args.no_cpu:
+            try:
+                cb = cpu_baseline(args, b, blocks)
+            except Exception as exc:  # the baseline must never take the GPU number down with it
+                cb = {"value": None, "unit": "body-substeps/s", "cores": os.cpu_count(), "kind": "reference",
+                      "sample": f"failed: {exc}"}
+            if cb:
+                out["cpu_baseline"] = cb
+        print(json.dumps(out))
+    b.close()
+    worlds.close()
+    if world_size > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

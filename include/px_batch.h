@@ -37,6 +37,7 @@ struct PxWorld; /* include/pdphyzx.h */
 /* PxBatchDesc.flags */
 #define PX_BATCH_FLAG_TRACE 1u        /* keep the last substep's ordered pair + manifold lists */
 #define PX_BATCH_FLAG_SERIAL_SOLVER 2u /* debug: one thread walks the manifolds in pool order */
+#define PX_BATCH_FLAG_PROFILE 4u       /* accumulate SM-clock cycles per kernel phase per world */
 
 /* PxWorldHeader.statOverflow bits */
 #define PX_BATCH_OVERFLOW_PAIRS 1u     /* more AABB-pass pairs than maxPairs: extra pairs dropped */
@@ -215,6 +216,9 @@ PX_API int pxBatchMutableD2H(PxBatch *b, void *host, uint32_t first, uint32_t n)
 PX_API int pxBatchImmutableH2D(PxBatch *b, const void *host, uint32_t first, uint32_t n);
 /* Copy the trace block of worlds [first, first + n) into `host` (n * traceStride bytes). */
 PX_API int pxBatchTraceD2H(PxBatch *b, void *host, uint32_t first, uint32_t n);
+/* PX_BATCH_FLAG_PROFILE: copy out u64[nWorlds][8] cycles per phase (A sort, B sweep, C narrowphase,
+ * D lists, E solver, F integrate/correct/sleep, 6-7 unused) accumulated since creation */
+PX_API int pxBatchProfileD2H(PxBatch *b, uint64_t *host);
 /* Device pointers (for zero-copy consumers on the same GPU), as integers */
 PX_API uint64_t pxBatchDeviceMutable(PxBatch *b);
 PX_API uint64_t pxBatchDeviceImmutable(PxBatch *b);

@@ -5,7 +5,7 @@ package is the Python-side plumbing used by the tests and the benchmark: scene g
 and a ctypes binding of the C ABI.
 """
 from . import scenes  # noqa: F401
-from .batch import (ALL_WORLDS, FLAG_SERIAL_SOLVER, FLAG_TRACE, OVERFLOW_MANIFOLDS, OVERFLOW_PAIRS, Batch, Blocks,  # noqa: F401
+from .batch import (ALL_WORLDS, FLAG_PROFILE, FLAG_SERIAL_SOLVER, FLAG_TRACE, OVERFLOW_MANIFOLDS, OVERFLOW_PAIRS, Batch, Blocks,  # noqa: F401
                     HostWorlds, PxError, Trace, compute_layout, core, host, make_desc, pack_worlds)
 
 __all__ = ["scenes", "Batch", "Blocks", "HostWorlds", "PxError", "Trace", "compute_layout", "core", "host",

@@ -20,6 +20,7 @@ _UNIT_TAG = {1.0: "m", 100.0: "cm", 1000.0: "mm"}
 ALL_WORLDS = 0xFFFFFFFF
 FLAG_TRACE = 1
 FLAG_SERIAL_SOLVER = 2
+FLAG_PROFILE = 4
 OVERFLOW_PAIRS = 1
 OVERFLOW_MANIFOLDS = 2
 
@@ -91,6 +92,7 @@ def core():
         "pxBatchMutableD2H": (i32, [vp, vp, u32, u32]),
         "pxBatchImmutableH2D": (i32, [vp, vp, u32, u32]),
         "pxBatchTraceD2H": (i32, [vp, vp, u32, u32]),
+        "pxBatchProfileD2H": (i32, [vp, vp]),
         "pxBatchDeviceMutable": (C.c_uint64, [vp]),
         "pxBatchDeviceImmutable": (C.c_uint64, [vp]),
         "pxBatchLaunchCount": (C.c_uint64, [vp]),
@@ -346,7 +348,7 @@ class Batch:
                               maxStatic=max_static, maxVertices=max_vertices, maxManifolds=max_manifolds,
                               maxPairs=max_pairs)
         if stream:
-            self.desc.stream = C.c_void_p(stream)
+            self.desc.stream = C.c_void_p(stream)  # NB: 0 (the legacy default stream) means "own stream"
         self._sin_keepalive = None
         if worlds is not None:
             self.desc.sinTable = worlds.lib.pxh_sin_table()
@@ -438,6 +440,12 @@ class Batch:
         buf = np.zeros(n * self.L.traceStride, np.uint8)
         _check(self.lib.pxBatchTraceD2H(self.h, buf.ctypes.data_as(C.c_void_p), first, n), "pxBatchTraceD2H")
         return Trace(self.L, buf)
+
+    def profile(self) -> np.ndarray:
+        """u64[nWorlds, 8] SM-clock cycles per phase (needs FLAG_PROFILE)."""
+        out = np.zeros((self.n, 8), np.uint64)
+        _check(self.lib.pxBatchProfileD2H(self.h, out.ctypes.data_as(C.c_void_p)), "pxBatchProfileD2H")
+        return out
 
     @property
     def launches(self) -> int:

@@ -29,6 +29,7 @@ struct PxBatch {
   uint32_t threads;
   uint8_t *dMut, *dImm, *dTrace;
   float *dSin;
+  unsigned long long *dProf;
   uint8_t *hMut, *hImm; /* pinned staging, same layout */
   float sinTable[256];
   /* control path */
@@ -64,6 +65,7 @@ extern "C" PxBatch *pxBatchCreate(uint32_t nWorlds, const PxBatchDesc *desc) {
   memset(&b->L, 0, sizeof(b->L));
   b->dMut = b->dImm = b->dTrace = nullptr;
   b->dSin = nullptr;
+  b->dProf = nullptr;
   b->hMut = b->hImm = nullptr;
   b->dCmds = b->dGlobal = nullptr;
   b->dWorldStart = nullptr;
@@ -125,6 +127,10 @@ extern "C" PxBatch *pxBatchCreate(uint32_t nWorlds, const PxBatchDesc *desc) {
     if ((e = cudaMalloc(&b->dTrace, traceBytes)) != cudaSuccess) return fail("cudaMalloc(trace)", e);
     if ((e = cudaMemsetAsync(b->dTrace, 0, traceBytes, b->stream)) != cudaSuccess) return fail("cudaMemset", e);
   }
+  if (b->flags & PX_BATCH_FLAG_PROFILE) {
+    if ((e = cudaMalloc(&b->dProf, (size_t)nWorlds * 64)) != cudaSuccess) return fail("cudaMalloc(prof)", e);
+    if ((e = cudaMemsetAsync(b->dProf, 0, (size_t)nWorlds * 64, b->stream)) != cudaSuccess) return fail("cudaMemset", e);
+  }
   if ((e = cudaMallocHost(&b->hMut, mutBytes)) != cudaSuccess) return fail("cudaMallocHost(mutable)", e);
   if ((e = cudaMallocHost(&b->hImm, immBytes)) != cudaSuccess) return fail("cudaMallocHost(immutable)", e);
   memset(b->hMut, 0, mutBytes);
@@ -175,6 +181,7 @@ extern "C" void pxBatchFree(PxBatch *b) {
   cudaFree(b->dImm);
   cudaFree(b->dTrace);
   cudaFree(b->dSin);
+  cudaFree(b->dProf);
   cudaFree(b->dCmds);
   cudaFree(b->dGlobal);
   cudaFree(b->dWorldStart);
@@ -347,6 +354,7 @@ extern "C" int pxBatchStep(PxBatch *b, uint32_t kSubsteps) {
   P.imm = b->dImm;
   P.trace = b->dTrace;
   P.sinTable = b->dSin;
+  P.prof = b->dProf;
   P.kSubsteps = kSubsteps;
   P.flags = b->flags;
   int rc = pxLaunchStep(&P, b->threads, b->stream);
@@ -373,6 +381,15 @@ extern "C" int pxBatchStepTimed(PxBatch *b, uint32_t kSubsteps, float *ms) {
   if (rc != 0) return rc;
   if (err != cudaSuccess) return pxSetError(-(int)err - 1000, "pxBatchStepTimed: %s", cudaGetErrorString(err));
   if (ms) *ms = t;
+  return 0;
+}
+
+extern "C" int pxBatchProfileD2H(PxBatch *b, uint64_t *host) {
+  if (!b || !host) return pxSetError(-1, "pxBatchProfileD2H: NULL argument");
+  if (!b->dProf) return pxSetError(-1, "pxBatchProfileD2H: the batch was created without PX_BATCH_FLAG_PROFILE");
+  if (useDevice(b)) return -1;
+  CU(cudaMemcpyAsync(host, b->dProf, (size_t)b->L.nWorlds * 64, cudaMemcpyDeviceToHost, b->stream));
+  CU(cudaStreamSynchronize(b->stream));
   return 0;
 }
 

@@ -607,6 +607,16 @@ __global__ void __launch_bounds__(NT) pxStepKernel(const PxStepParams P) {
   uint32_t overflow = 0;                         /* thread 0 accumulates the world's flags */
   uint32_t statPairs = 0, statManifolds = 0;
 
+  long long profT = 0;
+  unsigned long long *prof = P.prof ? P.prof + (size_t)world * 8 : nullptr;
+#define PROF_MARK(slot)                                   \
+  if (prof && tid == 0) {                                 \
+    long long now = clock64();                            \
+    prof[slot] += (unsigned long long)(now - profT);      \
+    profT = now;                                          \
+  }
+  if (prof && tid == 0) profT = clock64();
+
   for (uint32_t step = 0; step < P.kSubsteps; step++) {
     const bool traceNow = P.trace != nullptr && step + 1 == P.kSubsteps;
     uint8_t *gtrace = traceNow ? P.trace + (size_t)world * L.traceStride : nullptr;
@@ -669,6 +679,7 @@ __global__ void __launch_bounds__(NT) pxStepKernel(const PxStepParams P) {
     }
     __syncthreads();
 
+    PROF_MARK(0)
     /* ====================== phase B: sweep -> ordered pair list, binned by shape pair == */
     /* pass 1 counts, a packed 4x16-bit block scan gives every body its first sequence
      * number and its first index in each of the three type bins, pass 2 writes.  The
@@ -778,6 +789,7 @@ __global__ void __launch_bounds__(NT) pxStepKernel(const PxStepParams P) {
     }
     __syncthreads();
 
+    PROF_MARK(1)
     /* ====================== phase C: narrowphase, one pair per thread per bin ========= */
     {
       const uint32_t nAll = min(nCC + nCP + nPP, MP);
@@ -864,6 +876,7 @@ __global__ void __launch_bounds__(NT) pxStepKernel(const PxStepParams P) {
       }
     }
     __syncthreads();
+    PROF_MARK(2)
     const uint32_t mRaw = s.misc[MI_MCOUNT];
     const uint32_t M = min(mRaw, MM);
     if (tid == 0 && mRaw > MM) overflow |= PX_BATCH_OVERFLOW_MANIFOLDS;
@@ -956,6 +969,7 @@ __global__ void __launch_bounds__(NT) pxStepKernel(const PxStepParams P) {
     }
     __syncthreads();
 
+    PROF_MARK(3)
     /* ====================== phase E: sequential impulses, dataflow order ============== */
     if (P.flags & PX_BATCH_FLAG_SERIAL_SOLVER) {
       /* debug: literal pool-order walk by one thread (needs the ordered list: rebuild it
@@ -1029,6 +1043,7 @@ __global__ void __launch_bounds__(NT) pxStepKernel(const PxStepParams P) {
     }
     __syncthreads();
 
+    PROF_MARK(4)
     /* ====================== phase F: integrate velocities, correct positions, sleep ==== */
     uint32_t sleepingLocal = 0;
     for (uint32_t p = tid; p < nDyn; p += NT) {
@@ -1118,6 +1133,7 @@ __global__ void __launch_bounds__(NT) pxStepKernel(const PxStepParams P) {
       statManifolds = M;
     }
     __syncthreads();
+    PROF_MARK(5)
   }
 
   /* --------------------------------------------------------------- store (smem -> HBM) */

@@ -56,6 +56,7 @@ struct PxStepParams {
   const uint8_t *imm;
   uint8_t *trace; /* NULL unless PX_BATCH_FLAG_TRACE */
   const float *sinTable;
+  unsigned long long *prof; /* NULL, or u64[nWorlds][8] SM-clock cycles per phase (PX_BATCH_FLAG_PROFILE) */
   uint32_t kSubsteps;
   uint32_t flags;
 };

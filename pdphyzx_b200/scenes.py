@@ -134,27 +134,34 @@ def _pen(b: _Builder, cell: float, cols: int, rows_tall: int, e=0.5, sf=0.5, df=
     return width, floor_y
 
 
-def _regular_polygon(n: int, radius: float, seed, world, body) -> np.ndarray:
-    """n points at jittered angles / radii in [0.8, 1.0]*radius: convex with all points on the
-    hull for n <= 8 (the reference's gift-wrap hull drops any that are not)."""
-    i = np.arange(n)
-    ja = rand01(seed, world, body * 16 + i, 11) - np.float32(0.5)
-    jr = rand01(seed, world, body * 16 + i, 12)
-    ang = (i + np.float32(0.35) * ja) * np.float32(2.0 * np.pi / n)
-    rad = radius * (np.float32(0.8) + np.float32(0.2) * jr)
-    return np.stack([rad * np.cos(ang), rad * np.sin(ang)], axis=1).astype(np.float32)
+def _polygons(n: np.ndarray, radius: np.ndarray, seed, world, body: np.ndarray) -> np.ndarray:
+    """Per body: n[i] points at jittered angles / radii in [0.8, 1.0] * radius[i] -- convex with
+    (almost always) all points on the hull for n <= 8; the reference's gift-wrap hull drops
+    any that are not.  Returns float32 [len(n), 8, 2], rows beyond n[i] zero."""
+    k = np.arange(MAX_SCENE_VERTS)[None, :]
+    key = body[:, None] * 16 + k
+    ja = rand01(seed, world, key, 11) - np.float32(0.5)
+    jr = rand01(seed, world, key, 12)
+    nn = n[:, None].astype(np.float32)
+    ang = (k.astype(np.float32) + np.float32(0.35) * ja) * (np.float32(2.0 * np.pi) / nn)
+    rad = radius[:, None].astype(np.float32) * (np.float32(0.8) + np.float32(0.2) * jr)
+    v = np.stack([rad * np.cos(ang), rad * np.sin(ang)], axis=2).astype(np.float32)
+    v[k.repeat(len(n), 0) >= n[:, None]] = 0
+    return v
 
 
 def pile_scene(world: int, seed: int = 1, n_dynamic: int = 252, mix: str = "circles", unit: float = UNIT_M,
                iterations: int = 10, cell: float | None = None, gravity=None, cols: int = 18,
                peg: bool = True, fps: int = 50) -> Scene:
     """Penned pile: `n_dynamic` bodies dropped on a jittered grid `cols` wide into a pen of
-    3 static boxes (+1 static circle peg) -- BASELINE configs 1-4.
+    3 static boxes (+1 static ledge box) -- BASELINE configs 1-4.
 
     mix = "circles": all circles.  mix = "mixed": 1/3 circles, 1/3 boxes, 1/3 convex polygons
-    with 3-8 vertices, interleaved by body index.  `cell` is the grid pitch in world length
-    units (default 0.6 for UNIT_M, 12 for UNIT_MM/UNIT_CM pixel-like scenes); body radius is
-    ~0.42 * cell.  Gravity defaults to (0, 9.8) m/s^2 (scaled by the unit inside setGravity).
+    with 3-8 vertices, interleaved by body index.  mix = "polygons": boxes and polygons.
+    `cell` is the grid pitch in world length units (default 0.6 for UNIT_M, 12 for the
+    pixel-like UNIT_CM / UNIT_MM scenes); body radius is ~0.4 * cell.  Gravity defaults to
+    (0, 9.8) m/s^2 for UNIT_M and the examples' (0, 1.025) otherwise (scaled by the unit inside
+    setGravity).  Vectorised over bodies: a batch of thousands of worlds builds in seconds.
     """
     if cell is None:
         cell = 0.6 if unit == UNIT_M else 12.0
@@ -163,34 +170,52 @@ def pile_scene(world: int, seed: int = 1, n_dynamic: int = 252, mix: str = "circ
     rows_tall = (n_dynamic + cols - 1) // cols
     b = _Builder()
     width, floor_y = _pen(b, cell, cols, rows_tall, peg=peg)
+    stat = b.scene()
+    ns = stat.n_bodies
+
+    f32 = np.float32
     idx = np.arange(n_dynamic)
-    jx = rand01(seed, world, idx, 1) - np.float32(0.5)
-    jy = rand01(seed, world, idx, 2) - np.float32(0.5)
+    jx = rand01(seed, world, idx, 1) - f32(0.5)
+    jy = rand01(seed, world, idx, 2) - f32(0.5)
     jr = rand01(seed, world, idx, 3)
     jk = rand01(seed, world, idx, 4)
     ja = rand01(seed, world, idx, 5)
-    for i in range(n_dynamic):
-        cx = np.float32(cell) * np.float32(0.75 + (i % cols) + 0.2 * jx[i])
-        cy = np.float32(floor_y) - np.float32(cell) * np.float32(1.0 + (i // cols) * 1.05 + 0.2 * jy[i]) - np.float32(cell)
-        r = np.float32(cell) * np.float32(0.36 + 0.06 * jr[i])
-        kind = KIND_CIRCLE
-        if mix == "mixed":
-            kind = (KIND_CIRCLE, KIND_BOX, KIND_POLYGON)[i % 3]
-        elif mix == "polygons":
-            kind = (KIND_BOX, KIND_POLYGON)[i % 2]
-        if kind == KIND_CIRCLE:
-            b.add(1, KIND_CIRCLE, p0=float(r), density=1.0, x=float(cx), y=float(cy))
-        elif kind == KIND_BOX:
-            w = np.float32(2.0) * r * np.float32(0.75 + 0.2 * jk[i])
-            h = np.float32(2.0) * r * np.float32(0.95 - 0.2 * jk[i])
-            b.add(1, KIND_BOX, p0=float(w), p1=float(h), density=1.0, x=float(cx), y=float(cy),
-                  angle=float(np.float32(0.3) * (ja[i] - np.float32(0.5))))
-        else:
-            n = 3 + int(jk[i] * 6.0) % 6  # 3..8
-            v = _regular_polygon(n, float(r) * 1.1, seed, world, i)
-            b.add(1, KIND_POLYGON, verts=v, density=1.0, x=float(cx), y=float(cy),
-                  angle=float(np.float32(6.28) * ja[i]))
-    return b.scene(unit=unit, fps=fps, iterations=iterations, gravity=tuple(gravity))
+    cell32 = f32(cell)
+    cx = cell32 * (f32(0.75) + (idx % cols).astype(f32) + f32(0.2) * jx)
+    cy = f32(floor_y) - cell32 * (f32(2.0) + (idx // cols).astype(f32) * f32(1.05) + f32(0.2) * jy)
+    r = cell32 * (f32(0.36) + f32(0.06) * jr)
+    if mix == "mixed":
+        kind = np.array([KIND_CIRCLE, KIND_BOX, KIND_POLYGON], np.uint8)[idx % 3]
+    elif mix == "polygons":
+        kind = np.array([KIND_BOX, KIND_POLYGON], np.uint8)[idx % 2]
+    else:
+        kind = np.full(n_dynamic, KIND_CIRCLE, np.uint8)
+    is_c, is_b, is_p = kind == KIND_CIRCLE, kind == KIND_BOX, kind == KIND_POLYGON
+    p0 = np.zeros(n_dynamic, f32)
+    p1 = np.zeros(n_dynamic, f32)
+    p0[is_c] = r[is_c]
+    p0[is_b] = (f32(2.0) * r * (f32(0.75) + f32(0.2) * jk))[is_b]
+    p1[is_b] = (f32(2.0) * r * (f32(0.95) - f32(0.2) * jk))[is_b]
+    nverts = np.zeros(n_dynamic, np.uint8)
+    nverts[is_p] = (3 + (jk * f32(6.0)).astype(np.int64) % 6)[is_p]
+    verts = np.zeros((n_dynamic, MAX_SCENE_VERTS, 2), f32)
+    if is_p.any():
+        verts[is_p] = _polygons(nverts[is_p].astype(np.int64), (r * f32(1.1))[is_p], seed, world, idx[is_p])
+    angle = np.zeros(n_dynamic, f32)
+    angle[is_b] = (f32(0.3) * (ja - f32(0.5)))[is_b]
+    angle[is_p] = (f32(6.28) * ja)[is_p]
+
+    cat = lambda a, c: np.concatenate([a, c])
+    zeros = np.zeros(ns + n_dynamic, f32)
+    return Scene(
+        unit=unit, fps=fps, iterations=iterations, gravity=tuple(gravity),
+        dynamic=cat(stat.dynamic, np.ones(n_dynamic, np.uint8)), kind=cat(stat.kind, kind),
+        p0=cat(stat.p0, p0), p1=cat(stat.p1, p1), nverts=cat(stat.nverts, nverts), verts=cat(stat.verts, verts),
+        density=cat(stat.density, np.ones(n_dynamic, f32)), x=cat(stat.x, cx.astype(f32)), y=cat(stat.y, cy.astype(f32)),
+        restitution=cat(stat.restitution, np.full(n_dynamic, 0.2, f32)),
+        static_friction=cat(stat.static_friction, np.full(n_dynamic, 0.5, f32)),
+        dynamic_friction=cat(stat.dynamic_friction, np.full(n_dynamic, 0.3, f32)),
+        vx=zeros.copy(), vy=zeros.copy(), av=zeros.copy(), angle=cat(np.zeros(ns, f32), angle))
 
 
 def stack_scene(world: int, seed: int = 1, n_dynamic: int = 60, unit: float = UNIT_MM, iterations: int = 10,
@@ -210,7 +235,8 @@ def stack_scene(world: int, seed: int = 1, n_dynamic: int = 60, unit: float = UN
         cx = cell * (1.0 + 1.5 * col) + float(np.float32(0.04) * np.float32(cell) * jx[i])
         cy = floor_y - cell * (0.5 + row * 1.01)
         if (i + world) % 4 == 3:
-            v = _regular_polygon(6 + 2 * (i % 2), cell * 0.5, seed, world, i)
+            nv = 6 + 2 * (i % 2)
+            v = _polygons(np.array([nv]), np.array([cell * 0.5], np.float32), seed, world, np.array([i]))[0, :nv]
             b.add(1, KIND_POLYGON, verts=v, density=1.0, x=cx, y=cy, e=0.1, sf=0.6, df=0.4)
         else:
             w = cell * float(np.float32(0.9) + np.float32(0.1) * jk[i])
