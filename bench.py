@@ -335,6 +335,14 @@ def run_ours(args):
             tot = pr.sum()
             out["phase_share"] = {n: float(pr[:, i].sum() / tot) for i, n in enumerate(
                 ("A_sort", "B_sweep", "C_narrowphase", "D_lists", "E_solver", "F_integrate"))}
+            tot = pr[:, :6].sum()
+            out["phase_share"] = {n: float(pr[:, i].sum() / tot) for i, n in enumerate(
+                ("A_sort", "B_sweep", "C_narrowphase", "D_lists", "E_solver", "F_integrate"))}
+            nsub = float(blocks.header["substeps"].mean())
+            out["solver_rounds_per_substep"] = float(pr[:, 6].mean() / nsub)
+            out["solver_cycles_per_round"] = float(pr[:, 4].sum() / max(pr[:, 6].sum(), 1))
+            out["solver_apply_cycles_per_round"] = float(pr[:, 7].sum() / max(pr[:, 6].sum(), 1))
+            pr = pr[:, :6]
             out["cycles_per_world_substep"] = float(pr.sum(axis=1).mean() / float(blocks.header["substeps"].mean()))
         if e2e_ms is not None:
             out["e2e"] = {"value": body_substeps / (e2e_ms * 1e-3), "unit": "body-substeps/s",

@@ -81,7 +81,7 @@ extern "C" PxBatch *pxBatchCreate(uint32_t nWorlds, const PxBatchDesc *desc) {
     delete b;
     return nullptr;
   }
-  pxPlanSmem(&b->L, &b->plan);
+  pxPlanSmem(&b->L, 1, &b->plan);
 
   auto fail = [&](const char *what, cudaError_t e) -> PxBatch * {
     pxSetError(-(int)e - 1000, "pxBatchCreate: %s: %s", what, cudaGetErrorString(e));
@@ -98,25 +98,35 @@ extern "C" PxBatch *pxBatchCreate(uint32_t nWorlds, const PxBatchDesc *desc) {
   cudaDeviceProp prop;
   if ((e = cudaGetDeviceProperties(&prop, dev)) != cudaSuccess) return fail("cudaGetDeviceProperties", e);
   b->numSms = prop.multiProcessorCount;
-  if (b->plan.total > (uint32_t)prop.sharedMemPerBlockOptin) {
-    pxSetError(-2, "pxBatchCreate: a world needs %u bytes of shared memory, the device offers %zu per CTA; lower the capacities",
-               b->plan.total, (size_t)prop.sharedMemPerBlockOptin);
-    pxBatchFree(b);
-    return nullptr;
-  }
   if (desc->stream) {
     b->stream = (cudaStream_t)desc->stream;
   } else {
     if ((e = cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
     b->ownStream = true;
   }
-  b->threads = desc->threads ? desc->threads : 256;
+  b->threads = desc->threads ? desc->threads : 128;
   if (b->threads != 64 && b->threads != 128 && b->threads != 256) {
     pxSetError(-1, "PxBatchDesc.threads must be 64, 128 or 256");
     pxBatchFree(b);
     return nullptr;
   }
+  {
+    /* keep the polygon vertex pool in shared memory unless reading it through L1 instead
+     * lets one more world be resident per SM (the solver phase is latency-bound: resident
+     * worlds are what hides it) */
+    PxSmemPlan slim;
+    pxPlanSmem(&b->L, 0, &slim);
+    const size_t perSm = (size_t)prop.sharedMemPerMultiprocessor, reserve = (size_t)prop.reservedSharedMemPerBlock;
+    const size_t fat = perSm / (b->plan.total + reserve), thin = perSm / (slim.total + reserve);
+    if (b->plan.total > (uint32_t)prop.sharedMemPerBlockOptin || thin > fat) b->plan = slim;
+  }
 
+  if (b->plan.total > (uint32_t)prop.sharedMemPerBlockOptin) {
+    pxSetError(-2, "pxBatchCreate: a world needs %u bytes of shared memory, the device offers %zu per CTA; lower the capacities",
+               b->plan.total, (size_t)prop.sharedMemPerBlockOptin);
+    pxBatchFree(b);
+    return nullptr;
+  }
   const size_t mutBytes = (size_t)nWorlds * b->L.mutStride, immBytes = (size_t)nWorlds * b->L.immStride;
   if ((e = cudaMalloc(&b->dMut, mutBytes)) != cudaSuccess) return fail("cudaMalloc(mutable)", e);
   if ((e = cudaMalloc(&b->dImm, immBytes)) != cudaSuccess) return fail("cudaMalloc(immutable)", e);

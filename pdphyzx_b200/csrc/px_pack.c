@@ -37,7 +37,7 @@ int pxBatchComputeLayout(uint32_t nWorlds, const PxBatchDesc *desc, PxBatchLayou
   L->maxPairs = desc->maxPairs ? desc->maxPairs : 8 * L->maxDynamic + 64;
   L->maxManifolds = alignUp(L->maxManifolds, 32);
   L->maxPairs = alignUp(L->maxPairs, 32);
-  if (L->maxVertices >= (1u << 24) || L->maxPairs > 32767 || L->maxManifolds > 65535) {
+  if (L->maxVertices >= (1u << 24) || L->maxPairs > 32767 || L->maxManifolds > 1024) {
     return pxSetError(-1, "PxBatchDesc: capacity too large");
   }
   /* the sweep counts pairs in packed 16-bit fields: all-pairs worst case must fit */

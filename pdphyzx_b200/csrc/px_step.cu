@@ -2,10 +2,12 @@
  * px_step.cu -- the pdphyzx world substep as one fused sm_100a kernel.
  *
  * One CTA per world.  The CTA loads its world's SoA block from HBM with coalesced 16-byte
- * accesses, keeps all body and manifold state in shared memory across K fused substeps
- * (K x pxWorldStepWithDt, reference src/px_world.c:410-420) and stores the mutable rows back.
- * No tensor cores: nothing here is a dense contraction.  Compile with -fmad=false: every
- * multiply-add must round twice, exactly like the scalar CPU build.
+ * accesses, keeps body and manifold state in shared memory (and the per-body state only its
+ * owner thread needs -- angle, force, torque, sleep time -- in registers) across K fused
+ * substeps (K x pxWorldStepWithDt, reference src/px_world.c:410-420) and stores the mutable
+ * rows back.  No tensor cores: nothing here is a dense contraction.  Compile with
+ * -fmad=false: every multiply-add must round twice, exactly like the scalar CPU build
+ * (SURVEY 0.11).
  *
  * Phases of a substep and the reference code each one restates
  *   A  AABBs, stable order by aabb.min.x           px_body_array.c:81-102, px_circle.c:43-48
@@ -24,9 +26,9 @@
  * px_body.c:148).  Phase D builds, for every dynamic body, the list of manifolds touching it
  * in pool order; phase E is a dataflow execution of the visit DAG those lists define: a
  * visit runs when it is at the head of the lists of both its bodies.  One warp pops up to 32
- * ready visits per round, so lanes stay dense, and iterations pipeline into each other
- * exactly as far as the dependencies allow.  Any such schedule produces the same bits as the
- * sequential loop.  Positional correction (px_manifold.c:217-255) depends only on the
+ * ready contact visits per round, so lanes stay dense, and iterations pipeline into each
+ * other exactly as far as the dependencies allow.  Any such schedule produces the same bits
+ * as the sequential loop.  Positional correction (px_manifold.c:217-255) depends only on the
  * manifold's normal/penetration and inverse masses, so each body sums its terms in list
  * order on its own thread.
  */
@@ -97,38 +99,38 @@ __device__ __forceinline__ V2 normalize(V2 v, float eps) {
 struct Sm {
   float *px, *py, *m00, *m01, *m10, *m11, *rad, *e, *sf, *df;
   uint32_t *shape;
-  float *vx, *vy, *av, *iM, *iI, *angle, *fx, *fy, *tq, *slp;
-  uint8_t *flags, *order, *order2, *posOf, *restFlag, *wakeFlag;
-  float4 *verts;
-  float *sinT;
+  float *vx, *vy, *av, *iM, *iI;
+  uint8_t *flags, *order, *order2, *posOf, *restFlag, *wakeFlag, *sSlot;
   PxWorldHeader *hdr;
   uint32_t *misc;
   unsigned long long *scan;
   float *mnx, *mny, *mpen, *mc0x, *mc0y, *mc1x, *mc1y, *msf, *mdf, *me;
   uint32_t *mids;
+  uint16_t *validSlot, *base, *listStart, *cnt, *cntB;
+  uint32_t *fillB;
   float *sMinX, *sMaxX, *sMinY, *sMaxY;
-  uint8_t *sSlot, *sSleep;
+  uint8_t *sSleep;
   float *stMinX, *stMaxX, *stMinY, *stMaxY;
-  uint16_t *list;
-  uint8_t *arr;
-  uint16_t *queue;
   uint32_t *bins;
-  uint16_t *cnt, *cntB, *listStart, *cursor;
-  uint32_t *remaining;
-  unsigned long long *stash;
-  uint16_t *validSlot;
-  uint32_t *maskB;
-  uint16_t *base;
+  const float4 *verts; /* shared memory or, when the pool does not fit, global through L1 */
+  uint16_t *list, *nextw;
+  uint8_t *sig;
+  uint32_t *queue;
 };
 
 /* misc[] slots */
-enum { MI_MCOUNT = 0, MI_QTAIL, MI_OVERFLOW, MI_UNSORTED, MI_SLEEPING, MI_NPAIRS, MI_BIN0, MI_BIN1, MI_BIN2, MI_BIN3 };
+enum { MI_MCOUNT = 0, MI_QTAIL, MI_OVERFLOW, MI_UNSORTED, MI_SLEEPING, MI_VISITS };
 
-/* manifold ids word: slotA | bodyIdB << 8 | bIsDynamic << 17 | contactCount << 18 */
+/*
+ * Rich manifold word (mids[] and ready-queue entries):
+ *   slotA | bodyIdB << 8 | bIsDynamic << 17 | contactCount << 18 | manifoldSlot << 20 | contactIndex << 30
+ */
 #define MID_A(w) ((w) & 0xffu)
 #define MID_B(w) (((w) >> 8) & 0x1ffu)
 #define MID_BDYN(w) (((w) >> 17) & 1u)
 #define MID_COUNT(w) (((w) >> 18) & 3u)
+#define MID_SLOT(w) (((w) >> 20) & 0x3ffu)
+#define MID_CI(w) (((w) >> 30) & 1u)
 
 /* bins word: pairSeq << 17 | slotA << 9 | bodyIdB */
 #define BIN_SEQ(w) ((w) >> 17)
@@ -372,8 +374,10 @@ __device__ void collidePolygons(const DBody &A, const DBody &B, float eps, float
   m.count = n;
 }
 
+
+
 /* ------------------------------------------------------------------------- block scan */
-/* exclusive prefix sum of a packed 4 x 16-bit counter word over the CTA, in thread order */
+/* exclusive prefix sum of a packed counter word over the CTA, in thread order */
 template <int NT>
 __device__ __forceinline__ unsigned long long blockExclusiveScan(unsigned long long v, unsigned long long *scratch,
                                                                  unsigned long long &total) {
@@ -421,77 +425,76 @@ __device__ __forceinline__ uint32_t firstStaticAfterX(const float *stMaxX, uint3
   return low;
 }
 
-/* pxManifoldApplyImpulse, px_manifold.c:98-215, for one manifold slot.  The caller
- * guarantees nobody else touches the two bodies' velocities while this runs. */
-__device__ __forceinline__ void applyManifoldImpulse(const Sm &s, uint32_t ms, float eps) {
-  const uint32_t ids = s.mids[ms];
-  const uint32_t a = MID_A(ids), b = MID_B(ids), bdyn = MID_BDYN(ids), count = MID_COUNT(ids);
-  /* px_world.c:252-255: skip when both bodies sleep (statics never sleep) */
-  if (bdyn && (s.flags[a] & PX_FLAG_SLEEPING) && (s.flags[b] & PX_FLAG_SLEEPING)) return;
 
+
+/*
+ * One contact of pxManifoldApplyImpulse (px_manifold.c:98-215).  The two-contact loop of
+ * the reference is executed as two consecutive ready-queue visits of the same manifold
+ * (contact 0 then contact 1, nothing in between can touch either body), so every solver
+ * round costs one contact.  The caller guarantees nobody else touches the two bodies'
+ * velocities while this runs.
+ * px_world.c:252-255 skips a manifold when both bodies sleep; the sweep never creates one
+ * for two sleeping dynamic bodies (px_world.c:367-369), sleep flags do not change between
+ * the two, and statics never sleep, so the test is always false here.
+ */
+__device__ __forceinline__ void applyContactImpulse(const Sm &s, uint32_t w, float eps) {
+  const uint32_t ms = MID_SLOT(w), a = MID_A(w), b = MID_B(w), ci = MID_CI(w);
+  const bool bdyn = MID_BDYN(w) != 0;
+  /* every load below depends only on the queue word: one shared-memory round trip */
   const V2 n = v2(s.mnx[ms], s.mny[ms]);
   const float e = s.me[ms], sf = s.msf[ms], df = s.mdf[ms];
+  const float *cxp = ci ? s.mc1x : s.mc0x, *cyp = ci ? s.mc1y : s.mc0y;
+  const V2 c = v2(cxp[ms], cyp[ms]);
   const V2 pa = v2(s.px[a], s.py[a]), pb = v2(s.px[b], s.py[b]);
-  const float iMA = s.iM[a], iIA = s.iI[a];
-  float iMB = 0.0f, iIB = 0.0f;
-  V2 va = v2(s.vx[a], s.vy[a]);
-  float wa = s.av[a];
-  V2 vb = v2(0.0f, 0.0f);
-  float wb = 0.0f;
-  if (bdyn) {
-    iMB = s.iM[b];
-    iIB = s.iI[b];
-    vb = v2(s.vx[b], s.vy[b]);
-    wb = s.av[b];
+  const float iMA = s.iM[a], iIA = s.iI[a], iMB = s.iM[b], iIB = s.iI[b]; /* statics: 0 */
+  V2 va = v2(s.vx[a], s.vy[a]), vb = v2(s.vx[b], s.vy[b]);
+  float wa = s.av[a], wb = s.av[b];
+  const float fcount = (float)MID_COUNT(w);
+
+  const V2 ra = c - pa, rb = c - pb;
+  const V2 raPerp = v2(-ra.y, ra.x), rbPerp = v2(-rb.y, rb.x);
+  V2 rv = (vb + rbPerp * wb) - (va + raPerp * wa);
+  const float vn = dot(rv, n);
+  if (vn > 0) return;
+
+  const float raCrossN = cross(ra, n), rbCrossN = cross(rb, n);
+  const float invMassSum = iMA + iMB + raCrossN * raCrossN * iIA + rbCrossN * rbCrossN * iIB;
+  const float normalMag = -(1.0f + e) * vn;
+  const float denom = invMassSum * fcount;
+  const float rcpDenom = fRcp(denom);
+  const float j = normalMag * rcpDenom;
+  const V2 impulse = n * j;
+  { /* pxBodyApplyImpulse(bodyA, -impulse, ra), px_body.c:147-156 */
+    const V2 ni = -impulse;
+    va = v2(va.x + ni.x * iMA, va.y + ni.y * iMA);
+    wa = wa + cross(ra, ni) * iIA;
   }
-  const float fcount = (float)count;
+  { /* bodyB only if dynamic (px_manifold.c:165-167); a static keeps its exact zeros */
+    const V2 nvb = v2(vb.x + impulse.x * iMB, vb.y + impulse.y * iMB);
+    const float nwb = wb + cross(rb, impulse) * iIB;
+    vb = bdyn ? nvb : vb;
+    wb = bdyn ? nwb : wb;
+  }
 
-  for (uint32_t i = 0; i < count; i++) {
-    V2 c = i == 0 ? v2(s.mc0x[ms], s.mc0y[ms]) : v2(s.mc1x[ms], s.mc1y[ms]);
-    V2 ra = c - pa, rb = c - pb;
-    V2 raPerp = v2(-ra.y, ra.x), rbPerp = v2(-rb.y, rb.x);
-    V2 rv = (vb + rbPerp * wb) - (va + raPerp * wa);
-    float vn = dot(rv, n);
-    if (vn > 0) continue;
-
-    float raCrossN = cross(ra, n), rbCrossN = cross(rb, n);
-    float invMassSum = iMA + iMB + raCrossN * raCrossN * iIA + rbCrossN * rbCrossN * iIB;
-    float normalMag = -(1.0f + e) * vn;
-    float denom = invMassSum * fcount;
-    float rcpDenom = fRcp(denom);
-    float j = normalMag * rcpDenom;
-    V2 impulse = n * j;
-    { /* pxBodyApplyImpulse(bodyA, -impulse, ra), px_body.c:147-156 */
-      V2 ni = -impulse;
-      va = v2(va.x + ni.x * iMA, va.y + ni.y * iMA);
-      wa = wa + cross(ra, ni) * iIA;
-    }
-    if (bdyn) {
-      vb = v2(vb.x + impulse.x * iMB, vb.y + impulse.y * iMB);
-      wb = wb + cross(rb, impulse) * iIB;
-    }
-
-    rv = (vb + rbPerp * wb) - (va + raPerp * wa);
-    V2 tangent = rv - n * dot(rv, n);
-    float tlen = fSqrt(lensq(tangent));
-    if (!(tlen > eps)) continue;
+  rv = (vb + rbPerp * wb) - (va + raPerp * wa);
+  V2 tangent = rv - n * dot(rv, n);
+  const float tlen = fSqrt(lensq(tangent));
+  if (tlen > eps) {
     tangent = tangent * fRcp(tlen);
-    float tmag = -dot(rv, tangent);
-    float jt = tmag * rcpDenom; /* same denominator, same pxFastRcp value */
-    V2 friction;
-    if (fabsf(jt) < j * sf) {
-      friction = tangent * jt;
-    } else {
-      friction = tangent * (-j * df);
-    }
+    const float tmag = -dot(rv, tangent);
+    const float jt = tmag * rcpDenom; /* same denominator, same pxFastRcp value */
+    const float fmag = (fabsf(jt) < j * sf) ? jt : (-j * df);
+    const V2 friction = tangent * fmag;
     {
-      V2 nf = -friction;
+      const V2 nf = -friction;
       va = v2(va.x + nf.x * iMA, va.y + nf.y * iMA);
       wa = wa + cross(ra, nf) * iIA;
     }
-    if (bdyn) {
-      vb = v2(vb.x + friction.x * iMB, vb.y + friction.y * iMB);
-      wb = wb + cross(rb, friction) * iIB;
+    {
+      const V2 nvb = v2(vb.x + friction.x * iMB, vb.y + friction.y * iMB);
+      const float nwb = wb + cross(rb, friction) * iIB;
+      vb = bdyn ? nvb : vb;
+      wb = bdyn ? nwb : wb;
     }
   }
   s.vx[a] = va.x;
@@ -504,27 +507,24 @@ __device__ __forceinline__ void applyManifoldImpulse(const Sm &s, uint32_t ms, f
   }
 }
 
-__device__ __forceinline__ void bindSmem(Sm &s, uint8_t *base, const PxSmemPlan &S) {
+__device__ __forceinline__ void bindSmem(Sm &s, uint8_t *base, const PxSmemPlan &S, const float4 *globalVerts) {
 #define BIND(field, type) s.field = (type *)(base + S.field)
   BIND(px, float); BIND(py, float); BIND(m00, float); BIND(m01, float); BIND(m10, float); BIND(m11, float);
   BIND(rad, float); BIND(e, float); BIND(sf, float); BIND(df, float); BIND(shape, uint32_t);
   BIND(vx, float); BIND(vy, float); BIND(av, float); BIND(iM, float); BIND(iI, float);
-  BIND(angle, float); BIND(fx, float); BIND(fy, float); BIND(tq, float); BIND(slp, float);
   BIND(flags, uint8_t); BIND(order, uint8_t); BIND(order2, uint8_t); BIND(posOf, uint8_t);
-  BIND(restFlag, uint8_t); BIND(wakeFlag, uint8_t);
-  BIND(verts, float4); BIND(sinT, float); BIND(hdr, PxWorldHeader); BIND(misc, uint32_t);
-  BIND(scan, unsigned long long);
+  BIND(restFlag, uint8_t); BIND(wakeFlag, uint8_t); BIND(sSlot, uint8_t);
+  BIND(hdr, PxWorldHeader); BIND(misc, uint32_t); BIND(scan, unsigned long long);
   BIND(mnx, float); BIND(mny, float); BIND(mpen, float); BIND(mc0x, float); BIND(mc0y, float);
   BIND(mc1x, float); BIND(mc1y, float); BIND(msf, float); BIND(mdf, float); BIND(me, float); BIND(mids, uint32_t);
-  BIND(sMinX, float); BIND(sMaxX, float); BIND(sMinY, float); BIND(sMaxY, float);
-  BIND(sSlot, uint8_t); BIND(sSleep, uint8_t);
+  BIND(validSlot, uint16_t); BIND(base, uint16_t); BIND(listStart, uint16_t); BIND(cnt, uint16_t); BIND(cntB, uint16_t);
+  BIND(fillB, uint32_t);
+  BIND(sMinX, float); BIND(sMaxX, float); BIND(sMinY, float); BIND(sMaxY, float); BIND(sSleep, uint8_t);
   BIND(stMinX, float); BIND(stMaxX, float); BIND(stMinY, float); BIND(stMaxY, float);
-  BIND(list, uint16_t); BIND(arr, uint8_t); BIND(queue, uint16_t);
   BIND(bins, uint32_t);
-  BIND(cnt, uint16_t); BIND(cntB, uint16_t); BIND(listStart, uint16_t); BIND(cursor, uint16_t); BIND(remaining, uint32_t);
-  BIND(stash, unsigned long long);
-  BIND(validSlot, uint16_t); BIND(maskB, uint32_t); BIND(base, uint16_t);
+  BIND(list, uint16_t); BIND(nextw, uint16_t); BIND(sig, uint8_t); BIND(queue, uint32_t);
 #undef BIND
+  s.verts = S.vertsInSmem ? (const float4 *)(base + S.verts) : globalVerts;
 }
 
 template <int NT>
@@ -535,39 +535,37 @@ __device__ __forceinline__ void copyRows(float *dst, const float *src, uint32_t 
   for (uint32_t i = threadIdx.x; i < nFloats / 4; i += NT) d4[i] = s4[i];
 }
 
+#define PX_DMAX 256 /* dynamic slots per world (PX_MAX_BODIES rounded up to the copy granule) */
+
 /* ============================================================================ kernel ==== */
 template <int NT>
-__global__ void __launch_bounds__(NT) pxStepKernel(const PxStepParams P) {
+__global__ void __launch_bounds__(NT, 512 / NT) pxStepKernel(const PxStepParams P) {
+  constexpr int R = PX_DMAX / NT; /* body slots (and sorted positions) owned per thread */
   extern __shared__ __align__(16) uint8_t smemRaw[];
-  Sm s;
-  bindSmem(s, smemRaw, P.S);
-
   const PxBatchLayout &L = P.L;
   const uint32_t D = L.maxDynamic, S = L.maxStatic, MM = L.maxManifolds, MP = L.maxPairs;
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
   const uint32_t world = blockIdx.x;
   uint8_t *gmut = P.mut + (size_t)world * L.mutStride;
   const uint8_t *gimm = P.imm + (size_t)world * L.immStride;
+  Sm s;
+  bindSmem(s, smemRaw, P.S, (const float4 *)(gimm + L.offVerts));
   const float eps = L.epsilon, epsSq = L.epsilonSq, allowedPen = L.allowedPenetration;
   const uint32_t QMASK = P.S.qcap - 1;
+  const float *gdynC = (const float *)(gmut + L.offDyn);
+  float *gdyn = (float *)(gmut + L.offDyn);
 
   /* ---------------------------------------------------------------- load (HBM -> smem) */
   {
-    const float *gdyn = (const float *)(gmut + L.offDyn);
-    copyRows<NT>(s.px, gdyn + PX_DYN_PX * D, D);
-    copyRows<NT>(s.py, gdyn + PX_DYN_PY * D, D);
-    copyRows<NT>(s.vx, gdyn + PX_DYN_VX * D, D);
-    copyRows<NT>(s.vy, gdyn + PX_DYN_VY * D, D);
-    copyRows<NT>(s.av, gdyn + PX_DYN_AV * D, D);
-    copyRows<NT>(s.angle, gdyn + PX_DYN_ANGLE * D, D);
-    copyRows<NT>(s.fx, gdyn + PX_DYN_FX * D, D);
-    copyRows<NT>(s.fy, gdyn + PX_DYN_FY * D, D);
-    copyRows<NT>(s.tq, gdyn + PX_DYN_TORQUE * D, D);
-    copyRows<NT>(s.slp, gdyn + PX_DYN_SLEEP * D, D);
-    copyRows<NT>(s.m00, gdyn + PX_DYN_M00 * D, D);
-    copyRows<NT>(s.m01, gdyn + PX_DYN_M01 * D, D);
-    copyRows<NT>(s.m10, gdyn + PX_DYN_M10 * D, D);
-    copyRows<NT>(s.m11, gdyn + PX_DYN_M11 * D, D);
+    copyRows<NT>(s.px, gdynC + PX_DYN_PX * D, D);
+    copyRows<NT>(s.py, gdynC + PX_DYN_PY * D, D);
+    copyRows<NT>(s.vx, gdynC + PX_DYN_VX * D, D);
+    copyRows<NT>(s.vy, gdynC + PX_DYN_VY * D, D);
+    copyRows<NT>(s.av, gdynC + PX_DYN_AV * D, D);
+    copyRows<NT>(s.m00, gdynC + PX_DYN_M00 * D, D);
+    copyRows<NT>(s.m01, gdynC + PX_DYN_M01 * D, D);
+    copyRows<NT>(s.m10, gdynC + PX_DYN_M10 * D, D);
+    copyRows<NT>(s.m11, gdynC + PX_DYN_M11 * D, D);
     const float *gc = (const float *)(gimm + L.offDynConst);
     copyRows<NT>(s.iM, gc + PX_DYNC_IMASS * D, D);
     copyRows<NT>(s.iI, gc + PX_DYNC_IINERTIA * D, D);
@@ -588,12 +586,29 @@ __global__ void __launch_bounds__(NT) pxStepKernel(const PxStepParams P) {
     copyRows<NT>(s.df + D, gs + PX_STAT_DF * S, S);
     copyRows<NT>(s.rad + D, gs + PX_STAT_RADIUS * S, S);
     copyRows<NT>((float *)(s.shape + D), (const float *)(gimm + L.offStatShape), S);
+    for (uint32_t i = tid; i < S; i += NT) {
+      s.vx[D + i] = 0.0f;
+      s.vy[D + i] = 0.0f;
+      s.av[D + i] = 0.0f;
+      s.iM[D + i] = 0.0f;
+      s.iI[D + i] = 0.0f;
+    }
     copyRows<NT>((float *)s.flags, (const float *)(gmut + L.offDynFlags), D / 4);
     copyRows<NT>((float *)s.order, (const float *)(gmut + L.offDynOrder), D / 4);
-    copyRows<NT>((float *)s.verts, (const float *)(gimm + L.offVerts), L.maxVertices * 4);
-    copyRows<NT>(s.sinT, P.sinTable, 256);
     copyRows<NT>((float *)s.hdr, (const float *)(gmut + L.offHeader), sizeof(PxWorldHeader) / 4);
     if (tid < 16) s.misc[tid] = 0;
+  }
+  /* thread-private body state: slot x = tid + r * NT lives in this thread's registers */
+  float rAngle[R], rFx[R], rFy[R], rTq[R], rSlp[R];
+#pragma unroll
+  for (int r = 0; r < R; r++) {
+    const uint32_t x = tid + r * NT;
+    const bool in = x < D;
+    rAngle[r] = in ? gdynC[PX_DYN_ANGLE * D + x] : 0.0f;
+    rFx[r] = in ? gdynC[PX_DYN_FX * D + x] : 0.0f;
+    rFy[r] = in ? gdynC[PX_DYN_FY * D + x] : 0.0f;
+    rTq[r] = in ? gdynC[PX_DYN_TORQUE * D + x] : 0.0f;
+    rSlp[r] = in ? gdynC[PX_DYN_SLEEP * D + x] : 0.0f;
   }
   __syncthreads();
 
@@ -603,17 +618,16 @@ __global__ void __launch_bounds__(NT) pxStepKernel(const PxStepParams P) {
   const uint32_t iterations = s.hdr->iterations & 255u;
   const float linSleepSq = s.hdr->linearSleepThresholdSq, angSleep = s.hdr->angularSleepThreshold;
   const float timeToSleep = s.hdr->timeToSleep;
-  const uint32_t nRounds = (nDyn + NT - 1) / NT; /* sorted positions handled per thread */
-  uint32_t overflow = 0;                         /* thread 0 accumulates the world's flags */
+  uint32_t overflow = 0; /* thread 0 accumulates the world's flags */
   uint32_t statPairs = 0, statManifolds = 0;
 
   long long profT = 0;
   unsigned long long *prof = P.prof ? P.prof + (size_t)world * 8 : nullptr;
-#define PROF_MARK(slot)                                   \
-  if (prof && tid == 0) {                                 \
-    long long now = clock64();                            \
-    prof[slot] += (unsigned long long)(now - profT);      \
-    profT = now;                                          \
+#define PROF_MARK(slot)                              \
+  if (prof && tid == 0) {                            \
+    long long now = clock64();                       \
+    prof[slot] += (unsigned long long)(now - profT); \
+    profT = now;                                     \
   }
   if (prof && tid == 0) profT = clock64();
 
@@ -627,36 +641,56 @@ __global__ void __launch_bounds__(NT) pxStepKernel(const PxStepParams P) {
     for (uint32_t i = tid; i < D; i += NT) {
       s.restFlag[i] = 0;
       s.wakeFlag[i] = 0;
+      s.fillB[i] = 0;
     }
-    for (uint32_t i = tid; i < D * 8; i += NT) s.maskB[i] = 0;
-    __syncthreads();
     for (uint32_t p = tid; p < nDyn; p += NT) {
       uint32_t slot = s.order[p];
-      float key = s.px[slot] - s.rad[slot];
-      s.sMinX[p] = key;
+      s.sMinX[p] = s.px[slot] - s.rad[slot];
     }
     __syncthreads();
     {
+      /* Stable sort by key (px_body_array.c:81-102 moves an element left only past strictly
+       * greater keys, so equal keys keep their order and the result is the unique stable
+       * permutation).  The list is nearly sorted: odd-even transposition passes that swap
+       * only strictly out-of-order neighbours reach the same permutation in a few passes;
+       * rank-by-counting is the fallback. */
       bool unsorted = false;
       for (uint32_t p = tid; p + 1 < nDyn; p += NT) unsorted |= s.sMinX[p] > s.sMinX[p + 1];
-      if (unsorted) s.misc[MI_UNSORTED] = 1;
-    }
-    __syncthreads();
-    if (s.misc[MI_UNSORTED]) {
-      /* rank by counting = the permutation a stable insertion sort produces
-       * (px_body_array.c:81-102 moves an element left only past strictly greater keys) */
-      for (uint32_t p = tid; p < nDyn; p += NT) {
-        float key = s.sMinX[p];
-        uint32_t rank = 0;
-        for (uint32_t q = 0; q < nDyn; q++) {
-          float kq = s.sMinX[q];
-          rank += (kq < key || (kq == key && q < p)) ? 1u : 0u;
+      int dirty = __syncthreads_or(unsorted);
+      for (int pass = 0; dirty && pass < 12; pass++) {
+#pragma unroll
+        for (uint32_t parity = 0; parity < 2; parity++) {
+          for (uint32_t i = tid; 2 * i + parity + 1 < nDyn; i += NT) {
+            const uint32_t p0 = 2 * i + parity;
+            const float k0 = s.sMinX[p0], k1 = s.sMinX[p0 + 1];
+            if (k0 > k1) {
+              s.sMinX[p0] = k1;
+              s.sMinX[p0 + 1] = k0;
+              const uint8_t o0 = s.order[p0];
+              s.order[p0] = s.order[p0 + 1];
+              s.order[p0 + 1] = o0;
+            }
+          }
+          __syncthreads();
         }
-        s.order2[rank] = s.order[p];
+        unsorted = false;
+        for (uint32_t p = tid; p + 1 < nDyn; p += NT) unsorted |= s.sMinX[p] > s.sMinX[p + 1];
+        dirty = __syncthreads_or(unsorted);
       }
-      __syncthreads();
-      for (uint32_t p = tid; p < nDyn; p += NT) s.order[p] = s.order2[p];
-      __syncthreads();
+      if (dirty) {
+        for (uint32_t p = tid; p < nDyn; p += NT) {
+          float key = s.sMinX[p];
+          uint32_t rank = 0;
+          for (uint32_t q = 0; q < nDyn; q++) {
+            float kq = s.sMinX[q];
+            rank += (kq < key || (kq == key && q < p)) ? 1u : 0u;
+          }
+          s.order2[rank] = s.order[p];
+        }
+        __syncthreads();
+        for (uint32_t p = tid; p < nDyn; p += NT) s.order[p] = s.order2[p];
+        __syncthreads();
+      }
     }
     /* sorted-position arrays for the sweep */
     for (uint32_t p = tid; p < nDyn; p += NT) {
@@ -678,27 +712,25 @@ __global__ void __launch_bounds__(NT) pxStepKernel(const PxStepParams P) {
       s.stMaxY[q] = y + r;
     }
     __syncthreads();
-
     PROF_MARK(0)
+
     /* ====================== phase B: sweep -> ordered pair list, binned by shape pair == */
     /* pass 1 counts, a packed 4x16-bit block scan gives every body its first sequence
      * number and its first index in each of the three type bins, pass 2 writes.  The
      * reference's early-exit `break` acts as `continue`; over a sorted list
      * both give the same pairs, so the dynamic scan stops at the first min.x > A.max.x. */
-    unsigned long long carry = 0; /* running totals of earlier rounds */
-    for (uint32_t r = 0; r < nRounds; r++) {
+    unsigned long long exr[R];
+    uint32_t startStatR[R];
+    unsigned long long carry = 0;
+#pragma unroll
+    for (int r = 0; r < R; r++) {
       const uint32_t p = r * NT + tid;
       unsigned long long counts = 0; /* all | cc << 16 | cp << 32 | pp << 48 */
-      float aMinX = 0, aMaxX = 0, aMinY = 0, aMaxY = 0;
-      uint32_t aSlot = 0, aSleep = 0, aPoly = 0, startStat = 0;
+      uint32_t startStat = 0;
       if (p < nDyn) {
-        aMinX = s.sMinX[p];
-        aMaxX = s.sMaxX[p];
-        aMinY = s.sMinY[p];
-        aMaxY = s.sMaxY[p];
-        aSlot = s.sSlot[p];
-        aSleep = s.sSleep[p];
-        aPoly = PX_SHAPE_COUNT(s.shape[aSlot]) != 0;
+        const float aMinX = s.sMinX[p], aMaxX = s.sMaxX[p], aMinY = s.sMinY[p], aMaxY = s.sMaxY[p];
+        const uint32_t aSleep = s.sSleep[p];
+        const uint32_t aPoly = PX_SHAPE_COUNT(s.shape[s.sSlot[p]]) != 0;
         for (uint32_t q = p + 1; q < nDyn; q++) {
           float bMinX = s.sMinX[q];
           if (bMinX > aMaxX) break;
@@ -717,13 +749,10 @@ __global__ void __launch_bounds__(NT) pxStepKernel(const PxStepParams P) {
         }
       }
       unsigned long long total;
-      unsigned long long ex = blockExclusiveScan<NT>(counts, s.scan, total) + carry;
+      exr[r] = blockExclusiveScan<NT>(counts, s.scan, total) + carry;
       carry += total;
-      if (p < nDyn) {
-        s.base[p] = (uint16_t)min((uint32_t)(ex & 0xffffu), MP);
-        s.stash[p] = ex; /* per-type first indices for pass 2 */
-        s.order2[p] = (uint8_t)startStat;
-      }
+      startStatR[r] = startStat;
+      if (p < nDyn) s.base[p] = (uint16_t)min((uint32_t)(exr[r] & 0xffffu), MP);
     }
     const uint32_t totalPairsRaw = (uint32_t)(carry & 0xffffu);
     const uint32_t nPairs = min(totalPairsRaw, MP);
@@ -735,13 +764,15 @@ __global__ void __launch_bounds__(NT) pxStepKernel(const PxStepParams P) {
     }
     /* bin regions inside bins[]: [0,nCC) circle-circle, [nCC, nCC+nCP) circle-polygon (either
      * order), then polygon-polygon; entries whose sequence number is >= MP are dropped */
-    __syncthreads();
-    for (uint32_t p = tid; p < nDyn; p += NT) {
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+      const uint32_t p = r * NT + tid;
+      if (p >= nDyn) continue;
       const float aMinX = s.sMinX[p], aMaxX = s.sMaxX[p], aMinY = s.sMinY[p], aMaxY = s.sMaxY[p];
       const uint32_t aSlot = s.sSlot[p], aSleep = s.sSleep[p];
       const uint32_t aPoly = PX_SHAPE_COUNT(s.shape[aSlot]) != 0;
-      uint32_t seq = s.base[p];
-      const unsigned long long ex = s.stash[p];
+      const unsigned long long ex = exr[r];
+      uint32_t seq = (uint32_t)(ex & 0xffffu);
       uint32_t binAt[3] = {(uint32_t)((ex >> 16) & 0xffffu), nCC + (uint32_t)((ex >> 32) & 0xffffu),
                            nCC + nCP + (uint32_t)((ex >> 48) & 0xffffu)};
       uint16_t *tpA = gtrace ? (uint16_t *)(gtrace + L.offTracePairs) : nullptr;
@@ -767,7 +798,7 @@ __global__ void __launch_bounds__(NT) pxStepKernel(const PxStepParams P) {
         }
         seq++;
       }
-      for (uint32_t q = s.order2[p]; q < nStat; q++) {
+      for (uint32_t q = startStatR[r]; q < nStat; q++) {
         float bMinX = s.stMinX[q];
         if (bMinX > aMaxX) continue;
         if (!boxesOverlap(aMinX, aMinY, aMaxX, aMaxY, bMinX, s.stMinY[q], s.stMaxX[q], s.stMaxY[q])) continue;
@@ -787,21 +818,25 @@ __global__ void __launch_bounds__(NT) pxStepKernel(const PxStepParams P) {
         seq++;
       }
     }
+    if (P.S.vertsInSmem) {
+      /* region X holds the vertex pool during the narrowphase; the solver's region Y overlays
+       * it afterwards, so it is refreshed from L2 every substep */
+      copyRows<NT>((float *)(smemRaw + P.S.verts), (const float *)(gimm + L.offVerts), L.maxVertices * 4);
+    }
     __syncthreads();
-
     PROF_MARK(1)
+
     /* ====================== phase C: narrowphase, one pair per thread per bin ========= */
     {
       const uint32_t nAll = min(nCC + nCP + nPP, MP);
-      for (uint32_t idx = tid; idx < ((nAll + NT - 1) / NT) * NT; idx += NT) {
+      for (uint32_t idx = tid; idx < nAll; idx += NT) {
         Contact m;
         m.count = 0;
         m.c1 = v2(0.0f, 0.0f);
-        uint32_t word = 0xffffffffu, a = 0, b = 0;
-        if (idx < nAll) word = s.bins[idx];
-        if (word != 0xffffffffu) {
-          a = BIN_A(word);
-          b = BIN_B(word);
+        const uint32_t word = s.bins[idx];
+        if (word == 0xffffffffu) continue;
+        const uint32_t a = BIN_A(word), b = BIN_B(word);
+        {
           DBody A = loadBody(s, a), B = loadBody(s, b);
           if (idx < nCC) {
             collideCircles(A, B, eps, m);
@@ -818,61 +853,50 @@ __global__ void __launch_bounds__(NT) pxStepKernel(const PxStepParams P) {
             collidePolygons(A, B, eps, epsSq, m);
           }
         }
-        if (m.count) {
-          const uint32_t bdyn = b < D;
-          const uint32_t ms = atomicAdd(&s.misc[MI_MCOUNT], 1u);
-          if (ms < MM) {
-            /* pxManifoldInit, px_manifold.c:12-31: geometric-mean friction via pxFastSqrt */
-            s.msf[ms] = fSqrt(s.sf[a] * s.sf[b]);
-            s.mdf[ms] = fSqrt(s.df[a] * s.df[b]);
-            /* pxManifoldDetectRestingContact, px_manifold.c:46-92, on the velocities as they
-             * are before force integration */
-            float ea = s.e[a], eb = s.e[b];
-            float minE = ea < eb ? ea : eb;
-            V2 gstep = g * dt;
-            float gsq = lensq(gstep);
-            V2 pa = v2(s.px[a], s.py[a]), pb = v2(s.px[b], s.py[b]);
-            V2 va = v2(s.vx[a], s.vy[a]);
-            float wa = s.av[a];
-            V2 vb = v2(0.0f, 0.0f);
-            float wb = 0.0f;
-            if (bdyn) {
-              vb = v2(s.vx[b], s.vy[b]);
-              wb = s.av[b];
-            }
-            for (uint32_t i = 0; i < m.count; i++) {
-              V2 c = i == 0 ? m.c0 : m.c1;
-              V2 ra = c - pa, rb = c - pb;
-              V2 rv = (vb + v2(-rb.y, rb.x) * wb) - (va + v2(-ra.y, ra.x) * wa);
-              if (lensq(rv) < gsq + eps) {
-                minE = 0.0f;
-                break;
-              }
-            }
-            s.mnx[ms] = m.normal.x;
-            s.mny[ms] = m.normal.y;
-            s.mpen[ms] = m.pen;
-            s.mc0x[ms] = m.c0.x;
-            s.mc0y[ms] = m.c0.y;
-            s.mc1x[ms] = m.c1.x;
-            s.mc1y[ms] = m.c1.y;
-            s.me[ms] = minE;
-            s.mids[ms] = a | (b << 8) | (bdyn << 17) | (m.count << 18);
-            s.validSlot[BIN_SEQ(word)] = (uint16_t)(ms + 1);
-            /* manifold pass of pxUpdateSleepStates, px_world.c:147-177: flags set by SLOT */
-            const bool resting = (minE == 0.0f);
-            if (!bdyn && resting) {
-              s.restFlag[a] = 1;
-            } else if (bdyn && !resting) {
-              if (s.flags[a] & PX_FLAG_SLEEPING) s.wakeFlag[b] = 1;
-              if (s.flags[b] & PX_FLAG_SLEEPING) s.wakeFlag[a] = 1;
-            }
-            if (bdyn) { /* remember A's sorted position in B's partner mask */
-              uint32_t pa_ = s.posOf[a];
-              atomicOr(&s.maskB[b * 8 + (pa_ >> 5)], 1u << (pa_ & 31u));
-            }
+        if (!m.count) continue;
+        const uint32_t bdyn = b < D;
+        const uint32_t ms = atomicAdd(&s.misc[MI_MCOUNT], 1u);
+        if (ms >= MM) continue; /* manifold overflow, flagged below */
+        /* pxManifoldInit, px_manifold.c:12-31: geometric-mean friction via pxFastSqrt */
+        s.msf[ms] = fSqrt(s.sf[a] * s.sf[b]);
+        s.mdf[ms] = fSqrt(s.df[a] * s.df[b]);
+        /* pxManifoldDetectRestingContact, px_manifold.c:46-92, on the velocities as they are
+         * before force integration */
+        float ea = s.e[a], eb = s.e[b];
+        float minE = ea < eb ? ea : eb;
+        V2 gstep = g * dt;
+        float gsq = lensq(gstep);
+        V2 pa = v2(s.px[a], s.py[a]), pb = v2(s.px[b], s.py[b]);
+        const V2 va = v2(s.vx[a], s.vy[a]), vb = v2(s.vx[b], s.vy[b]); /* statics: exact zeros */
+        const float wa = s.av[a], wb = s.av[b];
+        for (uint32_t i = 0; i < m.count; i++) {
+          V2 c = i == 0 ? m.c0 : m.c1;
+          V2 ra = c - pa, rb = c - pb;
+          V2 rv = (vb + v2(-rb.y, rb.x) * wb) - (va + v2(-ra.y, ra.x) * wa);
+          if (lensq(rv) < gsq + eps) {
+            minE = 0.0f;
+            break;
           }
         }
+        s.mnx[ms] = m.normal.x;
+        s.mny[ms] = m.normal.y;
+        s.mpen[ms] = m.pen;
+        s.mc0x[ms] = m.c0.x;
+        s.mc0y[ms] = m.c0.y;
+        s.mc1x[ms] = m.c1.x;
+        s.mc1y[ms] = m.c1.y;
+        s.me[ms] = minE;
+        s.mids[ms] = a | (b << 8) | (bdyn << 17) | (m.count << 18) | (ms << 20);
+        s.validSlot[BIN_SEQ(word)] = (uint16_t)(ms + 1);
+        /* manifold pass of pxUpdateSleepStates, px_world.c:147-177: flags set by SLOT */
+        const bool resting = (minE == 0.0f);
+        if (!bdyn && resting) {
+          s.restFlag[a] = 1;
+        } else if (bdyn && !resting) {
+          if (s.flags[a] & PX_FLAG_SLEEPING) s.wakeFlag[b] = 1;
+          if (s.flags[b] & PX_FLAG_SLEEPING) s.wakeFlag[a] = 1;
+        }
+        if (bdyn) atomicAdd(&s.fillB[b], 1u); /* bodyB-role manifold count of b */
       }
     }
     __syncthreads();
@@ -884,31 +908,36 @@ __global__ void __launch_bounds__(NT) pxStepKernel(const PxStepParams P) {
     /* ====================== phase D: per-body manifold lists, integrate forces ======== */
     /* Body x (sorted position p) meets its manifolds in pool order: first the ones where it
      * is bodyB (their A-bodies come earlier in the sweep, ordered by A's sorted position),
-     * then its own block where it is bodyA, in sequence order. */
+     * then its own block where it is bodyA, in sequence order.  Region X is dead from here;
+     * region Y (list, nextw, sig, queue) overlays it. */
+    uint32_t rankStartR[R];
     carry = 0;
-    for (uint32_t r = 0; r < nRounds; r++) {
+#pragma unroll
+    for (int r = 0; r < R; r++) {
       const uint32_t p = r * NT + tid;
       uint32_t nA = 0, nB = 0, x = 0;
       if (p < nDyn) {
         x = s.sSlot[p];
         for (uint32_t seq = s.base[p]; seq < s.base[p + 1]; seq++) nA += s.validSlot[seq] != 0;
-#pragma unroll
-        for (int w = 0; w < 8; w++) nB += __popc(s.maskB[x * 8 + w]);
+        nB = s.fillB[x];
       }
       unsigned long long total;
       unsigned long long ex = blockExclusiveScan<NT>((unsigned long long)(nA + nB) | ((unsigned long long)nA << 32), s.scan, total) + carry;
       carry += total;
+      rankStartR[r] = (uint32_t)(ex >> 32);
       if (p < nDyn) {
         s.listStart[x] = (uint16_t)(ex & 0xffffffffu);
         s.cnt[x] = (uint16_t)(nA + nB);
         s.cntB[x] = (uint16_t)nB;
-        s.cursor[x] = 0;
-        s.remaining[x] = (nA + nB) * iterations;
-        s.stash[p] = ex >> 32; /* manifold rank of the block's first manifold (trace output) */
+        s.fillB[x] = 0;
       }
     }
+    for (uint32_t i = tid; i < (2 * M + 3) / 4; i += NT) ((uint32_t *)s.sig)[i] = 0;
     __syncthreads();
-    for (uint32_t p = tid; p < nDyn; p += NT) {
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+      const uint32_t p = r * NT + tid;
+      if (p >= nDyn) continue;
       const uint32_t x = s.sSlot[p];
       const uint32_t startX = s.listStart[x], nBx = s.cntB[x];
       uint32_t k = 0;
@@ -918,27 +947,12 @@ __global__ void __launch_bounds__(NT) pxStepKernel(const PxStepParams P) {
         const uint32_t ms = vs - 1;
         const uint32_t ids = s.mids[ms];
         s.list[startX + nBx + k] = (uint16_t)ms;
-        uint32_t arrivals = (nBx == 0 && k == 0) ? 1u : 0u, need = 1;
-        if (MID_BDYN(ids)) {
+        if (MID_BDYN(ids)) { /* unordered placement in B's bodyB segment, sorted below */
           const uint32_t y = MID_B(ids);
-          /* position of this manifold among y's B-role manifolds = partners of y that sit
-           * before p in the sorted order */
-          uint32_t ordB = 0;
-          const uint32_t wq = p >> 5;
-          for (uint32_t w = 0; w < wq; w++) ordB += __popc(s.maskB[y * 8 + w]);
-          ordB += __popc(s.maskB[y * 8 + wq] & ((1u << (p & 31u)) - 1u));
-          s.list[s.listStart[y] + ordB] = (uint16_t)ms;
-          arrivals += ordB == 0 ? 1u : 0u;
-          need = 2;
-        }
-        if (arrivals == need) {
-          s.arr[ms] = 0;
-          if (iterations) s.queue[atomicAdd(&s.misc[MI_QTAIL], 1u) & QMASK] = (uint16_t)ms;
-        } else {
-          s.arr[ms] = (uint8_t)arrivals;
+          s.list[s.listStart[y] + atomicAdd(&s.fillB[y], 1u)] = (uint16_t)ms;
         }
         if (gtrace) { /* ordered manifold dump */
-          const uint32_t rank = (uint32_t)s.stash[p] + k;
+          const uint32_t rank = rankStartR[r] + k;
           float *mf = (float *)(gtrace + L.offTraceManifolds);
           mf[0 * MM + rank] = s.mnx[ms];
           mf[1 * MM + rank] = s.mny[ms];
@@ -956,109 +970,194 @@ __global__ void __launch_bounds__(NT) pxStepKernel(const PxStepParams P) {
         }
         k++;
       }
+    }
+    __syncthreads();
+    /* by slot owner: order the bodyB segment by the A-body's sorted position, derive each
+     * manifold's successor on this body, signal the first manifold, integrate forces */
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+      const uint32_t x = tid + r * NT;
+      if (x >= D || !(s.flags[x] & 4u)) continue;
+      const uint32_t start = s.listStart[x], n = s.cnt[x], nBx = s.cntB[x];
+      for (uint32_t i = 1; i < nBx; i++) { /* insertion sort, a handful of entries */
+        const uint32_t cur = s.list[start + i];
+        const uint32_t key = s.posOf[MID_A(s.mids[cur])];
+        int jj = (int)i - 1;
+        while (jj >= 0) {
+          const uint32_t other = s.list[start + jj];
+          if (s.posOf[MID_A(s.mids[other])] <= key) break;
+          s.list[start + jj + 1] = (uint16_t)other;
+          jj--;
+        }
+        s.list[start + jj + 1] = (uint16_t)cur;
+      }
+      for (uint32_t i = 0; i < n; i++) {
+        const uint32_t ms = s.list[start + i];
+        const uint32_t side = i < nBx ? 1u : 0u;
+        const uint32_t in = i + 1 == n ? 0u : i + 1;
+        const uint32_t succ = s.list[start + in];
+        s.nextw[2 * ms + side] = (uint16_t)(succ | ((in < nBx ? 1u : 0u) << 15));
+      }
+      if (n) {
+        const uint32_t first = s.list[start];
+        s.sig[2 * first + (nBx ? 1u : 0u)] = 1;
+      }
       /* pxIntegrateForces, px_world.c:231-239 / px_body.c:167-179 (resting-contact detection
        * above already consumed the pre-integration velocities) */
       if (!(s.flags[x] & PX_FLAG_SLEEPING)) {
         float halfDt = fDiv(dt, 2.0f);
         float iM = s.iM[x], iI = s.iI[x];
-        V2 dv = (v2(s.fx[x], s.fy[x]) * iM + g) * halfDt;
+        V2 dv = (v2(rFx[r], rFy[r]) * iM + g) * halfDt;
         s.vx[x] = s.vx[x] + dv.x;
         s.vy[x] = s.vy[x] + dv.y;
-        s.av[x] = s.av[x] + s.tq[x] * iI * halfDt;
+        s.av[x] = s.av[x] + rTq[r] * iI * halfDt;
       }
     }
     __syncthreads();
-
+    /* manifolds at the head of the lists of all their dynamic bodies start the solver */
+    if (iterations && !(P.flags & PX_BATCH_FLAG_SERIAL_SOLVER)) {
+      for (uint32_t ms = tid; ms < M; ms += NT) {
+        const uint32_t w = s.mids[ms];
+        if (s.sig[2 * ms] == 1 && (!MID_BDYN(w) || s.sig[2 * ms + 1] == 1)) {
+          s.queue[atomicAdd(&s.misc[MI_QTAIL], 1u) & QMASK] = w;
+        }
+      }
+    }
+    __syncthreads();
     PROF_MARK(3)
+
     /* ====================== phase E: sequential impulses, dataflow order ============== */
     if (P.flags & PX_BATCH_FLAG_SERIAL_SOLVER) {
-      /* debug: literal pool-order walk by one thread (needs the ordered list: rebuild it
-       * from the blocks) */
+      /* debug: literal pool-order walk by one thread */
       if (tid == 0) {
         for (uint32_t it = 0; it < iterations; it++) {
           for (uint32_t p = 0; p < nDyn; p++) {
             for (uint32_t seq = s.base[p]; seq < s.base[p + 1]; seq++) {
               uint32_t vs = s.validSlot[seq];
-              if (vs) applyManifoldImpulse(s, vs - 1, eps);
+              if (!vs) continue;
+              const uint32_t w = s.mids[vs - 1];
+              applyContactImpulse(s, w, eps);
+              if (MID_COUNT(w) > 1) applyContactImpulse(s, w | (1u << 30), eps);
             }
           }
         }
       }
-    } else if (warp == 0) {
-      const uint32_t totalVisits = M * iterations;
-      uint32_t head = 0, tail = s.misc[MI_QTAIL], done = 0;
-      while (done < totalVisits) {
+    } else if (warp == 0 && iterations) {
+      /*
+       * Every manifold side counts the signals it has received (sig).  Visit v of a manifold
+       * may run once each of its dynamic bodies has delivered v + 1 signals: one from the
+       * body at list-build time if the manifold heads that body's list, one each time the
+       * body's previous manifold (cyclically) finishes a visit.  Signals whose target side is
+       * A are applied first, B-side signals after a warp barrier, and exactly one of the two
+       * signalers sees both counts equal and enqueues the visit -- no atomics.
+       */
+      uint32_t head = 0, tail = s.misc[MI_QTAIL], visits = 0;
+      unsigned long long profRounds = 0, profApply = 0;
+      const uint32_t NONE = 0xffffffffu;
+      while (head != tail) {
+        const long long tApply0 = prof ? clock64() : 0;
         const uint32_t n = min(tail - head, 32u);
-        if (n == 0) { /* cannot happen for a consistent list structure */
-          if (lane == 0) overflow |= PX_OVERFLOW_INTERNAL;
-          break;
-        }
-        uint32_t ms = 0, ids = 0;
         const bool active = lane < n;
+        uint32_t w = 0, wt0 = 0, wt1 = 0, mine0 = 0, mine1 = 0;
+        bool sigA0 = false, sigB0 = false, sigA1 = false, sigB1 = false, again = false;
         if (active) {
-          ms = s.queue[(head + lane) & QMASK];
-          ids = s.mids[ms];
-          applyManifoldImpulse(s, ms, eps);
+          w = s.queue[(head + lane) & QMASK];
+          const uint32_t ms = MID_SLOT(w);
+          /* successors of this manifold on body a / body b: static for the whole substep, so
+           * their rich words are fetched now and the latency hides behind the impulse math */
+          const uint32_t nx0 = s.nextw[2 * ms], nx1 = s.nextw[2 * ms + 1];
+          const bool last = MID_CI(w) + 1u >= MID_COUNT(w);
+          const bool two = MID_BDYN(w) != 0;
+          wt0 = s.mids[nx0 & 0x3ffu];
+          wt1 = s.mids[nx1 & 0x3ffu];
+          mine0 = 2u * (nx0 & 0x3ffu) + (nx0 >> 15); /* sig index of (successor, side of body a) */
+          mine1 = 2u * (nx1 & 0x3ffu) + (nx1 >> 15);
+          again = !last;
+          sigA0 = last && (nx0 >> 15) == 0;
+          sigB0 = last && (nx0 >> 15) == 1;
+          sigA1 = last && two && (nx1 >> 15) == 0;
+          sigB1 = last && two && (nx1 >> 15) == 1;
+          applyContactImpulse(s, w, eps);
         }
         __syncwarp();
-        /* release: advance each touched body's cursor, signal the next visit in its list */
-        uint32_t ready0 = 0xffffffffu, ready1 = 0xffffffffu;
-        if (active) {
-#pragma unroll
-          for (int side = 0; side < 2; side++) {
-            if (side == 1 && !MID_BDYN(ids)) break;
-            const uint32_t body = side == 0 ? MID_A(ids) : MID_B(ids);
-            uint32_t left = s.remaining[body] - 1u;
-            s.remaining[body] = left;
-            uint32_t c = s.cursor[body] + 1u;
-            if (c == s.cnt[body]) c = 0;
-            s.cursor[body] = (uint16_t)c;
-            if (left) {
-              const uint32_t nxt = s.list[s.listStart[body] + c];
-              const uint32_t need = 1u + MID_BDYN(s.mids[nxt]);
-              uint32_t got = 1;
-              if (need == 2) {
-                /* two arrivals per visit, possibly from two lanes of this round */
-                got = (uint32_t)atomicAdd((unsigned int *)(s.arr + (nxt & ~3u)), 1u << (8 * (nxt & 3u)));
-                got = ((got >> (8 * (nxt & 3u))) & 0xffu) + 1u;
-              }
-              if (got == need) {
-                if (need == 2) atomicAnd((unsigned int *)(s.arr + (nxt & ~3u)), ~(0xffu << (8 * (nxt & 3u))));
-                if (side == 0) ready0 = nxt; else ready1 = nxt;
-              }
-            }
+        if (prof) {
+          profApply += (unsigned long long)(clock64() - tApply0);
+          profRounds++;
+        }
+        uint32_t push0 = again ? (w | (1u << 30)) : NONE; /* second contact of the same manifold */
+        uint32_t push1 = NONE;
+        /* signals whose target side is A: the signaler pushes if the B side (when there is one)
+         * was complete BEFORE this round */
+        {
+          uint32_t c0 = 0, c1 = 0, o0 = 0, o1 = 0;
+          if (sigA0) {
+            c0 = s.sig[mine0] + 1u;
+            o0 = s.sig[mine0 + 1];
           }
+          if (sigA1) {
+            c1 = s.sig[mine1] + 1u;
+            o1 = s.sig[mine1 + 1];
+          }
+          if (sigA0) s.sig[mine0] = (uint8_t)c0;
+          if (sigA1) s.sig[mine1] = (uint8_t)c1;
+          if (sigA0 && c0 <= iterations && (!MID_BDYN(wt0) || o0 == c0)) push0 = wt0;
+          if (sigA1 && c1 <= iterations && (!MID_BDYN(wt1) || o1 == c1)) push1 = wt1;
         }
         __syncwarp();
-        const uint32_t b0 = __ballot_sync(0xffffffffu, ready0 != 0xffffffffu);
-        const uint32_t b1 = __ballot_sync(0xffffffffu, ready1 != 0xffffffffu);
+        /* signals whose target side is B: the signaler pushes if the A side is complete, be it
+         * from an earlier round or from the phase above */
+        {
+          uint32_t c0 = 0, c1 = 0, o0 = 0, o1 = 0;
+          if (sigB0) {
+            c0 = s.sig[mine0] + 1u;
+            o0 = s.sig[mine0 - 1];
+          }
+          if (sigB1) {
+            c1 = s.sig[mine1] + 1u;
+            o1 = s.sig[mine1 - 1];
+          }
+          if (sigB0) s.sig[mine0] = (uint8_t)c0;
+          if (sigB1) s.sig[mine1] = (uint8_t)c1;
+          if (sigB0 && c0 <= iterations && o0 == c0) push0 = wt0;
+          if (sigB1 && c1 <= iterations && o1 == c1) push1 = wt1;
+        }
+        const uint32_t b0 = __ballot_sync(0xffffffffu, push0 != NONE);
+        const uint32_t b1 = __ballot_sync(0xffffffffu, push1 != NONE);
         const uint32_t lt = (1u << lane) - 1u;
-        if (ready0 != 0xffffffffu) s.queue[(tail + __popc(b0 & lt)) & QMASK] = (uint16_t)ready0;
-        if (ready1 != 0xffffffffu) s.queue[(tail + __popc(b0) + __popc(b1 & lt)) & QMASK] = (uint16_t)ready1;
+        if (push0 != NONE) s.queue[(tail + __popc(b0 & lt)) & QMASK] = push0;
+        if (push1 != NONE) s.queue[(tail + __popc(b0) + __popc(b1 & lt)) & QMASK] = push1;
         tail += __popc(b0) + __popc(b1);
         head += n;
-        done += n;
+        visits += __popc(__ballot_sync(0xffffffffu, sigA0 || sigB0));
         __syncwarp();
+      }
+      if (lane == 0 && visits != M * iterations) overflow |= PX_OVERFLOW_INTERNAL;
+      if (prof && lane == 0) {
+        prof[6] += profRounds;
+        prof[7] += profApply;
       }
     }
     __syncthreads();
-
     PROF_MARK(4)
+
     /* ====================== phase F: integrate velocities, correct positions, sleep ==== */
     uint32_t sleepingLocal = 0;
-    for (uint32_t p = tid; p < nDyn; p += NT) {
-      const uint32_t x = s.sSlot[p];
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+      const uint32_t x = tid + r * NT;
+      if (x >= D || !(s.flags[x] & 4u)) continue;
+      const uint32_t p = s.posOf[x];
       uint32_t fl = s.flags[x];
       float posx = s.px[x], posy = s.py[x];
       /* pxBodyIntegrateVelocity, px_body.c:181-188 */
       if (!(fl & PX_FLAG_SLEEPING)) {
         posx = posx + s.vx[x] * dt;
         posy = posy + s.vy[x] * dt;
-        float radians = s.angle[x] + s.av[x] * dt;
+        float radians = rAngle[r] + s.av[x] * dt;
         radians = fmodf(radians, D_2PI);
         if (radians < 0) radians += D_2PI;
-        s.angle[x] = radians;
-        float c = fSin(s.sinT, radians + D_PI * 0.5f), sn = fSin(s.sinT, radians);
+        rAngle[r] = radians;
+        float c = fSin(P.sinTable, radians + D_PI * 0.5f), sn = fSin(P.sinTable, radians);
         s.m00[x] = c;
         s.m01[x] = -sn;
         s.m10[x] = sn;
@@ -1073,7 +1172,7 @@ __global__ void __launch_bounds__(NT) pxStepKernel(const PxStepParams P) {
           if (pen <= allowedPen) continue;
           const uint32_t ids = s.mids[ms];
           const float iMA = s.iM[MID_A(ids)];
-          const float iMB = MID_BDYN(ids) ? s.iM[MID_B(ids)] : 0.0f;
+          const float iMB = s.iM[MID_B(ids)];
           const float excess = pen - allowedPen;
           const float mag = fDiv(excess * 0.2f, iMA + iMB);
           const V2 corr = v2(s.mnx[ms], s.mny[ms]) * mag;
@@ -1093,7 +1192,7 @@ __global__ void __launch_bounds__(NT) pxStepKernel(const PxStepParams P) {
 
       /* body pass of pxUpdateSleepStates, px_world.c:179-219: the flags are TESTED by sorted
        * position p although they were set by slot -- the reference's behaviour */
-      float slp = s.slp[x];
+      float slp = rSlp[r];
       if (s.wakeFlag[p]) {
         slp = 0.0f;
         fl &= ~PX_FLAG_SLEEPING;
@@ -1110,20 +1209,20 @@ __global__ void __launch_bounds__(NT) pxStepKernel(const PxStepParams P) {
             s.vx[x] = 0.0f;
             s.vy[x] = 0.0f;
             s.av[x] = 0.0f;
-            s.fx[x] = 0.0f;
-            s.fy[x] = 0.0f;
-            s.tq[x] = 0.0f;
+            rFx[r] = 0.0f;
+            rFy[r] = 0.0f;
+            rTq[r] = 0.0f;
             fl |= PX_FLAG_SLEEPING;
           }
         }
       }
-      s.slp[x] = slp;
+      rSlp[r] = slp;
       s.flags[x] = (uint8_t)fl;
       /* pxClearForces, px_world.c:302-311 */
       if (!(slp >= timeToSleep)) {
-        s.fx[x] = 0.0f;
-        s.fy[x] = 0.0f;
-        s.tq[x] = 0.0f;
+        rFx[r] = 0.0f;
+        rFy[r] = 0.0f;
+        rTq[r] = 0.0f;
       }
       sleepingLocal += (fl & PX_FLAG_SLEEPING) ? 1u : 0u;
     }
@@ -1138,23 +1237,28 @@ __global__ void __launch_bounds__(NT) pxStepKernel(const PxStepParams P) {
 
   /* --------------------------------------------------------------- store (smem -> HBM) */
   {
-    float *gdyn = (float *)(gmut + L.offDyn);
     copyRows<NT>(gdyn + PX_DYN_PX * D, s.px, D);
     copyRows<NT>(gdyn + PX_DYN_PY * D, s.py, D);
     copyRows<NT>(gdyn + PX_DYN_VX * D, s.vx, D);
     copyRows<NT>(gdyn + PX_DYN_VY * D, s.vy, D);
     copyRows<NT>(gdyn + PX_DYN_AV * D, s.av, D);
-    copyRows<NT>(gdyn + PX_DYN_ANGLE * D, s.angle, D);
-    copyRows<NT>(gdyn + PX_DYN_FX * D, s.fx, D);
-    copyRows<NT>(gdyn + PX_DYN_FY * D, s.fy, D);
-    copyRows<NT>(gdyn + PX_DYN_TORQUE * D, s.tq, D);
-    copyRows<NT>(gdyn + PX_DYN_SLEEP * D, s.slp, D);
     copyRows<NT>(gdyn + PX_DYN_M00 * D, s.m00, D);
     copyRows<NT>(gdyn + PX_DYN_M01 * D, s.m01, D);
     copyRows<NT>(gdyn + PX_DYN_M10 * D, s.m10, D);
     copyRows<NT>(gdyn + PX_DYN_M11 * D, s.m11, D);
     copyRows<NT>((float *)(gmut + L.offDynFlags), (const float *)s.flags, D / 4);
     copyRows<NT>((float *)(gmut + L.offDynOrder), (const float *)s.order, D / 4);
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+      const uint32_t x = tid + r * NT;
+      if (x < D) {
+        gdyn[PX_DYN_ANGLE * D + x] = rAngle[r];
+        gdyn[PX_DYN_FX * D + x] = rFx[r];
+        gdyn[PX_DYN_FY * D + x] = rFy[r];
+        gdyn[PX_DYN_TORQUE * D + x] = rTq[r];
+        gdyn[PX_DYN_SLEEP * D + x] = rSlp[r];
+      }
+    }
     if (tid == 0) {
       PxWorldHeader *gh = (PxWorldHeader *)(gmut + L.offHeader);
       gh->statManifolds = statManifolds;
@@ -1213,10 +1317,12 @@ __global__ void pxCommandKernel(const PxBatchLayout L, uint8_t *mut, const uint8
   }
 }
 
+
+
 /* ---------------------------------------------------------------------- host launchers */
 static uint32_t alignUp(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
 
-extern "C" void pxPlanSmem(const PxBatchLayout *L, PxSmemPlan *S) {
+extern "C" void pxPlanSmem(const PxBatchLayout *L, int vertsInSmem, PxSmemPlan *S) {
   const uint32_t D = L->maxDynamic, St = L->maxStatic, NB = D + St, V = L->maxVertices;
   const uint32_t MM = L->maxManifolds, MP = L->maxPairs;
   uint32_t o = 0;
@@ -1228,45 +1334,37 @@ extern "C" void pxPlanSmem(const PxBatchLayout *L, PxSmemPlan *S) {
   S->px = take(NB * 4); S->py = take(NB * 4); S->m00 = take(NB * 4); S->m01 = take(NB * 4);
   S->m10 = take(NB * 4); S->m11 = take(NB * 4); S->rad = take(NB * 4); S->e = take(NB * 4);
   S->sf = take(NB * 4); S->df = take(NB * 4); S->shape = take(NB * 4);
-  S->vx = take(D * 4); S->vy = take(D * 4); S->av = take(D * 4); S->iM = take(D * 4); S->iI = take(D * 4);
-  S->angle = take(D * 4); S->fx = take(D * 4); S->fy = take(D * 4); S->tq = take(D * 4); S->slp = take(D * 4);
+  /* velocities / inverse masses cover the statics too (all zero, px_body.c:30-44) so the
+   * solver reads both bodies of a manifold without branching */
+  S->vx = take(NB * 4); S->vy = take(NB * 4); S->av = take(NB * 4); S->iM = take(NB * 4); S->iI = take(NB * 4);
   S->flags = take(D); S->order = take(D); S->order2 = take(D); S->posOf = take(D);
-  S->restFlag = take(D); S->wakeFlag = take(D);
-  S->verts = take(V * 16);
-  S->sinT = take(256 * 4);
+  S->restFlag = take(D); S->wakeFlag = take(D); S->sSlot = take(D);
   S->hdr = take(sizeof(PxWorldHeader));
   S->misc = take(16 * 4);
-  S->scan = take(32 * 8);
+  S->scan = take(8 * 8);
   S->mnx = take(MM * 4); S->mny = take(MM * 4); S->mpen = take(MM * 4); S->mc0x = take(MM * 4);
   S->mc0y = take(MM * 4); S->mc1x = take(MM * 4); S->mc1y = take(MM * 4); S->msf = take(MM * 4);
   S->mdf = take(MM * 4); S->me = take(MM * 4); S->mids = take(MM * 4);
+  S->validSlot = take(MP * 2);
+  S->base = take((D + 1) * 2);
+  S->listStart = take((D + 1) * 2);
+  S->cnt = take(D * 2); S->cntB = take(D * 2);
+  S->fillB = take(D * 4);
   uint32_t qcap = 32;
   while (qcap < MM) qcap <<= 1;
   S->qcap = qcap;
-  /* R1: sweep arrays | solver lists */
-  const uint32_t r1 = o;
+  /* region X (sweep + narrowphase) overlaid by region Y (solver) */
+  const uint32_t rx = o;
   S->sMinX = take(D * 4); S->sMaxX = take(D * 4); S->sMinY = take(D * 4); S->sMaxY = take(D * 4);
   S->sSleep = take(D);
   S->stMinX = take(St * 4); S->stMaxX = take(St * 4); S->stMinY = take(St * 4); S->stMaxY = take(St * 4);
-  const uint32_t r1a = o;
-  o = r1;
-  S->list = take(2 * MM * 2); S->arr = take(MM); S->queue = take(qcap * 2);
-  o = o > r1a ? o : r1a;
-  /* sSlot is read in phases D and F as well: keep it out of the aliased region */
-  S->sSlot = take(D);
-  /* R2: bins | per-body solver bookkeeping */
-  const uint32_t r2 = o;
   S->bins = take(MP * 4);
-  const uint32_t r2a = o;
-  o = r2;
-  S->cnt = take(D * 2); S->cntB = take(D * 2); S->listStart = take((D + 1) * 2); S->cursor = take(D * 2);
-  S->remaining = take(D * 4);
-  o = o > r2a ? o : r2a;
-  S->stash = take(D * 8);
-  /* R3 */
-  S->validSlot = take(MP * 2);
-  S->maskB = take(D * 8 * 4);
-  S->base = take((D + 1) * 2);
+  S->vertsInSmem = vertsInSmem ? 1u : 0u;
+  S->verts = vertsInSmem ? take(V * 16) : 0;
+  const uint32_t rxEnd = o;
+  o = rx;
+  S->list = take(2 * MM * 2); S->nextw = take(2 * MM * 2); S->sig = take(2 * MM); S->queue = take(qcap * 4);
+  o = o > rxEnd ? o : rxEnd;
   S->total = o;
 }
 
@@ -1293,24 +1391,20 @@ extern "C" int pxLaunchStep(const PxStepParams *P, uint32_t threads, void *strea
   }
 }
 
+template <int NT>
+static cudaError_t occupancyT(const PxStepParams *P, int *ctasPerSm) {
+  cudaError_t err = cudaFuncSetAttribute(pxStepKernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->S.total);
+  if (err != cudaSuccess) return err;
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctasPerSm, pxStepKernel<NT>, NT, P->S.total);
+}
+
 extern "C" int pxStepOccupancy(const PxStepParams *P, uint32_t threads, int *ctasPerSm) {
-  cudaError_t err;
   switch (threads) {
-  case 64:
-    cudaFuncSetAttribute(pxStepKernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->S.total);
-    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctasPerSm, pxStepKernel<64>, 64, P->S.total);
-    break;
-  case 128:
-    cudaFuncSetAttribute(pxStepKernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->S.total);
-    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctasPerSm, pxStepKernel<128>, 128, P->S.total);
-    break;
-  case 256:
-    cudaFuncSetAttribute(pxStepKernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->S.total);
-    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctasPerSm, pxStepKernel<256>, 256, P->S.total);
-    break;
+  case 64: return (int)occupancyT<64>(P, ctasPerSm);
+  case 128: return (int)occupancyT<128>(P, ctasPerSm);
+  case 256: return (int)occupancyT<256>(P, ctasPerSm);
   default: return (int)cudaErrorInvalidValue;
   }
-  return (int)err;
 }
 
 extern "C" int pxLaunchCommands(const PxBatchLayout *L, uint8_t *mut, const uint8_t *imm, const PxCommand *cmds,

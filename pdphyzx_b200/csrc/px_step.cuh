@@ -10,43 +10,40 @@
 #include "px_batch.h"
 
 /* Byte offsets of every shared-memory array of one world-CTA.  Computed once on the host
- * (pxPlanSmem) from the batch layout and handed to the kernel by value. */
+ * (pxPlanSmem) from the batch layout and handed to the kernel by value.
+ * Body-id space: dynamic slot s -> id s, static position q -> id D + q (NB = D + S). */
 struct PxSmemPlan {
-  /* persistent across the K fused substeps -------------------------------------------- */
-  /* body-id space: dynamic slot s -> id s, static position q -> id D + q (NB = D + S) */
+  /* persistent across the K fused substeps */
   uint32_t px, py, m00, m01, m10, m11, rad, e, sf, df; /* f32[NB] */
   uint32_t shape;                                       /* u32[NB] */
-  uint32_t vx, vy, av, iM, iI;                          /* f32[D] */
-  uint32_t angle, fx, fy, tq, slp;                      /* f32[D] */
-  uint32_t flags, order, order2, posOf, restFlag, wakeFlag; /* u8[D] */
-  uint32_t verts;                                       /* float4[V] */
-  uint32_t sinT;                                        /* f32[256] */
+  uint32_t vx, vy, av, iM, iI;                          /* f32[NB] (statics: zeros) */
+  uint32_t flags, order, order2, posOf, restFlag, wakeFlag, sSlot; /* u8[D] */
   uint32_t hdr;                                         /* PxWorldHeader */
-  uint32_t misc;                                        /* u32[16] counters / scan scratch */
-  uint32_t scan;                                        /* u64[32] block-scan scratch */
-  /* manifolds of the current substep, SoA by (unordered) manifold slot ------------------ */
+  uint32_t misc;                                        /* u32[16] counters */
+  uint32_t scan;                                        /* u64[8] block-scan scratch */
+  /* manifolds of the current substep, SoA by (unordered) manifold slot */
   uint32_t mnx, mny, mpen, mc0x, mc0y, mc1x, mc1y, msf, mdf, me; /* f32[MM] */
   uint32_t mids;                                                 /* u32[MM] */
-  /* phase-local, aliased ------------------------------------------------------------- */
-  /* R1: broadphase sorted arrays  |  solver lists */
-  uint32_t sMinX, sMaxX, sMinY, sMaxY; /* f32[D] by sorted position */
-  uint32_t sSlot;                      /* u8[D]  slot | sleeping << ... kept separate: */
-  uint32_t sSleep;                     /* u8[D] */
-  uint32_t stMinX, stMaxX, stMinY, stMaxY; /* f32[S] static boxes by static position */
-  uint32_t list;                       /* u16[2*MM] per-body manifold lists (CSR payload) */
-  uint32_t arr;                        /* u8[MM]   arrival counters */
-  uint32_t queue;                      /* u16[QCAP] ready ring */
-  /* R2: type bins | per-body solver bookkeeping */
-  uint32_t bins;                       /* u32[MP] */
-  uint32_t cnt, cntB, listStart, cursor; /* u16[D] (listStart u16[D+1]) */
-  uint32_t remaining;                    /* u32[D] visits left per body */
-  uint32_t stash;                        /* u64[D] per-position scan results carried between passes */
-  /* R3: narrowphase -> list build */
-  uint32_t validSlot;                  /* u16[MP] manifold slot + 1 by pair sequence number */
-  uint32_t maskB;                      /* u32[D][8] sorted positions of A-partners per body */
-  uint32_t base;                       /* u16[D+1] first pair sequence number by sorted position */
-  uint32_t total;                      /* bytes */
-  uint32_t qcap;                       /* ring capacity (power of two >= MM) */
+  /* sweep -> list build */
+  uint32_t validSlot; /* u16[MP] manifold slot + 1 by pair sequence number */
+  uint32_t base;      /* u16[D+1] first pair sequence number by sorted position */
+  uint32_t listStart; /* u16[D+1] by slot */
+  uint32_t cnt, cntB; /* u16[D] manifolds per body / of which as bodyB, by slot */
+  uint32_t fillB;     /* u32[D] atomic counters */
+  /* region X (sweep + narrowphase), aliased with region Y (solver) */
+  uint32_t sMinX, sMaxX, sMinY, sMaxY;     /* f32[D] by sorted position */
+  uint32_t sSleep;                         /* u8[D] */
+  uint32_t stMinX, stMaxX, stMinY, stMaxY; /* f32[S] */
+  uint32_t bins;                           /* u32[MP] pairs binned by shape-pair type */
+  uint32_t verts;                          /* float4[V] (only if vertsInSmem) */
+  /* region Y */
+  uint32_t list;   /* u16[2*MM] per-body manifold lists (CSR payload), persists to phase F */
+  uint32_t nextw;  /* u16[2*MM] successor of manifold ms on side s: slot | side << 15 */
+  uint32_t sig;    /* u8[2*MM]  signals received per manifold side */
+  uint32_t queue;  /* u32[QCAP] ready ring of rich manifold words */
+  uint32_t total;  /* bytes */
+  uint32_t qcap;   /* ring capacity (power of two >= MM) */
+  uint32_t vertsInSmem;
 };
 
 struct PxStepParams {
@@ -64,7 +61,8 @@ struct PxStepParams {
 #ifdef __cplusplus
 extern "C" {
 #endif
-void pxPlanSmem(const PxBatchLayout *L, PxSmemPlan *S);
+/* vertsInSmem: 1 keeps the polygon vertex pool in shared memory, 0 reads it through L1 */
+void pxPlanSmem(const PxBatchLayout *L, int vertsInSmem, PxSmemPlan *S);
 /* launches the step kernel for all worlds of the layout; returns cudaError_t as int */
 int pxLaunchStep(const PxStepParams *P, uint32_t threads, void *stream);
 /* occupancy query: resident CTAs per SM for this plan */
