@@ -341,7 +341,6 @@ def run_ours(args):
             nsub = float(blocks.header["substeps"].mean())
             out["solver_rounds_per_substep"] = float(pr[:, 6].mean() / nsub)
             out["solver_cycles_per_round"] = float(pr[:, 4].sum() / max(pr[:, 6].sum(), 1))
-            out["solver_apply_cycles_per_round"] = float(pr[:, 7].sum() / max(pr[:, 6].sum(), 1))
             pr = pr[:, :6]
             out["cycles_per_world_substep"] = float(pr.sum(axis=1).mean() / float(blocks.header["substeps"].mean()))
         if e2e_ms is not None:

@@ -33,8 +33,10 @@ int pxBatchComputeLayout(uint32_t nWorlds, const PxBatchDesc *desc, PxBatchLayou
   L->maxDynamic = alignUp(desc->maxDynamic, 16); /* byte rows are copied 16 bytes at a time */
   L->maxStatic = alignUp(desc->maxStatic ? desc->maxStatic : 1, 4);
   L->maxVertices = alignUp(desc->maxVertices ? desc->maxVertices : 4, 4);
-  L->maxManifolds = desc->maxManifolds ? desc->maxManifolds : 3 * L->maxDynamic + 64;
-  L->maxPairs = desc->maxPairs ? desc->maxPairs : 8 * L->maxDynamic + 64;
+  /* defaults sized from dense piles (about 2.5 manifolds and 5.5 AABB-pass pairs per body);
+   * a world that needs more sets its PX_BATCH_OVERFLOW_* flag and the caller raises these */
+  L->maxManifolds = desc->maxManifolds ? desc->maxManifolds : (11 * L->maxDynamic) / 4;
+  L->maxPairs = desc->maxPairs ? desc->maxPairs : 7 * L->maxDynamic;
   L->maxManifolds = alignUp(L->maxManifolds, 32);
   L->maxPairs = alignUp(L->maxPairs, 32);
   if (L->maxVertices >= (1u << 24) || L->maxPairs > 32767 || L->maxManifolds > 1024) {

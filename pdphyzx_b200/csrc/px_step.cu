@@ -96,25 +96,30 @@ __device__ __forceinline__ V2 normalize(V2 v, float eps) {
 }
 
 /* ----------------------------------------------------------------------- shared views */
+/* Body-id space: dynamic slot s -> id s, static position q -> id D + q (NB = D + S).
+ * Records are float4 so that one LDS.128 fetches what a phase needs of a body or manifold. */
 struct Sm {
-  float *px, *py, *m00, *m01, *m10, *m11, *rad, *e, *sf, *df;
-  uint32_t *shape;
-  float *vx, *vy, *av, *iM, *iI;
+  float4 *bodyP; /* {pos.x, pos.y, iMass, iInertia}                 statics: iM = iI = 0 */
+  float4 *bodyV; /* {vel.x, vel.y, angularVelocity, aabbRadius}     statics: zero velocity */
+  float4 *bodyR; /* orientation {m00, m01, m10, m11} */
+  float4 *bodyM; /* {restitution, staticFriction, dynamicFriction, shape word bits} */
   uint8_t *flags, *order, *order2, *posOf, *restFlag, *wakeFlag, *sSlot;
   PxWorldHeader *hdr;
   uint32_t *misc;
   unsigned long long *scan;
-  float *mnx, *mny, *mpen, *mc0x, *mc0y, *mc1x, *mc1y, *msf, *mdf, *me;
+  float4 *manA; /* {normal.x, normal.y, mixedRestitution, staticFriction} */
+  float4 *manB; /* {dynamicFriction, penetration, c0.x, c0.y} */
+  float4 *manC; /* {c1.x, c1.y, rcpDenom0, rcpDenom1} */
   uint32_t *mids;
   uint16_t *validSlot, *base, *listStart, *cnt, *cntB;
   uint32_t *fillB;
-  float *sMinX, *sMaxX, *sMinY, *sMaxY;
-  uint8_t *sSleep;
-  float *stMinX, *stMaxX, *stMinY, *stMaxY;
+  float4 *sBox;    /* {min.x, min.y, max.x, max.y} by sorted position */
+  uint32_t *sInfo; /* slot | sleeping << 8 | isPolygon << 9, by sorted position */
+  float4 *stBox;
   uint32_t *bins;
   const float4 *verts; /* shared memory or, when the pool does not fit, global through L1 */
   uint16_t *list, *nextw;
-  uint8_t *sig;
+  uint32_t *sig;
   uint32_t *queue;
 };
 
@@ -147,10 +152,11 @@ struct DBody {
 
 __device__ __forceinline__ DBody loadBody(const Sm &s, uint32_t id) {
   DBody b;
-  b.pos = v2(s.px[id], s.py[id]);
-  b.rot = M2{s.m00[id], s.m01[id], s.m10[id], s.m11[id]};
-  b.radius = s.rad[id];
-  uint32_t sh = s.shape[id];
+  const float4 p = s.bodyP[id], r = s.bodyR[id];
+  b.pos = v2(p.x, p.y);
+  b.rot = M2{r.x, r.y, r.z, r.w};
+  b.radius = s.bodyV[id].w;
+  const uint32_t sh = __float_as_uint(s.bodyM[id].w);
   b.nverts = PX_SHAPE_COUNT(sh);
   b.v = s.verts + PX_SHAPE_OFFSET(sh);
   return b;
@@ -403,20 +409,19 @@ __device__ __forceinline__ unsigned long long blockExclusiveScan(unsigned long l
 }
 
 /* pxBodyAABBsOverlap, px_body.c:126-145: strict comparisons, touching boxes overlap */
-__device__ __forceinline__ bool boxesOverlap(float aMinX, float aMinY, float aMaxX, float aMaxY, float bMinX, float bMinY,
-                                             float bMaxX, float bMaxY) {
-  if (aMaxX < bMinX || aMinX > bMaxX) return false;
-  if (aMaxY < bMinY || aMinY > bMaxY) return false;
+__device__ __forceinline__ bool boxesOverlap(const float4 a, const float4 b) {
+  if (a.z < b.x || a.x > b.z) return false;
+  if (a.w < b.y || a.y > b.w) return false;
   return true;
 }
 
 /* pxBodyArrayFindFirstIndexAfterX, px_body_array.c:104-131: predicate on max.x over a list
  * sorted by min.x, replicated literally */
-__device__ __forceinline__ uint32_t firstStaticAfterX(const float *stMaxX, uint32_t n, float minX) {
+__device__ __forceinline__ uint32_t firstStaticAfterX(const float4 *stBox, uint32_t n, float minX) {
   uint32_t low = 0, high = n;
   while (low < high) {
     uint32_t mid = low + (high - low) / 2;
-    if (stMaxX[mid] < minX) {
+    if (stBox[mid].z < minX) {
       low = mid + 1;
     } else {
       high = mid;
@@ -425,104 +430,97 @@ __device__ __forceinline__ uint32_t firstStaticAfterX(const float *stMaxX, uint3
   return low;
 }
 
-
-
 /*
  * One contact of pxManifoldApplyImpulse (px_manifold.c:98-215).  The two-contact loop of
  * the reference is executed as two consecutive ready-queue visits of the same manifold
  * (contact 0 then contact 1, nothing in between can touch either body), so every solver
  * round costs one contact.  The caller guarantees nobody else touches the two bodies'
  * velocities while this runs.
+ *
+ * rcpDenom = pxFastRcp(invMassSum * contactCount) (px_manifold.c:148-156) depends only on
+ * positions, the normal and the inverse masses, all frozen during the solver, so it is
+ * computed once per contact in the narrowphase epilogue; the friction impulse divides by the
+ * same denominator (px_manifold.c:193-194) and reuses it.
+ *
  * px_world.c:252-255 skips a manifold when both bodies sleep; the sweep never creates one
  * for two sleeping dynamic bodies (px_world.c:367-369), sleep flags do not change between
  * the two, and statics never sleep, so the test is always false here.
  */
 __device__ __forceinline__ void applyContactImpulse(const Sm &s, uint32_t w, float eps) {
-  const uint32_t ms = MID_SLOT(w), a = MID_A(w), b = MID_B(w), ci = MID_CI(w);
-  const bool bdyn = MID_BDYN(w) != 0;
+  const uint32_t ms = MID_SLOT(w), a = MID_A(w), b = MID_B(w);
+  const bool second = MID_CI(w) != 0, bdyn = MID_BDYN(w) != 0;
   /* every load below depends only on the queue word: one shared-memory round trip */
-  const V2 n = v2(s.mnx[ms], s.mny[ms]);
-  const float e = s.me[ms], sf = s.msf[ms], df = s.mdf[ms];
-  const float *cxp = ci ? s.mc1x : s.mc0x, *cyp = ci ? s.mc1y : s.mc0y;
-  const V2 c = v2(cxp[ms], cyp[ms]);
-  const V2 pa = v2(s.px[a], s.py[a]), pb = v2(s.px[b], s.py[b]);
-  const float iMA = s.iM[a], iIA = s.iI[a], iMB = s.iM[b], iIB = s.iI[b]; /* statics: 0 */
-  V2 va = v2(s.vx[a], s.vy[a]), vb = v2(s.vx[b], s.vy[b]);
-  float wa = s.av[a], wb = s.av[b];
-  const float fcount = (float)MID_COUNT(w);
+  const float4 mA = s.manA[ms], mB = s.manB[ms], mC = s.manC[ms];
+  const float4 pA = s.bodyP[a], pB = s.bodyP[b];
+  float4 vA = s.bodyV[a], vB = s.bodyV[b];
+  const V2 n = v2(mA.x, mA.y);
+  const float e = mA.z, sf = mA.w, df = mB.x;
+  const V2 c = second ? v2(mC.x, mC.y) : v2(mB.z, mB.w);
+  const float rcpDenom = second ? mC.w : mC.z;
+  const V2 pa = v2(pA.x, pA.y), pb = v2(pB.x, pB.y);
+  const float iMA = pA.z, iIA = pA.w, iMB = pB.z, iIB = pB.w; /* statics: 0 */
+  V2 va = v2(vA.x, vA.y), vb = v2(vB.x, vB.y);
+  float wa = vA.z, wb = vB.z;
 
   const V2 ra = c - pa, rb = c - pb;
   const V2 raPerp = v2(-ra.y, ra.x), rbPerp = v2(-rb.y, rb.x);
   V2 rv = (vb + rbPerp * wb) - (va + raPerp * wa);
   const float vn = dot(rv, n);
-  if (vn > 0) return;
+  /* The two early exits of the reference (`continue` when the bodies separate, skip friction
+   * when the tangent vanishes) are applied as selects at the end: a single warp runs this
+   * chain, and a branch costs it more than the few discarded operations. */
+  const bool approaching = !(vn > 0);
 
-  const float raCrossN = cross(ra, n), rbCrossN = cross(rb, n);
-  const float invMassSum = iMA + iMB + raCrossN * raCrossN * iIA + rbCrossN * rbCrossN * iIB;
   const float normalMag = -(1.0f + e) * vn;
-  const float denom = invMassSum * fcount;
-  const float rcpDenom = fRcp(denom);
   const float j = normalMag * rcpDenom;
   const V2 impulse = n * j;
-  { /* pxBodyApplyImpulse(bodyA, -impulse, ra), px_body.c:147-156 */
-    const V2 ni = -impulse;
-    va = v2(va.x + ni.x * iMA, va.y + ni.y * iMA);
-    wa = wa + cross(ra, ni) * iIA;
-  }
-  { /* bodyB only if dynamic (px_manifold.c:165-167); a static keeps its exact zeros */
-    const V2 nvb = v2(vb.x + impulse.x * iMB, vb.y + impulse.y * iMB);
-    const float nwb = wb + cross(rb, impulse) * iIB;
-    vb = bdyn ? nvb : vb;
-    wb = bdyn ? nwb : wb;
-  }
+  /* pxBodyApplyImpulse(bodyA, -impulse, ra), px_body.c:147-156 */
+  const V2 ni = -impulse;
+  const V2 va1 = v2(va.x + ni.x * iMA, va.y + ni.y * iMA);
+  const float wa1 = wa + cross(ra, ni) * iIA;
+  /* bodyB only if dynamic (px_manifold.c:165-167); a static keeps its exact zeros */
+  const V2 vb1 = bdyn ? v2(vb.x + impulse.x * iMB, vb.y + impulse.y * iMB) : vb;
+  const float wb1 = bdyn ? wb + cross(rb, impulse) * iIB : wb;
 
-  rv = (vb + rbPerp * wb) - (va + raPerp * wa);
+  rv = (vb1 + rbPerp * wb1) - (va1 + raPerp * wa1);
   V2 tangent = rv - n * dot(rv, n);
   const float tlen = fSqrt(lensq(tangent));
-  if (tlen > eps) {
-    tangent = tangent * fRcp(tlen);
-    const float tmag = -dot(rv, tangent);
-    const float jt = tmag * rcpDenom; /* same denominator, same pxFastRcp value */
-    const float fmag = (fabsf(jt) < j * sf) ? jt : (-j * df);
-    const V2 friction = tangent * fmag;
-    {
-      const V2 nf = -friction;
-      va = v2(va.x + nf.x * iMA, va.y + nf.y * iMA);
-      wa = wa + cross(ra, nf) * iIA;
-    }
-    {
-      const V2 nvb = v2(vb.x + friction.x * iMB, vb.y + friction.y * iMB);
-      const float nwb = wb + cross(rb, friction) * iIB;
-      vb = bdyn ? nvb : vb;
-      wb = bdyn ? nwb : wb;
-    }
-  }
-  s.vx[a] = va.x;
-  s.vy[a] = va.y;
-  s.av[a] = wa;
+  const bool slides = tlen > eps;
+  tangent = tangent * fRcp(tlen);
+  const float tmag = -dot(rv, tangent);
+  const float jt = tmag * rcpDenom;
+  const float fmag = (fabsf(jt) < j * sf) ? jt : (-j * df);
+  const V2 friction = tangent * fmag;
+  const V2 nf = -friction;
+  const V2 va2 = v2(va1.x + nf.x * iMA, va1.y + nf.y * iMA);
+  const float wa2 = wa1 + cross(ra, nf) * iIA;
+  const V2 vb2 = bdyn ? v2(vb1.x + friction.x * iMB, vb1.y + friction.y * iMB) : vb1;
+  const float wb2 = bdyn ? wb1 + cross(rb, friction) * iIB : wb1;
+
+  vA.x = approaching ? (slides ? va2.x : va1.x) : va.x;
+  vA.y = approaching ? (slides ? va2.y : va1.y) : va.y;
+  vA.z = approaching ? (slides ? wa2 : wa1) : wa;
+  s.bodyV[a] = vA;
   if (bdyn) {
-    s.vx[b] = vb.x;
-    s.vy[b] = vb.y;
-    s.av[b] = wb;
+    vB.x = approaching ? (slides ? vb2.x : vb1.x) : vb.x;
+    vB.y = approaching ? (slides ? vb2.y : vb1.y) : vb.y;
+    vB.z = approaching ? (slides ? wb2 : wb1) : wb;
+    s.bodyV[b] = vB;
   }
 }
 
 __device__ __forceinline__ void bindSmem(Sm &s, uint8_t *base, const PxSmemPlan &S, const float4 *globalVerts) {
 #define BIND(field, type) s.field = (type *)(base + S.field)
-  BIND(px, float); BIND(py, float); BIND(m00, float); BIND(m01, float); BIND(m10, float); BIND(m11, float);
-  BIND(rad, float); BIND(e, float); BIND(sf, float); BIND(df, float); BIND(shape, uint32_t);
-  BIND(vx, float); BIND(vy, float); BIND(av, float); BIND(iM, float); BIND(iI, float);
+  BIND(bodyP, float4); BIND(bodyV, float4); BIND(bodyR, float4); BIND(bodyM, float4);
   BIND(flags, uint8_t); BIND(order, uint8_t); BIND(order2, uint8_t); BIND(posOf, uint8_t);
   BIND(restFlag, uint8_t); BIND(wakeFlag, uint8_t); BIND(sSlot, uint8_t);
   BIND(hdr, PxWorldHeader); BIND(misc, uint32_t); BIND(scan, unsigned long long);
-  BIND(mnx, float); BIND(mny, float); BIND(mpen, float); BIND(mc0x, float); BIND(mc0y, float);
-  BIND(mc1x, float); BIND(mc1y, float); BIND(msf, float); BIND(mdf, float); BIND(me, float); BIND(mids, uint32_t);
+  BIND(manA, float4); BIND(manB, float4); BIND(manC, float4); BIND(mids, uint32_t);
   BIND(validSlot, uint16_t); BIND(base, uint16_t); BIND(listStart, uint16_t); BIND(cnt, uint16_t); BIND(cntB, uint16_t);
   BIND(fillB, uint32_t);
-  BIND(sMinX, float); BIND(sMaxX, float); BIND(sMinY, float); BIND(sMaxY, float); BIND(sSleep, uint8_t);
-  BIND(stMinX, float); BIND(stMaxX, float); BIND(stMinY, float); BIND(stMaxY, float);
+  BIND(sBox, float4); BIND(sInfo, uint32_t); BIND(stBox, float4);
   BIND(bins, uint32_t);
-  BIND(list, uint16_t); BIND(nextw, uint16_t); BIND(sig, uint8_t); BIND(queue, uint32_t);
+  BIND(list, uint16_t); BIND(nextw, uint16_t); BIND(sig, uint32_t); BIND(queue, uint32_t);
 #undef BIND
   s.verts = S.vertsInSmem ? (const float4 *)(base + S.verts) : globalVerts;
 }
@@ -555,43 +553,31 @@ __global__ void __launch_bounds__(NT, 512 / NT) pxStepKernel(const PxStepParams 
   const float *gdynC = (const float *)(gmut + L.offDyn);
   float *gdyn = (float *)(gmut + L.offDyn);
 
-  /* ---------------------------------------------------------------- load (HBM -> smem) */
+  /* -------------------------------------------- load (HBM SoA rows -> smem records) */
+  /* global rows are read coalesced (consecutive slots by consecutive threads); the record
+   * transpose happens on the shared-memory side */
   {
-    copyRows<NT>(s.px, gdynC + PX_DYN_PX * D, D);
-    copyRows<NT>(s.py, gdynC + PX_DYN_PY * D, D);
-    copyRows<NT>(s.vx, gdynC + PX_DYN_VX * D, D);
-    copyRows<NT>(s.vy, gdynC + PX_DYN_VY * D, D);
-    copyRows<NT>(s.av, gdynC + PX_DYN_AV * D, D);
-    copyRows<NT>(s.m00, gdynC + PX_DYN_M00 * D, D);
-    copyRows<NT>(s.m01, gdynC + PX_DYN_M01 * D, D);
-    copyRows<NT>(s.m10, gdynC + PX_DYN_M10 * D, D);
-    copyRows<NT>(s.m11, gdynC + PX_DYN_M11 * D, D);
     const float *gc = (const float *)(gimm + L.offDynConst);
-    copyRows<NT>(s.iM, gc + PX_DYNC_IMASS * D, D);
-    copyRows<NT>(s.iI, gc + PX_DYNC_IINERTIA * D, D);
-    copyRows<NT>(s.e, gc + PX_DYNC_E * D, D);
-    copyRows<NT>(s.sf, gc + PX_DYNC_SF * D, D);
-    copyRows<NT>(s.df, gc + PX_DYNC_DF * D, D);
-    copyRows<NT>(s.rad, gc + PX_DYNC_RADIUS * D, D);
-    copyRows<NT>((float *)s.shape, (const float *)(gimm + L.offDynShape), D);
+    const uint32_t *gshape = (const uint32_t *)(gimm + L.offDynShape);
+    for (uint32_t x = tid; x < D; x += NT) {
+      s.bodyP[x] = make_float4(gdynC[PX_DYN_PX * D + x], gdynC[PX_DYN_PY * D + x], gc[PX_DYNC_IMASS * D + x],
+                               gc[PX_DYNC_IINERTIA * D + x]);
+      s.bodyV[x] = make_float4(gdynC[PX_DYN_VX * D + x], gdynC[PX_DYN_VY * D + x], gdynC[PX_DYN_AV * D + x],
+                               gc[PX_DYNC_RADIUS * D + x]);
+      s.bodyR[x] = make_float4(gdynC[PX_DYN_M00 * D + x], gdynC[PX_DYN_M01 * D + x], gdynC[PX_DYN_M10 * D + x],
+                               gdynC[PX_DYN_M11 * D + x]);
+      s.bodyM[x] = make_float4(gc[PX_DYNC_E * D + x], gc[PX_DYNC_SF * D + x], gc[PX_DYNC_DF * D + x],
+                               __uint_as_float(gshape[x]));
+    }
     const float *gs = (const float *)(gimm + L.offStat);
-    copyRows<NT>(s.px + D, gs + PX_STAT_PX * S, S);
-    copyRows<NT>(s.py + D, gs + PX_STAT_PY * S, S);
-    copyRows<NT>(s.m00 + D, gs + PX_STAT_M00 * S, S);
-    copyRows<NT>(s.m01 + D, gs + PX_STAT_M01 * S, S);
-    copyRows<NT>(s.m10 + D, gs + PX_STAT_M10 * S, S);
-    copyRows<NT>(s.m11 + D, gs + PX_STAT_M11 * S, S);
-    copyRows<NT>(s.e + D, gs + PX_STAT_E * S, S);
-    copyRows<NT>(s.sf + D, gs + PX_STAT_SF * S, S);
-    copyRows<NT>(s.df + D, gs + PX_STAT_DF * S, S);
-    copyRows<NT>(s.rad + D, gs + PX_STAT_RADIUS * S, S);
-    copyRows<NT>((float *)(s.shape + D), (const float *)(gimm + L.offStatShape), S);
-    for (uint32_t i = tid; i < S; i += NT) {
-      s.vx[D + i] = 0.0f;
-      s.vy[D + i] = 0.0f;
-      s.av[D + i] = 0.0f;
-      s.iM[D + i] = 0.0f;
-      s.iI[D + i] = 0.0f;
+    const uint32_t *gsshape = (const uint32_t *)(gimm + L.offStatShape);
+    for (uint32_t q = tid; q < S; q += NT) {
+      s.bodyP[D + q] = make_float4(gs[PX_STAT_PX * S + q], gs[PX_STAT_PY * S + q], 0.0f, 0.0f);
+      s.bodyV[D + q] = make_float4(0.0f, 0.0f, 0.0f, gs[PX_STAT_RADIUS * S + q]);
+      s.bodyR[D + q] = make_float4(gs[PX_STAT_M00 * S + q], gs[PX_STAT_M01 * S + q], gs[PX_STAT_M10 * S + q],
+                                   gs[PX_STAT_M11 * S + q]);
+      s.bodyM[D + q] = make_float4(gs[PX_STAT_E * S + q], gs[PX_STAT_SF * S + q], gs[PX_STAT_DF * S + q],
+                                   __uint_as_float(gsshape[q]));
     }
     copyRows<NT>((float *)s.flags, (const float *)(gmut + L.offDynFlags), D / 4);
     copyRows<NT>((float *)s.order, (const float *)(gmut + L.offDynOrder), D / 4);
@@ -643,9 +629,10 @@ __global__ void __launch_bounds__(NT, 512 / NT) pxStepKernel(const PxStepParams 
       s.wakeFlag[i] = 0;
       s.fillB[i] = 0;
     }
+    float *keys = (float *)s.bins; /* region X scratch: sort keys by position */
     for (uint32_t p = tid; p < nDyn; p += NT) {
-      uint32_t slot = s.order[p];
-      s.sMinX[p] = s.px[slot] - s.rad[slot];
+      const uint32_t slot = s.order[p];
+      keys[p] = s.bodyP[slot].x - s.bodyV[slot].w;
     }
     __syncthreads();
     {
@@ -655,17 +642,17 @@ __global__ void __launch_bounds__(NT, 512 / NT) pxStepKernel(const PxStepParams 
        * only strictly out-of-order neighbours reach the same permutation in a few passes;
        * rank-by-counting is the fallback. */
       bool unsorted = false;
-      for (uint32_t p = tid; p + 1 < nDyn; p += NT) unsorted |= s.sMinX[p] > s.sMinX[p + 1];
+      for (uint32_t p = tid; p + 1 < nDyn; p += NT) unsorted |= keys[p] > keys[p + 1];
       int dirty = __syncthreads_or(unsorted);
       for (int pass = 0; dirty && pass < 12; pass++) {
 #pragma unroll
         for (uint32_t parity = 0; parity < 2; parity++) {
           for (uint32_t i = tid; 2 * i + parity + 1 < nDyn; i += NT) {
             const uint32_t p0 = 2 * i + parity;
-            const float k0 = s.sMinX[p0], k1 = s.sMinX[p0 + 1];
+            const float k0 = keys[p0], k1 = keys[p0 + 1];
             if (k0 > k1) {
-              s.sMinX[p0] = k1;
-              s.sMinX[p0 + 1] = k0;
+              keys[p0] = k1;
+              keys[p0 + 1] = k0;
               const uint8_t o0 = s.order[p0];
               s.order[p0] = s.order[p0 + 1];
               s.order[p0 + 1] = o0;
@@ -674,15 +661,15 @@ __global__ void __launch_bounds__(NT, 512 / NT) pxStepKernel(const PxStepParams 
           __syncthreads();
         }
         unsorted = false;
-        for (uint32_t p = tid; p + 1 < nDyn; p += NT) unsorted |= s.sMinX[p] > s.sMinX[p + 1];
+        for (uint32_t p = tid; p + 1 < nDyn; p += NT) unsorted |= keys[p] > keys[p + 1];
         dirty = __syncthreads_or(unsorted);
       }
       if (dirty) {
         for (uint32_t p = tid; p < nDyn; p += NT) {
-          float key = s.sMinX[p];
+          const float key = keys[p];
           uint32_t rank = 0;
           for (uint32_t q = 0; q < nDyn; q++) {
-            float kq = s.sMinX[q];
+            const float kq = keys[q];
             rank += (kq < key || (kq == key && q < p)) ? 1u : 0u;
           }
           s.order2[rank] = s.order[p];
@@ -692,24 +679,22 @@ __global__ void __launch_bounds__(NT, 512 / NT) pxStepKernel(const PxStepParams 
         __syncthreads();
       }
     }
-    /* sorted-position arrays for the sweep */
+    /* sorted-position records for the sweep: radius-based AABBs (px_circle.c:43-48,
+     * px_polygon.c:261-266) */
     for (uint32_t p = tid; p < nDyn; p += NT) {
-      uint32_t slot = s.order[p];
-      float x = s.px[slot], y = s.py[slot], r = s.rad[slot];
-      s.sMinX[p] = x - r;
-      s.sMaxX[p] = x + r;
-      s.sMinY[p] = y - r;
-      s.sMaxY[p] = y + r;
+      const uint32_t slot = s.order[p];
+      const float4 bp = s.bodyP[slot];
+      const float r = s.bodyV[slot].w;
+      s.sBox[p] = make_float4(bp.x - r, bp.y - r, bp.x + r, bp.y + r);
+      const uint32_t poly = PX_SHAPE_COUNT(__float_as_uint(s.bodyM[slot].w)) != 0;
+      s.sInfo[p] = slot | ((s.flags[slot] & PX_FLAG_SLEEPING) ? 0x100u : 0u) | (poly << 9);
       s.sSlot[p] = (uint8_t)slot;
-      s.sSleep[p] = (s.flags[slot] & PX_FLAG_SLEEPING) ? 1 : 0;
       s.posOf[slot] = (uint8_t)p;
     }
     for (uint32_t q = tid; q < nStat; q += NT) {
-      float x = s.px[D + q], y = s.py[D + q], r = s.rad[D + q];
-      s.stMinX[q] = x - r;
-      s.stMaxX[q] = x + r;
-      s.stMinY[q] = y - r;
-      s.stMaxY[q] = y + r;
+      const float4 bp = s.bodyP[D + q];
+      const float r = s.bodyV[D + q].w;
+      s.stBox[q] = make_float4(bp.x - r, bp.y - r, bp.x + r, bp.y + r);
     }
     __syncthreads();
     PROF_MARK(0)
@@ -718,104 +703,133 @@ __global__ void __launch_bounds__(NT, 512 / NT) pxStepKernel(const PxStepParams 
     /* pass 1 counts, a packed 4x16-bit block scan gives every body its first sequence
      * number and its first index in each of the three type bins, pass 2 writes.  The
      * reference's early-exit `break` acts as `continue`; over a sorted list
-     * both give the same pairs, so the dynamic scan stops at the first min.x > A.max.x. */
+     * both give the same pairs, so the dynamic scan stops at the first min.x > A.max.x.
+     * Pass 1 remembers which candidates of the scan window passed the AABB test in a bit
+     * mask, so pass 2 only revisits those. */
     unsigned long long exr[R];
-    uint32_t startStatR[R];
+    uint32_t startStatR[R], dynMaskR[R], statMaskR[R];
     unsigned long long carry = 0;
 #pragma unroll
     for (int r = 0; r < R; r++) {
       const uint32_t p = r * NT + tid;
       unsigned long long counts = 0; /* all | cc << 16 | cp << 32 | pp << 48 */
-      uint32_t startStat = 0;
+      uint32_t startStat = 0, dynMask = 0, statMask = 0;
       if (p < nDyn) {
-        const float aMinX = s.sMinX[p], aMaxX = s.sMaxX[p], aMinY = s.sMinY[p], aMaxY = s.sMaxY[p];
-        const uint32_t aSleep = s.sSleep[p];
-        const uint32_t aPoly = PX_SHAPE_COUNT(s.shape[s.sSlot[p]]) != 0;
+        const float4 a = s.sBox[p];
+        const uint32_t ai = s.sInfo[p];
+        const uint32_t aSleep = ai & 0x100u, aPoly = (ai >> 9) & 1u;
         for (uint32_t q = p + 1; q < nDyn; q++) {
-          float bMinX = s.sMinX[q];
-          if (bMinX > aMaxX) break;
-          if (aSleep && s.sSleep[q]) continue;
-          if (!boxesOverlap(aMinX, aMinY, aMaxX, aMaxY, bMinX, s.sMinY[q], s.sMaxX[q], s.sMaxY[q])) continue;
-          uint32_t bPoly = PX_SHAPE_COUNT(s.shape[s.sSlot[q]]) != 0;
-          counts += 1ull + (1ull << (16 * (1 + aPoly + bPoly)));
+          const float4 b = s.sBox[q];
+          if (b.x > a.z) break;
+          const uint32_t bi = s.sInfo[q];
+          if (aSleep & bi) continue; /* both sleeping */
+          if (!boxesOverlap(a, b)) continue;
+          counts += 1ull + (1ull << (16 * (1 + aPoly + ((bi >> 9) & 1u))));
+          const uint32_t k = q - p - 1;
+          dynMask |= k < 32 ? (1u << k) : 0u;
+          if (k >= 32) dynMask = 0xffffffffu, counts |= 1ull << 63; /* window too long: rescan */
         }
-        startStat = firstStaticAfterX(s.stMaxX, nStat, aMinX);
+        startStat = firstStaticAfterX(s.stBox, nStat, a.x);
         for (uint32_t q = startStat; q < nStat; q++) {
-          float bMinX = s.stMinX[q];
-          if (bMinX > aMaxX) continue;
-          if (!boxesOverlap(aMinX, aMinY, aMaxX, aMaxY, bMinX, s.stMinY[q], s.stMaxX[q], s.stMaxY[q])) continue;
-          uint32_t bPoly = PX_SHAPE_COUNT(s.shape[D + q]) != 0;
+          const float4 b = s.stBox[q];
+          if (b.x > a.z) continue;
+          if (!boxesOverlap(a, b)) continue;
+          const uint32_t bPoly = PX_SHAPE_COUNT(__float_as_uint(s.bodyM[D + q].w)) != 0;
           counts += 1ull + (1ull << (16 * (1 + aPoly + bPoly)));
+          const uint32_t k = q - startStat;
+          statMask |= k < 32 ? (1u << k) : 0u;
         }
       }
+      const bool rescan = (counts >> 63) != 0;
+      counts &= ~(1ull << 63);
       unsigned long long total;
       exr[r] = blockExclusiveScan<NT>(counts, s.scan, total) + carry;
       carry += total;
       startStatR[r] = startStat;
+      dynMaskR[r] = rescan ? 0xffffffffu : dynMask;
+      statMaskR[r] = statMask;
+      if (rescan) exr[r] |= 1ull << 63;
       if (p < nDyn) s.base[p] = (uint16_t)min((uint32_t)(exr[r] & 0xffffu), MP);
     }
     const uint32_t totalPairsRaw = (uint32_t)(carry & 0xffffu);
     const uint32_t nPairs = min(totalPairsRaw, MP);
     const uint32_t nCC = (uint32_t)((carry >> 16) & 0xffffu), nCP = (uint32_t)((carry >> 32) & 0xffffu);
-    const uint32_t nPP = (uint32_t)((carry >> 48) & 0xffffu);
+    const uint32_t nPP = (uint32_t)((carry >> 48) & 0x7fffu);
     if (tid == 0) {
       s.base[nDyn] = (uint16_t)nPairs;
       if (totalPairsRaw > MP) overflow |= PX_BATCH_OVERFLOW_PAIRS;
     }
     /* bin regions inside bins[]: [0,nCC) circle-circle, [nCC, nCC+nCP) circle-polygon (either
-     * order), then polygon-polygon; entries whose sequence number is >= MP are dropped */
+     * order), then polygon-polygon; entries whose sequence number is >= MP are dropped.
+     * bins[] doubles as the sort-key scratch of phase A: all key reads are behind us. */
+    __syncthreads();
 #pragma unroll
     for (int r = 0; r < R; r++) {
       const uint32_t p = r * NT + tid;
       if (p >= nDyn) continue;
-      const float aMinX = s.sMinX[p], aMaxX = s.sMaxX[p], aMinY = s.sMinY[p], aMaxY = s.sMaxY[p];
-      const uint32_t aSlot = s.sSlot[p], aSleep = s.sSleep[p];
-      const uint32_t aPoly = PX_SHAPE_COUNT(s.shape[aSlot]) != 0;
-      const unsigned long long ex = exr[r];
+      const uint32_t ai = s.sInfo[p];
+      const uint32_t aSlot = ai & 0xffu, aPoly = (ai >> 9) & 1u;
+      const bool rescan = (exr[r] >> 63) != 0;
+      const unsigned long long ex = exr[r] & ~(1ull << 63);
       uint32_t seq = (uint32_t)(ex & 0xffffu);
       uint32_t binAt[3] = {(uint32_t)((ex >> 16) & 0xffffu), nCC + (uint32_t)((ex >> 32) & 0xffffu),
-                           nCC + nCP + (uint32_t)((ex >> 48) & 0xffffu)};
+                           nCC + nCP + (uint32_t)((ex >> 48) & 0x7fffu)};
       uint16_t *tpA = gtrace ? (uint16_t *)(gtrace + L.offTracePairs) : nullptr;
-      for (uint32_t q = p + 1; q < nDyn; q++) {
-        float bMinX = s.sMinX[q];
-        if (bMinX > aMaxX) break;
-        if (aSleep && s.sSleep[q]) continue;
-        if (!boxesOverlap(aMinX, aMinY, aMaxX, aMaxY, bMinX, s.sMinY[q], s.sMaxX[q], s.sMaxY[q])) continue;
-        uint32_t bSlot = s.sSlot[q];
-        uint32_t t = aPoly + (PX_SHAPE_COUNT(s.shape[bSlot]) != 0);
-        uint32_t at = binAt[t]++;
+      auto emit = [&](uint32_t bId, uint32_t bPoly, uint32_t traceB) {
+        const uint32_t t = aPoly + bPoly;
+        const uint32_t at = binAt[t]++;
         if (at >= MP) {
           /* pair overflow (flagged): the world's results are unspecified from here on */
         } else if (seq < MP) {
-          s.bins[at] = (seq << 17) | (aSlot << 9) | bSlot;
+          s.bins[at] = (seq << 17) | (aSlot << 9) | bId;
           s.validSlot[seq] = 0;
           if (tpA) {
             tpA[seq] = (uint16_t)aSlot;
-            tpA[MP + seq] = (uint16_t)(0x8000u | bSlot);
+            tpA[MP + seq] = (uint16_t)traceB;
           }
         } else {
           s.bins[at] = 0xffffffffu;
         }
         seq++;
+      };
+      if (!rescan) {
+        uint32_t m = dynMaskR[r];
+        while (m) {
+          const uint32_t k = __ffs(m) - 1;
+          m &= m - 1;
+          const uint32_t bi = s.sInfo[p + 1 + k];
+          emit(bi & 0xffu, (bi >> 9) & 1u, 0x8000u | (bi & 0xffu));
+        }
+      } else {
+        const float4 a = s.sBox[p];
+        const uint32_t aSleep = ai & 0x100u;
+        for (uint32_t q = p + 1; q < nDyn; q++) {
+          const float4 b = s.sBox[q];
+          if (b.x > a.z) break;
+          const uint32_t bi = s.sInfo[q];
+          if (aSleep & bi) continue;
+          if (!boxesOverlap(a, b)) continue;
+          emit(bi & 0xffu, (bi >> 9) & 1u, 0x8000u | (bi & 0xffu));
+        }
       }
-      for (uint32_t q = startStatR[r]; q < nStat; q++) {
-        float bMinX = s.stMinX[q];
-        if (bMinX > aMaxX) continue;
-        if (!boxesOverlap(aMinX, aMinY, aMaxX, aMaxY, bMinX, s.stMinY[q], s.stMaxX[q], s.stMaxY[q])) continue;
-        uint32_t t = aPoly + (PX_SHAPE_COUNT(s.shape[D + q]) != 0);
-        uint32_t at = binAt[t]++;
-        if (at >= MP) {
-        } else if (seq < MP) {
-          s.bins[at] = (seq << 17) | (aSlot << 9) | (D + q);
-          s.validSlot[seq] = 0;
-          if (tpA) {
-            tpA[seq] = (uint16_t)aSlot;
-            tpA[MP + seq] = (uint16_t)(gimm + L.offStatSlot)[q];
-          }
-        } else {
-          s.bins[at] = 0xffffffffu;
+      if (nStat <= 32 + startStatR[r]) {
+        uint32_t m = statMaskR[r];
+        while (m) {
+          const uint32_t k = __ffs(m) - 1;
+          m &= m - 1;
+          const uint32_t q = startStatR[r] + k;
+          const uint32_t bPoly = PX_SHAPE_COUNT(__float_as_uint(s.bodyM[D + q].w)) != 0;
+          emit(D + q, bPoly, tpA ? (uint32_t)(gimm + L.offStatSlot)[q] : 0u);
         }
-        seq++;
+      } else {
+        const float4 a = s.sBox[p];
+        for (uint32_t q = startStatR[r]; q < nStat; q++) {
+          const float4 b = s.stBox[q];
+          if (b.x > a.z) continue;
+          if (!boxesOverlap(a, b)) continue;
+          const uint32_t bPoly = PX_SHAPE_COUNT(__float_as_uint(s.bodyM[D + q].w)) != 0;
+          emit(D + q, bPoly, tpA ? (uint32_t)(gimm + L.offStatSlot)[q] : 0u);
+        }
       }
     }
     if (P.S.vertsInSmem) {
@@ -829,6 +843,8 @@ __global__ void __launch_bounds__(NT, 512 / NT) pxStepKernel(const PxStepParams 
     /* ====================== phase C: narrowphase, one pair per thread per bin ========= */
     {
       const uint32_t nAll = min(nCC + nCP + nPP, MP);
+      const V2 gstep = g * dt;
+      const float gsq = lensq(gstep);
       for (uint32_t idx = tid; idx < nAll; idx += NT) {
         Contact m;
         m.count = 0;
@@ -857,35 +873,37 @@ __global__ void __launch_bounds__(NT, 512 / NT) pxStepKernel(const PxStepParams 
         const uint32_t bdyn = b < D;
         const uint32_t ms = atomicAdd(&s.misc[MI_MCOUNT], 1u);
         if (ms >= MM) continue; /* manifold overflow, flagged below */
+        const float4 mtA = s.bodyM[a], mtB = s.bodyM[b];
+        const float4 pA = s.bodyP[a], pB = s.bodyP[b], vA = s.bodyV[a], vB = s.bodyV[b];
         /* pxManifoldInit, px_manifold.c:12-31: geometric-mean friction via pxFastSqrt */
-        s.msf[ms] = fSqrt(s.sf[a] * s.sf[b]);
-        s.mdf[ms] = fSqrt(s.df[a] * s.df[b]);
+        const float sfm = fSqrt(mtA.y * mtB.y), dfm = fSqrt(mtA.z * mtB.z);
         /* pxManifoldDetectRestingContact, px_manifold.c:46-92, on the velocities as they are
-         * before force integration */
-        float ea = s.e[a], eb = s.e[b];
-        float minE = ea < eb ? ea : eb;
-        V2 gstep = g * dt;
-        float gsq = lensq(gstep);
-        V2 pa = v2(s.px[a], s.py[a]), pb = v2(s.px[b], s.py[b]);
-        const V2 va = v2(s.vx[a], s.vy[a]), vb = v2(s.vx[b], s.vy[b]); /* statics: exact zeros */
-        const float wa = s.av[a], wb = s.av[b];
-        for (uint32_t i = 0; i < m.count; i++) {
-          V2 c = i == 0 ? m.c0 : m.c1;
-          V2 ra = c - pa, rb = c - pb;
-          V2 rv = (vb + v2(-rb.y, rb.x) * wb) - (va + v2(-ra.y, ra.x) * wa);
-          if (lensq(rv) < gsq + eps) {
-            minE = 0.0f;
-            break;
+         * before force integration (a static's are exact zeros) */
+        float minE = mtA.x < mtB.x ? mtA.x : mtB.x;
+        const V2 pa = v2(pA.x, pA.y), pb = v2(pB.x, pB.y);
+        const V2 va = v2(vA.x, vA.y), vb = v2(vB.x, vB.y);
+        const float wa = vA.z, wb = vB.z;
+        const float fcount = (float)m.count;
+        float rcp[2] = {0.0f, 0.0f};
+        bool restingHit = false;
+#pragma unroll
+        for (uint32_t i = 0; i < 2; i++) {
+          if (i < m.count) {
+            const V2 c = i == 0 ? m.c0 : m.c1;
+            const V2 ra = c - pa, rb = c - pb;
+            const V2 rv = (vb + v2(-rb.y, rb.x) * wb) - (va + v2(-ra.y, ra.x) * wa);
+            /* the reference stops at the first hit; later contacts cannot un-hit it */
+            restingHit = restingHit || (lensq(rv) < gsq + eps);
+            /* per-contact solver denominator, px_manifold.c:142-156 */
+            const float raCrossN = cross(ra, m.normal), rbCrossN = cross(rb, m.normal);
+            const float invMassSum = pA.z + pB.z + raCrossN * raCrossN * pA.w + rbCrossN * rbCrossN * pB.w;
+            rcp[i] = fRcp(invMassSum * fcount);
           }
         }
-        s.mnx[ms] = m.normal.x;
-        s.mny[ms] = m.normal.y;
-        s.mpen[ms] = m.pen;
-        s.mc0x[ms] = m.c0.x;
-        s.mc0y[ms] = m.c0.y;
-        s.mc1x[ms] = m.c1.x;
-        s.mc1y[ms] = m.c1.y;
-        s.me[ms] = minE;
+        if (restingHit) minE = 0.0f;
+        s.manA[ms] = make_float4(m.normal.x, m.normal.y, minE, sfm);
+        s.manB[ms] = make_float4(dfm, m.pen, m.c0.x, m.c0.y);
+        s.manC[ms] = make_float4(m.c1.x, m.c1.y, rcp[0], rcp[1]);
         s.mids[ms] = a | (b << 8) | (bdyn << 17) | (m.count << 18) | (ms << 20);
         s.validSlot[BIN_SEQ(word)] = (uint16_t)(ms + 1);
         /* manifold pass of pxUpdateSleepStates, px_world.c:147-177: flags set by SLOT */
@@ -932,7 +950,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) pxStepKernel(const PxStepParams 
         s.fillB[x] = 0;
       }
     }
-    for (uint32_t i = tid; i < (2 * M + 3) / 4; i += NT) ((uint32_t *)s.sig)[i] = 0;
+    for (uint32_t i = tid; i < M; i += NT) s.sig[i] = 0;
     __syncthreads();
 #pragma unroll
     for (int r = 0; r < R; r++) {
@@ -953,17 +971,18 @@ __global__ void __launch_bounds__(NT, 512 / NT) pxStepKernel(const PxStepParams 
         }
         if (gtrace) { /* ordered manifold dump */
           const uint32_t rank = rankStartR[r] + k;
+          const float4 mA = s.manA[ms], mB = s.manB[ms], mC = s.manC[ms];
           float *mf = (float *)(gtrace + L.offTraceManifolds);
-          mf[0 * MM + rank] = s.mnx[ms];
-          mf[1 * MM + rank] = s.mny[ms];
-          mf[2 * MM + rank] = s.mpen[ms];
-          mf[3 * MM + rank] = s.msf[ms];
-          mf[4 * MM + rank] = s.mdf[ms];
-          mf[5 * MM + rank] = s.me[ms];
-          mf[6 * MM + rank] = s.mc0x[ms];
-          mf[7 * MM + rank] = s.mc0y[ms];
-          mf[8 * MM + rank] = s.mc1x[ms];
-          mf[9 * MM + rank] = s.mc1y[ms];
+          mf[0 * MM + rank] = mA.x;
+          mf[1 * MM + rank] = mA.y;
+          mf[2 * MM + rank] = mB.y;
+          mf[3 * MM + rank] = mA.w;
+          mf[4 * MM + rank] = mB.x;
+          mf[5 * MM + rank] = mA.z;
+          mf[6 * MM + rank] = mB.z;
+          mf[7 * MM + rank] = mB.w;
+          mf[8 * MM + rank] = mC.x;
+          mf[9 * MM + rank] = mC.y;
           uint32_t bId = MID_B(ids);
           uint32_t slotB = MID_BDYN(ids) ? bId : (uint32_t)(gimm + L.offStatSlot)[bId - D];
           ((uint32_t *)(mf + (size_t)PX_TRACE_M_F32 * MM))[rank] = MID_A(ids) | (slotB << 8) | (MID_BDYN(ids) << 16) | (MID_COUNT(ids) << 24);
@@ -998,19 +1017,21 @@ __global__ void __launch_bounds__(NT, 512 / NT) pxStepKernel(const PxStepParams 
         const uint32_t succ = s.list[start + in];
         s.nextw[2 * ms + side] = (uint16_t)(succ | ((in < nBx ? 1u : 0u) << 15));
       }
-      if (n) {
+      if (n) { /* the body's first manifold receives its first signal from the body itself */
         const uint32_t first = s.list[start];
-        s.sig[2 * first + (nBx ? 1u : 0u)] = 1;
+        atomicAdd(&s.sig[first], nBx ? 0x10000u : 1u);
       }
       /* pxIntegrateForces, px_world.c:231-239 / px_body.c:167-179 (resting-contact detection
        * above already consumed the pre-integration velocities) */
       if (!(s.flags[x] & PX_FLAG_SLEEPING)) {
-        float halfDt = fDiv(dt, 2.0f);
-        float iM = s.iM[x], iI = s.iI[x];
-        V2 dv = (v2(rFx[r], rFy[r]) * iM + g) * halfDt;
-        s.vx[x] = s.vx[x] + dv.x;
-        s.vy[x] = s.vy[x] + dv.y;
-        s.av[x] = s.av[x] + rTq[r] * iI * halfDt;
+        const float halfDt = fDiv(dt, 2.0f);
+        const float4 bp = s.bodyP[x];
+        float4 bv = s.bodyV[x];
+        const V2 dv = (v2(rFx[r], rFy[r]) * bp.z + g) * halfDt;
+        bv.x = bv.x + dv.x;
+        bv.y = bv.y + dv.y;
+        bv.z = bv.z + rTq[r] * bp.w * halfDt;
+        s.bodyV[x] = bv;
       }
     }
     __syncthreads();
@@ -1018,7 +1039,8 @@ __global__ void __launch_bounds__(NT, 512 / NT) pxStepKernel(const PxStepParams 
     if (iterations && !(P.flags & PX_BATCH_FLAG_SERIAL_SOLVER)) {
       for (uint32_t ms = tid; ms < M; ms += NT) {
         const uint32_t w = s.mids[ms];
-        if (s.sig[2 * ms] == 1 && (!MID_BDYN(w) || s.sig[2 * ms + 1] == 1)) {
+        const uint32_t sg = s.sig[ms];
+        if ((sg & 0xffffu) == 1u && (!MID_BDYN(w) || (sg >> 16) == 1u)) {
           s.queue[atomicAdd(&s.misc[MI_QTAIL], 1u) & QMASK] = w;
         }
       }
@@ -1044,82 +1066,48 @@ __global__ void __launch_bounds__(NT, 512 / NT) pxStepKernel(const PxStepParams 
       }
     } else if (warp == 0 && iterations) {
       /*
-       * Every manifold side counts the signals it has received (sig).  Visit v of a manifold
-       * may run once each of its dynamic bodies has delivered v + 1 signals: one from the
-       * body at list-build time if the manifold heads that body's list, one each time the
-       * body's previous manifold (cyclically) finishes a visit.  Signals whose target side is
-       * A are applied first, B-side signals after a warp barrier, and exactly one of the two
-       * signalers sees both counts equal and enqueues the visit -- no atomics.
+       * sig[m] counts the signals manifold m has received from its A body (low half) and its
+       * B body (high half).  Visit v of a manifold may run once each of its dynamic bodies has
+       * delivered v + 1 signals: one from the body at list-build time if the manifold heads
+       * that body's list, one each time the body's previous manifold (cyclically) finishes a
+       * visit.  A signal is one shared-memory atomicAdd; its return value shows both counts
+       * as they were, so exactly one of the (at most two) signalers sees the other side
+       * already complete and enqueues the visit.
        */
-      uint32_t head = 0, tail = s.misc[MI_QTAIL], visits = 0;
-      unsigned long long profRounds = 0, profApply = 0;
+      uint32_t head = 0, tail = s.misc[MI_QTAIL], visits = 0, rounds = 0;
       const uint32_t NONE = 0xffffffffu;
       while (head != tail) {
-        const long long tApply0 = prof ? clock64() : 0;
         const uint32_t n = min(tail - head, 32u);
-        const bool active = lane < n;
-        uint32_t w = 0, wt0 = 0, wt1 = 0, mine0 = 0, mine1 = 0;
-        bool sigA0 = false, sigB0 = false, sigA1 = false, sigB1 = false, again = false;
-        if (active) {
-          w = s.queue[(head + lane) & QMASK];
+        uint32_t push0 = NONE, push1 = NONE;
+        bool lastVisit = false;
+        if (lane < n) {
+          const uint32_t w = s.queue[(head + lane) & QMASK];
           const uint32_t ms = MID_SLOT(w);
-          /* successors of this manifold on body a / body b: static for the whole substep, so
-           * their rich words are fetched now and the latency hides behind the impulse math */
-          const uint32_t nx0 = s.nextw[2 * ms], nx1 = s.nextw[2 * ms + 1];
-          const bool last = MID_CI(w) + 1u >= MID_COUNT(w);
-          const bool two = MID_BDYN(w) != 0;
-          wt0 = s.mids[nx0 & 0x3ffu];
-          wt1 = s.mids[nx1 & 0x3ffu];
-          mine0 = 2u * (nx0 & 0x3ffu) + (nx0 >> 15); /* sig index of (successor, side of body a) */
-          mine1 = 2u * (nx1 & 0x3ffu) + (nx1 >> 15);
-          again = !last;
-          sigA0 = last && (nx0 >> 15) == 0;
-          sigB0 = last && (nx0 >> 15) == 1;
-          sigA1 = last && two && (nx1 >> 15) == 0;
-          sigB1 = last && two && (nx1 >> 15) == 1;
+          /* successors of this manifold on body a / body b are fixed for the substep: their
+           * rich words are fetched now and the latency hides behind the impulse math */
+          const uint32_t nx = *(const uint32_t *)(s.nextw + 2 * ms); /* side a | side b << 16 */
+          const uint32_t t0 = nx & 0x3ffu, t1 = MID_BDYN(w) ? (nx >> 16) & 0x3ffu : 0u;
+          const uint32_t wt0 = s.mids[t0], wt1 = s.mids[t1];
           applyContactImpulse(s, w, eps);
-        }
-        __syncwarp();
-        if (prof) {
-          profApply += (unsigned long long)(clock64() - tApply0);
-          profRounds++;
-        }
-        uint32_t push0 = again ? (w | (1u << 30)) : NONE; /* second contact of the same manifold */
-        uint32_t push1 = NONE;
-        /* signals whose target side is A: the signaler pushes if the B side (when there is one)
-         * was complete BEFORE this round */
-        {
-          uint32_t c0 = 0, c1 = 0, o0 = 0, o1 = 0;
-          if (sigA0) {
-            c0 = s.sig[mine0] + 1u;
-            o0 = s.sig[mine0 + 1];
+          lastVisit = MID_CI(w) + 1u >= MID_COUNT(w);
+          if (!lastVisit) {
+            push0 = w | (1u << 30); /* second contact of the same manifold */
+          } else {
+            {
+              const uint32_t sideB = (nx >> 15) & 1u;
+              const uint32_t old = atomicAdd(&s.sig[t0], sideB ? 0x10000u : 1u);
+              const uint32_t mine = (sideB ? (old >> 16) : (old & 0xffffu)) + 1u;
+              const uint32_t other = sideB ? (old & 0xffffu) : (old >> 16);
+              if (mine <= iterations && (!MID_BDYN(wt0) || other == mine)) push0 = wt0;
+            }
+            if (MID_BDYN(w)) {
+              const uint32_t sideB = nx >> 31;
+              const uint32_t old = atomicAdd(&s.sig[t1], sideB ? 0x10000u : 1u);
+              const uint32_t mine = (sideB ? (old >> 16) : (old & 0xffffu)) + 1u;
+              const uint32_t other = sideB ? (old & 0xffffu) : (old >> 16);
+              if (mine <= iterations && (!MID_BDYN(wt1) || other == mine)) push1 = wt1;
+            }
           }
-          if (sigA1) {
-            c1 = s.sig[mine1] + 1u;
-            o1 = s.sig[mine1 + 1];
-          }
-          if (sigA0) s.sig[mine0] = (uint8_t)c0;
-          if (sigA1) s.sig[mine1] = (uint8_t)c1;
-          if (sigA0 && c0 <= iterations && (!MID_BDYN(wt0) || o0 == c0)) push0 = wt0;
-          if (sigA1 && c1 <= iterations && (!MID_BDYN(wt1) || o1 == c1)) push1 = wt1;
-        }
-        __syncwarp();
-        /* signals whose target side is B: the signaler pushes if the A side is complete, be it
-         * from an earlier round or from the phase above */
-        {
-          uint32_t c0 = 0, c1 = 0, o0 = 0, o1 = 0;
-          if (sigB0) {
-            c0 = s.sig[mine0] + 1u;
-            o0 = s.sig[mine0 - 1];
-          }
-          if (sigB1) {
-            c1 = s.sig[mine1] + 1u;
-            o1 = s.sig[mine1 - 1];
-          }
-          if (sigB0) s.sig[mine0] = (uint8_t)c0;
-          if (sigB1) s.sig[mine1] = (uint8_t)c1;
-          if (sigB0 && c0 <= iterations && o0 == c0) push0 = wt0;
-          if (sigB1 && c1 <= iterations && o1 == c1) push1 = wt1;
         }
         const uint32_t b0 = __ballot_sync(0xffffffffu, push0 != NONE);
         const uint32_t b1 = __ballot_sync(0xffffffffu, push1 != NONE);
@@ -1128,14 +1116,13 @@ __global__ void __launch_bounds__(NT, 512 / NT) pxStepKernel(const PxStepParams 
         if (push1 != NONE) s.queue[(tail + __popc(b0) + __popc(b1 & lt)) & QMASK] = push1;
         tail += __popc(b0) + __popc(b1);
         head += n;
-        visits += __popc(__ballot_sync(0xffffffffu, sigA0 || sigB0));
+        visits += lastVisit ? 1u : 0u;
+        rounds++;
         __syncwarp();
       }
+      visits = __reduce_add_sync(0xffffffffu, visits);
       if (lane == 0 && visits != M * iterations) overflow |= PX_OVERFLOW_INTERNAL;
-      if (prof && lane == 0) {
-        prof[6] += profRounds;
-        prof[7] += profApply;
-      }
+      if (prof && lane == 0) prof[6] += rounds;
     }
     __syncthreads();
     PROF_MARK(4)
@@ -1148,47 +1135,46 @@ __global__ void __launch_bounds__(NT, 512 / NT) pxStepKernel(const PxStepParams 
       if (x >= D || !(s.flags[x] & 4u)) continue;
       const uint32_t p = s.posOf[x];
       uint32_t fl = s.flags[x];
-      float posx = s.px[x], posy = s.py[x];
+      float4 bp = s.bodyP[x];
+      float4 bv = s.bodyV[x];
+      float posx = bp.x, posy = bp.y;
       /* pxBodyIntegrateVelocity, px_body.c:181-188 */
       if (!(fl & PX_FLAG_SLEEPING)) {
-        posx = posx + s.vx[x] * dt;
-        posy = posy + s.vy[x] * dt;
-        float radians = rAngle[r] + s.av[x] * dt;
+        posx = posx + bv.x * dt;
+        posy = posy + bv.y * dt;
+        float radians = rAngle[r] + bv.z * dt;
         radians = fmodf(radians, D_2PI);
         if (radians < 0) radians += D_2PI;
         rAngle[r] = radians;
-        float c = fSin(P.sinTable, radians + D_PI * 0.5f), sn = fSin(P.sinTable, radians);
-        s.m00[x] = c;
-        s.m01[x] = -sn;
-        s.m10[x] = sn;
-        s.m11[x] = c;
+        const float c = fSin(P.sinTable, radians + D_PI * 0.5f), sn = fSin(P.sinTable, radians);
+        s.bodyR[x] = make_float4(c, -sn, sn, c);
       }
       /* pxCorrectPositions, px_world.c:288-292: this body's terms, in pool order */
       {
         const uint32_t start = s.listStart[x], n = s.cnt[x], nBx = s.cntB[x];
         for (uint32_t i = 0; i < n; i++) {
           const uint32_t ms = s.list[start + i];
-          const float pen = s.mpen[ms];
+          const float pen = s.manB[ms].y;
           if (pen <= allowedPen) continue;
           const uint32_t ids = s.mids[ms];
-          const float iMA = s.iM[MID_A(ids)];
-          const float iMB = s.iM[MID_B(ids)];
+          const float4 mA = s.manA[ms];
+          const float iMA = s.bodyP[MID_A(ids)].z, iMB = s.bodyP[MID_B(ids)].z;
           const float excess = pen - allowedPen;
           const float mag = fDiv(excess * 0.2f, iMA + iMB);
-          const V2 corr = v2(s.mnx[ms], s.mny[ms]) * mag;
+          const V2 corr = v2(mA.x, mA.y) * mag;
           if (i >= nBx) { /* bodyA: moveBy(-(corr * iMA)) */
-            V2 d = -(corr * iMA);
+            const V2 d = -(corr * iMA);
             posx = posx + d.x;
             posy = posy + d.y;
           } else {
-            V2 d = corr * iMB;
+            const V2 d = corr * iMB;
             posx = posx + d.x;
             posy = posy + d.y;
           }
         }
       }
-      s.px[x] = posx;
-      s.py[x] = posy;
+      bp.x = posx;
+      bp.y = posy;
 
       /* body pass of pxUpdateSleepStates, px_world.c:179-219: the flags are TESTED by sorted
        * position p although they were set by slot -- the reference's behaviour */
@@ -1197,8 +1183,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) pxStepKernel(const PxStepParams 
         slp = 0.0f;
         fl &= ~PX_FLAG_SLEEPING;
       } else {
-        const float vx = s.vx[x], vy = s.vy[x];
-        const bool below = (vx * vx + vy * vy <= linSleepSq) && (fabsf(s.av[x]) <= angSleep);
+        const bool below = (bv.x * bv.x + bv.y * bv.y <= linSleepSq) && (fabsf(bv.z) <= angSleep);
         if (!below) {
           slp = 0.0f;
           fl &= ~PX_FLAG_SLEEPING;
@@ -1206,9 +1191,9 @@ __global__ void __launch_bounds__(NT, 512 / NT) pxStepKernel(const PxStepParams 
           slp = slp + dt;
           if (s.restFlag[p]) slp = slp + dt;
           if (slp >= timeToSleep) {
-            s.vx[x] = 0.0f;
-            s.vy[x] = 0.0f;
-            s.av[x] = 0.0f;
+            bv.x = 0.0f;
+            bv.y = 0.0f;
+            bv.z = 0.0f;
             rFx[r] = 0.0f;
             rFy[r] = 0.0f;
             rTq[r] = 0.0f;
@@ -1217,7 +1202,6 @@ __global__ void __launch_bounds__(NT, 512 / NT) pxStepKernel(const PxStepParams 
         }
       }
       rSlp[r] = slp;
-      s.flags[x] = (uint8_t)fl;
       /* pxClearForces, px_world.c:302-311 */
       if (!(slp >= timeToSleep)) {
         rFx[r] = 0.0f;
@@ -1225,6 +1209,11 @@ __global__ void __launch_bounds__(NT, 512 / NT) pxStepKernel(const PxStepParams 
         rTq[r] = 0.0f;
       }
       sleepingLocal += (fl & PX_FLAG_SLEEPING) ? 1u : 0u;
+      /* positions are read by other bodies' correction terms?  No: corrections use only the
+       * manifold and inverse masses, so the record can be written back right away */
+      s.bodyP[x] = bp;
+      s.bodyV[x] = bv;
+      s.flags[x] = (uint8_t)fl;
     }
     if (step + 1 == P.kSubsteps) {
       if (sleepingLocal) atomicAdd(&s.misc[MI_SLEEPING], sleepingLocal);
@@ -1235,30 +1224,31 @@ __global__ void __launch_bounds__(NT, 512 / NT) pxStepKernel(const PxStepParams 
     PROF_MARK(5)
   }
 
-  /* --------------------------------------------------------------- store (smem -> HBM) */
+  /* ------------------------------------------- store (smem records -> HBM SoA rows) */
   {
-    copyRows<NT>(gdyn + PX_DYN_PX * D, s.px, D);
-    copyRows<NT>(gdyn + PX_DYN_PY * D, s.py, D);
-    copyRows<NT>(gdyn + PX_DYN_VX * D, s.vx, D);
-    copyRows<NT>(gdyn + PX_DYN_VY * D, s.vy, D);
-    copyRows<NT>(gdyn + PX_DYN_AV * D, s.av, D);
-    copyRows<NT>(gdyn + PX_DYN_M00 * D, s.m00, D);
-    copyRows<NT>(gdyn + PX_DYN_M01 * D, s.m01, D);
-    copyRows<NT>(gdyn + PX_DYN_M10 * D, s.m10, D);
-    copyRows<NT>(gdyn + PX_DYN_M11 * D, s.m11, D);
-    copyRows<NT>((float *)(gmut + L.offDynFlags), (const float *)s.flags, D / 4);
-    copyRows<NT>((float *)(gmut + L.offDynOrder), (const float *)s.order, D / 4);
 #pragma unroll
     for (int r = 0; r < R; r++) {
       const uint32_t x = tid + r * NT;
       if (x < D) {
+        const float4 bp = s.bodyP[x], bv = s.bodyV[x], br = s.bodyR[x];
+        gdyn[PX_DYN_PX * D + x] = bp.x;
+        gdyn[PX_DYN_PY * D + x] = bp.y;
+        gdyn[PX_DYN_VX * D + x] = bv.x;
+        gdyn[PX_DYN_VY * D + x] = bv.y;
+        gdyn[PX_DYN_AV * D + x] = bv.z;
         gdyn[PX_DYN_ANGLE * D + x] = rAngle[r];
         gdyn[PX_DYN_FX * D + x] = rFx[r];
         gdyn[PX_DYN_FY * D + x] = rFy[r];
         gdyn[PX_DYN_TORQUE * D + x] = rTq[r];
         gdyn[PX_DYN_SLEEP * D + x] = rSlp[r];
+        gdyn[PX_DYN_M00 * D + x] = br.x;
+        gdyn[PX_DYN_M01 * D + x] = br.y;
+        gdyn[PX_DYN_M10 * D + x] = br.z;
+        gdyn[PX_DYN_M11 * D + x] = br.w;
       }
     }
+    copyRows<NT>((float *)(gmut + L.offDynFlags), (const float *)s.flags, D / 4);
+    copyRows<NT>((float *)(gmut + L.offDynOrder), (const float *)s.order, D / 4);
     if (tid == 0) {
       PxWorldHeader *gh = (PxWorldHeader *)(gmut + L.offHeader);
       gh->statManifolds = statManifolds;
@@ -1331,20 +1321,13 @@ extern "C" void pxPlanSmem(const PxBatchLayout *L, int vertsInSmem, PxSmemPlan *
     o += alignUp(bytes, 16);
     return at;
   };
-  S->px = take(NB * 4); S->py = take(NB * 4); S->m00 = take(NB * 4); S->m01 = take(NB * 4);
-  S->m10 = take(NB * 4); S->m11 = take(NB * 4); S->rad = take(NB * 4); S->e = take(NB * 4);
-  S->sf = take(NB * 4); S->df = take(NB * 4); S->shape = take(NB * 4);
-  /* velocities / inverse masses cover the statics too (all zero, px_body.c:30-44) so the
-   * solver reads both bodies of a manifold without branching */
-  S->vx = take(NB * 4); S->vy = take(NB * 4); S->av = take(NB * 4); S->iM = take(NB * 4); S->iI = take(NB * 4);
+  S->bodyP = take(NB * 16); S->bodyV = take(NB * 16); S->bodyR = take(NB * 16); S->bodyM = take(NB * 16);
   S->flags = take(D); S->order = take(D); S->order2 = take(D); S->posOf = take(D);
   S->restFlag = take(D); S->wakeFlag = take(D); S->sSlot = take(D);
   S->hdr = take(sizeof(PxWorldHeader));
   S->misc = take(16 * 4);
   S->scan = take(8 * 8);
-  S->mnx = take(MM * 4); S->mny = take(MM * 4); S->mpen = take(MM * 4); S->mc0x = take(MM * 4);
-  S->mc0y = take(MM * 4); S->mc1x = take(MM * 4); S->mc1y = take(MM * 4); S->msf = take(MM * 4);
-  S->mdf = take(MM * 4); S->me = take(MM * 4); S->mids = take(MM * 4);
+  S->manA = take(MM * 16); S->manB = take(MM * 16); S->manC = take(MM * 16); S->mids = take(MM * 4);
   S->validSlot = take(MP * 2);
   S->base = take((D + 1) * 2);
   S->listStart = take((D + 1) * 2);
@@ -1355,15 +1338,13 @@ extern "C" void pxPlanSmem(const PxBatchLayout *L, int vertsInSmem, PxSmemPlan *
   S->qcap = qcap;
   /* region X (sweep + narrowphase) overlaid by region Y (solver) */
   const uint32_t rx = o;
-  S->sMinX = take(D * 4); S->sMaxX = take(D * 4); S->sMinY = take(D * 4); S->sMaxY = take(D * 4);
-  S->sSleep = take(D);
-  S->stMinX = take(St * 4); S->stMaxX = take(St * 4); S->stMinY = take(St * 4); S->stMaxY = take(St * 4);
-  S->bins = take(MP * 4);
+  S->sBox = take(D * 16); S->sInfo = take(D * 4); S->stBox = take(St * 16);
+  S->bins = take((MP > D ? MP : D) * 4);
   S->vertsInSmem = vertsInSmem ? 1u : 0u;
   S->verts = vertsInSmem ? take(V * 16) : 0;
   const uint32_t rxEnd = o;
   o = rx;
-  S->list = take(2 * MM * 2); S->nextw = take(2 * MM * 2); S->sig = take(2 * MM); S->queue = take(qcap * 4);
+  S->list = take(2 * MM * 2); S->nextw = take(2 * MM * 2); S->sig = take(MM * 4); S->queue = take(qcap * 4);
   o = o > rxEnd ? o : rxEnd;
   S->total = o;
 }

@@ -13,17 +13,14 @@
  * (pxPlanSmem) from the batch layout and handed to the kernel by value.
  * Body-id space: dynamic slot s -> id s, static position q -> id D + q (NB = D + S). */
 struct PxSmemPlan {
-  /* persistent across the K fused substeps */
-  uint32_t px, py, m00, m01, m10, m11, rad, e, sf, df; /* f32[NB] */
-  uint32_t shape;                                       /* u32[NB] */
-  uint32_t vx, vy, av, iM, iI;                          /* f32[NB] (statics: zeros) */
+  /* persistent across the K fused substeps: float4 records by body id */
+  uint32_t bodyP, bodyV, bodyR, bodyM;
   uint32_t flags, order, order2, posOf, restFlag, wakeFlag, sSlot; /* u8[D] */
-  uint32_t hdr;                                         /* PxWorldHeader */
-  uint32_t misc;                                        /* u32[16] counters */
-  uint32_t scan;                                        /* u64[8] block-scan scratch */
-  /* manifolds of the current substep, SoA by (unordered) manifold slot */
-  uint32_t mnx, mny, mpen, mc0x, mc0y, mc1x, mc1y, msf, mdf, me; /* f32[MM] */
-  uint32_t mids;                                                 /* u32[MM] */
+  uint32_t hdr;                                                     /* PxWorldHeader */
+  uint32_t misc;                                                    /* u32[16] counters */
+  uint32_t scan;                                                    /* u64[8] block-scan scratch */
+  /* manifolds of the current substep: three float4 records + one id word per slot */
+  uint32_t manA, manB, manC, mids;
   /* sweep -> list build */
   uint32_t validSlot; /* u16[MP] manifold slot + 1 by pair sequence number */
   uint32_t base;      /* u16[D+1] first pair sequence number by sorted position */
@@ -31,18 +28,18 @@ struct PxSmemPlan {
   uint32_t cnt, cntB; /* u16[D] manifolds per body / of which as bodyB, by slot */
   uint32_t fillB;     /* u32[D] atomic counters */
   /* region X (sweep + narrowphase), aliased with region Y (solver) */
-  uint32_t sMinX, sMaxX, sMinY, sMaxY;     /* f32[D] by sorted position */
-  uint32_t sSleep;                         /* u8[D] */
-  uint32_t stMinX, stMaxX, stMinY, stMaxY; /* f32[S] */
-  uint32_t bins;                           /* u32[MP] pairs binned by shape-pair type */
-  uint32_t verts;                          /* float4[V] (only if vertsInSmem) */
+  uint32_t sBox;  /* float4[D] AABB by sorted position */
+  uint32_t sInfo; /* u32[D] slot | sleeping << 8 | polygon << 9 by sorted position */
+  uint32_t stBox; /* float4[S] */
+  uint32_t bins;  /* u32[max(MP, D)] pairs binned by shape-pair type (sort keys in phase A) */
+  uint32_t verts; /* float4[V] (only if vertsInSmem) */
   /* region Y */
-  uint32_t list;   /* u16[2*MM] per-body manifold lists (CSR payload), persists to phase F */
-  uint32_t nextw;  /* u16[2*MM] successor of manifold ms on side s: slot | side << 15 */
-  uint32_t sig;    /* u8[2*MM]  signals received per manifold side */
-  uint32_t queue;  /* u32[QCAP] ready ring of rich manifold words */
-  uint32_t total;  /* bytes */
-  uint32_t qcap;   /* ring capacity (power of two >= MM) */
+  uint32_t list;  /* u16[2*MM] per-body manifold lists (CSR payload), persists to phase F */
+  uint32_t nextw; /* u16[2*MM] successor of manifold ms on side s: slot | side << 15 */
+  uint32_t sig;   /* u32[MM]   signals received: A side low half, B side high half */
+  uint32_t queue; /* u32[QCAP] ready ring of rich manifold words */
+  uint32_t total; /* bytes */
+  uint32_t qcap;  /* ring capacity (power of two >= MM) */
   uint32_t vertsInSmem;
 };
 
