@@ -179,7 +179,8 @@ PX_API int pxBatchStep(PxBatch *b, uint32_t kSubsteps);
 /* Same, bracketed by CUDA events on the launching stream; blocks; *ms = device time. */
 PX_API int pxBatchStepTimed(PxBatch *b, uint32_t kSubsteps, float *ms);
 
-/* Wait for the stream; returns the number of worlds with statOverflow != 0 (or < 0). */
+/* Wait for the stream; 0 or < 0.  Capacity overflows are reported per world by
+ * pxBatchReadback (return value and PxContactStats.overflow). */
 PX_API int pxBatchSync(PxBatch *b);
 
 /* Sync, then write position, velocity, angularVelocity, orientationAngle, orientation, aabb,
@@ -236,6 +237,13 @@ PX_API int pxPackWorlds(const PxBatchLayout *layout, struct PxWorld *const *worl
 PX_API int pxUnpackWorlds(const PxBatchLayout *layout, struct PxWorld *const *worlds, uint32_t n, const void *mut, uint32_t flags);
 /* Capacities the given worlds need (fills desc.max* that are 0). */
 PX_API int pxBatchFitDesc(struct PxWorld *const *worlds, uint32_t n, PxBatchDesc *desc);
+
+/* Arithmetic self-tests on the current device (parity tier T0): op 0 rsqrt, 1 rcp, 2 sqrt,
+ * 3 div(a, b), 4 sin, 5 cos -- the device restatement of reference px_math.h:50-114, 226-252
+ * applied to host arrays; and pxFastRsqrt over all 2^32 bit patterns as 4096 block sums of the
+ * result bit patterns (block i covers patterns [i << 20, (i + 1) << 20)). */
+PX_API int pxSelfTestMath(int op, const float *a, const float *b, const float *sinTable256, float *out, uint32_t n);
+PX_API int pxSelfTestRsqrtSweep(uint64_t *sums4096);
 
 PX_API const char *pxBatchLastError(void);
 PX_API const char *pxBatchVersion(void);

@@ -26,6 +26,8 @@ def load():
         lib.pxOracleTimeSubsteps.argtypes = [vp, vp, vp, vp, C.c_uint32, C.c_uint32, C.c_uint32]
         lib.pxOracleMath.restype = None
         lib.pxOracleMath.argtypes = [C.c_int, vp, vp, vp, vp, C.c_uint32]
+        lib.pxOracleRsqrtSweep.restype = None
+        lib.pxOracleRsqrtSweep.argtypes = [vp, C.c_uint32, C.c_uint32]
         _lib = lib
     return _lib
 
@@ -50,4 +52,11 @@ def math(op: int, a: np.ndarray, b: np.ndarray | None, sin_table: np.ndarray) ->
     b = np.ascontiguousarray(b if b is not None else a, np.float32)
     out = np.zeros_like(a)
     load().pxOracleMath(op, _ptr(a), _ptr(b), _ptr(sin_table), _ptr(out), a.size)
+    return out
+
+
+def rsqrt_sweep(first: int, n: int) -> np.ndarray:
+    """Block sums of pxFastRsqrt result bit patterns for 2^20-pattern blocks [first, first+n)."""
+    out = np.zeros(n, np.uint64)
+    load().pxOracleRsqrtSweep(_ptr(out), first, n)
     return out

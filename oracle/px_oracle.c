@@ -890,3 +890,22 @@ void pxOracleMath(int op, const float *a, const float *b, const float *sinTable,
     }
   }
 }
+
+/* pxFastRsqrt over bit patterns [first << 20, (first + n) << 20): one 64-bit sum of the result
+ * bit patterns per 2^20 block (same reduction as the device self-test) */
+void pxOracleRsqrtSweep(uint64_t *sums, uint32_t first, uint32_t n) {
+  for (uint32_t b = 0; b < n; b++) {
+    uint64_t acc = 0;
+    uint32_t base = (first + b) << 20;
+    for (uint32_t k = 0; k < (1u << 20); k++) {
+      union {
+        float f;
+        uint32_t u;
+      } c;
+      c.u = base + k;
+      c.f = fastRsqrt(c.f);
+      acc += (c.f != c.f) ? 0x7fc00000u : c.u; /* NaN payloads are outside the contract */
+    }
+    sums[b] = acc;
+  }
+}

@@ -22,4 +22,6 @@ ORACLE_API double pxOracleTimeSubsteps(const PxBatchLayout *L, void *mut, const 
 /* op: 0 rsqrt 1 rcp 2 sqrt 3 div 4 sin 5 cos */
 ORACLE_API void pxOracleMath(int op, const float *a, const float *b, const float *sinTable, float *out, uint32_t n);
 
+ORACLE_API void pxOracleRsqrtSweep(uint64_t *sums, uint32_t first, uint32_t n);
+
 #endif

@@ -101,6 +101,8 @@ def core():
         "pxPackWorlds": (i32, [C.POINTER(PxBatchLayout), pp, u32, vp, vp]),
         "pxUnpackWorlds": (i32, [C.POINTER(PxBatchLayout), pp, u32, vp, u32]),
         "pxBatchFitDesc": (i32, [pp, u32, C.POINTER(PxBatchDesc)]),
+        "pxSelfTestMath": (i32, [C.c_int, vp, vp, vp, vp, u32]),
+        "pxSelfTestRsqrtSweep": (i32, [vp]),
         "pxBatchLastError": (C.c_char_p, []),
         "pxBatchVersion": (C.c_char_p, []),
     }
@@ -455,3 +457,20 @@ class Batch:
         a, b, c, d = C.c_int(0), C.c_int(0), C.c_int(0), C.c_int(0)
         _check(self.lib.pxBatchKernelInfo(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(d)), "pxBatchKernelInfo")
         return dict(ctas_per_sm=a.value, smem_bytes=b.value, threads=c.value, num_sms=d.value)
+
+
+def device_math(op: int, a: np.ndarray, b: np.ndarray | None = None, sin_table: np.ndarray | None = None) -> np.ndarray:
+    """Element-wise device evaluation of the fast-math contract (T0 tier); needs a GPU."""
+    a = np.ascontiguousarray(a, np.float32)
+    bb = np.ascontiguousarray(b if b is not None else a, np.float32)
+    out = np.zeros_like(a)
+    tp = sin_table.ctypes.data_as(C.c_void_p) if sin_table is not None else None
+    _check(core().pxSelfTestMath(op, a.ctypes.data_as(C.c_void_p), bb.ctypes.data_as(C.c_void_p), tp,
+                                 out.ctypes.data_as(C.c_void_p), a.size), "pxSelfTestMath")
+    return out
+
+
+def device_rsqrt_sweep() -> np.ndarray:
+    out = np.zeros(4096, np.uint64)
+    _check(core().pxSelfTestRsqrtSweep(out.ctypes.data_as(C.c_void_p)), "pxSelfTestRsqrtSweep")
+    return out

@@ -256,7 +256,8 @@ extern "C" int pxBatchUpload(PxBatch *b, struct PxWorld *const *worlds, uint32_t
 extern "C" int pxBatchSync(PxBatch *b) {
   if (!b) return pxSetError(-1, "pxBatchSync: NULL batch");
   if (useDevice(b)) return -1;
-  CU(cudaStreamSynchronize(b->stream));
+  cudaError_t e = cudaStreamSynchronize(b->stream);
+  if (e != cudaSuccess) return pxSetError(-(int)e - 1000, "pxBatchSync: %s", cudaGetErrorString(e));
   return 0;
 }
 
@@ -400,6 +401,48 @@ extern "C" int pxBatchProfileD2H(PxBatch *b, uint64_t *host) {
   if (useDevice(b)) return -1;
   CU(cudaMemcpyAsync(host, b->dProf, (size_t)b->L.nWorlds * 64, cudaMemcpyDeviceToHost, b->stream));
   CU(cudaStreamSynchronize(b->stream));
+  return 0;
+}
+
+/* ---------------------------------------------------------------------------- self-tests */
+extern "C" int pxSelfTestMath(int op, const float *a, const float *b, const float *sinTable256, float *out, uint32_t n) {
+  if (!a || !out || n == 0 || op < 0 || op > 5) return pxSetError(-1, "pxSelfTestMath: bad argument");
+  float *dA = nullptr, *dB = nullptr, *dT = nullptr, *dO = nullptr;
+  float table[256];
+  if (sinTable256) {
+    memcpy(table, sinTable256, sizeof(table));
+  } else {
+    for (int i = 0; i < 256; i++) table[i] = sinf((i * 3.141592741f * 2.0f) / 256);
+  }
+  int rc = 0;
+  cudaError_t e = cudaSuccess;
+  do {
+    if ((e = cudaMalloc(&dA, n * sizeof(float))) != cudaSuccess) break;
+    if ((e = cudaMalloc(&dB, n * sizeof(float))) != cudaSuccess) break;
+    if ((e = cudaMalloc(&dO, n * sizeof(float))) != cudaSuccess) break;
+    if ((e = cudaMalloc(&dT, sizeof(table))) != cudaSuccess) break;
+    if ((e = cudaMemcpy(dA, a, n * sizeof(float), cudaMemcpyHostToDevice)) != cudaSuccess) break;
+    if ((e = cudaMemcpy(dB, b ? b : a, n * sizeof(float), cudaMemcpyHostToDevice)) != cudaSuccess) break;
+    if ((e = cudaMemcpy(dT, table, sizeof(table), cudaMemcpyHostToDevice)) != cudaSuccess) break;
+    if ((e = (cudaError_t)pxLaunchMath(op, dA, dB, dT, dO, n, nullptr)) != cudaSuccess) break;
+    if ((e = cudaMemcpy(out, dO, n * sizeof(float), cudaMemcpyDeviceToHost)) != cudaSuccess) break;
+  } while (0);
+  if (e != cudaSuccess) rc = pxSetError(-(int)e - 1000, "pxSelfTestMath: %s", cudaGetErrorString(e));
+  cudaFree(dA);
+  cudaFree(dB);
+  cudaFree(dO);
+  cudaFree(dT);
+  return rc;
+}
+
+extern "C" int pxSelfTestRsqrtSweep(uint64_t *sums4096) {
+  if (!sums4096) return pxSetError(-1, "pxSelfTestRsqrtSweep: NULL argument");
+  unsigned long long *d = nullptr;
+  cudaError_t e = cudaMalloc(&d, 4096 * sizeof(unsigned long long));
+  if (e == cudaSuccess) e = (cudaError_t)pxLaunchRsqrtSweep(d, nullptr);
+  if (e == cudaSuccess) e = cudaMemcpy(sums4096, d, 4096 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  if (e != cudaSuccess) return pxSetError(-(int)e - 1000, "pxSelfTestRsqrtSweep: %s", cudaGetErrorString(e));
   return 0;
 }
 

@@ -24,8 +24,9 @@ int pxBatchComputeLayout(uint32_t nWorlds, const PxBatchDesc *desc, PxBatchLayou
   if (!(desc->unit == 1.0f || desc->unit == 100.0f || desc->unit == 1000.0f)) {
     return pxSetError(-1, "PxBatchDesc.unit must be 1, 100 or 1000 (got %g)", (double)desc->unit);
   }
-  if (desc->maxDynamic == 0 || desc->maxDynamic > PX_MAX_BODIES || desc->maxStatic > PX_MAX_BODIES) {
-    return pxSetError(-1, "PxBatchDesc: maxDynamic must be 1..255 and maxStatic 0..255 (got %u, %u)",
+  /* 256 is accepted so that a padded capacity read back from a layout can be fed in again */
+  if (desc->maxDynamic == 0 || desc->maxDynamic > 256 || desc->maxStatic > 256) {
+    return pxSetError(-1, "PxBatchDesc: maxDynamic must be 1..256 and maxStatic 0..256 (got %u, %u)",
                       desc->maxDynamic, desc->maxStatic);
   }
   memset(L, 0, sizeof(*L));

@@ -1309,6 +1309,58 @@ __global__ void pxCommandKernel(const PxBatchLayout L, uint8_t *mut, const uint8
 
 
 
+/* ------------------------------------------------------------------- arithmetic self-test */
+/* T0 parity tier: the device's restatement of the reference's inline math (px_math.h:50-114,
+ * 226-252) evaluated element-wise, and an exhaustive sweep of pxFastRsqrt over all 2^32 bit
+ * patterns reduced to one 64-bit sum per 2^20-pattern block. */
+__global__ void pxMathKernel(int op, const float *a, const float *b, const float *sinTable, float *out, uint32_t n) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float x = a[i];
+  float y = 0.0f;
+  switch (op) {
+  case 0: y = fRsqrt(x); break;
+  case 1: y = fRcp(x); break;
+  case 2: y = fSqrt(x); break;
+  case 3: y = fDiv(x, b[i]); break;
+  case 4: y = fSin(sinTable, x); break;
+  case 5: y = fSin(sinTable, x + D_PI * 0.5f); break;
+  }
+  out[i] = y;
+}
+
+__global__ void pxRsqrtSweepKernel(unsigned long long *sums /*[4096]*/) {
+  /* block b covers bit patterns [b << 20, (b + 1) << 20) */
+  const uint32_t base = blockIdx.x << 20;
+  unsigned long long acc = 0;
+  for (uint32_t k = threadIdx.x; k < (1u << 20); k += blockDim.x) {
+    /* NaN payloads are outside the contract (x86 keeps the operand's payload, the GPU returns
+     * the canonical NaN); NaNs only arise from negative or NaN inputs, which the step never
+     * produces.  NaN-ness itself must agree. */
+    const float y = fRsqrt(__uint_as_float(base + k));
+    acc += (y != y) ? 0x7fc00000u : __float_as_uint(y);
+  }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+  __shared__ unsigned long long part[32];
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long t = 0;
+    for (uint32_t w = 0; w < blockDim.x / 32; w++) t += part[w];
+    sums[blockIdx.x] = t;
+  }
+}
+
+extern "C" int pxLaunchMath(int op, const float *a, const float *b, const float *sinTable, float *out, uint32_t n, void *stream) {
+  pxMathKernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(op, a, b, sinTable, out, n);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int pxLaunchRsqrtSweep(unsigned long long *sums, void *stream) {
+  pxRsqrtSweepKernel<<<4096, 256, 0, (cudaStream_t)stream>>>(sums);
+  return (int)cudaGetLastError();
+}
+
 /* ---------------------------------------------------------------------- host launchers */
 static uint32_t alignUp(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
 

@@ -77,6 +77,9 @@ enum { PX_CMD_IMPULSE = 1, PX_CMD_FORCE = 2, PX_CMD_GRAVITY = 3, PX_CMD_ITERATIO
  * `global` list (PX_ALL_WORLDS, in seq order) is merged in by sequence number */
 int pxLaunchCommands(const PxBatchLayout *L, uint8_t *mut, const uint8_t *imm, const struct PxCommand *cmds,
                      const uint32_t *worldStart, const struct PxCommand *global, uint32_t nGlobal, void *stream);
+/* arithmetic self-tests (device pointers) */
+int pxLaunchMath(int op, const float *a, const float *b, const float *sinTable, float *out, uint32_t n, void *stream);
+int pxLaunchRsqrtSweep(unsigned long long *sums4096, void *stream);
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,122 @@
+"""GPU tests of the host-driven control path (BASELINE config 5) and of the px->world->step
+facade: queued applyImpulse / applyForce / setGravity / setIterations and the clock-driven step
+against the reference's own API calls."""
+import numpy as np
+import pytest
+
+import parity
+from oracle import refbind
+from pdphyzx_b200 import batch as pxb
+from pdphyzx_b200 import scenes
+
+pytestmark = pytest.mark.gpu
+bits = parity.bits
+
+
+def compare_with_reference(refs, worlds, b):
+    assert b.readback(worlds) == 0
+    for w, ref in enumerate(refs):
+        rr, rf, ro = ref.bodies(True)
+        hr, hf, ho = worlds.bodies(w, True)
+        np.testing.assert_array_equal(ro, ho, err_msg=f"world {w}: order")
+        np.testing.assert_array_equal(bits(rr[ro][:, :18]), bits(hr[ro][:, :18]), err_msg=f"world {w}: state")
+        np.testing.assert_array_equal(rf[ro], hf[ro], err_msg=f"world {w}: flags")
+
+
+@pytest.mark.parametrize("fused", [1, 8])
+def test_rl_style_control_matches_reference(reflib_available, fused):
+    """Every batch step the host enqueues a per-world applyImpulse on one body, an applyForce on
+    another and a setGravity, then steps K substeps (config 5: K=1 vs fused K=8), UNIT_MM."""
+    n = 6
+    sc = [scenes.stack_scene(w, n_dynamic=30) for w in range(n)]
+    refs = [refbind.RefWorld(s, "wide") for s in sc]
+    worlds = pxb.HostWorlds(sc)
+    b = pxb.Batch(worlds)
+    rng = np.random.default_rng(1)
+    for it in range(60):
+        for w in range(n):
+            body = int(rng.integers(0, 30))
+            ix, iy = float(np.float32(rng.uniform(-3, 3))), float(np.float32(rng.uniform(-8, 0)))
+            cx, cy = float(np.float32(rng.uniform(-2, 2))), float(np.float32(rng.uniform(-2, 2)))
+            b.apply_impulse(w, body, ix, iy, cx, cy)
+            refs[w].lib.ref_body_apply_impulse(refs[w].w, body, ix, iy, cx, cy)
+            body2 = int(rng.integers(0, 30))
+            fx = float(np.float32(rng.uniform(-50, 50)))
+            b.apply_force(w, body2, fx, 0.0, 0.0, cy)
+            refs[w].lib.ref_body_apply_force(refs[w].w, body2, fx, 0.0, 0.0, cy)
+            gx = float(np.float32(rng.uniform(-1, 1)))
+            b.set_gravity(w, gx, 9.8)
+            refs[w].lib.ref_set_gravity(refs[w].w, gx, 9.8)
+        b.step(fused)
+        for ref in refs:
+            ref.substep(fused)
+        if it % 10 == 9:
+            compare_with_reference(refs, worlds, b)
+    compare_with_reference(refs, worlds, b)
+    b.close()
+    worlds.close()
+
+
+def test_batch_wide_setters_and_ordering(reflib_available):
+    n = 4
+    sc = [scenes.pile_scene(w, mix="mixed", n_dynamic=40, cols=6) for w in range(n)]
+    refs = [refbind.RefWorld(s, "wide") for s in sc]
+    worlds = pxb.HostWorlds(sc)
+    b = pxb.Batch(worlds)
+    b.step(100)
+    for r in refs:
+        r.substep(100)
+    # ALL-worlds gravity, then a per-world override submitted later must win for that world
+    b.set_gravity(pxb.ALL_WORLDS, 1.0, 5.0)
+    b.set_gravity(2, -1.0, 3.0)
+    b.set_iterations(pxb.ALL_WORLDS, 4)
+    b.set_iterations(1, 12)
+    for w, r in enumerate(refs):
+        r.lib.ref_set_gravity(r.w, *((-1.0, 3.0) if w == 2 else (1.0, 5.0)))
+        r.lib.ref_set_iterations(r.w, 12 if w == 1 else 4)
+    # a sleeping-or-not body is woken by an impulse (px_body_api.c:37-42)
+    b.apply_impulse(0, 3, 0.5, -0.5, 0.0, 0.0)
+    refs[0].lib.ref_body_apply_impulse(refs[0].w, 3, 0.5, -0.5, 0.0, 0.0)
+    b.step(150)
+    for r in refs:
+        r.substep(150)
+    compare_with_reference(refs, worlds, b)
+    with pytest.raises(pxb.PxError):
+        b.apply_impulse(99, 0, 1, 1, 0, 0)
+    b.close()
+    worlds.close()
+
+
+def test_world_step_facade_keeps_the_clock_semantics(reflib_available):
+    """px->world->step on our host API (1-world device batch behind it) against the reference's
+    px->world->step under the same stub clock: first call never steps, 0-3 fixed steps per call,
+    5 substeps each (px_clock.c:25-52, px_world.c:422-445)."""
+    sc = scenes.pile_scene(3, mix="mixed", n_dynamic=40, cols=6, unit=100.0)
+    ref = refbind.RefWorld(sc, "wide")
+    worlds = pxb.HostWorlds([sc])
+    h, w = worlds.lib, worlds.ptrs[0]
+    t = 1000
+    fired_ref = fired_dev = 0
+    schedule = [20] * 30 + [3, 3, 3, 70, 250, 20, 20, 1, 45] + [20] * 20
+    for k, dt_ms in enumerate([0] + schedule):
+        t += dt_ms
+        ref.lib.ref_set_time_ms(t)
+        h.pxh_set_time_ms(t)
+        a = ref.lib.ref_step(ref.w)
+        b = h.pxh_step(w)
+        assert a == b, f"call {k}: stepped flag {a} vs {b}"
+        fired_ref += a
+        fired_dev += b
+        rr, rf, ro = ref.bodies(True)
+        hr, hf, ho = worlds.bodies(0, True)
+        np.testing.assert_array_equal(ro, ho)
+        np.testing.assert_array_equal(bits(rr[ro][:, :18]), bits(hr[ro][:, :18]), err_msg=f"call {k}")
+        if k == 20:  # host-side edits between frames are carried to the device by the facade
+            ref.lib.ref_body_apply_impulse(ref.w, 5, 40.0, -60.0, 0.0, 0.0)
+            h.pxh_body_apply_impulse(w, 5, 40.0, -60.0, 0.0, 0.0)
+            ref.lib.ref_body_set_position(ref.w, 1, 7, 300.0, 100.0)
+            h.pxh_body_set_position(w, 1, 7, 300.0, 100.0)
+    assert fired_dev > 40
+    h.pxh_draw_debug(w)  # "Contacts: %d  Sleeping: %d" comes from the device statistics
+    assert worlds.stats(0)["manifolds"] == len(ref.manifolds()[1])
+    worlds.close()
