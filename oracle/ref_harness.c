@@ -65,8 +65,18 @@ static inline PxManifold *refLoggedAcquire(PxManifoldPool *pool, PxBody *bodyA, 
   return pxManifoldPoolAcquire(pool);
 }
 #define pxManifoldPoolAcquire(pool) refLoggedAcquire((pool), bodyA, bodyB)
+#ifdef PXREF_B200
+/* "b200" variant: the reference with the one-function binding of integration/px_world_b200.c
+ * (INTEGRATION.md): its own pxWorldStep is renamed, the binding's definition is what
+ * px_world_api.c binds into PxWorldAPI.step.  Everything else is the reference, verbatim. */
+#define pxWorldStep pxWorldStepCpu
+#endif
 #include "px_world.c"
 #undef pxManifoldPoolAcquire
+#ifdef PXREF_B200
+#undef pxWorldStep
+#include "../integration/px_world_b200.c"
+#endif
 
 /* ---- flat C ABI for the test harness ------------------------------------------------ */
 
@@ -94,7 +104,19 @@ REF_EXPORT PxWorld *ref_world_new(int fps) {
   ref_init();
   return g_px->world->new((uint8_t)fps);
 }
-REF_EXPORT void ref_world_free(PxWorld *w) { g_px->world->free(w); }
+REF_EXPORT void ref_world_free(PxWorld *w) {
+#ifdef PXREF_B200
+  pxWorldB200Release(w);
+#endif
+  g_px->world->free(w);
+}
+REF_EXPORT int ref_is_b200(void) {
+#ifdef PXREF_B200
+  return 1;
+#else
+  return 0;
+#endif
+}
 REF_EXPORT void ref_set_gravity(PxWorld *w, float x, float y) { g_px->world->setGravity(w, x, y); }
 REF_EXPORT void ref_set_iterations(PxWorld *w, int it) { g_px->world->setIterations(w, (uint8_t)it); }
 REF_EXPORT void ref_set_sleep_params(PxWorld *w, float linSq, float ang, float tts) {

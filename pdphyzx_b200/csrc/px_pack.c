@@ -15,6 +15,12 @@
 #include "px_batch.h"
 #include "px_internal.h"
 
+/* the per-world AoS <-> SoA conversion is shared, by field name, with the reference-side
+ * binding (integration/px_world_b200.c): include/px_pack_inl.h */
+#define PX_PACK_FAIL(rc, ...) return pxSetError((rc), __VA_ARGS__)
+#define PX_PACK_WORLD_HAS_STATS 1
+#include "px_pack_inl.h"
+
 static uint32_t alignUp(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
 
 int pxBatchComputeLayout(uint32_t nWorlds, const PxBatchDesc *desc, PxBatchLayout *L) {
@@ -94,31 +100,16 @@ int pxBatchComputeLayout(uint32_t nWorlds, const PxBatchDesc *desc, PxBatchLayou
   return 0;
 }
 
-static uint32_t bodyVertexCount(const PxBody *b) {
-  return b->collider.type == PX_POLYGON ? b->collider.shape.polygon.vertices.length : 0;
-}
-
 int pxBatchFitDesc(struct PxWorld *const *worlds, uint32_t n, PxBatchDesc *desc) {
   if (!worlds || !desc) {
     return pxSetError(-1, "pxBatchFitDesc: NULL argument");
   }
   uint32_t maxDyn = 1, maxStat = 1, maxVerts = 4;
   for (uint32_t w = 0; w < n; w++) {
-    const PxWorld *world = worlds[w];
-    if (!world) {
+    if (!worlds[w]) {
       return pxSetError(-1, "pxBatchFitDesc: world %u is NULL", w);
     }
-    uint32_t verts = 0;
-    for (uint32_t i = 0; i < world->dynamicBodies.length; i++) {
-      uint32_t slot = world->dynamicBodies.activeIndices[i];
-      if (slot + 1 > maxDyn) maxDyn = slot + 1;
-      verts += bodyVertexCount(&world->dynamicBodies.items[slot]);
-    }
-    for (uint32_t i = 0; i < world->staticBodies.length; i++) {
-      verts += bodyVertexCount(&world->staticBodies.items[world->staticBodies.activeIndices[i]]);
-    }
-    if (world->staticBodies.length > maxStat) maxStat = world->staticBodies.length;
-    if (verts > maxVerts) maxVerts = verts;
+    pxPackWorldNeeds(worlds[w], &maxDyn, &maxStat, &maxVerts);
   }
   if (!desc->maxDynamic) desc->maxDynamic = maxDyn;
   if (!desc->maxStatic) desc->maxStatic = maxStat;
@@ -130,128 +121,19 @@ int pxBatchFitDesc(struct PxWorld *const *worlds, uint32_t n, PxBatchDesc *desc)
   return 0;
 }
 
-static uint32_t packShape(const PxBody *b, float *verts4, uint32_t *cursor, uint32_t cap, int *err) {
-  uint32_t count = bodyVertexCount(b);
-  if (count == 0) {
-    return PX_SHAPE_PACK(0, 0);
-  }
-  if (*cursor + count > cap) {
-    *err = 1;
-    return PX_SHAPE_PACK(0, 0);
-  }
-  const PxPolygonData *p = &b->collider.shape.polygon;
-  uint32_t off = *cursor;
-  for (uint32_t i = 0; i < count; i++) {
-    float *v = verts4 + (size_t)(off + i) * 4;
-    v[0] = p->vertices.items[i].x;
-    v[1] = p->vertices.items[i].y;
-    v[2] = p->normals.items[i].x;
-    v[3] = p->normals.items[i].y;
-  }
-  *cursor += count;
-  return PX_SHAPE_PACK(off, count);
-}
-
-static float bodyRadius(const PxBody *b) {
-  /* the AABB half-extent: circle radius or the polygon's pre-recentring maxRadius
-   * (px_circle.c:43-48, px_polygon.c:261-266) */
-  return b->collider.type == PX_CIRCLE ? b->collider.shape.circle.radius : b->collider.shape.polygon.maxRadius;
-}
-
 int pxPackWorlds(const PxBatchLayout *L, struct PxWorld *const *worlds, uint32_t n, void *mutBase, void *immBase) {
   if (!L || !worlds || !mutBase || !immBase) {
     return pxSetError(-1, "pxPackWorlds: NULL argument");
   }
-  const uint32_t D = L->maxDynamic, S = L->maxStatic;
   for (uint32_t w = 0; w < n; w++) {
-    const PxWorld *world = worlds[w];
-    if (!world) {
+    if (!worlds[w]) {
       return pxSetError(-1, "pxPackWorlds: world %u is NULL", w);
     }
-    uint8_t *mut = (uint8_t *)mutBase + (size_t)w * L->mutStride;
-    uint8_t *imm = (uint8_t *)immBase + (size_t)w * L->immStride;
-    memset(mut, 0, L->mutStride);
-    memset(imm, 0, L->immStride);
-
-    const PxBodyArray *dyn = &world->dynamicBodies;
-    const PxBodyArray *stat = &world->staticBodies;
-    if (stat->length > S) {
-      return pxSetError(-1, "world %u: %u static bodies exceed maxStatic %u", w, stat->length, S);
+    int rc = pxPackOneWorld(L, worlds[w], w, (uint8_t *)mutBase + (size_t)w * L->mutStride,
+                            (uint8_t *)immBase + (size_t)w * L->immStride);
+    if (rc != 0) {
+      return rc;
     }
-
-    PxWorldHeader *h = (PxWorldHeader *)(mut + L->offHeader);
-    h->gravityX = world->gravity.x;
-    h->gravityY = world->gravity.y;
-    h->dt = pxFastDiv(world->clock.fixedTimestep, PX_SUBSTEPS_PER_STEP); /* px_world.c:432 */
-    h->linearSleepThresholdSq = world->linearSleepThresholdSq;
-    h->angularSleepThreshold = world->angularSleepThreshold;
-    h->timeToSleep = world->timeToSleep;
-    h->iterations = world->iterations;
-    h->nDynamic = dyn->length;
-    h->nStatic = stat->length;
-
-    float *dynF = (float *)(mut + L->offDyn);
-    uint8_t *dynFlags = mut + L->offDynFlags;
-    uint8_t *dynOrder = mut + L->offDynOrder;
-    float *dynC = (float *)(imm + L->offDynConst);
-    uint32_t *dynShape = (uint32_t *)(imm + L->offDynShape);
-    float *statF = (float *)(imm + L->offStat);
-    uint32_t *statShape = (uint32_t *)(imm + L->offStatShape);
-    uint8_t *statSlot = imm + L->offStatSlot;
-    float *verts4 = (float *)(imm + L->offVerts);
-    uint32_t vcursor = 0;
-    int verr = 0;
-
-    for (uint32_t i = 0; i < dyn->length; i++) {
-      uint32_t slot = dyn->activeIndices[i];
-      if (slot >= D) {
-        return pxSetError(-1, "world %u: dynamic slot %u exceeds maxDynamic %u", w, slot, D);
-      }
-      const PxBody *b = &dyn->items[slot];
-      dynOrder[i] = (uint8_t)slot;
-      dynF[PX_DYN_PX * D + slot] = b->position.x;
-      dynF[PX_DYN_PY * D + slot] = b->position.y;
-      dynF[PX_DYN_VX * D + slot] = b->velocity.x;
-      dynF[PX_DYN_VY * D + slot] = b->velocity.y;
-      dynF[PX_DYN_AV * D + slot] = b->angularVelocity;
-      dynF[PX_DYN_ANGLE * D + slot] = b->orientationAngle;
-      dynF[PX_DYN_FX * D + slot] = b->force.x;
-      dynF[PX_DYN_FY * D + slot] = b->force.y;
-      dynF[PX_DYN_TORQUE * D + slot] = b->torque;
-      dynF[PX_DYN_SLEEP * D + slot] = b->sleepTime;
-      dynF[PX_DYN_M00 * D + slot] = b->orientation.m00;
-      dynF[PX_DYN_M01 * D + slot] = b->orientation.m01;
-      dynF[PX_DYN_M10 * D + slot] = b->orientation.m10;
-      dynF[PX_DYN_M11 * D + slot] = b->orientation.m11;
-      dynFlags[slot] = b->flags;
-      dynC[PX_DYNC_IMASS * D + slot] = b->iMass;
-      dynC[PX_DYNC_IINERTIA * D + slot] = b->iMomentOfInertia;
-      dynC[PX_DYNC_E * D + slot] = b->restitution;
-      dynC[PX_DYNC_SF * D + slot] = b->staticFriction;
-      dynC[PX_DYNC_DF * D + slot] = b->dynamicFriction;
-      dynC[PX_DYNC_RADIUS * D + slot] = bodyRadius(b);
-      dynShape[slot] = packShape(b, verts4, &vcursor, L->maxVertices, &verr);
-    }
-    for (uint32_t i = 0; i < stat->length; i++) {
-      uint32_t slot = stat->activeIndices[i];
-      const PxBody *b = &stat->items[slot];
-      statSlot[i] = (uint8_t)slot;
-      statF[PX_STAT_PX * S + i] = b->position.x;
-      statF[PX_STAT_PY * S + i] = b->position.y;
-      statF[PX_STAT_M00 * S + i] = b->orientation.m00;
-      statF[PX_STAT_M01 * S + i] = b->orientation.m01;
-      statF[PX_STAT_M10 * S + i] = b->orientation.m10;
-      statF[PX_STAT_M11 * S + i] = b->orientation.m11;
-      statF[PX_STAT_E * S + i] = b->restitution;
-      statF[PX_STAT_SF * S + i] = b->staticFriction;
-      statF[PX_STAT_DF * S + i] = b->dynamicFriction;
-      statF[PX_STAT_RADIUS * S + i] = bodyRadius(b);
-      statShape[i] = packShape(b, verts4, &vcursor, L->maxVertices, &verr);
-    }
-    if (verr) {
-      return pxSetError(-1, "world %u: polygon vertices exceed maxVertices %u", w, L->maxVertices);
-    }
-    h->nVertices = vcursor;
   }
   return 0;
 }
@@ -260,55 +142,16 @@ int pxUnpackWorlds(const PxBatchLayout *L, struct PxWorld *const *worlds, uint32
   if (!L || !worlds || !mutBase) {
     return pxSetError(-1, "pxUnpackWorlds: NULL argument");
   }
-  const uint32_t D = L->maxDynamic;
   int overflowed = 0;
   for (uint32_t w = 0; w < n; w++) {
-    PxWorld *world = worlds[w];
-    if (!world) {
+    if (!worlds[w]) {
       return pxSetError(-1, "pxUnpackWorlds: world %u is NULL", w);
     }
-    const uint8_t *mut = (const uint8_t *)mutBase + (size_t)w * L->mutStride;
-    const PxWorldHeader *h = (const PxWorldHeader *)(mut + L->offHeader);
-    world->contacts.length = (uint16_t)h->statManifolds;
-    world->contacts.sleeping = (uint16_t)h->statSleeping;
-    world->contacts.overflow = h->statOverflow;
-    if (h->statOverflow) {
-      overflowed++;
+    int rc = pxUnpackOneWorld(L, worlds[w], w, (const uint8_t *)mutBase + (size_t)w * L->mutStride, flags);
+    if (rc < 0) {
+      return rc;
     }
-    if (flags & PX_READBACK_STATS_ONLY) {
-      continue;
-    }
-    PxBodyArray *dyn = &world->dynamicBodies;
-    if (h->nDynamic != dyn->length) {
-      return pxSetError(-1, "world %u: body count changed on the host since upload (%u vs %u)", w, dyn->length, h->nDynamic);
-    }
-    const float *dynF = (const float *)(mut + L->offDyn);
-    const uint8_t *dynFlags = mut + L->offDynFlags;
-    const uint8_t *dynOrder = mut + L->offDynOrder;
-    for (uint32_t i = 0; i < dyn->length; i++) {
-      uint32_t slot = dynOrder[i];
-      dyn->activeIndices[i] = (uint8_t)slot;
-      PxBody *b = &dyn->items[slot];
-      b->position.x = dynF[PX_DYN_PX * D + slot];
-      b->position.y = dynF[PX_DYN_PY * D + slot];
-      b->velocity.x = dynF[PX_DYN_VX * D + slot];
-      b->velocity.y = dynF[PX_DYN_VY * D + slot];
-      b->angularVelocity = dynF[PX_DYN_AV * D + slot];
-      b->orientationAngle = dynF[PX_DYN_ANGLE * D + slot];
-      b->force.x = dynF[PX_DYN_FX * D + slot];
-      b->force.y = dynF[PX_DYN_FY * D + slot];
-      b->torque = dynF[PX_DYN_TORQUE * D + slot];
-      b->sleepTime = dynF[PX_DYN_SLEEP * D + slot];
-      b->orientation.m00 = dynF[PX_DYN_M00 * D + slot];
-      b->orientation.m01 = dynF[PX_DYN_M01 * D + slot];
-      b->orientation.m10 = dynF[PX_DYN_M10 * D + slot];
-      b->orientation.m11 = dynF[PX_DYN_M11 * D + slot];
-      b->flags = dynFlags[slot];
-      /* the AABB always follows the position (pxBodyMoveBy, px_body.c:95-102) */
-      float r = bodyRadius(b);
-      b->aabb.min = pxVec2Subf(b->position, r);
-      b->aabb.max = pxVec2Addf(b->position, r);
-    }
+    overflowed += rc;
   }
   return overflowed;
 }

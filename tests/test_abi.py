@@ -105,3 +105,16 @@ def test_no_cpu_fallback():
         pxb.Batch(worlds)
     assert "cuda" in str(exc.value).lower()
     worlds.close()
+
+
+def test_reference_side_binding_builds_and_loads():
+    """integration/px_world_b200.c compiled into the reference's translation unit
+    (oracle/_ref/libpxref_b200_*.so, INTEGRATION.md) loads and links the C-ABI library;
+    stepping it needs a GPU (tests/test_gpu_control.py)."""
+    from oracle import refbind
+    if not refbind.available("b200", 1.0):
+        pytest.skip("oracle/_ref/libpxref_b200_m.so not built (needs /root/reference at build time)")
+    lib = refbind.load("b200", 1.0)
+    lib.ref_is_b200.restype = C.c_int
+    assert lib.ref_is_b200() == 1
+    assert refbind.load("wide", 1.0).ref_is_b200() == 0

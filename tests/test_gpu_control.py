@@ -120,3 +120,41 @@ def test_world_step_facade_keeps_the_clock_semantics(reflib_available):
     h.pxh_draw_debug(w)  # "Contacts: %d  Sleeping: %d" comes from the device statistics
     assert worlds.stats(0)["manifolds"] == len(ref.manifolds()[1])
     worlds.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("unit,mix", [(1.0, "mixed"), (1000.0, "circles")])
+def test_reference_side_binding_is_a_drop_in(reflib_available, unit, mix):
+    """the reference itself, built with integration/px_world_b200.c in place of
+    its pxWorldStep (oracle/_ref/libpxref_b200_*.so), steps reference-built PxWorld structs on
+    the GPU through the C ABI.  Same scenes, same stub clock, same host-side edits as the
+    unmodified reference on the CPU: every body field bit-identical after every call."""
+    if not refbind.available("b200", unit):
+        pytest.skip("oracle/_ref/libpxref_b200_*.so not built")
+    sc = scenes.pile_scene(5, mix=mix, n_dynamic=70, cols=8, unit=unit)
+    cpu = refbind.RefWorld(sc, "wide")
+    gpu = refbind.RefWorld(sc, "b200")
+    t = 5000
+    fired = 0
+    schedule = [20] * 40 + [3, 70, 250, 20, 1, 45] + [20] * 30
+    for k, dt_ms in enumerate([0] + schedule):
+        t += dt_ms
+        cpu.lib.ref_set_time_ms(t)
+        gpu.lib.ref_set_time_ms(t)
+        a = cpu.lib.ref_step(cpu.w)
+        b = gpu.lib.ref_step(gpu.w)
+        assert a == b, f"call {k}: stepped flag {a} vs {b}"
+        fired += b
+        cr, cf, co = cpu.bodies(True)
+        gr, gf, go = gpu.bodies(True)
+        np.testing.assert_array_equal(co, go, err_msg=f"call {k}: iteration order")
+        np.testing.assert_array_equal(cf, gf, err_msg=f"call {k}: flags")
+        np.testing.assert_array_equal(bits(cr[co][:, :18]), bits(gr[co][:, :18]), err_msg=f"call {k}")
+        if k == 25:  # host-side API calls and field pokes between frames travel with the world
+            for r in (cpu, gpu):
+                r.lib.ref_body_apply_impulse(r.w, 9, 3.0, -6.0, 0.0, 0.0)
+                r.lib.ref_body_set_position(r.w, 1, 11, 2.0 * unit, 1.0 * unit)
+                r.lib.ref_set_gravity(r.w, 0.5, 9.0)
+    assert fired > 50
+    cpu.close()
+    gpu.close()
