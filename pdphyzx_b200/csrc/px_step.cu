@@ -124,7 +124,9 @@ struct Sm {
 };
 
 /* misc[] slots */
-enum { MI_MCOUNT = 0, MI_QTAIL, MI_OVERFLOW, MI_UNSORTED, MI_SLEEPING, MI_VISITS };
+enum { MI_MCOUNT = 0, MI_QTAIL, MI_OVERFLOW, MI_UNSORTED, MI_SLEEPING, MI_VISITS, MI_MATHROUND, MI_RDESC = 16 };
+#define PX_RING 16u /* round descriptors in flight (misc[MI_RDESC..]) */
+#define PX_LAG 8u   /* rounds the scheduler warp may run ahead of the math warp */
 
 /*
  * Rich manifold word (mids[] and ready-queue entries):
@@ -446,13 +448,30 @@ __device__ __forceinline__ uint32_t firstStaticAfterX(const float4 *stBox, uint3
  * for two sleeping dynamic bodies (px_world.c:367-369), sleep flags do not change between
  * the two, and statics never sleep, so the test is always false here.
  */
-__device__ __forceinline__ void applyContactImpulse(const Sm &s, uint32_t w, float eps) {
+struct ContactIn {
+  float4 mA, mB, mC, pA, pB, vA, vB;
+};
+
+/* every load of a contact visit depends only on the queue word: one shared-memory round trip */
+__device__ __forceinline__ ContactIn loadContact(const Sm &s, uint32_t w) {
   const uint32_t ms = MID_SLOT(w), a = MID_A(w), b = MID_B(w);
+  ContactIn in;
+  in.mA = s.manA[ms];
+  in.mB = s.manB[ms];
+  in.mC = s.manC[ms];
+  in.pA = s.bodyP[a];
+  in.pB = s.bodyP[b];
+  in.vA = s.bodyV[a];
+  in.vB = s.bodyV[b];
+  return in;
+}
+
+__device__ __forceinline__ void solveContact(const Sm &s, uint32_t w, const ContactIn &in, float eps) {
+  const uint32_t a = MID_A(w), b = MID_B(w);
   const bool second = MID_CI(w) != 0, bdyn = MID_BDYN(w) != 0;
-  /* every load below depends only on the queue word: one shared-memory round trip */
-  const float4 mA = s.manA[ms], mB = s.manB[ms], mC = s.manC[ms];
-  const float4 pA = s.bodyP[a], pB = s.bodyP[b];
-  float4 vA = s.bodyV[a], vB = s.bodyV[b];
+  const float4 mA = in.mA, mB = in.mB, mC = in.mC;
+  const float4 pA = in.pA, pB = in.pB;
+  float4 vA = in.vA, vB = in.vB;
   const V2 n = v2(mA.x, mA.y);
   const float e = mA.z, sf = mA.w, df = mB.x;
   const V2 c = second ? v2(mC.x, mC.y) : v2(mB.z, mB.w);
@@ -467,8 +486,8 @@ __device__ __forceinline__ void applyContactImpulse(const Sm &s, uint32_t w, flo
   V2 rv = (vb + rbPerp * wb) - (va + raPerp * wa);
   const float vn = dot(rv, n);
   /* The two early exits of the reference (`continue` when the bodies separate, skip friction
-   * when the tangent vanishes) are applied as selects at the end: a single warp runs this
-   * chain, and a branch costs it more than the few discarded operations. */
+   * when the tangent vanishes) are applied as selects at the end: the visit sits on the
+   * solver's critical chain, and a branch costs it more than the few discarded operations. */
   const bool approaching = !(vn > 0);
 
   const float normalMag = -(1.0f + e) * vn;
@@ -507,6 +526,11 @@ __device__ __forceinline__ void applyContactImpulse(const Sm &s, uint32_t w, flo
     vB.z = approaching ? (slides ? wb2 : wb1) : wb;
     s.bodyV[b] = vB;
   }
+}
+
+__device__ __forceinline__ void applyContactImpulse(const Sm &s, uint32_t w, float eps) {
+  const ContactIn in = loadContact(s, w);
+  solveContact(s, w, in, eps);
 }
 
 __device__ __forceinline__ void bindSmem(Sm &s, uint8_t *base, const PxSmemPlan &S, const float4 *globalVerts) {
@@ -582,7 +606,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) pxStepKernel(const PxStepParams 
     copyRows<NT>((float *)s.flags, (const float *)(gmut + L.offDynFlags), D / 4);
     copyRows<NT>((float *)s.order, (const float *)(gmut + L.offDynOrder), D / 4);
     copyRows<NT>((float *)s.hdr, (const float *)(gmut + L.offHeader), sizeof(PxWorldHeader) / 4);
-    if (tid < 16) s.misc[tid] = 0;
+    if (tid < 32) s.misc[tid] = 0;
   }
   /* thread-private body state: slot x = tid + r * NT lives in this thread's registers */
   float rAngle[R], rFx[R], rFy[R], rTq[R], rSlp[R];
@@ -623,7 +647,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) pxStepKernel(const PxStepParams 
 
     /* ====================== phase A: AABB keys, stable order by aabb.min.x ============ */
     /* the order persists across substeps, so it is almost always already sorted */
-    if (tid < 16 && tid != MI_OVERFLOW) s.misc[tid] = 0;
+    if (tid < 32 && tid != MI_OVERFLOW) s.misc[tid] = 0;
     for (uint32_t i = tid; i < D; i += NT) {
       s.restFlag[i] = 0;
       s.wakeFlag[i] = 0;
@@ -1015,7 +1039,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) pxStepKernel(const PxStepParams 
         const uint32_t side = i < nBx ? 1u : 0u;
         const uint32_t in = i + 1 == n ? 0u : i + 1;
         const uint32_t succ = s.list[start + in];
-        s.nextw[2 * ms + side] = (uint16_t)(succ | ((in < nBx ? 1u : 0u) << 15));
+        s.nextw[2 * ms + side] = (uint16_t)(succ | (MID_BDYN(s.mids[succ]) << 14) | ((in < nBx ? 1u : 0u) << 15));
       }
       if (n) { /* the body's first manifold receives its first signal from the body itself */
         const uint32_t first = s.list[start];
@@ -1066,6 +1090,14 @@ __global__ void __launch_bounds__(NT, 512 / NT) pxStepKernel(const PxStepParams 
       }
     } else if (warp == 0 && iterations) {
       /*
+       * Scheduler warp.  The ORDER in which contact visits may run depends only on the
+       * manifold lists, never on a velocity, so scheduling is split from the arithmetic:
+       * this warp runs the dataflow bookkeeping and publishes rounds of up to 32 mutually
+       * independent visits; warp 1 (below) executes them.  The solver is bound by its
+       * dependency chain (about 21 rounds per iteration in a 252-body pile whatever the round
+       * width), so what matters is the latency of one round; the two chains -- ready
+       * queue/signals here, load/impulse/store there -- run side by side instead of adding up.
+       *
        * sig[m] counts the signals manifold m has received from its A body (low half) and its
        * B body (high half).  Visit v of a manifold may run once each of its dynamic bodies has
        * delivered v + 1 signals: one from the body at list-build time if the manifold heads
@@ -1073,58 +1105,95 @@ __global__ void __launch_bounds__(NT, 512 / NT) pxStepKernel(const PxStepParams 
        * visit.  A signal is one shared-memory atomicAdd; its return value shows both counts
        * as they were, so exactly one of the (at most two) signalers sees the other side
        * already complete and enqueues the visit.
+       *
+       * Round r is the queue segment [head_r, head_r + n_r); rdesc[r % PX_RING] = (r + 1) << 16
+       * | n_r publishes it (release store; the segment's words were stored in earlier rounds).
+       * Everything signalled in round r is pushed behind the segments of rounds <= r, so a
+       * visit is always published in a later round than the visits it depends on.  The
+       * scheduler stays at most PX_LAG rounds ahead, which bounds the descriptor ring and keeps
+       * unexecuted segments from being overwritten (qcap >= MM + 32 * (PX_LAG + 1)).
+       * The loop body is branch-free: idle lanes and absent pushes go to a dummy slot.
        */
       uint32_t head = 0, tail = s.misc[MI_QTAIL], visits = 0, rounds = 0;
-      const uint32_t NONE = 0xffffffffu;
+      const uint32_t NONE = 0xffffffffu, DUMMY = P.S.qcap; /* queue[qcap] is a write-only sink */
+      volatile uint32_t *mathRound = s.misc + MI_MATHROUND;
+      const uint32_t rdescAddr = (uint32_t)__cvta_generic_to_shared(s.misc + MI_RDESC);
+      const uint32_t lt = (1u << lane) - 1u;
+      uint32_t mr = 0;
       while (head != tail) {
         const uint32_t n = min(tail - head, 32u);
-        uint32_t push0 = NONE, push1 = NONE;
-        bool lastVisit = false;
-        if (lane < n) {
-          const uint32_t w = s.queue[(head + lane) & QMASK];
-          const uint32_t ms = MID_SLOT(w);
-          /* successors of this manifold on body a / body b are fixed for the substep: their
-           * rich words are fetched now and the latency hides behind the impulse math */
-          const uint32_t nx = *(const uint32_t *)(s.nextw + 2 * ms); /* side a | side b << 16 */
-          const uint32_t t0 = nx & 0x3ffu, t1 = MID_BDYN(w) ? (nx >> 16) & 0x3ffu : 0u;
-          const uint32_t wt0 = s.mids[t0], wt1 = s.mids[t1];
-          applyContactImpulse(s, w, eps);
-          lastVisit = MID_CI(w) + 1u >= MID_COUNT(w);
-          if (!lastVisit) {
-            push0 = w | (1u << 30); /* second contact of the same manifold */
-          } else {
-            {
-              const uint32_t sideB = (nx >> 15) & 1u;
-              const uint32_t old = atomicAdd(&s.sig[t0], sideB ? 0x10000u : 1u);
-              const uint32_t mine = (sideB ? (old >> 16) : (old & 0xffffu)) + 1u;
-              const uint32_t other = sideB ? (old & 0xffffu) : (old >> 16);
-              if (mine <= iterations && (!MID_BDYN(wt0) || other == mine)) push0 = wt0;
-            }
-            if (MID_BDYN(w)) {
-              const uint32_t sideB = nx >> 31;
-              const uint32_t old = atomicAdd(&s.sig[t1], sideB ? 0x10000u : 1u);
-              const uint32_t mine = (sideB ? (old >> 16) : (old & 0xffffu)) + 1u;
-              const uint32_t other = sideB ? (old & 0xffffu) : (old >> 16);
-              if (mine <= iterations && (!MID_BDYN(wt1) || other == mine)) push1 = wt1;
-            }
-          }
-        }
-        const uint32_t b0 = __ballot_sync(0xffffffffu, push0 != NONE);
-        const uint32_t b1 = __ballot_sync(0xffffffffu, push1 != NONE);
-        const uint32_t lt = (1u << lane) - 1u;
-        if (push0 != NONE) s.queue[(tail + __popc(b0 & lt)) & QMASK] = push0;
-        if (push1 != NONE) s.queue[(tail + __popc(b0) + __popc(b1 & lt)) & QMASK] = push1;
-        tail += __popc(b0) + __popc(b1);
+        while (rounds - mr >= PX_LAG) mr = *mathRound;
+        asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(rdescAddr + 4u * (rounds & (PX_RING - 1u))),
+                     "r"(((rounds + 1u) << 16) | n)
+                     : "memory");
+        const bool active = lane < n;
+        const uint32_t qw = s.queue[(head + lane) & QMASK];
+        const uint32_t w = active ? qw : 0u; /* idle lanes: a harmless word, every index in range */
+        const uint32_t ms = MID_SLOT(w);
+        const bool again = active && (MID_CI(w) + 1u < MID_COUNT(w)); /* second contact follows */
+        const bool sigA = active && !again, sigB = sigA && MID_BDYN(w);
+        /* successors of this manifold on body a / body b are fixed for the substep:
+         * slot | successor has a dynamic B << 14 | successor's side for this body << 15 */
+        const uint32_t nx = *(const uint32_t *)(s.nextw + 2 * ms); /* side a | side b << 16 */
+        /* (the b half is unset when B is static, the a half when no manifold 0 exists) */
+        const uint32_t t0 = sigA ? (nx & 0x3ffu) : 0u, t1 = sigB ? ((nx >> 16) & 0x3ffu) : 0u;
+        const uint32_t wt0 = s.mids[t0], wt1 = s.mids[t1];
+        uint32_t old0 = 0, old1 = 0;
+        if (sigA) old0 = atomicAdd(&s.sig[t0], (nx & 0x8000u) ? 0x10000u : 1u);
+        if (sigB) old1 = atomicAdd(&s.sig[t1], (nx & 0x80000000u) ? 0x10000u : 1u);
+        const uint32_t mine0 = ((nx & 0x8000u) ? (old0 >> 16) : (old0 & 0xffffu)) + 1u;
+        const uint32_t other0 = (nx & 0x8000u) ? (old0 & 0xffffu) : (old0 >> 16);
+        const uint32_t mine1 = ((nx & 0x80000000u) ? (old1 >> 16) : (old1 & 0xffffu)) + 1u;
+        const uint32_t other1 = (nx & 0x80000000u) ? (old1 & 0xffffu) : (old1 >> 16);
+        const bool ready0 = sigA && mine0 <= iterations && (!(nx & 0x4000u) || other0 == mine0);
+        const bool ready1 = sigB && mine1 <= iterations && (!(nx & 0x40000000u) || other1 == mine1);
+        const bool has0 = again || ready0;
+        const uint32_t push0 = again ? (w | (1u << 30)) : wt0;
+        const uint32_t b0 = __ballot_sync(0xffffffffu, has0);
+        const uint32_t b1 = __ballot_sync(0xffffffffu, ready1);
+        const uint32_t c0 = __popc(b0);
+        s.queue[has0 ? ((tail + __popc(b0 & lt)) & QMASK) : DUMMY] = push0;
+        s.queue[ready1 ? ((tail + c0 + __popc(b1 & lt)) & QMASK) : DUMMY] = wt1;
+        tail += c0 + __popc(b1);
         head += n;
-        visits += lastVisit ? 1u : 0u;
+        visits += sigA ? 1u : 0u;
         rounds++;
+        mr = *mathRound;
         __syncwarp();
       }
+      asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(rdescAddr + 4u * (rounds & (PX_RING - 1u))),
+                   "r"(((rounds + 1u) << 16) | 0xffffu) /* end of schedule */
+                   : "memory");
       visits = __reduce_add_sync(0xffffffffu, visits);
-      if (lane == 0 && visits != M * iterations) overflow |= PX_OVERFLOW_INTERNAL;
+      if (lane == 0) s.misc[MI_VISITS] = visits;
       if (prof && lane == 0) prof[6] += rounds;
+    } else if (warp == 1 && iterations) {
+      /* Math warp: executes the published rounds in order, one contact visit per lane.  The
+       * next round's descriptor is fetched before this round's arithmetic, so in the steady
+       * state (scheduler ahead) a round starts with its queue word already on the way. */
+      volatile uint32_t *mathRound = s.misc + MI_MATHROUND;
+      const uint32_t rdescAddr = (uint32_t)__cvta_generic_to_shared(s.misc + MI_RDESC);
+      uint32_t head = 0, d;
+      asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(d) : "r"(rdescAddr) : "memory");
+      for (uint32_t r = 0;; r++) {
+        while ((d >> 16) != ((r + 1u) & 0xffffu))
+          asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(d) : "r"(rdescAddr + 4u * (r & (PX_RING - 1u))) : "memory");
+        const uint32_t n = d & 0xffffu;
+        if (n == 0xffffu) break;
+        const uint32_t w = s.queue[(head + lane) & QMASK];
+        asm volatile("ld.acquire.cta.shared.u32 %0, [%1];"
+                     : "=r"(d)
+                     : "r"(rdescAddr + 4u * ((r + 1u) & (PX_RING - 1u)))
+                     : "memory");
+        if (lane < n) applyContactImpulse(s, w, eps);
+        head += n;
+        __syncwarp();
+        *mathRound = r + 1u;
+      }
     }
     __syncthreads();
+    if (tid == 0 && iterations && !(P.flags & PX_BATCH_FLAG_SERIAL_SOLVER) && s.misc[MI_VISITS] != M * iterations)
+      overflow |= PX_OVERFLOW_INTERNAL;
     PROF_MARK(4)
 
     /* ====================== phase F: integrate velocities, correct positions, sleep ==== */
@@ -1377,7 +1446,7 @@ extern "C" void pxPlanSmem(const PxBatchLayout *L, int vertsInSmem, PxSmemPlan *
   S->flags = take(D); S->order = take(D); S->order2 = take(D); S->posOf = take(D);
   S->restFlag = take(D); S->wakeFlag = take(D); S->sSlot = take(D);
   S->hdr = take(sizeof(PxWorldHeader));
-  S->misc = take(16 * 4);
+  S->misc = take(32 * 4);
   S->scan = take(8 * 8);
   S->manA = take(MM * 16); S->manB = take(MM * 16); S->manC = take(MM * 16); S->mids = take(MM * 4);
   S->validSlot = take(MP * 2);
@@ -1386,7 +1455,7 @@ extern "C" void pxPlanSmem(const PxBatchLayout *L, int vertsInSmem, PxSmemPlan *
   S->cnt = take(D * 2); S->cntB = take(D * 2);
   S->fillB = take(D * 4);
   uint32_t qcap = 32;
-  while (qcap < MM) qcap <<= 1;
+  while (qcap < MM + 32 * (PX_LAG + 1)) qcap <<= 1; /* ready visits + published, unexecuted rounds */
   S->qcap = qcap;
   /* region X (sweep + narrowphase) overlaid by region Y (solver) */
   const uint32_t rx = o;
@@ -1396,7 +1465,7 @@ extern "C" void pxPlanSmem(const PxBatchLayout *L, int vertsInSmem, PxSmemPlan *
   S->verts = vertsInSmem ? take(V * 16) : 0;
   const uint32_t rxEnd = o;
   o = rx;
-  S->list = take(2 * MM * 2); S->nextw = take(2 * MM * 2); S->sig = take(MM * 4); S->queue = take(qcap * 4);
+  S->list = take(2 * MM * 2); S->nextw = take(2 * MM * 2); S->sig = take(MM * 4); S->queue = take((qcap + 4) * 4); /* + the dummy sink at [qcap] */
   o = o > rxEnd ? o : rxEnd;
   S->total = o;
 }

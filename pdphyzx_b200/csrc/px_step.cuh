@@ -17,7 +17,7 @@ struct PxSmemPlan {
   uint32_t bodyP, bodyV, bodyR, bodyM;
   uint32_t flags, order, order2, posOf, restFlag, wakeFlag, sSlot; /* u8[D] */
   uint32_t hdr;                                                     /* PxWorldHeader */
-  uint32_t misc;                                                    /* u32[16] counters */
+  uint32_t misc;                                                    /* u32[32] counters + round descriptors */
   uint32_t scan;                                                    /* u64[8] block-scan scratch */
   /* manifolds of the current substep: three float4 records + one id word per slot */
   uint32_t manA, manB, manC, mids;
@@ -35,7 +35,7 @@ struct PxSmemPlan {
   uint32_t verts; /* float4[V] (only if vertsInSmem) */
   /* region Y */
   uint32_t list;  /* u16[2*MM] per-body manifold lists (CSR payload), persists to phase F */
-  uint32_t nextw; /* u16[2*MM] successor of manifold ms on side s: slot | side << 15 */
+  uint32_t nextw; /* u16[2*MM] successor of manifold ms on side s: slot | successor has a dynamic B << 14 | side << 15 */
   uint32_t sig;   /* u32[MM]   signals received: A side low half, B side high half */
   uint32_t queue; /* u32[QCAP] ready ring of rich manifold words */
   uint32_t total; /* bytes */
