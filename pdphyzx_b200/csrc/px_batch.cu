@@ -104,7 +104,9 @@ extern "C" PxBatch *pxBatchCreate(uint32_t nWorlds, const PxBatchDesc *desc) {
     if ((e = cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
     b->ownStream = true;
   }
-  b->threads = desc->threads ? desc->threads : 128;
+  /* 256 threads (3 CTAs/SM at <= 85 registers) for full-size worlds: the sweep, narrowphase and
+   * list phases are throughput-bound and the solver only ever uses two warps */
+  b->threads = desc->threads ? desc->threads : (b->L.maxDynamic > 128 ? 256 : 128);
   if (b->threads != 64 && b->threads != 128 && b->threads != 256) {
     pxSetError(-1, "PxBatchDesc.threads must be 64, 128 or 256");
     pxBatchFree(b);

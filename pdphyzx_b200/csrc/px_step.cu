@@ -69,6 +69,53 @@ __device__ __forceinline__ float fSin(const float *table, float radians) {
   return table[i1] * (1.0f - fraction) + table[i2] * fraction;
 }
 
+/* ------------------------------------------------- explicit shared-memory accesses */
+/* The solver's two loops are single-warp dependency chains: every instruction on them is
+ * latency.  They address shared memory by 32-bit window offsets computed once outside the
+ * loop (generic pointers make the compiler rebuild the window base every iteration) and use
+ * predicated stores instead of branches. */
+__device__ __forceinline__ uint32_t sAddr(const void *p) {
+  /* the asm pins the offset in a register: rebuilding it from the window base and a kernel
+   * parameter every loop iteration is cheaper in registers but sits on the chain */
+  uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+  asm volatile("" : "+r"(a));
+  return a;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ float4 lds128(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
+/* flags another warp writes: acquire keeps later loads behind it, volatile keeps it a real load */
+__device__ __forceinline__ uint32_t ldsAcquire(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t ldsVolatile(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void stsVolatile(uint32_t a, uint32_t v) {
+  asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+__device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v)); }
+__device__ __forceinline__ void sts128If(uint32_t a, float4 v, bool p) {
+  asm volatile("{ .reg .pred q; setp.ne.u32 q, %5, 0; @q st.shared.v4.f32 [%0], {%1, %2, %3, %4}; }" ::"r"(a), "f"(v.x),
+               "f"(v.y), "f"(v.z), "f"(v.w), "r"((uint32_t)p));
+}
+__device__ __forceinline__ uint32_t atomAddS(uint32_t a, uint32_t v) {
+  uint32_t old;
+  asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(a), "r"(v) : "memory");
+  return old;
+}
+
 struct V2 {
   float x, y;
 };
@@ -253,40 +300,61 @@ __device__ void collideCirclePolygon(const DBody &C, const DBody &P, float eps, 
   m.count = 1;
 }
 
-/* pxFindAxisLeastPenetration (px_collision.c:180-218) with pxPolygonGetSupport
- * (px_polygon.c:326-347) inlined */
-__device__ float leastPenetration(uint32_t &faceIndex, const DBody &A, const DBody &B, float epsSq) {
-  float bestD = -FLT_MAX;
-  uint32_t bestI = 0;
-  for (uint32_t i = 0; i < A.nverts; i++) {
-    float4 an = A.v[i];
-    V2 nw = mul(A.rot, v2(an.z, an.w));
-    V2 n = mulT(B.rot, nw);
-    V2 dir = -n;
-    V2 sup = v2(0.0f, 0.0f);
-    if (!(lensq(dir) < epsSq)) {
-      float best = -FLT_MAX;
-      float4 b0 = B.v[0];
-      sup = v2(b0.x, b0.y);
-      for (uint32_t k = 0; k < B.nverts; k++) {
-        float4 bv = B.v[k];
-        float proj = bv.x * dir.x + bv.y * dir.y;
-        if (proj > best) {
-          best = proj;
-          sup = v2(bv.x, bv.y);
-        }
+/* One face of pxFindAxisLeastPenetration (px_collision.c:180-218, loop body :190-214) with
+ * pxPolygonGetSupport (px_polygon.c:326-347) inlined: the separation of B's support point
+ * along the normal of face i of A. */
+__device__ __forceinline__ float faceSeparation(const DBody &A, const DBody &B, uint32_t i, float epsSq) {
+  float4 an = A.v[i];
+  V2 nw = mul(A.rot, v2(an.z, an.w));
+  V2 n = mulT(B.rot, nw);
+  V2 dir = -n;
+  V2 sup = v2(0.0f, 0.0f);
+  if (!(lensq(dir) < epsSq)) {
+    float best = -FLT_MAX;
+    float4 b0 = B.v[0];
+    sup = v2(b0.x, b0.y);
+    for (uint32_t k = 0; k < B.nverts; k++) {
+      float4 bv = B.v[k];
+      float proj = bv.x * dir.x + bv.y * dir.y;
+      if (proj > best) {
+        best = proj;
+        sup = v2(bv.x, bv.y);
       }
     }
-    V2 v = mul(A.rot, v2(an.x, an.y)) + A.pos;
-    v = v - B.pos;
-    v = mulT(B.rot, v);
-    float d = dot(n, sup - v);
-    if (d > bestD) {
-      bestD = d;
-      bestI = i;
+  }
+  V2 v = mul(A.rot, v2(an.x, an.y)) + A.pos;
+  v = v - B.pos;
+  v = mulT(B.rot, v);
+  return dot(n, sup - v);
+}
+
+/* pxFindAxisLeastPenetration evaluated by the PX_SAT_LANES lanes of a pair group: lane q takes
+ * faces q, q + PX_SAT_LANES, ...; the reference keeps the FIRST face among the maxima (strict
+ * `>` while scanning upwards), which the (value, lowest index) reduction reproduces. */
+#define PX_SAT_LANES 4u
+__device__ __forceinline__ float leastPenetrationGroup(uint32_t &faceIndex, const DBody &A, const DBody &B, uint32_t q,
+                                                       bool valid, float epsSq) {
+  float bestD = -FLT_MAX;
+  uint32_t bestI = 0xffu;
+  if (valid) {
+    for (uint32_t i = q; i < A.nverts; i += PX_SAT_LANES) {
+      const float d = faceSeparation(A, B, i, epsSq);
+      if (d > bestD) {
+        bestD = d;
+        bestI = i;
+      }
     }
   }
-  faceIndex = bestI;
+#pragma unroll
+  for (uint32_t o = 1; o < PX_SAT_LANES; o <<= 1) {
+    const float od = __shfl_xor_sync(0xffffffffu, bestD, o);
+    const uint32_t oi = __shfl_xor_sync(0xffffffffu, bestI, o);
+    if (od > bestD || (od == bestD && oi < bestI)) {
+      bestD = od;
+      bestI = oi;
+    }
+  }
+  faceIndex = bestI == 0xffu ? 0u : bestI;
   return bestD;
 }
 
@@ -307,19 +375,12 @@ __device__ __forceinline__ int clipSegment(V2 out[2], const V2 in0, const V2 in1
   return sp;
 }
 
-/* pxCollidePolygons, px_collision.c:299-435 (pxFindIncidentFace :220-259 inlined) */
-__device__ void collidePolygons(const DBody &A, const DBody &B, float eps, float epsSq, Contact &m) {
+/* pxCollidePolygons after the two SAT passes, px_collision.c:312-435 (pxFindIncidentFace
+ * :220-259 inlined): `flip` says B owns the reference face (pxBiasGt, :322-337) */
+__device__ void clipPolygons(const DBody &A, const DBody &B, bool flip, uint32_t refIndex, float eps, Contact &m) {
   m.count = 0;
-  uint32_t faceA, faceB;
-  float penA = leastPenetration(faceA, A, B, epsSq);
-  if (penA >= 0.0f) return;
-  float penB = leastPenetration(faceB, B, A, epsSq);
-  if (penB >= 0.0f) return;
-
-  const bool flip = !(penA >= penB * 0.95f + penA * 0.01f); /* pxBiasGt */
   const DBody &ref = flip ? B : A;
   const DBody &inc = flip ? A : B;
-  uint32_t refIndex = flip ? faceB : faceA;
 
   /* incident face: most anti-parallel normal */
   float4 rf = ref.v[refIndex];
@@ -466,12 +527,12 @@ __device__ __forceinline__ ContactIn loadContact(const Sm &s, uint32_t w) {
   return in;
 }
 
-__device__ __forceinline__ void solveContact(const Sm &s, uint32_t w, const ContactIn &in, float eps) {
-  const uint32_t a = MID_A(w), b = MID_B(w);
+/* the arithmetic of one contact visit: in.vA / in.vB come back updated */
+__device__ __forceinline__ void contactImpulse(uint32_t w, ContactIn &in, float eps) {
   const bool second = MID_CI(w) != 0, bdyn = MID_BDYN(w) != 0;
   const float4 mA = in.mA, mB = in.mB, mC = in.mC;
   const float4 pA = in.pA, pB = in.pB;
-  float4 vA = in.vA, vB = in.vB;
+  float4 &vA = in.vA, &vB = in.vB;
   const V2 n = v2(mA.x, mA.y);
   const float e = mA.z, sf = mA.w, df = mB.x;
   const V2 c = second ? v2(mC.x, mC.y) : v2(mB.z, mB.w);
@@ -519,17 +580,19 @@ __device__ __forceinline__ void solveContact(const Sm &s, uint32_t w, const Cont
   vA.x = approaching ? (slides ? va2.x : va1.x) : va.x;
   vA.y = approaching ? (slides ? va2.y : va1.y) : va.y;
   vA.z = approaching ? (slides ? wa2 : wa1) : wa;
-  s.bodyV[a] = vA;
-  if (bdyn) {
-    vB.x = approaching ? (slides ? vb2.x : vb1.x) : vb.x;
-    vB.y = approaching ? (slides ? vb2.y : vb1.y) : vb.y;
-    vB.z = approaching ? (slides ? wb2 : wb1) : wb;
-    s.bodyV[b] = vB;
-  }
+  vB.x = approaching ? (slides ? vb2.x : vb1.x) : vb.x; /* a static B: vb2 == vb1 == vb, exact zeros */
+  vB.y = approaching ? (slides ? vb2.y : vb1.y) : vb.y;
+  vB.z = approaching ? (slides ? wb2 : wb1) : wb;
+}
+
+__device__ __forceinline__ void solveContact(const Sm &s, uint32_t w, ContactIn &in, float eps) {
+  contactImpulse(w, in, eps);
+  s.bodyV[MID_A(w)] = in.vA;
+  if (MID_BDYN(w)) s.bodyV[MID_B(w)] = in.vB;
 }
 
 __device__ __forceinline__ void applyContactImpulse(const Sm &s, uint32_t w, float eps) {
-  const ContactIn in = loadContact(s, w);
+  ContactIn in = loadContact(s, w);
   solveContact(s, w, in, eps);
 }
 
@@ -561,7 +624,7 @@ __device__ __forceinline__ void copyRows(float *dst, const float *src, uint32_t 
 
 /* ============================================================================ kernel ==== */
 template <int NT>
-__global__ void __launch_bounds__(NT, 512 / NT) pxStepKernel(const PxStepParams P) {
+__global__ void __launch_bounds__(NT, NT == 256 ? 3 : 512 / NT) pxStepKernel(const PxStepParams P) {
   constexpr int R = PX_DMAX / NT; /* body slots (and sorted positions) owned per thread */
   extern __shared__ __align__(16) uint8_t smemRaw[];
   const PxBatchLayout &L = P.L;
@@ -864,39 +927,19 @@ __global__ void __launch_bounds__(NT, 512 / NT) pxStepKernel(const PxStepParams 
     __syncthreads();
     PROF_MARK(1)
 
-    /* ====================== phase C: narrowphase, one pair per thread per bin ========= */
+    /* ====================== phase C: narrowphase ===================================== */
     {
-      const uint32_t nAll = min(nCC + nCP + nPP, MP);
+      const uint32_t nAll = min(nCC + nCP + nPP, MP), nCircle = min(nCC + nCP, nAll);
       const V2 gstep = g * dt;
       const float gsq = lensq(gstep);
-      for (uint32_t idx = tid; idx < nAll; idx += NT) {
-        Contact m;
-        m.count = 0;
-        m.c1 = v2(0.0f, 0.0f);
-        const uint32_t word = s.bins[idx];
-        if (word == 0xffffffffu) continue;
-        const uint32_t a = BIN_A(word), b = BIN_B(word);
-        {
-          DBody A = loadBody(s, a), B = loadBody(s, b);
-          if (idx < nCC) {
-            collideCircles(A, B, eps, m);
-          } else if (idx < nCC + nCP) {
-            /* pxCollide, px_collision.c:445-459: the polygon-circle order swaps the arguments
-             * and flips the normal */
-            if (A.nverts == 0) {
-              collideCirclePolygon(A, B, eps, m);
-            } else {
-              collideCirclePolygon(B, A, eps, m);
-              m.normal = -m.normal;
-            }
-          } else {
-            collidePolygons(A, B, eps, epsSq, m);
-          }
-        }
-        if (!m.count) continue;
+      /* manifold slot + pxManifoldInit + resting contact + sleep flags for a pair with contacts */
+      auto keep = [&](uint32_t word, uint32_t a, uint32_t b, const Contact &m) {
         const uint32_t bdyn = b < D;
         const uint32_t ms = atomicAdd(&s.misc[MI_MCOUNT], 1u);
-        if (ms >= MM) continue; /* manifold overflow, flagged below */
+        if (ms >= MM) { /* manifold overflow, flagged below */
+          s.validSlot[BIN_SEQ(word)] = 0;
+          return;
+        }
         const float4 mtA = s.bodyM[a], mtB = s.bodyM[b];
         const float4 pA = s.bodyP[a], pB = s.bodyP[b], vA = s.bodyV[a], vB = s.bodyV[b];
         /* pxManifoldInit, px_manifold.c:12-31: geometric-mean friction via pxFastSqrt */
@@ -939,6 +982,78 @@ __global__ void __launch_bounds__(NT, 512 / NT) pxStepKernel(const PxStepParams 
           if (s.flags[b] & PX_FLAG_SLEEPING) s.wakeFlag[a] = 1;
         }
         if (bdyn) atomicAdd(&s.fillB[b], 1u); /* bodyB-role manifold count of b */
+      };
+
+      /* C1: circle-circle and circle-polygon pairs, one pair per thread */
+      for (uint32_t idx = tid; idx < nCircle; idx += NT) {
+        const uint32_t word = s.bins[idx];
+        if (word == 0xffffffffu) continue;
+        const uint32_t a = BIN_A(word), b = BIN_B(word);
+        Contact m;
+        m.count = 0;
+        m.c1 = v2(0.0f, 0.0f);
+        {
+          DBody A = loadBody(s, a), B = loadBody(s, b);
+          if (idx < nCC) {
+            collideCircles(A, B, eps, m);
+          } else if (A.nverts == 0) {
+            /* pxCollide, px_collision.c:445-459: the polygon-circle order swaps the arguments
+             * and flips the normal */
+            collideCirclePolygon(A, B, eps, m);
+          } else {
+            collideCirclePolygon(B, A, eps, m);
+            m.normal = -m.normal;
+          }
+        }
+        if (m.count) keep(word, a, b, m);
+      }
+
+      /* C2: polygon-polygon SAT, PX_SAT_LANES lanes per pair (the faces of a polygon are spread
+       * over the lanes of its group, so a triangle-box pair and an octagon-octagon pair keep a
+       * warp about equally busy).  Survivors leave {1 << 15 | flip << 8 | reference face} in
+       * validSlot[seq] for the clip pass; separated pairs leave 0. */
+      {
+        const uint32_t q = tid & (PX_SAT_LANES - 1u), grp = tid / PX_SAT_LANES;
+        const uint32_t nPoly = nAll - nCircle;
+        for (uint32_t base = 0; base < nPoly; base += NT / PX_SAT_LANES) {
+          const uint32_t k = base + grp;
+          uint32_t word = 0xffffffffu;
+          if (k < nPoly) word = s.bins[nCircle + k];
+          const bool valid = word != 0xffffffffu;
+          const uint32_t a = valid ? BIN_A(word) : 0u, b = valid ? BIN_B(word) : 0u;
+          const DBody A = loadBody(s, a), B = loadBody(s, b);
+          uint32_t faceA, faceB = 0;
+          const float penA = leastPenetrationGroup(faceA, A, B, q, valid, epsSq);
+          const bool alive = valid && !(penA >= 0.0f);
+          /* the second pass is skipped only when no pair of the warp needs it */
+          float penB = 0.0f;
+          if (__any_sync(0xffffffffu, alive)) penB = leastPenetrationGroup(faceB, B, A, q, alive, epsSq);
+          if (alive && !(penB >= 0.0f) && q == 0) {
+            const bool flip = !(penA >= penB * 0.95f + penA * 0.01f); /* pxBiasGt */
+            s.validSlot[BIN_SEQ(word)] = (uint16_t)(0x8000u | (flip ? 0x100u : 0u) | (flip ? faceB : faceA));
+          }
+        }
+      }
+      __syncthreads();
+
+      /* C3: reference-face clipping for the SAT survivors, one pair per thread */
+      for (uint32_t idx = nCircle + tid; idx < nAll; idx += NT) {
+        const uint32_t word = s.bins[idx];
+        if (word == 0xffffffffu) continue;
+        const uint32_t sat = s.validSlot[BIN_SEQ(word)];
+        if (!sat) continue;
+        const uint32_t a = BIN_A(word), b = BIN_B(word);
+        Contact m;
+        m.c1 = v2(0.0f, 0.0f);
+        {
+          DBody A = loadBody(s, a), B = loadBody(s, b);
+          clipPolygons(A, B, (sat & 0x100u) != 0, sat & 0xffu, eps, m);
+        }
+        if (m.count) {
+          keep(word, a, b, m);
+        } else {
+          s.validSlot[BIN_SEQ(word)] = 0;
+        }
       }
     }
     __syncthreads();
@@ -1115,32 +1230,35 @@ __global__ void __launch_bounds__(NT, 512 / NT) pxStepKernel(const PxStepParams 
        * The loop body is branch-free: idle lanes and absent pushes go to a dummy slot.
        */
       uint32_t head = 0, tail = s.misc[MI_QTAIL], visits = 0, rounds = 0;
-      const uint32_t NONE = 0xffffffffu, DUMMY = P.S.qcap; /* queue[qcap] is a write-only sink */
-      volatile uint32_t *mathRound = s.misc + MI_MATHROUND;
-      const uint32_t rdescAddr = (uint32_t)__cvta_generic_to_shared(s.misc + MI_RDESC);
+      const uint32_t aQueue = sAddr(s.queue), aNext = sAddr(s.nextw), aMids = sAddr(s.mids), aSig = sAddr(s.sig);
+      const uint32_t aDesc = sAddr(s.misc + MI_RDESC), aMathRound = sAddr(s.misc + MI_MATHROUND);
+      const uint32_t aDummy = aQueue + 4u * P.S.qcap; /* queue[qcap] is a write-only sink */
       const uint32_t lt = (1u << lane) - 1u;
       uint32_t mr = 0;
+#pragma unroll 2
       while (head != tail) {
         const uint32_t n = min(tail - head, 32u);
-        while (rounds - mr >= PX_LAG) mr = *mathRound;
-        asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(rdescAddr + 4u * (rounds & (PX_RING - 1u))),
+        while (rounds - mr >= PX_LAG) { /* far enough ahead: leave the issue slots to the others */
+          __nanosleep(64);
+          mr = ldsVolatile(aMathRound);
+        }
+        asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(aDesc + 4u * (rounds & (PX_RING - 1u))),
                      "r"(((rounds + 1u) << 16) | n)
                      : "memory");
         const bool active = lane < n;
-        const uint32_t qw = s.queue[(head + lane) & QMASK];
+        const uint32_t qw = lds32(aQueue + 4u * ((head + lane) & QMASK));
         const uint32_t w = active ? qw : 0u; /* idle lanes: a harmless word, every index in range */
-        const uint32_t ms = MID_SLOT(w);
         const bool again = active && (MID_CI(w) + 1u < MID_COUNT(w)); /* second contact follows */
         const bool sigA = active && !again, sigB = sigA && MID_BDYN(w);
         /* successors of this manifold on body a / body b are fixed for the substep:
          * slot | successor has a dynamic B << 14 | successor's side for this body << 15 */
-        const uint32_t nx = *(const uint32_t *)(s.nextw + 2 * ms); /* side a | side b << 16 */
+        const uint32_t nx = lds32(aNext + 4u * MID_SLOT(w)); /* side a | side b << 16 */
         /* (the b half is unset when B is static, the a half when no manifold 0 exists) */
         const uint32_t t0 = sigA ? (nx & 0x3ffu) : 0u, t1 = sigB ? ((nx >> 16) & 0x3ffu) : 0u;
-        const uint32_t wt0 = s.mids[t0], wt1 = s.mids[t1];
-        uint32_t old0 = 0, old1 = 0;
-        if (sigA) old0 = atomicAdd(&s.sig[t0], (nx & 0x8000u) ? 0x10000u : 1u);
-        if (sigB) old1 = atomicAdd(&s.sig[t1], (nx & 0x80000000u) ? 0x10000u : 1u);
+        const uint32_t wt0 = lds32(aMids + 4u * t0), wt1 = lds32(aMids + 4u * t1);
+        /* an idle side adds 0: no branch around the atomics */
+        const uint32_t old0 = atomAddS(aSig + 4u * t0, sigA ? ((nx & 0x8000u) ? 0x10000u : 1u) : 0u);
+        const uint32_t old1 = atomAddS(aSig + 4u * t1, sigB ? ((nx & 0x80000000u) ? 0x10000u : 1u) : 0u);
         const uint32_t mine0 = ((nx & 0x8000u) ? (old0 >> 16) : (old0 & 0xffffu)) + 1u;
         const uint32_t other0 = (nx & 0x8000u) ? (old0 & 0xffffu) : (old0 >> 16);
         const uint32_t mine1 = ((nx & 0x80000000u) ? (old1 >> 16) : (old1 & 0xffffu)) + 1u;
@@ -1152,16 +1270,16 @@ __global__ void __launch_bounds__(NT, 512 / NT) pxStepKernel(const PxStepParams 
         const uint32_t b0 = __ballot_sync(0xffffffffu, has0);
         const uint32_t b1 = __ballot_sync(0xffffffffu, ready1);
         const uint32_t c0 = __popc(b0);
-        s.queue[has0 ? ((tail + __popc(b0 & lt)) & QMASK) : DUMMY] = push0;
-        s.queue[ready1 ? ((tail + c0 + __popc(b1 & lt)) & QMASK) : DUMMY] = wt1;
+        sts32(has0 ? aQueue + 4u * ((tail + __popc(b0 & lt)) & QMASK) : aDummy, push0);
+        sts32(ready1 ? aQueue + 4u * ((tail + c0 + __popc(b1 & lt)) & QMASK) : aDummy, wt1);
         tail += c0 + __popc(b1);
         head += n;
         visits += sigA ? 1u : 0u;
         rounds++;
-        mr = *mathRound;
+        mr = ldsVolatile(aMathRound);
         __syncwarp();
       }
-      asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(rdescAddr + 4u * (rounds & (PX_RING - 1u))),
+      asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(aDesc + 4u * (rounds & (PX_RING - 1u))),
                    "r"(((rounds + 1u) << 16) | 0xffffu) /* end of schedule */
                    : "memory");
       visits = __reduce_add_sync(0xffffffffu, visits);
@@ -1170,25 +1288,45 @@ __global__ void __launch_bounds__(NT, 512 / NT) pxStepKernel(const PxStepParams 
     } else if (warp == 1 && iterations) {
       /* Math warp: executes the published rounds in order, one contact visit per lane.  The
        * next round's descriptor is fetched before this round's arithmetic, so in the steady
-       * state (scheduler ahead) a round starts with its queue word already on the way. */
-      volatile uint32_t *mathRound = s.misc + MI_MATHROUND;
-      const uint32_t rdescAddr = (uint32_t)__cvta_generic_to_shared(s.misc + MI_RDESC);
-      uint32_t head = 0, d;
-      asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(d) : "r"(rdescAddr) : "memory");
+       * state (scheduler ahead) a round starts with its queue word already on the way.  Idle
+       * lanes run the arithmetic on manifold 0 and store nothing. */
+      const uint32_t aQueue = sAddr(s.queue), aDesc = sAddr(s.misc + MI_RDESC), aMathRound = sAddr(s.misc + MI_MATHROUND);
+      const uint32_t aManA = sAddr(s.manA), aManB = sAddr(s.manB), aManC = sAddr(s.manC);
+      const uint32_t aBodyP = sAddr(s.bodyP), aBodyV = sAddr(s.bodyV);
+      uint32_t head = 0, d = ldsAcquire(aDesc);
+#pragma unroll 4
       for (uint32_t r = 0;; r++) {
-        while ((d >> 16) != ((r + 1u) & 0xffffu))
-          asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(d) : "r"(rdescAddr + 4u * (r & (PX_RING - 1u))) : "memory");
+        const uint32_t expect = ((r + 1u) & 0xffffu) << 16;
+        /* d ^ expect == n (<= 32) when the descriptor is the one of round r; 0xffff ends */
+        bool done = false;
+        while ((d ^ expect) > 32u) {
+          if ((d ^ expect) == 0xffffu) {
+            done = true;
+            break;
+          }
+          d = ldsAcquire(aDesc + 4u * (r & (PX_RING - 1u)));
+        }
+        if (done) break;
         const uint32_t n = d & 0xffffu;
-        if (n == 0xffffu) break;
-        const uint32_t w = s.queue[(head + lane) & QMASK];
-        asm volatile("ld.acquire.cta.shared.u32 %0, [%1];"
-                     : "=r"(d)
-                     : "r"(rdescAddr + 4u * ((r + 1u) & (PX_RING - 1u)))
-                     : "memory");
-        if (lane < n) applyContactImpulse(s, w, eps);
+        const uint32_t qw = lds32(aQueue + 4u * ((head + lane) & QMASK));
+        d = ldsAcquire(aDesc + 4u * ((r + 1u) & (PX_RING - 1u)));
+        const bool active = lane < n;
+        const uint32_t w = active ? qw : 0u;
+        const uint32_t ms16 = MID_SLOT(w) * 16u, a16 = MID_A(w) * 16u, b16 = MID_B(w) * 16u;
+        ContactIn in;
+        in.mA = lds128(aManA + ms16);
+        in.mB = lds128(aManB + ms16);
+        in.mC = lds128(aManC + ms16);
+        in.pA = lds128(aBodyP + a16);
+        in.pB = lds128(aBodyP + b16);
+        in.vA = lds128(aBodyV + a16);
+        in.vB = lds128(aBodyV + b16);
+        contactImpulse(w, in, eps);
+        sts128If(aBodyV + a16, in.vA, active);
+        sts128If(aBodyV + b16, in.vB, active && MID_BDYN(w));
         head += n;
         __syncwarp();
-        *mathRound = r + 1u;
+        stsVolatile(aMathRound, r + 1u);
       }
     }
     __syncthreads();
