@@ -30,6 +30,8 @@ struct PxBatch {
   uint8_t *dMut, *dImm, *dTrace;
   float *dSin;
   unsigned long long *dProf;
+  float4 *dScratch;   /* manifold records of the resident CTAs (px_step.cuh) */
+  uint32_t *dSlotMask;
   uint8_t *hMut, *hImm; /* pinned staging, same layout */
   float sinTable[256];
   /* control path */
@@ -66,6 +68,8 @@ extern "C" PxBatch *pxBatchCreate(uint32_t nWorlds, const PxBatchDesc *desc) {
   b->dMut = b->dImm = b->dTrace = nullptr;
   b->dSin = nullptr;
   b->dProf = nullptr;
+  b->dScratch = nullptr;
+  b->dSlotMask = nullptr;
   b->hMut = b->hImm = nullptr;
   b->dCmds = b->dGlobal = nullptr;
   b->dWorldStart = nullptr;
@@ -143,6 +147,12 @@ extern "C" PxBatch *pxBatchCreate(uint32_t nWorlds, const PxBatchDesc *desc) {
     if ((e = cudaMalloc(&b->dProf, (size_t)nWorlds * 64)) != cudaSuccess) return fail("cudaMalloc(prof)", e);
     if ((e = cudaMemsetAsync(b->dProf, 0, (size_t)nWorlds * 64, b->stream)) != cudaSuccess) return fail("cudaMemset", e);
   }
+  {
+    const size_t scratchBytes = (size_t)PX_SCRATCH_SMIDS * PX_SCRATCH_SLOTS * b->L.maxManifolds * 3 * sizeof(float4);
+    if ((e = cudaMalloc(&b->dScratch, scratchBytes)) != cudaSuccess) return fail("cudaMalloc(scratch)", e);
+    if ((e = cudaMalloc(&b->dSlotMask, PX_SCRATCH_SMIDS * sizeof(uint32_t))) != cudaSuccess) return fail("cudaMalloc(slotMask)", e);
+    if ((e = cudaMemsetAsync(b->dSlotMask, 0, PX_SCRATCH_SMIDS * sizeof(uint32_t), b->stream)) != cudaSuccess) return fail("cudaMemset", e);
+  }
   if ((e = cudaMallocHost(&b->hMut, mutBytes)) != cudaSuccess) return fail("cudaMallocHost(mutable)", e);
   if ((e = cudaMallocHost(&b->hImm, immBytes)) != cudaSuccess) return fail("cudaMallocHost(immutable)", e);
   memset(b->hMut, 0, mutBytes);
@@ -194,6 +204,8 @@ extern "C" void pxBatchFree(PxBatch *b) {
   cudaFree(b->dTrace);
   cudaFree(b->dSin);
   cudaFree(b->dProf);
+  cudaFree(b->dScratch);
+  cudaFree(b->dSlotMask);
   cudaFree(b->dCmds);
   cudaFree(b->dGlobal);
   cudaFree(b->dWorldStart);
@@ -368,6 +380,8 @@ extern "C" int pxBatchStep(PxBatch *b, uint32_t kSubsteps) {
   P.trace = b->dTrace;
   P.sinTable = b->dSin;
   P.prof = b->dProf;
+  P.scratch = b->dScratch;
+  P.slotMask = b->dSlotMask;
   P.kSubsteps = kSubsteps;
   P.flags = b->flags;
   int rc = pxLaunchStep(&P, b->threads, b->stream);

@@ -105,6 +105,12 @@ __device__ __forceinline__ uint32_t ldsVolatile(uint32_t a) {
 __device__ __forceinline__ void stsVolatile(uint32_t a, uint32_t v) {
   asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
 }
+/* a global load the compiler may not sink below later volatile asm statements */
+__device__ __forceinline__ float4 ldcgPinned(const float4 *p) {
+  float4 v;
+  asm volatile("ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
 __device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v)); }
 __device__ __forceinline__ void sts128If(uint32_t a, float4 v, bool p) {
   asm volatile("{ .reg .pred q; setp.ne.u32 q, %5, 0; @q st.shared.v4.f32 [%0], {%1, %2, %3, %4}; }" ::"r"(a), "f"(v.x),
@@ -149,14 +155,17 @@ struct Sm {
   float4 *bodyP; /* {pos.x, pos.y, iMass, iInertia}                 statics: iM = iI = 0 */
   float4 *bodyV; /* {vel.x, vel.y, angularVelocity, aabbRadius}     statics: zero velocity */
   float4 *bodyR; /* orientation {m00, m01, m10, m11} */
-  float4 *bodyM; /* {restitution, staticFriction, dynamicFriction, shape word bits} */
+  uint32_t *shape; /* PX_SHAPE_PACK word by body id */
+  const float *dynMat, *statMat; /* global immutable rows: materials are only read at manifold creation */
   uint8_t *flags, *order, *order2, *posOf, *restFlag, *wakeFlag, *sSlot;
   PxWorldHeader *hdr;
   uint32_t *misc;
   unsigned long long *scan;
-  float4 *manA; /* {normal.x, normal.y, mixedRestitution, staticFriction} */
-  float4 *manB; /* {dynamicFriction, penetration, c0.x, c0.y} */
-  float4 *manC; /* {c1.x, c1.y, rcpDenom0, rcpDenom1} */
+  /* manifold records, float4[3] per slot, in this CTA's L2-resident scratch slot (global):
+   *   [0] {normal.x, normal.y, mixedRestitution, staticFriction}
+   *   [1] {dynamicFriction, penetration, c0.x, c0.y}
+   *   [2] {c1.x, c1.y, rcpDenom0, rcpDenom1} */
+  float4 *man;
   uint32_t *mids;
   uint16_t *validSlot, *base, *listStart, *cnt, *cntB;
   uint32_t *fillB;
@@ -170,8 +179,23 @@ struct Sm {
   uint32_t *queue;
 };
 
+/* manifold records bypass L1 (.cg): the slot is rewritten every substep and read by other
+ * threads of the CTA, and L2 is where it lives anyway */
+__device__ __forceinline__ float4 manLoad(const Sm &s, uint32_t ms, uint32_t k) { return __ldcg(s.man + 3u * ms + k); }
+__device__ __forceinline__ void manStore(const Sm &s, uint32_t ms, float4 a, float4 b, float4 c) {
+  __stcg(s.man + 3u * ms + 0u, a);
+  __stcg(s.man + 3u * ms + 1u, b);
+  __stcg(s.man + 3u * ms + 2u, c);
+}
+/* {restitution, staticFriction, dynamicFriction} of a body id, from the immutable block */
+__device__ __forceinline__ float3 materialOf(const Sm &s, uint32_t id, uint32_t D, uint32_t S) {
+  if (id < D) return make_float3(__ldg(s.dynMat + PX_DYNC_E * D + id), __ldg(s.dynMat + PX_DYNC_SF * D + id), __ldg(s.dynMat + PX_DYNC_DF * D + id));
+  const uint32_t q = id - D;
+  return make_float3(__ldg(s.statMat + PX_STAT_E * S + q), __ldg(s.statMat + PX_STAT_SF * S + q), __ldg(s.statMat + PX_STAT_DF * S + q));
+}
+
 /* misc[] slots */
-enum { MI_MCOUNT = 0, MI_QTAIL, MI_OVERFLOW, MI_UNSORTED, MI_SLEEPING, MI_VISITS, MI_MATHROUND, MI_RDESC = 16 };
+enum { MI_MCOUNT = 0, MI_QTAIL, MI_OVERFLOW, MI_UNSORTED, MI_SLEEPING, MI_VISITS, MI_MATHROUND, MI_SLOT, MI_RDESC = 16 };
 #define PX_RING 16u /* round descriptors in flight (misc[MI_RDESC..]) */
 #define PX_LAG 8u   /* rounds the scheduler warp may run ahead of the math warp */
 
@@ -205,7 +229,7 @@ __device__ __forceinline__ DBody loadBody(const Sm &s, uint32_t id) {
   b.pos = v2(p.x, p.y);
   b.rot = M2{r.x, r.y, r.z, r.w};
   b.radius = s.bodyV[id].w;
-  const uint32_t sh = __float_as_uint(s.bodyM[id].w);
+  const uint32_t sh = s.shape[id];
   b.nverts = PX_SHAPE_COUNT(sh);
   b.v = s.verts + PX_SHAPE_OFFSET(sh);
   return b;
@@ -517,9 +541,9 @@ struct ContactIn {
 __device__ __forceinline__ ContactIn loadContact(const Sm &s, uint32_t w) {
   const uint32_t ms = MID_SLOT(w), a = MID_A(w), b = MID_B(w);
   ContactIn in;
-  in.mA = s.manA[ms];
-  in.mB = s.manB[ms];
-  in.mC = s.manC[ms];
+  in.mA = manLoad(s, ms, 0);
+  in.mB = manLoad(s, ms, 1);
+  in.mC = manLoad(s, ms, 2);
   in.pA = s.bodyP[a];
   in.pB = s.bodyP[b];
   in.vA = s.bodyV[a];
@@ -598,11 +622,11 @@ __device__ __forceinline__ void applyContactImpulse(const Sm &s, uint32_t w, flo
 
 __device__ __forceinline__ void bindSmem(Sm &s, uint8_t *base, const PxSmemPlan &S, const float4 *globalVerts) {
 #define BIND(field, type) s.field = (type *)(base + S.field)
-  BIND(bodyP, float4); BIND(bodyV, float4); BIND(bodyR, float4); BIND(bodyM, float4);
+  BIND(bodyP, float4); BIND(bodyV, float4); BIND(bodyR, float4); BIND(shape, uint32_t);
   BIND(flags, uint8_t); BIND(order, uint8_t); BIND(order2, uint8_t); BIND(posOf, uint8_t);
   BIND(restFlag, uint8_t); BIND(wakeFlag, uint8_t); BIND(sSlot, uint8_t);
   BIND(hdr, PxWorldHeader); BIND(misc, uint32_t); BIND(scan, unsigned long long);
-  BIND(manA, float4); BIND(manB, float4); BIND(manC, float4); BIND(mids, uint32_t);
+  BIND(mids, uint32_t);
   BIND(validSlot, uint16_t); BIND(base, uint16_t); BIND(listStart, uint16_t); BIND(cnt, uint16_t); BIND(cntB, uint16_t);
   BIND(fillB, uint32_t);
   BIND(sBox, float4); BIND(sInfo, uint32_t); BIND(stBox, float4);
@@ -624,7 +648,7 @@ __device__ __forceinline__ void copyRows(float *dst, const float *src, uint32_t 
 
 /* ============================================================================ kernel ==== */
 template <int NT>
-__global__ void __launch_bounds__(NT, NT == 256 ? 3 : 512 / NT) pxStepKernel(const PxStepParams P) {
+__global__ void __launch_bounds__(NT, NT == 64 ? 6 : (NT == 128 ? 5 : 3)) pxStepKernel(const PxStepParams P) {
   constexpr int R = PX_DMAX / NT; /* body slots (and sorted positions) owned per thread */
   extern __shared__ __align__(16) uint8_t smemRaw[];
   const PxBatchLayout &L = P.L;
@@ -635,6 +659,8 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 3 : 512 / NT) pxStepKernel(con
   const uint8_t *gimm = P.imm + (size_t)world * L.immStride;
   Sm s;
   bindSmem(s, smemRaw, P.S, (const float4 *)(gimm + L.offVerts));
+  s.dynMat = (const float *)(gimm + L.offDynConst);
+  s.statMat = (const float *)(gimm + L.offStat);
   const float eps = L.epsilon, epsSq = L.epsilonSq, allowedPen = L.allowedPenetration;
   const uint32_t QMASK = P.S.qcap - 1;
   const float *gdynC = (const float *)(gmut + L.offDyn);
@@ -653,8 +679,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 3 : 512 / NT) pxStepKernel(con
                                gc[PX_DYNC_RADIUS * D + x]);
       s.bodyR[x] = make_float4(gdynC[PX_DYN_M00 * D + x], gdynC[PX_DYN_M01 * D + x], gdynC[PX_DYN_M10 * D + x],
                                gdynC[PX_DYN_M11 * D + x]);
-      s.bodyM[x] = make_float4(gc[PX_DYNC_E * D + x], gc[PX_DYNC_SF * D + x], gc[PX_DYNC_DF * D + x],
-                               __uint_as_float(gshape[x]));
+      s.shape[x] = gshape[x];
     }
     const float *gs = (const float *)(gimm + L.offStat);
     const uint32_t *gsshape = (const uint32_t *)(gimm + L.offStatShape);
@@ -663,13 +688,31 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 3 : 512 / NT) pxStepKernel(con
       s.bodyV[D + q] = make_float4(0.0f, 0.0f, 0.0f, gs[PX_STAT_RADIUS * S + q]);
       s.bodyR[D + q] = make_float4(gs[PX_STAT_M00 * S + q], gs[PX_STAT_M01 * S + q], gs[PX_STAT_M10 * S + q],
                                    gs[PX_STAT_M11 * S + q]);
-      s.bodyM[D + q] = make_float4(gs[PX_STAT_E * S + q], gs[PX_STAT_SF * S + q], gs[PX_STAT_DF * S + q],
-                                   __uint_as_float(gsshape[q]));
+      s.shape[D + q] = gsshape[q];
     }
     copyRows<NT>((float *)s.flags, (const float *)(gmut + L.offDynFlags), D / 4);
     copyRows<NT>((float *)s.order, (const float *)(gmut + L.offDynOrder), D / 4);
     copyRows<NT>((float *)s.hdr, (const float *)(gmut + L.offHeader), sizeof(PxWorldHeader) / 4);
-    if (tid < 32) s.misc[tid] = 0;
+    if (tid < 32 && tid != MI_SLOT) s.misc[tid] = 0;
+    if (tid == 0) {
+      /* claim a manifold scratch slot of this SM: lowest free bit of slotMask[smid] */
+      uint32_t smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      smid &= PX_SCRATCH_SMIDS - 1u;
+      uint32_t bit = 0, old = 0xffffffffu;
+      for (uint32_t tries = 0; tries < (1u << 22); tries++) { /* bounded: never hang the GPU on a bookkeeping bug */
+        bit = __ffs(~*(volatile uint32_t *)(P.slotMask + smid)) - 1u;
+        if (bit >= PX_SCRATCH_SLOTS) continue;
+        old = atomicOr(P.slotMask + smid, 1u << bit);
+        if (!(old & (1u << bit))) break;
+        old = 0xffffffffu;
+      }
+      if (old == 0xffffffffu) { /* no slot: results of this world are unspecified, and flagged */
+        bit = PX_SCRATCH_SLOTS - 1u;
+        s.misc[MI_OVERFLOW] = PX_OVERFLOW_INTERNAL;
+      }
+      s.misc[MI_SLOT] = smid * PX_SCRATCH_SLOTS + bit;
+    }
   }
   /* thread-private body state: slot x = tid + r * NT lives in this thread's registers */
   float rAngle[R], rFx[R], rFy[R], rTq[R], rSlp[R];
@@ -685,6 +728,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 3 : 512 / NT) pxStepKernel(con
   }
   __syncthreads();
 
+  s.man = P.scratch + (size_t)s.misc[MI_SLOT] * MM * 3u;
   const uint32_t nDyn = min(s.hdr->nDynamic, D), nStat = min(s.hdr->nStatic, S);
   const float dt = s.hdr->dt;
   const V2 g = v2(s.hdr->gravityX, s.hdr->gravityY);
@@ -710,7 +754,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 3 : 512 / NT) pxStepKernel(con
 
     /* ====================== phase A: AABB keys, stable order by aabb.min.x ============ */
     /* the order persists across substeps, so it is almost always already sorted */
-    if (tid < 32 && tid != MI_OVERFLOW) s.misc[tid] = 0;
+    if (tid < 32 && tid != MI_OVERFLOW && tid != MI_SLOT) s.misc[tid] = 0;
     for (uint32_t i = tid; i < D; i += NT) {
       s.restFlag[i] = 0;
       s.wakeFlag[i] = 0;
@@ -773,7 +817,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 3 : 512 / NT) pxStepKernel(con
       const float4 bp = s.bodyP[slot];
       const float r = s.bodyV[slot].w;
       s.sBox[p] = make_float4(bp.x - r, bp.y - r, bp.x + r, bp.y + r);
-      const uint32_t poly = PX_SHAPE_COUNT(__float_as_uint(s.bodyM[slot].w)) != 0;
+      const uint32_t poly = PX_SHAPE_COUNT(s.shape[slot]) != 0;
       s.sInfo[p] = slot | ((s.flags[slot] & PX_FLAG_SLEEPING) ? 0x100u : 0u) | (poly << 9);
       s.sSlot[p] = (uint8_t)slot;
       s.posOf[slot] = (uint8_t)p;
@@ -821,7 +865,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 3 : 512 / NT) pxStepKernel(con
           const float4 b = s.stBox[q];
           if (b.x > a.z) continue;
           if (!boxesOverlap(a, b)) continue;
-          const uint32_t bPoly = PX_SHAPE_COUNT(__float_as_uint(s.bodyM[D + q].w)) != 0;
+          const uint32_t bPoly = PX_SHAPE_COUNT(s.shape[D + q]) != 0;
           counts += 1ull + (1ull << (16 * (1 + aPoly + bPoly)));
           const uint32_t k = q - startStat;
           statMask |= k < 32 ? (1u << k) : 0u;
@@ -905,7 +949,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 3 : 512 / NT) pxStepKernel(con
           const uint32_t k = __ffs(m) - 1;
           m &= m - 1;
           const uint32_t q = startStatR[r] + k;
-          const uint32_t bPoly = PX_SHAPE_COUNT(__float_as_uint(s.bodyM[D + q].w)) != 0;
+          const uint32_t bPoly = PX_SHAPE_COUNT(s.shape[D + q]) != 0;
           emit(D + q, bPoly, tpA ? (uint32_t)(gimm + L.offStatSlot)[q] : 0u);
         }
       } else {
@@ -914,7 +958,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 3 : 512 / NT) pxStepKernel(con
           const float4 b = s.stBox[q];
           if (b.x > a.z) continue;
           if (!boxesOverlap(a, b)) continue;
-          const uint32_t bPoly = PX_SHAPE_COUNT(__float_as_uint(s.bodyM[D + q].w)) != 0;
+          const uint32_t bPoly = PX_SHAPE_COUNT(s.shape[D + q]) != 0;
           emit(D + q, bPoly, tpA ? (uint32_t)(gimm + L.offStatSlot)[q] : 0u);
         }
       }
@@ -940,7 +984,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 3 : 512 / NT) pxStepKernel(con
           s.validSlot[BIN_SEQ(word)] = 0;
           return;
         }
-        const float4 mtA = s.bodyM[a], mtB = s.bodyM[b];
+        const float3 mtA = materialOf(s, a, D, S), mtB = materialOf(s, b, D, S);
         const float4 pA = s.bodyP[a], pB = s.bodyP[b], vA = s.bodyV[a], vB = s.bodyV[b];
         /* pxManifoldInit, px_manifold.c:12-31: geometric-mean friction via pxFastSqrt */
         const float sfm = fSqrt(mtA.y * mtB.y), dfm = fSqrt(mtA.z * mtB.z);
@@ -968,9 +1012,8 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 3 : 512 / NT) pxStepKernel(con
           }
         }
         if (restingHit) minE = 0.0f;
-        s.manA[ms] = make_float4(m.normal.x, m.normal.y, minE, sfm);
-        s.manB[ms] = make_float4(dfm, m.pen, m.c0.x, m.c0.y);
-        s.manC[ms] = make_float4(m.c1.x, m.c1.y, rcp[0], rcp[1]);
+        manStore(s, ms, make_float4(m.normal.x, m.normal.y, minE, sfm), make_float4(dfm, m.pen, m.c0.x, m.c0.y),
+                 make_float4(m.c1.x, m.c1.y, rcp[0], rcp[1]));
         s.mids[ms] = a | (b << 8) | (bdyn << 17) | (m.count << 18) | (ms << 20);
         s.validSlot[BIN_SEQ(word)] = (uint16_t)(ms + 1);
         /* manifold pass of pxUpdateSleepStates, px_world.c:147-177: flags set by SLOT */
@@ -1110,7 +1153,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 3 : 512 / NT) pxStepKernel(con
         }
         if (gtrace) { /* ordered manifold dump */
           const uint32_t rank = rankStartR[r] + k;
-          const float4 mA = s.manA[ms], mB = s.manB[ms], mC = s.manC[ms];
+          const float4 mA = manLoad(s, ms, 0), mB = manLoad(s, ms, 1), mC = manLoad(s, ms, 2);
           float *mf = (float *)(gtrace + L.offTraceManifolds);
           mf[0 * MM + rank] = mA.x;
           mf[1 * MM + rank] = mA.y;
@@ -1291,42 +1334,65 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 3 : 512 / NT) pxStepKernel(con
        * state (scheduler ahead) a round starts with its queue word already on the way.  Idle
        * lanes run the arithmetic on manifold 0 and store nothing. */
       const uint32_t aQueue = sAddr(s.queue), aDesc = sAddr(s.misc + MI_RDESC), aMathRound = sAddr(s.misc + MI_MATHROUND);
-      const uint32_t aManA = sAddr(s.manA), aManB = sAddr(s.manB), aManC = sAddr(s.manC);
       const uint32_t aBodyP = sAddr(s.bodyP), aBodyV = sAddr(s.bodyV);
-      uint32_t head = 0, d = ldsAcquire(aDesc);
-#pragma unroll 4
-      for (uint32_t r = 0;; r++) {
-        const uint32_t expect = ((r + 1u) & 0xffffu) << 16;
-        /* d ^ expect == n (<= 32) when the descriptor is the one of round r; 0xffff ends */
-        bool done = false;
-        while ((d ^ expect) > 32u) {
-          if ((d ^ expect) == 0xffffu) {
-            done = true;
-            break;
-          }
-          d = ldsAcquire(aDesc + 4u * (r & (PX_RING - 1u)));
+      const float4 *man = s.man;
+      /* software pipeline: while round r runs, the queue word and the three manifold records of
+       * round r + 1 are already in flight from L2 (the scheduler is rounds ahead, so its
+       * descriptor is normally there); only velocities and the frozen body rows are read at the
+       * last moment, from shared memory */
+      uint32_t head = 0, r = 0, d = ldsAcquire(aDesc);
+      uint32_t w = 0, n = 0;
+      float4 mA, mB, mC;
+      bool have = false; /* w / n / m* hold round r */
+      for (;; r++) {
+        if (!have) {
+          const uint32_t expect = ((r + 1u) & 0xffffu) << 16;
+          while ((d ^ expect) > 0xffffu) d = ldsAcquire(aDesc + 4u * (r & (PX_RING - 1u)));
+          n = d & 0xffffu;
+          if (n == 0xffffu) break;
+          const uint32_t qw = lds32(aQueue + 4u * ((head + lane) & QMASK));
+          w = lane < n ? qw : 0u;
+          mA = __ldcg(man + 3u * MID_SLOT(w));
+          mB = __ldcg(man + 3u * MID_SLOT(w) + 1u);
+          mC = __ldcg(man + 3u * MID_SLOT(w) + 2u);
         }
-        if (done) break;
-        const uint32_t n = d & 0xffffu;
-        const uint32_t qw = lds32(aQueue + 4u * ((head + lane) & QMASK));
-        d = ldsAcquire(aDesc + 4u * ((r + 1u) & (PX_RING - 1u)));
         const bool active = lane < n;
-        const uint32_t w = active ? qw : 0u;
-        const uint32_t ms16 = MID_SLOT(w) * 16u, a16 = MID_A(w) * 16u, b16 = MID_B(w) * 16u;
+        const uint32_t a16 = MID_A(w) * 16u, b16 = MID_B(w) * 16u;
         ContactIn in;
-        in.mA = lds128(aManA + ms16);
-        in.mB = lds128(aManB + ms16);
-        in.mC = lds128(aManC + ms16);
+        in.mA = mA;
+        in.mB = mB;
+        in.mC = mC;
         in.pA = lds128(aBodyP + a16);
         in.pB = lds128(aBodyP + b16);
         in.vA = lds128(aBodyV + a16);
         in.vB = lds128(aBodyV + b16);
+        /* next round: descriptor, queue word, records */
+        const uint32_t headNext = head + n;
+        const uint32_t dn = ldsAcquire(aDesc + 4u * ((r + 1u) & (PX_RING - 1u)));
+        const uint32_t expectN = ((r + 2u) & 0xffffu) << 16;
+        const bool haveNext = (dn ^ expectN) <= 32u;
+        const uint32_t nNext = dn & 0xffffu;
+        /* issued unconditionally (an unpublished round reads manifold 0 and is redone above) and
+         * pinned ahead of the arithmetic, so the L2 round trip runs under this round's chain */
+        const uint32_t qwN = lds32(aQueue + 4u * ((headNext + lane) & QMASK));
+        const uint32_t wNext = (haveNext && lane < nNext) ? qwN : 0u;
+        const float4 nA = ldcgPinned(man + 3u * MID_SLOT(wNext));
+        const float4 nB = ldcgPinned(man + 3u * MID_SLOT(wNext) + 1u);
+        const float4 nC = ldcgPinned(man + 3u * MID_SLOT(wNext) + 2u);
+        asm volatile("" : "+f"(in.vA.x), "+f"(in.vB.x), "+f"(in.pA.x), "+f"(in.pB.x));
         contactImpulse(w, in, eps);
         sts128If(aBodyV + a16, in.vA, active);
         sts128If(aBodyV + b16, in.vB, active && MID_BDYN(w));
-        head += n;
+        head = headNext;
         __syncwarp();
         stsVolatile(aMathRound, r + 1u);
+        have = haveNext;
+        d = dn;
+        w = wNext;
+        n = nNext;
+        mA = nA;
+        mB = nB;
+        mC = nC;
       }
     }
     __syncthreads();
@@ -1361,10 +1427,10 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 3 : 512 / NT) pxStepKernel(con
         const uint32_t start = s.listStart[x], n = s.cnt[x], nBx = s.cntB[x];
         for (uint32_t i = 0; i < n; i++) {
           const uint32_t ms = s.list[start + i];
-          const float pen = s.manB[ms].y;
+          const float pen = manLoad(s, ms, 1).y;
           if (pen <= allowedPen) continue;
           const uint32_t ids = s.mids[ms];
-          const float4 mA = s.manA[ms];
+          const float4 mA = manLoad(s, ms, 0);
           const float iMA = s.bodyP[MID_A(ids)].z, iMB = s.bodyP[MID_B(ids)].z;
           const float excess = pen - allowedPen;
           const float mag = fDiv(excess * 0.2f, iMA + iMB);
@@ -1463,6 +1529,9 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 3 : 512 / NT) pxStepKernel(con
       gh->statSleeping = s.misc[MI_SLEEPING];
       gh->statOverflow = s.hdr->statOverflow | overflow | s.misc[MI_OVERFLOW];
       gh->substeps = s.hdr->substeps + P.kSubsteps;
+      /* every read of the scratch slot is behind the last barrier of the substep loop */
+      const uint32_t slot = s.misc[MI_SLOT];
+      atomicAnd(P.slotMask + slot / PX_SCRATCH_SLOTS, ~(1u << (slot % PX_SCRATCH_SLOTS)));
     }
   }
 }
@@ -1580,13 +1649,13 @@ extern "C" void pxPlanSmem(const PxBatchLayout *L, int vertsInSmem, PxSmemPlan *
     o += alignUp(bytes, 16);
     return at;
   };
-  S->bodyP = take(NB * 16); S->bodyV = take(NB * 16); S->bodyR = take(NB * 16); S->bodyM = take(NB * 16);
+  S->bodyP = take(NB * 16); S->bodyV = take(NB * 16); S->bodyR = take(NB * 16); S->shape = take(NB * 4);
   S->flags = take(D); S->order = take(D); S->order2 = take(D); S->posOf = take(D);
   S->restFlag = take(D); S->wakeFlag = take(D); S->sSlot = take(D);
   S->hdr = take(sizeof(PxWorldHeader));
   S->misc = take(32 * 4);
   S->scan = take(8 * 8);
-  S->manA = take(MM * 16); S->manB = take(MM * 16); S->manC = take(MM * 16); S->mids = take(MM * 4);
+  S->mids = take(MM * 4);
   S->validSlot = take(MP * 2);
   S->base = take((D + 1) * 2);
   S->listStart = take((D + 1) * 2);

@@ -14,13 +14,15 @@
  * Body-id space: dynamic slot s -> id s, static position q -> id D + q (NB = D + S). */
 struct PxSmemPlan {
   /* persistent across the K fused substeps: float4 records by body id */
-  uint32_t bodyP, bodyV, bodyR, bodyM;
+  uint32_t bodyP, bodyV, bodyR;
+  uint32_t shape;                                                   /* u32[NB] PX_SHAPE_PACK word by body id */
   uint32_t flags, order, order2, posOf, restFlag, wakeFlag, sSlot; /* u8[D] */
   uint32_t hdr;                                                     /* PxWorldHeader */
   uint32_t misc;                                                    /* u32[32] counters + round descriptors */
   uint32_t scan;                                                    /* u64[8] block-scan scratch */
-  /* manifolds of the current substep: three float4 records + one id word per slot */
-  uint32_t manA, manB, manC, mids;
+  /* manifolds of the current substep: one id word per slot here; the three float4 records per
+   * slot live in the CTA's L2-resident scratch slot (PxStepParams.scratch) */
+  uint32_t mids;
   /* sweep -> list build */
   uint32_t validSlot; /* u16[MP] manifold slot + 1 by pair sequence number */
   uint32_t base;      /* u16[D+1] first pair sequence number by sorted position */
@@ -51,9 +53,17 @@ struct PxStepParams {
   uint8_t *trace; /* NULL unless PX_BATCH_FLAG_TRACE */
   const float *sinTable;
   unsigned long long *prof; /* NULL, or u64[nWorlds][8] SM-clock cycles per phase (PX_BATCH_FLAG_PROFILE) */
+  /* manifold records {normal, e, sf | df, pen, c0 | c1, rcpDenom0, rcpDenom1}: float4[3] per manifold,
+   * maxManifolds per slot, PX_SCRATCH_SLOTS slots per SM id.  A CTA claims a free slot of its SM in
+   * slotMask[smid] for its lifetime, so the same few MB are rewritten every substep and stay in L2. */
+  float4 *scratch;
+  uint32_t *slotMask;
   uint32_t kSubsteps;
   uint32_t flags;
 };
+
+#define PX_SCRATCH_SLOTS 16u  /* >= resident CTAs per SM */
+#define PX_SCRATCH_SMIDS 256u /* >= %nsmid */
 
 #ifdef __cplusplus
 extern "C" {
