@@ -10,9 +10,8 @@ of 256 mixed-shape bodies (252 dynamic: 1/3 circles, 1/3 boxes, 1/3 3-8-gons; 4 
 
 value   = body-substeps/s, device-timed with CUDA events on the launching stream, state
           resident in HBM, whole job (all ranks), max over ranks.
-e2e     = same metric through the C ABI with HOST buffers: every step copies the mutable
-          blocks pinned-host -> HBM, steps, and copies them back (pxBatchMutableH2D /
-          pxBatchStep / pxBatchMutableD2H).
+e2e     = same metric through the C ABI with HOST buffers (pxBatchStepHost): every step copies
+          the mutable blocks pinned-host -> HBM, steps, copies them back and waits.
 --impl reference = the reference's own CPU step (oracle/_ref, the unmodified sources compiled
           under the PlaydateAPI host stub) on all host threads, bounded sample of the workload.
 
@@ -56,6 +55,7 @@ def parse_args():
     ap.add_argument("--max-manifolds", type=int, default=0, help="per-world manifold capacity (0 = library default)")
     ap.add_argument("--max-pairs", type=int, default=0, help="per-world AABB-pass pair capacity (0 = library default)")
     ap.add_argument("--cpu-worlds", type=int, default=0, help="worlds in the CPU baseline sample (0 = 2 per core)")
+    ap.add_argument("--e2e-chunks", type=int, default=8, help="world ranges pipelined per host-buffer step")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--profile", action="store_true", help="per-phase SM-cycle breakdown (adds clock reads)")
@@ -264,22 +264,22 @@ def run_ours(args):
     clocks = sampler.stop()
 
     # ---- end to end through the C ABI with host buffers -------------------------------
+    # pxBatchStepHost: pinned host blocks -> HBM -> FUSED substeps -> pinned host blocks, per world
+    # range, copies of one range pipelined under the substeps of another; the host waits for
+    # (and can read) the result of every step
     e2e_ms = None
     mut_bytes = b.n * b.L.mutStride
     if not args.no_e2e:
         b.mutable_d2h()
         b.sync()
         for _ in range(2):
-            b.mutable_h2d()
-            b.step(args.fused)
-            b.mutable_d2h()
+            b.step_host(args.fused, args.e2e_chunks)
+            b.sync()
         barrier()
         t0 = time.perf_counter()
         e0.record()
         for _ in range(args.steps):
-            b.mutable_h2d()
-            b.step(args.fused)
-            b.mutable_d2h()
+            b.step_host(args.fused, args.e2e_chunks)
             b.sync()  # the host reads the result of every step
         e1.record()
         barrier()

@@ -78,6 +78,7 @@ def core():
         "pxBatchUpload": (i32, [vp, pp, u32, u32]),
         "pxBatchFree": (None, [vp]),
         "pxBatchStep": (i32, [vp, u32]),
+        "pxBatchStepHost": (i32, [vp, u32, vp, u32]),
         "pxBatchStepTimed": (i32, [vp, u32, C.POINTER(C.c_float)]),
         "pxBatchSync": (i32, [vp]),
         "pxBatchReadback": (i32, [vp, pp, u32, u32, u32]),
@@ -390,6 +391,10 @@ class Batch:
     def step(self, k: int = 1):
         _check(self.lib.pxBatchStep(self.h, int(k)), "pxBatchStep")
 
+    def step_host(self, k: int = 1, chunks: int = 0, host_ptr: int | None = None):
+        """pxBatchStepHost: host buffers in, host buffers out, copies pipelined under compute."""
+        _check(self.lib.pxBatchStepHost(self.h, int(k), host_ptr, int(chunks)), "pxBatchStepHost")
+
     def step_timed(self, k: int = 1) -> float:
         ms = C.c_float(0)
         _check(self.lib.pxBatchStepTimed(self.h, int(k), C.byref(ms)), "pxBatchStepTimed")
@@ -430,6 +435,10 @@ class Batch:
 
     def immutable_h2d(self, first=0, n=None, host_ptr=None):
         _check(self.lib.pxBatchImmutableH2D(self.h, host_ptr, first, self.n - first if n is None else n), "pxBatchImmutableH2D")
+
+    def host_blocks(self) -> Blocks:
+        """Views over the pinned staging as it is (no copy, no sync)."""
+        return Blocks(self.L, self.host_mutable(), self.host_immutable())
 
     def download_blocks(self) -> Blocks:
         """Sync copy of the device state into the pinned staging; returns views over it."""

@@ -45,6 +45,10 @@ struct PxBatch {
   size_t hCmdCap;
   uint64_t launches;
   int ctasPerSm, numSms;
+  /* pxBatchStepHost: two helper streams pipeline the chunks of a host-buffer step */
+  cudaStream_t aux[2];
+  cudaEvent_t evFork, evJoin[2];
+  bool auxReady;
 };
 
 #define CU(call)                                                                                        \
@@ -69,6 +73,7 @@ extern "C" PxBatch *pxBatchCreate(uint32_t nWorlds, const PxBatchDesc *desc) {
   b->dSin = nullptr;
   b->dProf = nullptr;
   b->dScratch = nullptr;
+  b->auxReady = false;
   b->dSlotMask = nullptr;
   b->hMut = b->hImm = nullptr;
   b->dCmds = b->dGlobal = nullptr;
@@ -108,9 +113,9 @@ extern "C" PxBatch *pxBatchCreate(uint32_t nWorlds, const PxBatchDesc *desc) {
     if ((e = cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
     b->ownStream = true;
   }
-  /* 256 threads (3 CTAs/SM at <= 85 registers) for full-size worlds: the sweep, narrowphase and
-   * list phases are throughput-bound and the solver only ever uses two warps */
-  b->threads = desc->threads ? desc->threads : (b->L.maxDynamic > 128 ? 256 : 128);
+  /* 128 threads: 5 CTAs/SM (37.6 KB of shared memory and <= 102 registers each) keep the SM's
+   * issue slots busier than 3 CTAs of 256 threads */
+  b->threads = desc->threads ? desc->threads : 128;
   if (b->threads != 64 && b->threads != 128 && b->threads != 256) {
     pxSetError(-1, "PxBatchDesc.threads must be 64, 128 or 256");
     pxBatchFree(b);
@@ -124,7 +129,8 @@ extern "C" PxBatch *pxBatchCreate(uint32_t nWorlds, const PxBatchDesc *desc) {
     pxPlanSmem(&b->L, 0, &slim);
     const size_t perSm = (size_t)prop.sharedMemPerMultiprocessor, reserve = (size_t)prop.reservedSharedMemPerBlock;
     const size_t fat = perSm / (b->plan.total + reserve), thin = perSm / (slim.total + reserve);
-    if (b->plan.total > (uint32_t)prop.sharedMemPerBlockOptin || thin > fat) b->plan = slim;
+    const char *force = getenv("PX_VERTS_SMEM"); /* experiment switch: 1 = keep them in shared memory, 0 = never */
+    if (b->plan.total > (uint32_t)prop.sharedMemPerBlockOptin || (force ? force[0] == '0' : thin > fat)) b->plan = slim;
   }
 
   if (b->plan.total > (uint32_t)prop.sharedMemPerBlockOptin) {
@@ -205,6 +211,13 @@ extern "C" void pxBatchFree(PxBatch *b) {
   cudaFree(b->dSin);
   cudaFree(b->dProf);
   cudaFree(b->dScratch);
+  if (b->auxReady) {
+    for (int i = 0; i < 2; i++) {
+      cudaStreamDestroy(b->aux[i]);
+      cudaEventDestroy(b->evJoin[i]);
+    }
+    cudaEventDestroy(b->evFork);
+  }
   cudaFree(b->dSlotMask);
   cudaFree(b->dCmds);
   cudaFree(b->dGlobal);
@@ -367,26 +380,69 @@ static int flushCommands(PxBatch *b) {
 }
 
 /* --------------------------------------------------------------------------- stepping */
+/* K substeps for worlds [first, first + n) on `stream` */
+static int launchRange(PxBatch *b, uint32_t kSubsteps, uint32_t first, uint32_t n, cudaStream_t stream) {
+  PxStepParams P;
+  P.L = b->L;
+  P.L.nWorlds = n;
+  P.S = b->plan;
+  P.mut = b->dMut + (size_t)first * b->L.mutStride;
+  P.imm = b->dImm + (size_t)first * b->L.immStride;
+  P.trace = b->dTrace ? b->dTrace + (size_t)first * b->L.traceStride : nullptr;
+  P.sinTable = b->dSin;
+  P.prof = b->dProf ? b->dProf + (size_t)first * 8 : nullptr;
+  P.scratch = b->dScratch;
+  P.slotMask = b->dSlotMask;
+  P.kSubsteps = kSubsteps;
+  P.flags = b->flags;
+  int rc = pxLaunchStep(&P, b->threads, stream);
+  if (rc != 0) return pxSetError(-rc - 1000, "step kernel launch: %s", cudaGetErrorString((cudaError_t)rc));
+  b->launches++;
+  return 0;
+}
+
 extern "C" int pxBatchStep(PxBatch *b, uint32_t kSubsteps) {
   if (!b) return pxSetError(-1, "pxBatchStep: NULL batch");
   if (useDevice(b)) return -1;
   if (flushCommands(b)) return -1;
   if (kSubsteps == 0) return 0;
-  PxStepParams P;
-  P.L = b->L;
-  P.S = b->plan;
-  P.mut = b->dMut;
-  P.imm = b->dImm;
-  P.trace = b->dTrace;
-  P.sinTable = b->dSin;
-  P.prof = b->dProf;
-  P.scratch = b->dScratch;
-  P.slotMask = b->dSlotMask;
-  P.kSubsteps = kSubsteps;
-  P.flags = b->flags;
-  int rc = pxLaunchStep(&P, b->threads, b->stream);
-  if (rc != 0) return pxSetError(-rc - 1000, "step kernel launch: %s", cudaGetErrorString((cudaError_t)rc));
-  b->launches++;
+  return launchRange(b, kSubsteps, 0, b->L.nWorlds, b->stream);
+}
+
+extern "C" int pxBatchStepHost(PxBatch *b, uint32_t kSubsteps, void *hostMut, uint32_t chunks) {
+  if (!b) return pxSetError(-1, "pxBatchStepHost: NULL batch");
+  if (useDevice(b)) return -1;
+  if (flushCommands(b)) return -1;
+  uint8_t *host = hostMut ? (uint8_t *)hostMut : b->hMut;
+  const uint32_t W = b->L.nWorlds;
+  if (chunks == 0) chunks = 8;
+  if (chunks > W) chunks = W;
+  if (!b->auxReady) {
+    for (int i = 0; i < 2; i++) {
+      CU(cudaStreamCreateWithFlags(&b->aux[i], cudaStreamNonBlocking));
+      CU(cudaEventCreateWithFlags(&b->evJoin[i], cudaEventDisableTiming));
+    }
+    CU(cudaEventCreateWithFlags(&b->evFork, cudaEventDisableTiming));
+    b->auxReady = true;
+  }
+  /* fork: the helper streams start after everything already queued on the batch's stream */
+  CU(cudaEventRecord(b->evFork, b->stream));
+  for (int i = 0; i < 2; i++) CU(cudaStreamWaitEvent(b->aux[i], b->evFork, 0));
+  const size_t stride = b->L.mutStride;
+  for (uint32_t c = 0; c < chunks; c++) {
+    const uint32_t first = (uint32_t)((uint64_t)W * c / chunks), last = (uint32_t)((uint64_t)W * (c + 1) / chunks);
+    const uint32_t n = last - first;
+    if (!n) continue;
+    cudaStream_t st = b->aux[c & 1];
+    CU(cudaMemcpyAsync(b->dMut + first * stride, host + first * stride, n * stride, cudaMemcpyHostToDevice, st));
+    if (kSubsteps && launchRange(b, kSubsteps, first, n, st)) return -1;
+    CU(cudaMemcpyAsync(host + first * stride, b->dMut + first * stride, n * stride, cudaMemcpyDeviceToHost, st));
+  }
+  /* join: later work on the batch's stream (and pxBatchSync) waits for both helpers */
+  for (int i = 0; i < 2; i++) {
+    CU(cudaEventRecord(b->evJoin[i], b->aux[i]));
+    CU(cudaStreamWaitEvent(b->stream, b->evJoin[i], 0));
+  }
   return 0;
 }
 

@@ -158,3 +158,30 @@ def test_reference_side_binding_is_a_drop_in(reflib_available, unit, mix):
     assert fired > 50
     cpu.close()
     gpu.close()
+
+
+@pytest.mark.parametrize("chunks", [1, 3, 8])
+def test_host_buffer_step_is_the_same_step(chunks):
+    """pxBatchStepHost (H2D, K substeps, D2H per world range, pipelined on helper streams) leaves
+    exactly the bytes that separate H2D / step / D2H calls leave, in host memory and in HBM."""
+    sc = [scenes.pile_scene(w, mix="mixed", n_dynamic=40, cols=6) for w in range(13)]
+    wa, wb = pxb.HostWorlds(sc), pxb.HostWorlds(sc)
+    a, b = pxb.Batch(wa), pxb.Batch(wb)
+    for _ in range(6):
+        a.mutable_h2d()
+        a.step(5)
+        a.mutable_d2h()
+        a.sync()
+        b.step_host(5, chunks)
+        b.sync()
+        ha, hb = a.host_blocks(), b.host_blocks()
+        np.testing.assert_array_equal(np.asarray(ha.dyn).view(np.uint32), np.asarray(hb.dyn).view(np.uint32))
+        np.testing.assert_array_equal(ha.order, hb.order)
+        np.testing.assert_array_equal(ha.flags, hb.flags)
+    da, db = a.download_blocks(), b.download_blocks()
+    np.testing.assert_array_equal(np.asarray(da.dyn).view(np.uint32), np.asarray(db.dyn).view(np.uint32))
+    assert int(da.header["substeps"][0]) == 30
+    for x in (a, b):
+        x.close()
+    for x in (wa, wb):
+        x.close()
