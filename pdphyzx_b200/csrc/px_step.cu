@@ -106,9 +106,9 @@ __device__ __forceinline__ void stsVolatile(uint32_t a, uint32_t v) {
   asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
 }
 /* a global load the compiler may not sink below later volatile asm statements */
-__device__ __forceinline__ float4 ldcgPinned(const float4 *p) {
+__device__ __forceinline__ float4 ldgPinned(const float4 *p) {
   float4 v;
-  asm volatile("ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  asm volatile("ld.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
   return v;
 }
 __device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v)); }
@@ -179,13 +179,15 @@ struct Sm {
   uint32_t *queue;
 };
 
-/* manifold records bypass L1 (.cg): the slot is rewritten every substep and read by other
- * threads of the CTA, and L2 is where it lives anyway */
-__device__ __forceinline__ float4 manLoad(const Sm &s, uint32_t ms, uint32_t k) { return __ldcg(s.man + 3u * ms + k); }
+/* Manifold records use ordinary (L1-allocating) accesses: a slot is only ever touched by CTAs of
+ * one SM, i.e. through one L1, and writers and readers inside the CTA are separated by
+ * __syncthreads, which makes global writes visible block-wide.  A record is read once per
+ * solver iteration, so L1 hits pay. */
+__device__ __forceinline__ float4 manLoad(const Sm &s, uint32_t ms, uint32_t k) { return s.man[3u * ms + k]; }
 __device__ __forceinline__ void manStore(const Sm &s, uint32_t ms, float4 a, float4 b, float4 c) {
-  __stcg(s.man + 3u * ms + 0u, a);
-  __stcg(s.man + 3u * ms + 1u, b);
-  __stcg(s.man + 3u * ms + 2u, c);
+  s.man[3u * ms + 0u] = a;
+  s.man[3u * ms + 1u] = b;
+  s.man[3u * ms + 2u] = c;
 }
 /* {restitution, staticFriction, dynamicFriction} of a body id, from the immutable block */
 __device__ __forceinline__ float3 materialOf(const Sm &s, uint32_t id, uint32_t D, uint32_t S) {
@@ -1352,9 +1354,9 @@ __global__ void __launch_bounds__(NT, NT == 64 ? 6 : (NT == 128 ? 5 : 3)) pxStep
           if (n == 0xffffu) break;
           const uint32_t qw = lds32(aQueue + 4u * ((head + lane) & QMASK));
           w = lane < n ? qw : 0u;
-          mA = __ldcg(man + 3u * MID_SLOT(w));
-          mB = __ldcg(man + 3u * MID_SLOT(w) + 1u);
-          mC = __ldcg(man + 3u * MID_SLOT(w) + 2u);
+          mA = ldgPinned(man + 3u * MID_SLOT(w));
+          mB = ldgPinned(man + 3u * MID_SLOT(w) + 1u);
+          mC = ldgPinned(man + 3u * MID_SLOT(w) + 2u);
         }
         const bool active = lane < n;
         const uint32_t a16 = MID_A(w) * 16u, b16 = MID_B(w) * 16u;
@@ -1376,9 +1378,9 @@ __global__ void __launch_bounds__(NT, NT == 64 ? 6 : (NT == 128 ? 5 : 3)) pxStep
          * pinned ahead of the arithmetic, so the L2 round trip runs under this round's chain */
         const uint32_t qwN = lds32(aQueue + 4u * ((headNext + lane) & QMASK));
         const uint32_t wNext = (haveNext && lane < nNext) ? qwN : 0u;
-        const float4 nA = ldcgPinned(man + 3u * MID_SLOT(wNext));
-        const float4 nB = ldcgPinned(man + 3u * MID_SLOT(wNext) + 1u);
-        const float4 nC = ldcgPinned(man + 3u * MID_SLOT(wNext) + 2u);
+        const float4 nA = ldgPinned(man + 3u * MID_SLOT(wNext));
+        const float4 nB = ldgPinned(man + 3u * MID_SLOT(wNext) + 1u);
+        const float4 nC = ldgPinned(man + 3u * MID_SLOT(wNext) + 2u);
         asm volatile("" : "+f"(in.vA.x), "+f"(in.vB.x), "+f"(in.pA.x), "+f"(in.pB.x));
         contactImpulse(w, in, eps);
         sts128If(aBodyV + a16, in.vA, active);
