@@ -117,6 +117,21 @@ def measured_peak_hbm():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def kernel_facts(args):
+    """profiles/*_kernel_facts.json written by profiles/summarize.py from an ncu capture of the
+    default command line; only used when this run IS that configuration."""
+    if (args.worlds, args.mix, args.iterations, args.fused, args.threads) != (8192, "mixed", 10, 5, 0):
+        return None
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_kernel_facts.json")))
+    if not files:
+        return None
+    with open(files[-1]) as f:
+        facts = json.load(f)
+    facts["_file"] = os.path.basename(files[-1])
+    return facts
+
+
 def build_scenes(args, rank: int, n_worlds: int):
     from pdphyzx_b200 import scenes
     base = rank * args.worlds
@@ -327,9 +342,28 @@ def run_ours(args):
             "clocks": clocks, "gpu_launches": int(gpu_launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_source": peak_src,
-                         "note": "HBM is not what binds this path: the solver's dependency chain and fp32 issue do "
-                                 "(SURVEY 8d); see DESIGN.md and profiles/"},
+                         "algorithmic_bytes_per_launch": args.worlds * BODIES_PER_WORLD * alg,
+                         "note": "HBM is the nominal bound of this path (SURVEY 8d) but not the binding one: the "
+                                 "solver's dependency chain and non-FMA fp32 issue are; see roofline_issue, "
+                                 "DESIGN.md and profiles/"},
         }
+        facts = kernel_facts(args)
+        if facts:
+            # ncu of this very command line (profiles/summarize.py): DRAM bytes of one launch, and
+            # the warp instructions one world-substep costs -> issue-slot utilisation at the
+            # rate measured live above
+            out["roofline"]["traffic"] = facts["dram_bytes_per_launch"]
+            out["roofline"]["traffic_source"] = "profiles/" + facts["_file"]
+            sm_hz = (clocks.get("sm_mhz") or 1965.0) * 1e6
+            n_sms = info.get("num_sms", 148)
+            issue_peak = n_sms * 4 * sm_hz  # one warp instruction per scheduler per cycle
+            issue_rate = facts["warp_instructions_per_world_substep"] * (value / world_size) / BODIES_PER_WORLD
+            out["roofline_issue"] = {
+                "bound": "issue", "achieved": issue_rate / 1e12, "peak": issue_peak / 1e12, "unit": "T warp-instr/s",
+                "frac": issue_rate / issue_peak,
+                "warp_instructions_per_world_substep": facts["warp_instructions_per_world_substep"],
+                "lanes_per_instruction": facts["lanes_per_instruction"],
+                "note": "per GPU; instruction count from ncu (smsp__inst_executed.sum), rate from this run"}
         if args.profile:
             pr = b.profile().astype(np.float64)
             tot = pr.sum()

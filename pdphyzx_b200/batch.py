@@ -14,7 +14,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIBDIR = os.path.join(_HERE, "lib")
+_LIBDIR = os.environ.get("PX_LIBDIR") or os.path.join(_HERE, "lib")  # PX_LIBDIR: experiment builds
 _UNIT_TAG = {1.0: "m", 100.0: "cm", 1000.0: "mm"}
 
 ALL_WORLDS = 0xFFFFFFFF

@@ -395,6 +395,10 @@ static int launchRange(PxBatch *b, uint32_t kSubsteps, uint32_t first, uint32_t 
   P.slotMask = b->dSlotMask;
   P.kSubsteps = kSubsteps;
   P.flags = b->flags;
+  {
+    static const char *ns = getenv("PX_LAG_SLEEP_NS"); /* experiment switch */
+    P.lagSleepNs = ns ? (uint32_t)atoi(ns) : 500u;
+  }
   int rc = pxLaunchStep(&P, b->threads, stream);
   if (rc != 0) return pxSetError(-rc - 1000, "step kernel launch: %s", cudaGetErrorString((cudaError_t)rc));
   b->launches++;

@@ -199,7 +199,10 @@ __device__ __forceinline__ float3 materialOf(const Sm &s, uint32_t id, uint32_t 
 /* misc[] slots */
 enum { MI_MCOUNT = 0, MI_QTAIL, MI_OVERFLOW, MI_UNSORTED, MI_SLEEPING, MI_VISITS, MI_MATHROUND, MI_SLOT, MI_RDESC = 16 };
 #define PX_RING 16u /* round descriptors in flight (misc[MI_RDESC..]) */
-#define PX_LAG 8u   /* rounds the scheduler warp may run ahead of the math warp */
+#ifndef PX_LAG
+#define PX_LAG 8u
+#endif
+//   /* rounds the scheduler warp may run ahead of the math warp */
 
 /*
  * Rich manifold word (mids[] and ready-queue entries):
@@ -357,7 +360,9 @@ __device__ __forceinline__ float faceSeparation(const DBody &A, const DBody &B, 
 /* pxFindAxisLeastPenetration evaluated by the PX_SAT_LANES lanes of a pair group: lane q takes
  * faces q, q + PX_SAT_LANES, ...; the reference keeps the FIRST face among the maxima (strict
  * `>` while scanning upwards), which the (value, lowest index) reduction reproduces. */
-#define PX_SAT_LANES 4u
+#ifndef PX_SAT_LANES
+#define PX_SAT_LANES 2u
+#endif
 __device__ __forceinline__ float leastPenetrationGroup(uint32_t &faceIndex, const DBody &A, const DBody &B, uint32_t q,
                                                        bool valid, float epsSq) {
   float bestD = -FLT_MAX;
@@ -1284,7 +1289,7 @@ __global__ void __launch_bounds__(NT, NT == 64 ? 6 : (NT == 128 ? 5 : 3)) pxStep
       while (head != tail) {
         const uint32_t n = min(tail - head, 32u);
         while (rounds - mr >= PX_LAG) { /* far enough ahead: leave the issue slots to the others */
-          __nanosleep(64);
+          __nanosleep(P.lagSleepNs);
           mr = ldsVolatile(aMathRound);
         }
         asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(aDesc + 4u * (rounds & (PX_RING - 1u))),

@@ -60,6 +60,7 @@ struct PxStepParams {
   uint32_t *slotMask;
   uint32_t kSubsteps;
   uint32_t flags;
+  uint32_t lagSleepNs; /* scheduler warp: nanosleep while it is PX_LAG rounds ahead of the math warp */
 };
 
 #define PX_SCRATCH_SLOTS 16u  /* >= resident CTAs per SM */

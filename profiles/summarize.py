@@ -1,0 +1,119 @@
+#!/usr/bin/env python
+"""Turn an `ncu --set full --import-source on` report of the step kernel into the tracked
+summaries under profiles/ (the .ncu-rep itself stays in gpurun_out/, which is scratch).
+
+    python profiles/summarize.py gpurun_out/r01_full.ncu-rep r01 --worlds 8192 --fused 5
+
+writes
+    profiles/<tag>_ncu_raw.csv          every raw metric of the launch (metric,unit,value)
+    profiles/<tag>_segments.txt         SASS segments between barriers: share of samples and of
+                                        instructions, stall mix, lanes per instruction
+    profiles/<tag>_hot_instructions.txt the 60 most-sampled SASS instructions with their stalls
+    profiles/<tag>_kernel_facts.json    the numbers bench.py folds into its JSON line
+                                        (DRAM bytes and warp instructions per launch)
+Runs here (no GPU): needs only the `ncu` CLI to read the report.
+"""
+from __future__ import annotations
+
+import argparse
+import collections
+import csv
+import io
+import json
+import os
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def ncu_csv(rep: str, *args: str):
+    out = subprocess.run(["ncu", "-i", rep, "--csv", *args], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True).stdout
+    return list(csv.reader(io.StringIO(out)))
+
+
+def to_bytes(value: str, unit: str) -> float:
+    scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[unit]
+    return float(value) * scale
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("report")
+    ap.add_argument("tag")
+    ap.add_argument("--worlds", type=int, required=True)
+    ap.add_argument("--fused", type=int, required=True)
+    a = ap.parse_args()
+    world_substeps = a.worlds * a.fused
+
+    raw = ncu_csv(a.report, "--page", "raw")
+    hdr, units, vals = raw[0], raw[1], raw[2]
+    metrics = {h: (units[i], vals[i]) for i, h in enumerate(hdr)}
+    with open(os.path.join(HERE, f"{a.tag}_ncu_raw.csv"), "w") as f:
+        f.write("metric,unit,value\n")
+        for h in sorted(metrics):
+            if "__" in h or h.startswith("launch"):
+                f.write(f"{h},{metrics[h][0]},{metrics[h][1]}\n")
+
+    def m(name):
+        return float(metrics[name][1])
+
+    rd = to_bytes(metrics["dram__bytes_read.sum"][1], metrics["dram__bytes_read.sum"][0])
+    wr = to_bytes(metrics["dram__bytes_write.sum"][1], metrics["dram__bytes_write.sum"][0])
+    facts = {
+        "kernel": "pxStepKernel",
+        "worlds": a.worlds, "fused_substeps": a.fused,
+        "gpu_time_ms_under_ncu": m("gpu__time_duration.sum") * (1e-6 if metrics["gpu__time_duration.sum"][0] == "ns" else 1.0),
+        "dram_bytes_read": rd, "dram_bytes_write": wr, "dram_bytes_per_launch": rd + wr,
+        "warp_instructions_per_launch": m("smsp__inst_executed.sum"),
+        "warp_instructions_per_world_substep": m("smsp__inst_executed.sum") / world_substeps,
+        "issue_active_pct": m("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+        "lanes_per_instruction": m("smsp__thread_inst_executed_per_inst_executed.ratio"),
+        "registers_per_thread": m("launch__registers_per_thread"),
+        "shared_mem_per_block_bytes": m("launch__shared_mem_per_block_dynamic") * 1e3,
+        "l2_hit_rate_pct": m("lts__t_sector_hit_rate.pct"),
+        "source": os.path.basename(a.report),
+    }
+    with open(os.path.join(HERE, f"{a.tag}_kernel_facts.json"), "w") as f:
+        json.dump(facts, f, indent=1)
+        f.write("\n")
+
+    src = ncu_csv(a.report, "--page", "source")
+    hdr, data = src[1], src[2:]
+    i_src, i_smp, i_ie, i_te = (hdr.index(x) for x in ("Source", "# Samples", "Instructions Executed", "Thread Instructions Executed"))
+    stalls = [(i, h[6:]) for i, h in enumerate(hdr) if h.startswith("stall_") and "Not Issued" not in h]
+    total_smp = sum(int(r[i_smp]) for r in data) or 1
+    total_ie = sum(int(r[i_ie]) for r in data) or 1
+    bars = [k for k, r in enumerate(data) if "BAR.SYNC" in r[i_src] or "BAR.RED" in r[i_src]]
+    with open(os.path.join(HERE, f"{a.tag}_segments.txt"), "w") as f:
+        f.write(f"# SASS segments between CTA barriers of pxStepKernel ({len(data)} instructions); samples attributed to a\n"
+                f"# barrier wait show up on the first instruction AFTER the barrier.  {os.path.basename(a.report)}\n"
+                f"# columns: first-last SASS index, share of warp samples, share of executed warp instructions,\n"
+                f"#          warp instructions per world-substep, lanes per instruction, top stall reasons (% of segment)\n")
+        prev = 0
+        for b in bars + [len(data) - 1]:
+            seg = data[prev:b + 1]
+            smp = sum(int(r[i_smp]) for r in seg)
+            ie = sum(int(r[i_ie]) for r in seg)
+            te = sum(int(r[i_te]) for r in seg)
+            if smp > 0.004 * total_smp or ie > 0.004 * total_ie:
+                c = collections.Counter()
+                for r in seg:
+                    for i, name in stalls:
+                        c[name] += int(r[i])
+                tot = sum(c.values()) or 1
+                mix = " ".join(f"{k}:{100 * v / tot:.0f}" for k, v in c.most_common(5))
+                f.write(f"{prev:6d}-{b:6d}  samples {100 * smp / total_smp:5.1f}%  instr {100 * ie / total_ie:5.1f}%  "
+                        f"{ie / world_substeps:9.0f}/ws  lanes {te / max(ie, 1):4.1f}  {mix}\n")
+            prev = b + 1
+    with open(os.path.join(HERE, f"{a.tag}_hot_instructions.txt"), "w") as f:
+        f.write("# most-sampled SASS instructions: index, executions, share of samples, top stalls, instruction\n")
+        for k in sorted(range(len(data)), key=lambda k: -int(data[k][i_smp]))[:60]:
+            r = data[k]
+            st = sorted(((int(r[i]), name) for i, name in stalls), reverse=True)[:3]
+            f.write(f"{k:6d} {int(r[i_ie]):11d} {100 * int(r[i_smp]) / total_smp:5.2f}%  "
+                    + " ".join(f"{name}:{v}" for v, name in st if v) + "  | " + r[i_src].strip()[:90] + "\n")
+    print(json.dumps(facts))
+
+
+if __name__ == "__main__":
+    main()
