@@ -56,6 +56,9 @@ def parse_args():
     ap.add_argument("--max-pairs", type=int, default=0, help="per-world AABB-pass pair capacity (0 = library default)")
     ap.add_argument("--cpu-worlds", type=int, default=0, help="worlds in the CPU baseline sample (0 = 2 per core)")
     ap.add_argument("--e2e-chunks", type=int, default=8, help="world ranges pipelined per host-buffer step")
+    ap.add_argument("--control", action="store_true",
+                    help="BASELINE config 5: polygon stacks, PDPHYZX_UNIT_MM, every step the host queues one applyImpulse per "
+                         "world and a setGravity before stepping --fused substeps (compare --fused 1 with --fused 8)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--profile", action="store_true", help="per-phase SM-cycle breakdown (adds clock reads)")
@@ -135,11 +138,18 @@ def kernel_facts(args):
 def build_scenes(args, rank: int, n_worlds: int):
     from pdphyzx_b200 import scenes
     base = rank * args.worlds
+    if args.control:
+        return [scenes.stack_scene(base + w, seed=args.seed, n_dynamic=N_DYNAMIC, iterations=args.iterations, cols=21)
+                for w in range(n_worlds)]
     return [scenes.pile_scene(base + w, seed=args.seed, mix=args.mix, iterations=args.iterations, n_dynamic=N_DYNAMIC)
             for w in range(n_worlds)]
 
 
 def workload_name(args, n_gpus):
+    if args.control:
+        return (f"{args.worlds} worlds/GPU x polygon stacks ({N_DYNAMIC} dynamic bodies), {args.iterations} iterations, "
+                f"PDPHYZX_UNIT_MM, host-driven applyImpulse per world + setGravity before every step of "
+                f"{args.fused} substeps (BASELINE config 5)")
     return (f"{args.worlds} worlds/GPU x {BODIES_PER_WORLD} {args.mix} bodies ({N_DYNAMIC} dynamic + 4 static), "
             f"{args.iterations} iterations, PDPHYZX_UNIT_M, penned pile settled {args.settle} substeps "
             f"(north_star target scene: 65,536 worlds on 8 GPUs)")
@@ -269,11 +279,29 @@ def run_ours(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = b.launches
     barrier()
+    ctl = None
+    if args.control:
+        rng = np.random.default_rng(args.seed + rank)
+        ctl = (np.arange(b.n, dtype=np.uint32), rng.integers(0, N_DYNAMIC, b.n).astype(np.uint32),
+               rng.uniform(-2.0, 2.0, (b.n, 2)).astype(np.float32))
+
+    def control(i):
+        if ctl is not None:  # the commands are queued on the host and applied by a kernel before the substeps
+            b.apply_impulses(ctl[0], ctl[1], ctl[2])
+            b.set_gravity(0xFFFFFFFF, 0.0, 9.8 + 0.001 * (i % 7))
+
+    control(0)
+    b.step(args.fused)
+    barrier()
+    launches0 = b.launches
+    t_host0 = time.perf_counter()
     e0.record()
-    for _ in range(args.steps):
+    for i in range(args.steps):
+        control(i)
         b.step(args.fused)
     e1.record()
     barrier()
+    host_ms = 1e3 * (time.perf_counter() - t_host0)
     ms = e0.elapsed_time(e1)
     gpu_launches = b.launches - launches0
     clocks = sampler.stop()
@@ -338,6 +366,7 @@ def run_ours(args):
                 "smem_bytes_per_cta": info["smem_bytes"], "seed": args.seed,
                 "avg_manifolds_per_world": stats[0], "avg_pairs_per_world": stats[1],
                 "avg_sleeping_per_world": stats[2], "worlds_overflowed": int(stats[3]),
+                **({"host_wall_ms_per_step": host_ms / args.steps} if args.control else {}),
             },
             "clocks": clocks, "gpu_launches": int(gpu_launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -399,6 +428,8 @@ def run_ours(args):
 
 def main():
     args = parse_args()
+    if args.control:  # the control bench reports the device-timed rate and the host-side queueing time only
+        args.no_cpu = args.no_e2e = True
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)

@@ -206,6 +206,11 @@ PX_API int pxBatchReadback(PxBatch *b, struct PxWorld *const *worlds, uint32_t f
 /* px->body->applyImpulse: scales by the unit, v += J*iM, w += cross(c, J)*iI, wakes the body
  * (src/px_body_api.c:37-42, src/px_body.c:147-156, 195-202) */
 PX_API int pxBatchApplyImpulse(PxBatch *b, uint32_t world, uint32_t body, float ix, float iy, float cx, float cy);
+/* n applyImpulse calls in one (per-step control of many worlds): element i acts on body bodies[i]
+ * of world worlds[i] with impulse impulseXY[2i..], contact contactXY[2i..] (NULL = body centre);
+ * queued and ordered exactly like n single calls */
+PX_API int pxBatchApplyImpulses(PxBatch *b, uint32_t n, const uint32_t *worlds, const uint32_t *bodies, const float *impulseXY,
+                                const float *contactXY);
 /* px->body->applyForce (src/px_body_api.c:20-26, src/px_body.c:158-165) */
 PX_API int pxBatchApplyForce(PxBatch *b, uint32_t world, uint32_t body, float fx, float fy, float cx, float cy);
 /* px->world->setGravity: stores (x, y) * unit (src/px_world.c:57-63) */

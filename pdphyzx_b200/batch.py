@@ -83,6 +83,7 @@ def core():
         "pxBatchSync": (i32, [vp]),
         "pxBatchReadback": (i32, [vp, pp, u32, u32, u32]),
         "pxBatchApplyImpulse": (i32, [vp, u32, u32, f, f, f, f]),
+        "pxBatchApplyImpulses": (i32, [vp, u32, vp, vp, vp, vp]),
         "pxBatchApplyForce": (i32, [vp, u32, u32, f, f, f, f]),
         "pxBatchSetGravity": (i32, [vp, u32, f, f]),
         "pxBatchSetIterations": (i32, [vp, u32, u32]),
@@ -406,6 +407,16 @@ class Batch:
     # -- control -------------------------------------------------------------------------
     def apply_impulse(self, world, body, ix, iy, cx, cy):
         _check(self.lib.pxBatchApplyImpulse(self.h, world, body, ix, iy, cx, cy), "pxBatchApplyImpulse")
+
+    def apply_impulses(self, worlds, bodies, impulse_xy, contact_xy=None):
+        """pxBatchApplyImpulses: one applyImpulse per element, queued in order."""
+        w = np.ascontiguousarray(worlds, np.uint32)
+        bd = np.ascontiguousarray(bodies, np.uint32)
+        imp = np.ascontiguousarray(impulse_xy, np.float32).reshape(-1, 2)
+        con = None if contact_xy is None else np.ascontiguousarray(contact_xy, np.float32).reshape(-1, 2)
+        assert w.size == bd.size == imp.shape[0] and (con is None or con.shape[0] == w.size)
+        _check(self.lib.pxBatchApplyImpulses(self.h, w.size, w.ctypes.data, bd.ctypes.data, imp.ctypes.data,
+                                             None if con is None else con.ctypes.data), "pxBatchApplyImpulses")
 
     def apply_force(self, world, body, fx, fy, cx, cy):
         _check(self.lib.pxBatchApplyForce(self.h, world, body, fx, fy, cx, cy), "pxBatchApplyForce")

@@ -324,6 +324,17 @@ extern "C" int pxBatchApplyForce(PxBatch *b, uint32_t world, uint32_t body, floa
   if (world == PX_ALL_WORLDS) return pxSetError(-1, "pxBatchApplyForce: needs a world index");
   return pushCommand(b, world, PX_CMD_FORCE, body, fx, fy, cx, cy, "pxBatchApplyForce");
 }
+extern "C" int pxBatchApplyImpulses(PxBatch *b, uint32_t n, const uint32_t *worlds, const uint32_t *bodies, const float *impulseXY,
+                                    const float *contactXY) {
+  if (!worlds || !bodies || !impulseXY) return pxSetError(-1, "pxBatchApplyImpulses: NULL argument");
+  for (uint32_t i = 0; i < n; i++) {
+    if (worlds[i] == PX_ALL_WORLDS) return pxSetError(-1, "pxBatchApplyImpulses: element %u needs a world index", i);
+    int rc = pushCommand(b, worlds[i], PX_CMD_IMPULSE, bodies[i], impulseXY[2 * i], impulseXY[2 * i + 1],
+                         contactXY ? contactXY[2 * i] : 0.0f, contactXY ? contactXY[2 * i + 1] : 0.0f, "pxBatchApplyImpulses");
+    if (rc) return rc;
+  }
+  return 0;
+}
 extern "C" int pxBatchSetGravity(PxBatch *b, uint32_t world, float x, float y) {
   return pushCommand(b, world, PX_CMD_GRAVITY, 0, x, y, 0, 0, "pxBatchSetGravity");
 }

@@ -185,3 +185,69 @@ def test_host_buffer_step_is_the_same_step(chunks):
         x.close()
     for x in (wa, wb):
         x.close()
+
+
+def test_spawn_and_despawn_between_frames(reflib_available):
+    """px->world->newDynamicBody / freeBody on a world that is being stepped on
+    the device (examples/draw spawns and frees circles while running).  Slot reuse, the
+    swap-remove of activeIndices and the re-sort change the iteration order and with it the
+    solver order; the facade re-packs the world, so every frame must still match the reference."""
+    sc = scenes.pile_scene(9, mix="mixed", n_dynamic=50, cols=8, unit=1000.0)
+    ref = refbind.RefWorld(sc, "wide")
+    worlds = pxb.HostWorlds([sc])
+    h, w = worlds.lib, worlds.ptrs[0]
+    rng = np.random.default_rng(3)
+    empty = np.zeros(2, np.float32)
+    t = 100
+    live = [s for s, d in zip(ref.slots, sc.dynamic) if d]
+    for frame in range(90):
+        t += 20
+        ref.lib.ref_set_time_ms(t)
+        h.pxh_set_time_ms(t)
+        assert ref.lib.ref_step(ref.w) == h.pxh_step(w)
+        rr, rf, ro = ref.bodies(True)
+        hr, hf, ho = worlds.bodies(0, True)
+        np.testing.assert_array_equal(ro, ho, err_msg=f"frame {frame}: order")
+        np.testing.assert_array_equal(bits(rr[ro][:, :18]), bits(hr[ro][:, :18]), err_msg=f"frame {frame}")
+        if frame % 7 == 3 and live:  # despawn a random live body
+            slot = live.pop(int(rng.integers(0, len(live))))
+            ref.lib.ref_free_body(ref.w, 1, slot)
+            h.pxh_free_body(w, 1, slot)
+        if frame % 5 == 1:  # spawn a circle or a box above the pile; slots are reused
+            kind = int(rng.integers(0, 2))
+            x, y = float(np.float32(rng.uniform(3000, 9000))), float(np.float32(-2000.0))
+            p0, p1 = (250.0, 0.0) if kind == 0 else (400.0, 300.0)
+            a = ref.lib.ref_add_body(ref.w, 1, kind, p0, p1, empty, 0, 1.0, x, y, 0.2, 0.5, 0.3)
+            b = h.pxh_add_body(w, 1, kind, p0, p1, empty, 0, 1.0, x, y, 0.2, 0.5, 0.3)
+            assert a == b
+            if a >= 0:
+                live.append(a)
+    worlds.close()
+    ref.close()
+
+
+def test_vectorised_impulses_equal_single_calls():
+    """pxBatchApplyImpulses(n, ...) queues exactly what n pxBatchApplyImpulse calls queue."""
+    n = 9
+    sc = [scenes.stack_scene(w, n_dynamic=20) for w in range(n)]
+    wa, wb = pxb.HostWorlds(sc), pxb.HostWorlds(sc)
+    a, b = pxb.Batch(wa), pxb.Batch(wb)
+    rng = np.random.default_rng(11)
+    for it in range(25):
+        ws = rng.integers(0, n, 2 * n).astype(np.uint32)  # several commands per world, any order
+        bodies = rng.integers(0, 20, ws.size).astype(np.uint32)
+        imp = rng.uniform(-4, 4, (ws.size, 2)).astype(np.float32)
+        con = rng.uniform(-2, 2, (ws.size, 2)).astype(np.float32)
+        for i in range(ws.size):
+            a.apply_impulse(int(ws[i]), int(bodies[i]), float(imp[i, 0]), float(imp[i, 1]), float(con[i, 0]), float(con[i, 1]))
+        b.apply_impulses(ws, bodies, imp, con)
+        a.set_gravity(pxb.ALL_WORLDS, 0.0, 9.0 + it * 0.01)
+        b.set_gravity(pxb.ALL_WORLDS, 0.0, 9.0 + it * 0.01)
+        a.step(3)
+        b.step(3)
+    da, db = a.download_blocks(), b.download_blocks()
+    np.testing.assert_array_equal(np.asarray(da.mut), np.asarray(db.mut))
+    for x in (a, b):
+        x.close()
+    for x in (wa, wb):
+        x.close()
