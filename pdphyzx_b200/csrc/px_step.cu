@@ -651,6 +651,141 @@ __device__ __forceinline__ void copyRows(float *dst, const float *src, uint32_t 
   for (uint32_t i = threadIdx.x; i < nFloats / 4; i += NT) d4[i] = s4[i];
 }
 
+/* ------------------------------------------------------------------ solver warps */
+/* The two solver loops are functions of their own (never inlined): their register allocation
+ * is then independent of the rest of the kernel, whose pressure (narrowphase, sweep) would
+ * otherwise spill into these latency-critical chains. */
+struct SolverCtx {
+  uint32_t aQueue, aNext, aMids, aSig, aDesc, aMathRound, aBodyP, aBodyV;
+  uint32_t qmask, qcap, iterations, tail0, lagSleepNs;
+  const float4 *man;
+  float eps;
+};
+
+/* returns rounds | (visits is left in *visitsOut) */
+__device__ __noinline__ uint32_t solverSchedule(const SolverCtx c, uint32_t *visitsOut) {
+  const uint32_t lane = threadIdx.x & 31u, QMASK = c.qmask, iterations = c.iterations;
+  const uint32_t aQueue = c.aQueue, aNext = c.aNext, aMids = c.aMids, aSig = c.aSig, aDesc = c.aDesc, aMathRound = c.aMathRound;
+  uint32_t head = 0, tail = c.tail0, visits = 0, rounds = 0;
+  const uint32_t aDummy = aQueue + 4u * c.qcap; /* queue[qcap] is a write-only sink */
+  const uint32_t lt = (1u << lane) - 1u;
+  uint32_t mr = 0;
+#pragma unroll 2
+  while (head != tail) {
+    const uint32_t n = min(tail - head, 32u);
+    while (rounds - mr >= PX_LAG) { /* far enough ahead: leave the issue slots to the others */
+      __nanosleep(c.lagSleepNs);
+      mr = ldsVolatile(aMathRound);
+    }
+    asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(aDesc + 4u * (rounds & (PX_RING - 1u))),
+                 "r"(((rounds + 1u) << 16) | n)
+                 : "memory");
+    const bool active = lane < n;
+    const uint32_t qw = lds32(aQueue + 4u * ((head + lane) & QMASK));
+    const uint32_t w = active ? qw : 0u; /* idle lanes: a harmless word, every index in range */
+    const bool again = active && (MID_CI(w) + 1u < MID_COUNT(w)); /* second contact follows */
+    const bool sigA = active && !again, sigB = sigA && MID_BDYN(w);
+    /* successors of this manifold on body a / body b are fixed for the substep:
+     * slot | successor has a dynamic B << 14 | successor's side for this body << 15 */
+    const uint32_t nx = lds32(aNext + 4u * MID_SLOT(w)); /* side a | side b << 16 */
+    /* (the b half is unset when B is static, the a half when no manifold 0 exists) */
+    const uint32_t t0 = sigA ? (nx & 0x3ffu) : 0u, t1 = sigB ? ((nx >> 16) & 0x3ffu) : 0u;
+    const uint32_t wt0 = lds32(aMids + 4u * t0), wt1 = lds32(aMids + 4u * t1);
+    /* an idle side adds 0: no branch around the atomics */
+    const uint32_t old0 = atomAddS(aSig + 4u * t0, sigA ? ((nx & 0x8000u) ? 0x10000u : 1u) : 0u);
+    const uint32_t old1 = atomAddS(aSig + 4u * t1, sigB ? ((nx & 0x80000000u) ? 0x10000u : 1u) : 0u);
+    const uint32_t mine0 = ((nx & 0x8000u) ? (old0 >> 16) : (old0 & 0xffffu)) + 1u;
+    const uint32_t other0 = (nx & 0x8000u) ? (old0 & 0xffffu) : (old0 >> 16);
+    const uint32_t mine1 = ((nx & 0x80000000u) ? (old1 >> 16) : (old1 & 0xffffu)) + 1u;
+    const uint32_t other1 = (nx & 0x80000000u) ? (old1 & 0xffffu) : (old1 >> 16);
+    const bool ready0 = sigA && mine0 <= iterations && (!(nx & 0x4000u) || other0 == mine0);
+    const bool ready1 = sigB && mine1 <= iterations && (!(nx & 0x40000000u) || other1 == mine1);
+    const bool has0 = again || ready0;
+    const uint32_t push0 = again ? (w | (1u << 30)) : wt0;
+    const uint32_t b0 = __ballot_sync(0xffffffffu, has0);
+    const uint32_t b1 = __ballot_sync(0xffffffffu, ready1);
+    const uint32_t c0 = __popc(b0);
+    sts32(has0 ? aQueue + 4u * ((tail + __popc(b0 & lt)) & QMASK) : aDummy, push0);
+    sts32(ready1 ? aQueue + 4u * ((tail + c0 + __popc(b1 & lt)) & QMASK) : aDummy, wt1);
+    tail += c0 + __popc(b1);
+    head += n;
+    visits += sigA ? 1u : 0u;
+    rounds++;
+    mr = ldsVolatile(aMathRound);
+    __syncwarp();
+  }
+  asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(aDesc + 4u * (rounds & (PX_RING - 1u))),
+               "r"(((rounds + 1u) << 16) | 0xffffu) /* end of schedule */
+               : "memory");
+  *visitsOut = visits;
+  return rounds;
+}
+
+__device__ __noinline__ void solverMath(const SolverCtx c) {
+  const uint32_t lane = threadIdx.x & 31u, QMASK = c.qmask;
+  const uint32_t aQueue = c.aQueue, aDesc = c.aDesc, aMathRound = c.aMathRound, aBodyP = c.aBodyP, aBodyV = c.aBodyV;
+  const float4 *man = c.man;
+  const float eps = c.eps;
+  /* software pipeline: while round r runs, the queue word and the three manifold records of
+   * round r + 1 are already in flight from L2 (the scheduler is rounds ahead, so its
+   * descriptor is normally there); only velocities and the frozen body rows are read at the
+   * last moment, from shared memory */
+  uint32_t head = 0, r = 0, d = ldsAcquire(aDesc);
+  uint32_t w = 0, n = 0;
+  float4 mA, mB, mC;
+  bool have = false; /* w / n / m* hold round r */
+  for (;; r++) {
+    if (!have) {
+      const uint32_t expect = ((r + 1u) & 0xffffu) << 16;
+      while ((d ^ expect) > 0xffffu) d = ldsAcquire(aDesc + 4u * (r & (PX_RING - 1u)));
+      n = d & 0xffffu;
+      if (n == 0xffffu) break;
+      const uint32_t qw = lds32(aQueue + 4u * ((head + lane) & QMASK));
+      w = lane < n ? qw : 0u;
+      mA = ldgPinned(man + 3u * MID_SLOT(w));
+      mB = ldgPinned(man + 3u * MID_SLOT(w) + 1u);
+      mC = ldgPinned(man + 3u * MID_SLOT(w) + 2u);
+    }
+    const bool active = lane < n;
+    const uint32_t a16 = MID_A(w) * 16u, b16 = MID_B(w) * 16u;
+    ContactIn in;
+    in.mA = mA;
+    in.mB = mB;
+    in.mC = mC;
+    in.pA = lds128(aBodyP + a16);
+    in.pB = lds128(aBodyP + b16);
+    in.vA = lds128(aBodyV + a16);
+    in.vB = lds128(aBodyV + b16);
+    /* next round: descriptor, queue word, records */
+    const uint32_t headNext = head + n;
+    const uint32_t dn = ldsAcquire(aDesc + 4u * ((r + 1u) & (PX_RING - 1u)));
+    const uint32_t expectN = ((r + 2u) & 0xffffu) << 16;
+    const bool haveNext = (dn ^ expectN) <= 32u;
+    const uint32_t nNext = dn & 0xffffu;
+    /* issued unconditionally (an unpublished round reads manifold 0 and is redone above) and
+     * pinned ahead of the arithmetic, so the L2 round trip runs under this round's chain */
+    const uint32_t qwN = lds32(aQueue + 4u * ((headNext + lane) & QMASK));
+    const uint32_t wNext = (haveNext && lane < nNext) ? qwN : 0u;
+    const float4 nA = ldgPinned(man + 3u * MID_SLOT(wNext));
+    const float4 nB = ldgPinned(man + 3u * MID_SLOT(wNext) + 1u);
+    const float4 nC = ldgPinned(man + 3u * MID_SLOT(wNext) + 2u);
+    asm volatile("" : "+f"(in.vA.x), "+f"(in.vB.x), "+f"(in.pA.x), "+f"(in.pB.x));
+    contactImpulse(w, in, eps);
+    sts128If(aBodyV + a16, in.vA, active);
+    sts128If(aBodyV + b16, in.vB, active && MID_BDYN(w));
+    head = headNext;
+    __syncwarp();
+    stsVolatile(aMathRound, r + 1u);
+    have = haveNext;
+    d = dn;
+    w = wNext;
+    n = nNext;
+    mA = nA;
+    mB = nB;
+    mC = nC;
+  }
+}
+
 #define PX_DMAX 256 /* dynamic slots per world (PX_MAX_BODIES rounded up to the copy granule) */
 
 /* ============================================================================ kernel ==== */
@@ -916,16 +1051,17 @@ __global__ void __launch_bounds__(NT, NT == 64 ? 6 : (NT == 128 ? 5 : 3)) pxStep
       auto emit = [&](uint32_t bId, uint32_t bPoly, uint32_t traceB) {
         const uint32_t t = aPoly + bPoly;
         const uint32_t at = binAt[t]++;
-        if (at >= MP) {
-          /* pair overflow (flagged): the world's results are unspecified from here on */
-        } else if (seq < MP) {
-          s.bins[at] = (seq << 17) | (aSlot << 9) | bId;
+        /* pair overflow (flagged): pairs beyond either capacity are dropped and the world's
+         * results are unspecified from here on -- but every sequence number below MP must still
+         * be reset, or phase D would link last substep's manifold slot to it */
+        if (seq < MP) {
           s.validSlot[seq] = 0;
+          if (at < MP) s.bins[at] = (seq << 17) | (aSlot << 9) | bId;
           if (tpA) {
             tpA[seq] = (uint16_t)aSlot;
             tpA[MP + seq] = (uint16_t)traceB;
           }
-        } else {
+        } else if (at < MP) {
           s.bins[at] = 0xffffffffu;
         }
         seq++;
@@ -1279,59 +1415,14 @@ __global__ void __launch_bounds__(NT, NT == 64 ? 6 : (NT == 128 ? 5 : 3)) pxStep
        * unexecuted segments from being overwritten (qcap >= MM + 32 * (PX_LAG + 1)).
        * The loop body is branch-free: idle lanes and absent pushes go to a dummy slot.
        */
-      uint32_t head = 0, tail = s.misc[MI_QTAIL], visits = 0, rounds = 0;
-      const uint32_t aQueue = sAddr(s.queue), aNext = sAddr(s.nextw), aMids = sAddr(s.mids), aSig = sAddr(s.sig);
-      const uint32_t aDesc = sAddr(s.misc + MI_RDESC), aMathRound = sAddr(s.misc + MI_MATHROUND);
-      const uint32_t aDummy = aQueue + 4u * P.S.qcap; /* queue[qcap] is a write-only sink */
-      const uint32_t lt = (1u << lane) - 1u;
-      uint32_t mr = 0;
-#pragma unroll 2
-      while (head != tail) {
-        const uint32_t n = min(tail - head, 32u);
-        while (rounds - mr >= PX_LAG) { /* far enough ahead: leave the issue slots to the others */
-          __nanosleep(P.lagSleepNs);
-          mr = ldsVolatile(aMathRound);
-        }
-        asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(aDesc + 4u * (rounds & (PX_RING - 1u))),
-                     "r"(((rounds + 1u) << 16) | n)
-                     : "memory");
-        const bool active = lane < n;
-        const uint32_t qw = lds32(aQueue + 4u * ((head + lane) & QMASK));
-        const uint32_t w = active ? qw : 0u; /* idle lanes: a harmless word, every index in range */
-        const bool again = active && (MID_CI(w) + 1u < MID_COUNT(w)); /* second contact follows */
-        const bool sigA = active && !again, sigB = sigA && MID_BDYN(w);
-        /* successors of this manifold on body a / body b are fixed for the substep:
-         * slot | successor has a dynamic B << 14 | successor's side for this body << 15 */
-        const uint32_t nx = lds32(aNext + 4u * MID_SLOT(w)); /* side a | side b << 16 */
-        /* (the b half is unset when B is static, the a half when no manifold 0 exists) */
-        const uint32_t t0 = sigA ? (nx & 0x3ffu) : 0u, t1 = sigB ? ((nx >> 16) & 0x3ffu) : 0u;
-        const uint32_t wt0 = lds32(aMids + 4u * t0), wt1 = lds32(aMids + 4u * t1);
-        /* an idle side adds 0: no branch around the atomics */
-        const uint32_t old0 = atomAddS(aSig + 4u * t0, sigA ? ((nx & 0x8000u) ? 0x10000u : 1u) : 0u);
-        const uint32_t old1 = atomAddS(aSig + 4u * t1, sigB ? ((nx & 0x80000000u) ? 0x10000u : 1u) : 0u);
-        const uint32_t mine0 = ((nx & 0x8000u) ? (old0 >> 16) : (old0 & 0xffffu)) + 1u;
-        const uint32_t other0 = (nx & 0x8000u) ? (old0 & 0xffffu) : (old0 >> 16);
-        const uint32_t mine1 = ((nx & 0x80000000u) ? (old1 >> 16) : (old1 & 0xffffu)) + 1u;
-        const uint32_t other1 = (nx & 0x80000000u) ? (old1 & 0xffffu) : (old1 >> 16);
-        const bool ready0 = sigA && mine0 <= iterations && (!(nx & 0x4000u) || other0 == mine0);
-        const bool ready1 = sigB && mine1 <= iterations && (!(nx & 0x40000000u) || other1 == mine1);
-        const bool has0 = again || ready0;
-        const uint32_t push0 = again ? (w | (1u << 30)) : wt0;
-        const uint32_t b0 = __ballot_sync(0xffffffffu, has0);
-        const uint32_t b1 = __ballot_sync(0xffffffffu, ready1);
-        const uint32_t c0 = __popc(b0);
-        sts32(has0 ? aQueue + 4u * ((tail + __popc(b0 & lt)) & QMASK) : aDummy, push0);
-        sts32(ready1 ? aQueue + 4u * ((tail + c0 + __popc(b1 & lt)) & QMASK) : aDummy, wt1);
-        tail += c0 + __popc(b1);
-        head += n;
-        visits += sigA ? 1u : 0u;
-        rounds++;
-        mr = ldsVolatile(aMathRound);
-        __syncwarp();
-      }
-      asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(aDesc + 4u * (rounds & (PX_RING - 1u))),
-                   "r"(((rounds + 1u) << 16) | 0xffffu) /* end of schedule */
-                   : "memory");
+      SolverCtx c;
+      c.aQueue = sAddr(s.queue); c.aNext = sAddr(s.nextw); c.aMids = sAddr(s.mids); c.aSig = sAddr(s.sig);
+      c.aDesc = sAddr(s.misc + MI_RDESC); c.aMathRound = sAddr(s.misc + MI_MATHROUND);
+      c.aBodyP = sAddr(s.bodyP); c.aBodyV = sAddr(s.bodyV);
+      c.qmask = QMASK; c.qcap = P.S.qcap; c.iterations = iterations; c.tail0 = s.misc[MI_QTAIL]; c.lagSleepNs = P.lagSleepNs;
+      c.man = s.man; c.eps = eps;
+      uint32_t visits = 0;
+      const uint32_t rounds = solverSchedule(c, &visits);
       visits = __reduce_add_sync(0xffffffffu, visits);
       if (lane == 0) s.misc[MI_VISITS] = visits;
       if (prof && lane == 0) prof[6] += rounds;
@@ -1340,67 +1431,13 @@ __global__ void __launch_bounds__(NT, NT == 64 ? 6 : (NT == 128 ? 5 : 3)) pxStep
        * next round's descriptor is fetched before this round's arithmetic, so in the steady
        * state (scheduler ahead) a round starts with its queue word already on the way.  Idle
        * lanes run the arithmetic on manifold 0 and store nothing. */
-      const uint32_t aQueue = sAddr(s.queue), aDesc = sAddr(s.misc + MI_RDESC), aMathRound = sAddr(s.misc + MI_MATHROUND);
-      const uint32_t aBodyP = sAddr(s.bodyP), aBodyV = sAddr(s.bodyV);
-      const float4 *man = s.man;
-      /* software pipeline: while round r runs, the queue word and the three manifold records of
-       * round r + 1 are already in flight from L2 (the scheduler is rounds ahead, so its
-       * descriptor is normally there); only velocities and the frozen body rows are read at the
-       * last moment, from shared memory */
-      uint32_t head = 0, r = 0, d = ldsAcquire(aDesc);
-      uint32_t w = 0, n = 0;
-      float4 mA, mB, mC;
-      bool have = false; /* w / n / m* hold round r */
-      for (;; r++) {
-        if (!have) {
-          const uint32_t expect = ((r + 1u) & 0xffffu) << 16;
-          while ((d ^ expect) > 0xffffu) d = ldsAcquire(aDesc + 4u * (r & (PX_RING - 1u)));
-          n = d & 0xffffu;
-          if (n == 0xffffu) break;
-          const uint32_t qw = lds32(aQueue + 4u * ((head + lane) & QMASK));
-          w = lane < n ? qw : 0u;
-          mA = ldgPinned(man + 3u * MID_SLOT(w));
-          mB = ldgPinned(man + 3u * MID_SLOT(w) + 1u);
-          mC = ldgPinned(man + 3u * MID_SLOT(w) + 2u);
-        }
-        const bool active = lane < n;
-        const uint32_t a16 = MID_A(w) * 16u, b16 = MID_B(w) * 16u;
-        ContactIn in;
-        in.mA = mA;
-        in.mB = mB;
-        in.mC = mC;
-        in.pA = lds128(aBodyP + a16);
-        in.pB = lds128(aBodyP + b16);
-        in.vA = lds128(aBodyV + a16);
-        in.vB = lds128(aBodyV + b16);
-        /* next round: descriptor, queue word, records */
-        const uint32_t headNext = head + n;
-        const uint32_t dn = ldsAcquire(aDesc + 4u * ((r + 1u) & (PX_RING - 1u)));
-        const uint32_t expectN = ((r + 2u) & 0xffffu) << 16;
-        const bool haveNext = (dn ^ expectN) <= 32u;
-        const uint32_t nNext = dn & 0xffffu;
-        /* issued unconditionally (an unpublished round reads manifold 0 and is redone above) and
-         * pinned ahead of the arithmetic, so the L2 round trip runs under this round's chain */
-        const uint32_t qwN = lds32(aQueue + 4u * ((headNext + lane) & QMASK));
-        const uint32_t wNext = (haveNext && lane < nNext) ? qwN : 0u;
-        const float4 nA = ldgPinned(man + 3u * MID_SLOT(wNext));
-        const float4 nB = ldgPinned(man + 3u * MID_SLOT(wNext) + 1u);
-        const float4 nC = ldgPinned(man + 3u * MID_SLOT(wNext) + 2u);
-        asm volatile("" : "+f"(in.vA.x), "+f"(in.vB.x), "+f"(in.pA.x), "+f"(in.pB.x));
-        contactImpulse(w, in, eps);
-        sts128If(aBodyV + a16, in.vA, active);
-        sts128If(aBodyV + b16, in.vB, active && MID_BDYN(w));
-        head = headNext;
-        __syncwarp();
-        stsVolatile(aMathRound, r + 1u);
-        have = haveNext;
-        d = dn;
-        w = wNext;
-        n = nNext;
-        mA = nA;
-        mB = nB;
-        mC = nC;
-      }
+      SolverCtx c;
+      c.aQueue = sAddr(s.queue); c.aNext = sAddr(s.nextw); c.aMids = sAddr(s.mids); c.aSig = sAddr(s.sig);
+      c.aDesc = sAddr(s.misc + MI_RDESC); c.aMathRound = sAddr(s.misc + MI_MATHROUND);
+      c.aBodyP = sAddr(s.bodyP); c.aBodyV = sAddr(s.bodyV);
+      c.qmask = QMASK; c.qcap = P.S.qcap; c.iterations = iterations; c.tail0 = 0; c.lagSleepNs = P.lagSleepNs;
+      c.man = s.man; c.eps = eps;
+      solverMath(c);
     }
     __syncthreads();
     if (tid == 0 && iterations && !(P.flags & PX_BATCH_FLAG_SERIAL_SOLVER) && s.misc[MI_VISITS] != M * iterations)

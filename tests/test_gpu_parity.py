@@ -78,6 +78,9 @@ def test_capacity_overflow_is_flagged_not_fatal():
             b.step(50)
         blocks = b.download_blocks()
         assert int(blocks.header[0]["statOverflow"]) & want
+        # dropping the excess must leave the step internally consistent (bit 31 = a solver visit
+        # count that does not add up, e.g. a manifold slot of an earlier substep linked by mistake)
+        assert not int(blocks.header[0]["statOverflow"]) & 0x80000000
         assert b.readback(worlds) == 1  # one world overflowed
         assert worlds.stats(0)["overflow"] & want
         b.close()
