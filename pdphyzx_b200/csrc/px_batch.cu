@@ -129,7 +129,7 @@ extern "C" PxBatch *pxBatchCreate(uint32_t nWorlds, const PxBatchDesc *desc) {
     pxPlanSmem(&b->L, 0, &slim);
     const size_t perSm = (size_t)prop.sharedMemPerMultiprocessor, reserve = (size_t)prop.reservedSharedMemPerBlock;
     const size_t fat = perSm / (b->plan.total + reserve), thin = perSm / (slim.total + reserve);
-    const char *force = getenv("PX_VERTS_SMEM"); /* experiment switch: 1 = keep them in shared memory, 0 = never */
+    const char *force = getenv("PX_VERTS_SMEM"); /* tuning switch, undocumented on purpose: 1 = keep them in shared memory, 0 = never */
     if (b->plan.total > (uint32_t)prop.sharedMemPerBlockOptin || (force ? force[0] == '0' : thin > fat)) b->plan = slim;
   }
 
@@ -407,7 +407,7 @@ static int launchRange(PxBatch *b, uint32_t kSubsteps, uint32_t first, uint32_t 
   P.kSubsteps = kSubsteps;
   P.flags = b->flags;
   {
-    static const char *ns = getenv("PX_LAG_SLEEP_NS"); /* experiment switch */
+    static const char *ns = getenv("PX_LAG_SLEEP_NS"); /* tuning switch (500 ns: throughput is flat from 64 to 2000) */
     P.lagSleepNs = ns ? (uint32_t)atoi(ns) : 500u;
   }
   int rc = pxLaunchStep(&P, b->threads, stream);

@@ -1,13 +1,15 @@
 /*
  * px_step.cu -- the pdphyzx world substep as one fused sm_100a kernel.
  *
- * One CTA per world.  The CTA loads its world's SoA block from HBM with coalesced 16-byte
- * accesses, keeps body and manifold state in shared memory (and the per-body state only its
- * owner thread needs -- angle, force, torque, sleep time -- in registers) across K fused
- * substeps (K x pxWorldStepWithDt, reference src/px_world.c:410-420) and stores the mutable
- * rows back.  No tensor cores: nothing here is a dense contraction.  Compile with
- * -fmad=false: every multiply-add must round twice, exactly like the scalar CPU build
- * (SURVEY 0.11).
+ * One CTA per world.  The CTA loads its world's SoA block from HBM with coalesced accesses,
+ * keeps body state in shared memory (and the per-body state only its owner thread needs --
+ * angle, force, torque, sleep time -- in registers) across K fused substeps
+ * (K x pxWorldStepWithDt, reference src/px_world.c:410-420) and stores the mutable rows back.
+ * The float records of the substep's manifolds live in an L2-resident scratch slot the CTA
+ * claims on its SM (they were half of a world's shared-memory footprint): 37.6 KB of shared
+ * memory per 252-body world, five resident worlds per SM.  No tensor cores: nothing here is a
+ * dense contraction.  Compile with -fmad=false: every multiply-add must round twice, exactly
+ * like the scalar CPU build.
  *
  * Phases of a substep and the reference code each one restates
  *   A  AABBs, stable order by aabb.min.x           px_body_array.c:81-102, px_circle.c:43-48
@@ -25,8 +27,9 @@
  * visits commute bit-exactly iff they share no dynamic body (statics are never written,
  * px_body.c:148).  Phase D builds, for every dynamic body, the list of manifolds touching it
  * in pool order; phase E is a dataflow execution of the visit DAG those lists define: a
- * visit runs when it is at the head of the lists of both its bodies.  One warp pops up to 32
- * ready contact visits per round, so lanes stay dense, and iterations pipeline into each
+ * visit runs when it is at the head of the lists of both its bodies.  A scheduler warp keeps
+ * the ready queue and publishes rounds of up to 32 mutually independent contact visits, a
+ * math warp executes them (solverSchedule / solverMath), and iterations pipeline into each
  * other exactly as far as the dependencies allow.  Any such schedule produces the same bits
  * as the sequential loop.  Positional correction (px_manifold.c:217-255) depends only on the
  * manifold's normal/penetration and inverse masses, so each body sums its terms in list
