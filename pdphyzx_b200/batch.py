@@ -162,7 +162,7 @@ def host(unit: float = 1.0):
         "pxh_world_stats": (None, [vp, np.ctypeslib.ndpointer(np.uint32, flags="C_CONTIGUOUS")]),
         "pxh_add_body": (i, [vp, i, i, f, f, f32p, i, f, f, f, f, f, f]),
         "pxh_build_worlds": (i, [C.POINTER(vp), i, i32p, i, i, f, f, u8p, u8p, f32p, f32p, u8p, f32p, f32p, f32p, f32p,
-                                 f32p, f32p, f32p, C.c_void_p]),
+                                 f32p, f32p, f32p, C.c_void_p, i]),
         "pxh_body_set_motion": (None, [vp, i, i, f, f, f, f]),
         "pxh_body_apply_impulse": (None, [vp, i, f, f, f, f]),
         "pxh_body_apply_force": (None, [vp, i, f, f, f, f]),
@@ -209,13 +209,15 @@ class HostWorlds:
             motion = np.ascontiguousarray(np.concatenate([
                 np.stack([s.vx, s.vy, s.av, s.angle], axis=1) if s.vx is not None else np.zeros((s.n_bodies, 4), np.float32)
                 for s in scenes]).astype(np.float32))
-        verts = np.ascontiguousarray(np.concatenate([s.verts for s in scenes]).astype(np.float32).reshape(-1))
+        vmax = max(int(s.verts.shape[1]) for s in scenes)  # vertices per body slot (8 by default, up to 32)
+        pad = lambda v: v if v.shape[1] == vmax else np.concatenate([v, np.zeros((v.shape[0], vmax - v.shape[1], 2), v.dtype)], axis=1)
+        verts = np.ascontiguousarray(np.concatenate([pad(s.verts) for s in scenes]).astype(np.float32).reshape(-1))
         built = self.lib.pxh_build_worlds(
             self.ptrs, self.n, start, int(s0.fps), int(s0.iterations), float(s0.gravity[0]), float(s0.gravity[1]),
             cat("dynamic", np.uint8), cat("kind", np.uint8), cat("p0", np.float32), cat("p1", np.float32),
             cat("nverts", np.uint8), verts, cat("density", np.float32), cat("x", np.float32), cat("y", np.float32),
             cat("restitution", np.float32), cat("static_friction", np.float32), cat("dynamic_friction", np.float32),
-            motion.ctypes.data_as(C.c_void_p) if motion is not None else None)
+            motion.ctypes.data_as(C.c_void_p) if motion is not None else None, vmax)
         if built != self.n:
             for k in range(built):
                 self.lib.pxh_world_free(self.ptrs[k])

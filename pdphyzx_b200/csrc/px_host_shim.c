@@ -88,15 +88,15 @@ PXH int pxh_add_body(PxWorld *w, int dynamic, int kind, float p0, float p1, cons
  */
 PXH int pxh_build_worlds(PxWorld **out, int nWorlds, const int *bodyStart, int fps, int iterations, float gx, float gy,
                          const uint8_t *dynamic, const uint8_t *kind, const float *p0, const float *p1,
-                         const uint8_t *nverts, const float *verts /*[n][8][2]*/, const float *density, const float *x,
-                         const float *y, const float *e, const float *sf, const float *df, const float *motion) {
+                         const uint8_t *nverts, const float *verts /*[n][vertsPerBody][2]*/, const float *density, const float *x,
+                         const float *y, const float *e, const float *sf, const float *df, const float *motion, int vertsPerBody) {
   pxh_init();
   for (int w = 0; w < nWorlds; w++) {
     PxWorld *world = g_px->world->new((uint8_t)fps);
     g_px->world->setIterations(world, (uint8_t)iterations);
     g_px->world->setGravity(world, gx, gy);
     for (int k = bodyStart[w]; k < bodyStart[w + 1]; k++) {
-      int slot = pxh_add_body(world, dynamic[k], kind[k], p0[k], p1[k], verts + (size_t)k * 16, nverts[k], density[k],
+      int slot = pxh_add_body(world, dynamic[k], kind[k], p0[k], p1[k], verts + (size_t)k * 2 * (size_t)vertsPerBody, nverts[k], density[k],
                               x[k], y[k], e[k], sf[k], df[k]);
       if (slot < 0) {
         g_px->world->free(world);

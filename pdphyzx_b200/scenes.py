@@ -86,16 +86,26 @@ class Scene:
         return self.n_bodies - self.n_dynamic
 
 
+def _stack_verts(rows) -> np.ndarray:
+    """[n_bodies, widest, 2]: bodies with few vertices are zero-padded to the widest polygon."""
+    if not rows:
+        return np.zeros((0, MAX_SCENE_VERTS, 2), np.float32)
+    wide = max(v.shape[0] for v in rows)
+    out = np.zeros((len(rows), wide, 2), np.float32)
+    for i, v in enumerate(rows):
+        out[i, :v.shape[0]] = v
+    return out
+
+
 class _Builder:
     def __init__(self):
         self.rows = []
 
     def add(self, dynamic, kind, p0=0.0, p1=0.0, verts=None, density=0.0, x=0.0, y=0.0, e=0.2, sf=0.5,
             df=0.3, vx=0.0, vy=0.0, av=0.0, angle=0.0):
-        v = np.zeros((MAX_SCENE_VERTS, 2), np.float32)
-        n = 0
+        n = 0 if verts is None else len(verts)
+        v = np.zeros((max(MAX_SCENE_VERTS, n), 2), np.float32)
         if verts is not None:
-            n = len(verts)
             v[:n] = np.asarray(verts, np.float32)
         self.rows.append((dynamic, kind, p0, p1, n, v, density, x, y, e, sf, df, vx, vy, av, angle))
 
@@ -105,7 +115,7 @@ class _Builder:
         s = Scene(
             dynamic=col(0, np.uint8), kind=col(1, np.uint8), p0=col(2, np.float32), p1=col(3, np.float32),
             nverts=col(4, np.uint8),
-            verts=np.stack([row[5] for row in r]).astype(np.float32) if r else np.zeros((0, MAX_SCENE_VERTS, 2), np.float32),
+            verts=_stack_verts([row[5] for row in r]),
             density=col(6, np.float32), x=col(7, np.float32), y=col(8, np.float32),
             restitution=col(9, np.float32), static_friction=col(10, np.float32),
             dynamic_friction=col(11, np.float32), vx=col(12, np.float32), vy=col(13, np.float32),
@@ -249,3 +259,46 @@ def drop_scene(world: int, seed: int = 1, n_dynamic: int = 20, mix: str = "mixed
     """Small pile that fits the UNMODIFIED reference (<=64 bodies, <=64 manifolds)."""
     return pile_scene(world, seed=seed, n_dynamic=n_dynamic, mix=mix, unit=unit, iterations=iterations,
                       cols=5, peg=False)
+
+
+def edge_scene(world: int, seed: int = 1, n_dynamic: int = 60, n_static: int = 40, unit: float = UNIT_M,
+               iterations: int = 10, max_verts: int = 32) -> Scene:
+    """Edge cases of the step in one world: polygons with 9..`max_verts` vertices (the vertex cap
+    of the reference is 32, src/includes/px_vec2.h:481), many static boxes of uneven sizes along x
+    -- the reference's lower-bound search over statics tests aabb.max.x on a list sorted by
+    aabb.min.x (src/px_body_array.c:104-131), which is not monotone here, and more than 32 statics
+    exercise the long static window of the sweep -- plus circles and boxes falling through them."""
+    b = _Builder()
+    cell = 0.6 if unit == UNIT_M else 12.0  # as pile_scene: pixel-like lengths for the CM / MM builds
+    f32 = np.float32
+    cols = 10
+    width = cell * (cols + 1.5)
+    rows_tall = (n_dynamic + cols - 1) // cols
+    floor_y = cell * (rows_tall + 8)
+    b.add(0, KIND_BOX, p0=width * 1.2, p1=cell, x=width * 0.5, y=floor_y + cell * 0.5, e=0.4)
+    sidx = np.arange(n_static - 1)
+    sx = rand01(seed, world, sidx, 21) * f32(width)
+    sy = f32(floor_y) - rand01(seed, world, sidx, 22) * f32(cell * 4.0)
+    sw = f32(cell) * (f32(0.2) + f32(2.5) * rand01(seed, world, sidx, 23) ** 2)
+    for i in range(n_static - 1):
+        b.add(0, KIND_BOX, p0=float(sw[i]), p1=float(cell * 0.3), x=float(sx[i]), y=float(sy[i]), e=0.3, sf=0.6, df=0.4)
+    idx = np.arange(n_dynamic)
+    jx = rand01(seed, world, idx, 1) - f32(0.5)
+    jk = rand01(seed, world, idx, 4)
+    for i in range(n_dynamic):
+        x = float(cell * (0.75 + (i % cols) + 0.2 * jx[i]))
+        y = float(floor_y - cell * (6.0 + (i // cols) * 1.05))
+        r = float(cell * 0.38)
+        kind = i % 3
+        if kind == 0:
+            b.add(1, KIND_CIRCLE, p0=r, density=1.0, x=x, y=y)
+        elif kind == 1:
+            b.add(1, KIND_BOX, p0=1.5 * r, p1=1.8 * r, density=1.0, x=x, y=y, angle=float(0.3 * jx[i]))
+        else:
+            n = 9 + int(jk[i] * (max_verts - 8)) % (max_verts - 8)
+            ang = (np.arange(n, dtype=f32) + f32(0.3) * (rand01(seed, world, i * 64 + np.arange(n), 11) - f32(0.5))) * f32(2 * np.pi / n)
+            rad = f32(r * 1.1) * (f32(0.9) + f32(0.1) * rand01(seed, world, i * 64 + np.arange(n), 12))
+            b.add(1, KIND_POLYGON, verts=np.stack([rad * np.cos(ang), rad * np.sin(ang)], axis=1), density=1.0, x=x, y=y,
+                  angle=float(6.28 * jk[i]))
+    g = (0.0, 9.8) if unit == UNIT_M else (0.0, 1.025)
+    return b.scene(unit=unit, iterations=iterations, gravity=g)

@@ -208,3 +208,16 @@ def test_config3_mixed_worlds_sharded_checksum():
         shard.close()
     assert parts == total
     worlds.close()
+
+
+@pytest.mark.parametrize("unit", [1.0, 1000.0])
+def test_edge_scene_big_polygons_and_many_statics(unit):
+    """Polygons with 9..32 vertices (the generic SAT loops), 40 statics (long static window, the
+    literal non-monotone lower-bound search), all three shape classes -- every 3rd substep."""
+    stats = side_by_side([scenes.edge_scene(w, unit=unit) for w in range(3)], substeps=450, check_every=3)
+    assert stats["manifolds"].max() > 40
+
+
+def test_maximum_body_count():
+    """255 dynamic bodies: the uint8 slot / sentinel ceiling of the reference."""
+    side_by_side([scenes.pile_scene(w, mix="mixed", n_dynamic=255) for w in range(2)], substeps=300, check_every=10)

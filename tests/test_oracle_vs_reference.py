@@ -135,3 +135,13 @@ def test_oracle_rsqrt_sweep_matches_reference_on_a_slice(reflib_available):
         ref.ref_math_rsqrt(x, out, x.size)
         words = np.where(np.isnan(out), np.uint32(0x7FC00000), out.view(np.uint32))
         assert int(words.astype(np.uint64).sum()) == int(oraclebind.rsqrt_sweep(block, 1)[0])
+
+
+@pytest.mark.parametrize("unit", [1.0, 1000.0])
+def test_edge_scene_big_polygons_and_many_statics(reflib_available, unit):
+    """Polygons with 9..32 vertices, 40 static boxes with a non-monotone max.x along the min.x
+    order (the reference's static lower-bound search is literal, px_body_array.c:104-131)."""
+    sc = scenes.edge_scene(5, unit=unit)
+    assert int(sc.nverts.max()) > 20 and sc.n_static == 40
+    m, _ = run_vs_reference(sc, 450, every=3)
+    assert m > 40
