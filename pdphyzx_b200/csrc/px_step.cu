@@ -119,6 +119,16 @@ __device__ __forceinline__ void sts128If(uint32_t a, float4 v, bool p) {
   asm volatile("{ .reg .pred q; setp.ne.u32 q, %5, 0; @q st.shared.v4.f32 [%0], {%1, %2, %3, %4}; }" ::"r"(a), "f"(v.x),
                "f"(v.y), "f"(v.z), "f"(v.w), "r"((uint32_t)p));
 }
+/* predicated: idle lanes issue nothing (an unconditional add of 0 would pile every idle lane of
+ * the warp onto one address, and same-address shared atomics serialise) */
+__device__ __forceinline__ uint32_t atomAddSIf(uint32_t a, uint32_t v, bool p) {
+  uint32_t old = 0;
+  asm volatile("{ .reg .pred q; setp.ne.u32 q, %3, 0; @q atom.shared.add.u32 %0, [%1], %2; }"
+               : "+r"(old)
+               : "r"(a), "r"(v), "r"((uint32_t)p)
+               : "memory");
+  return old;
+}
 __device__ __forceinline__ uint32_t atomAddS(uint32_t a, uint32_t v) {
   uint32_t old;
   asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(a), "r"(v) : "memory");
@@ -694,9 +704,9 @@ __device__ __noinline__ uint32_t solverSchedule(const SolverCtx c, uint32_t *vis
     /* (the b half is unset when B is static, the a half when no manifold 0 exists) */
     const uint32_t t0 = sigA ? (nx & 0x3ffu) : 0u, t1 = sigB ? ((nx >> 16) & 0x3ffu) : 0u;
     const uint32_t wt0 = lds32(aMids + 4u * t0), wt1 = lds32(aMids + 4u * t1);
-    /* an idle side adds 0: no branch around the atomics */
-    const uint32_t old0 = atomAddS(aSig + 4u * t0, sigA ? ((nx & 0x8000u) ? 0x10000u : 1u) : 0u);
-    const uint32_t old1 = atomAddS(aSig + 4u * t1, sigB ? ((nx & 0x80000000u) ? 0x10000u : 1u) : 0u);
+    /* predicated, not branched around */
+    const uint32_t old0 = atomAddSIf(aSig + 4u * t0, (nx & 0x8000u) ? 0x10000u : 1u, sigA);
+    const uint32_t old1 = atomAddSIf(aSig + 4u * t1, (nx & 0x80000000u) ? 0x10000u : 1u, sigB);
     const uint32_t mine0 = ((nx & 0x8000u) ? (old0 >> 16) : (old0 & 0xffffu)) + 1u;
     const uint32_t other0 = (nx & 0x8000u) ? (old0 & 0xffffu) : (old0 >> 16);
     const uint32_t mine1 = ((nx & 0x80000000u) ? (old1 >> 16) : (old1 & 0xffffu)) + 1u;
