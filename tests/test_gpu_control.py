@@ -251,3 +251,33 @@ def test_vectorised_impulses_equal_single_calls():
         x.close()
     for x in (wa, wb):
         x.close()
+
+
+def test_config1_single_world_1000_step_calls(reflib_available):
+    """BASELINE config 1: one world, 252 circles dropped into the pen (+ 4 static boxes = 256
+    bodies), 10 iterations, 50 fps, 1000 px->world->step calls with the stub clock advancing
+    20 ms per call -- the reference on the CPU, this repo's px->world->step on the device
+    (a 1-world batch behind the facade).  996 of the 1000 calls fire; the state is
+    compared bit for bit every 50 calls and at the end."""
+    sc = scenes.pile_scene(0, mix="circles", n_dynamic=252)
+    ref = refbind.RefWorld(sc, "wide")
+    worlds = pxb.HostWorlds([sc])
+    h, w = worlds.lib, worlds.ptrs[0]
+    t, fired = 1000, 0
+    for call in range(1000):
+        ref.lib.ref_set_time_ms(t)
+        h.pxh_set_time_ms(t)
+        a, b = ref.lib.ref_step(ref.w), h.pxh_step(w)
+        assert a == b, f"call {call}: stepped flag"
+        fired += b
+        t += 20
+        if call % 50 == 49 or call == 999:
+            rr, rf, ro = ref.bodies(True)
+            hr, hf, ho = worlds.bodies(0, True)
+            np.testing.assert_array_equal(ro, ho, err_msg=f"call {call}: order")
+            np.testing.assert_array_equal(bits(rr[ro][:, :18]), bits(hr[ro][:, :18]), err_msg=f"call {call}")
+            np.testing.assert_array_equal(rf[ro], hf[ro], err_msg=f"call {call}: flags")
+    assert fired == 996
+    assert worlds.stats(0)["manifolds"] == len(ref.manifolds()[1]) > 300
+    worlds.close()
+    ref.close()
