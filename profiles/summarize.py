@@ -71,6 +71,18 @@ def main():
         "registers_per_thread": m("launch__registers_per_thread"),
         "shared_mem_per_block_bytes": m("launch__shared_mem_per_block_dynamic") * 1e3,
         "l2_hit_rate_pct": m("lts__t_sector_hit_rate.pct"),
+        # pipe utilisation, % of peak while active: ALU (integer / compare / select / logic), FMA pipe
+        # (the non-fused FMUL / FADD of this kernel issue there), LSU instruction issue, and the
+        # L1 / shared-memory DATA pipe in wavefronts -- the busiest unit
+        "pipe_alu_pct": m("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"),
+        "pipe_fma_pct": m("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active"),
+        "pipe_lsu_pct": m("sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active"),
+        "l1_data_pipe_wavefronts_pct": m("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed"),
+        "shared_wavefronts_pct": m("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed"),
+        "shared_bank_conflict_wavefronts": m("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum"),
+        "shared_wavefronts": m("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum"),
+        "achieved_warps_pct_of_max": m("sm__warps_active.avg.pct_of_peak_sustained_active"),
+        "eligible_warps_per_scheduler_cycle": m("smsp__warps_eligible.avg.per_cycle_active"),
         "source": os.path.basename(a.report),
     }
     with open(os.path.join(HERE, f"{a.tag}_kernel_facts.json"), "w") as f:
