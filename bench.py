@@ -266,6 +266,11 @@ def run_ours(args):
     for _ in range(max(args.warmup, 3)):
         b.step(args.fused)
     b.sync()
+    prof0 = prof0_raw = nsub0 = None
+    if args.profile:  # phase shares of the settled piles only: subtract what the free fall accumulated
+        prof0_raw = b.profile()
+        prof0 = prof0_raw.astype(np.float64)
+        nsub0 = float(b.download_blocks().header["substeps"].mean())
 
     def barrier():
         torch.cuda.synchronize()
@@ -394,18 +399,20 @@ def run_ours(args):
                 "lanes_per_instruction": facts["lanes_per_instruction"],
                 "note": "per GPU; instruction count from ncu (smsp__inst_executed.sum), rate from this run"}
         if args.profile:
-            pr = b.profile().astype(np.float64)
-            tot = pr.sum()
-            out["phase_share"] = {n: float(pr[:, i].sum() / tot) for i, n in enumerate(
-                ("A_sort", "B_sweep", "C_narrowphase", "D_lists", "E_solver", "F_integrate"))}
+            pr = b.profile().astype(np.float64) - prof0
+            nsub = float(blocks.header["substeps"].mean()) - nsub0
             tot = pr[:, :6].sum()
             out["phase_share"] = {n: float(pr[:, i].sum() / tot) for i, n in enumerate(
                 ("A_sort", "B_sweep", "C_narrowphase", "D_lists", "E_solver", "F_integrate"))}
-            nsub = float(blocks.header["substeps"].mean())
             out["solver_rounds_per_substep"] = float(pr[:, 6].mean() / nsub)
             out["solver_cycles_per_round"] = float(pr[:, 4].sum() / max(pr[:, 6].sum(), 1))
-            pr = pr[:, :6]
-            out["cycles_per_world_substep"] = float(pr.sum(axis=1).mean() / float(blocks.header["substeps"].mean()))
+            out["cycles_per_world_substep"] = float(pr[:, :6].sum(axis=1).mean() / nsub)
+            c = pr[:, 8:12].sum(axis=0) / pr[:, 2].sum()
+            out["narrowphase_stage_share"] = {"C1_circle_pairs": float(c[0]), "C2a_quick_reject": float(c[1]), "C2b_sat": float(c[2]),
+                                              "C3_clip": float(c[3]), "C4_manifold_init": float(1.0 - c.sum())}
+            raw7 = b.profile()[:, 7] - prof0_raw[:, 7]
+            out["polygon_pairs_per_substep"] = float((raw7 >> np.uint64(32)).mean() / nsub)
+            out["polygon_pairs_after_quick_reject_per_substep"] = float((raw7 & np.uint64(0xFFFFFFFF)).mean() / nsub)
         if e2e_ms is not None:
             out["e2e"] = {"value": body_substeps / (e2e_ms * 1e-3), "unit": "body-substeps/s",
                           "h2d_bytes_per_step": int(mut_bytes), "d2h_bytes_per_step": int(mut_bytes),

@@ -231,8 +231,10 @@ PX_API int pxBatchMutableD2H(PxBatch *b, void *host, uint32_t first, uint32_t n)
 PX_API int pxBatchImmutableH2D(PxBatch *b, const void *host, uint32_t first, uint32_t n);
 /* Copy the trace block of worlds [first, first + n) into `host` (n * traceStride bytes). */
 PX_API int pxBatchTraceD2H(PxBatch *b, void *host, uint32_t first, uint32_t n);
-/* PX_BATCH_FLAG_PROFILE: copy out u64[nWorlds][8] cycles per phase (A sort, B sweep, C narrowphase,
- * D lists, E solver, F integrate/correct/sleep, 6-7 unused) accumulated since creation */
+/* PX_BATCH_FLAG_PROFILE: copy out u64[nWorlds][16] accumulated since creation: SM-clock cycles per
+ * phase (0 A sort, 1 B sweep, 2 C narrowphase, 3 D lists, 4 E solver, 5 F integrate/correct/sleep),
+ * 6 solver rounds, 7 polygon pairs << 32 | pairs left after the quick rejection, 8-11 cycles of the
+ * narrowphase stages (circle pairs, quick rejection, SAT, clipping; the rest of 2 is manifold init) */
 PX_API int pxBatchProfileD2H(PxBatch *b, uint64_t *host);
 /* Device pointers (for zero-copy consumers on the same GPU), as integers */
 PX_API uint64_t pxBatchDeviceMutable(PxBatch *b);

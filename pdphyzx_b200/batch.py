@@ -466,8 +466,8 @@ class Batch:
         return Trace(self.L, buf)
 
     def profile(self) -> np.ndarray:
-        """u64[nWorlds, 8] SM-clock cycles per phase (needs FLAG_PROFILE)."""
-        out = np.zeros((self.n, 8), np.uint64)
+        """u64[nWorlds, 16] per-phase SM-clock cycles and counters (px_batch.h, needs FLAG_PROFILE)."""
+        out = np.zeros((self.n, 16), np.uint64)
         _check(self.lib.pxBatchProfileD2H(self.h, out.ctypes.data_as(C.c_void_p)), "pxBatchProfileD2H")
         return out
 

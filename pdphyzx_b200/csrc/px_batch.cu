@@ -19,6 +19,9 @@
 #include "px_internal.h"
 #include "px_step.cuh"
 
+#define PX_REGIONS 3u       /* scratch regions: the batch's stream and the two helper streams of pxBatchStepHost */
+#define PX_COUNTER_RING 64u /* >= launches that can be in flight at once */
+
 struct PxBatch {
   PxBatchLayout L;
   PxSmemPlan plan;
@@ -30,8 +33,9 @@ struct PxBatch {
   uint8_t *dMut, *dImm, *dTrace;
   float *dSin;
   unsigned long long *dProf;
-  float4 *dScratch;   /* manifold records of the resident CTAs (px_step.cuh) */
-  uint32_t *dSlotMask;
+  float4 *dScratch;   /* manifold records of the resident CTAs (px_step.cuh): PX_REGIONS regions of gridMax slots */
+  uint32_t *dCounters; /* world counters of the persistent grids, one per launch in flight (ring) */
+  uint32_t gridMax;    /* CTAs of a full launch: resident capacity of the device, at most nWorlds */
   uint8_t *hMut, *hImm; /* pinned staging, same layout */
   float sinTable[256];
   /* control path */
@@ -74,7 +78,8 @@ extern "C" PxBatch *pxBatchCreate(uint32_t nWorlds, const PxBatchDesc *desc) {
   b->dProf = nullptr;
   b->dScratch = nullptr;
   b->auxReady = false;
-  b->dSlotMask = nullptr;
+  b->dCounters = nullptr;
+  b->gridMax = 0;
   b->hMut = b->hImm = nullptr;
   b->dCmds = b->dGlobal = nullptr;
   b->dWorldStart = nullptr;
@@ -116,8 +121,8 @@ extern "C" PxBatch *pxBatchCreate(uint32_t nWorlds, const PxBatchDesc *desc) {
   /* 128 threads: 5 CTAs/SM (37.6 KB of shared memory and <= 102 registers each) keep the SM's
    * issue slots busier than 3 CTAs of 256 threads */
   b->threads = desc->threads ? desc->threads : 128;
-  if (b->threads != 64 && b->threads != 128 && b->threads != 256) {
-    pxSetError(-1, "PxBatchDesc.threads must be 64, 128 or 256");
+  if (b->threads != 128 && b->threads != 256) { /* the solver alone occupies four specialised warps */
+    pxSetError(-1, "PxBatchDesc.threads must be 128 or 256");
     pxBatchFree(b);
     return nullptr;
   }
@@ -150,14 +155,29 @@ extern "C" PxBatch *pxBatchCreate(uint32_t nWorlds, const PxBatchDesc *desc) {
     if ((e = cudaMemsetAsync(b->dTrace, 0, traceBytes, b->stream)) != cudaSuccess) return fail("cudaMemset", e);
   }
   if (b->flags & PX_BATCH_FLAG_PROFILE) {
-    if ((e = cudaMalloc(&b->dProf, (size_t)nWorlds * 64)) != cudaSuccess) return fail("cudaMalloc(prof)", e);
-    if ((e = cudaMemsetAsync(b->dProf, 0, (size_t)nWorlds * 64, b->stream)) != cudaSuccess) return fail("cudaMemset", e);
+    if ((e = cudaMalloc(&b->dProf, (size_t)nWorlds * PX_PROF_SLOTS * 8)) != cudaSuccess) return fail("cudaMalloc(prof)", e);
+    if ((e = cudaMemsetAsync(b->dProf, 0, (size_t)nWorlds * PX_PROF_SLOTS * 8, b->stream)) != cudaSuccess) return fail("cudaMemset", e);
   }
   {
-    const size_t scratchBytes = (size_t)PX_SCRATCH_SMIDS * PX_SCRATCH_SLOTS * b->L.maxManifolds * 3 * sizeof(float4);
+    /* the step kernel runs as ONE wave of persistent CTAs (px_step.cu); each owns a scratch slot */
+    PxStepParams P;
+    memset(&P, 0, sizeof(P));
+    P.L = b->L;
+    P.S = b->plan;
+    int occ = 0;
+    int rc = pxStepOccupancy(&P, b->threads, &occ);
+    if (rc != 0) return fail("occupancy query of the step kernel", (cudaError_t)rc);
+    if (occ < 1) {
+      pxSetError(-2, "pxBatchCreate: the step kernel does not fit an SM with %u bytes of shared memory per world", b->plan.total);
+      pxBatchFree(b);
+      return nullptr;
+    }
+    b->ctasPerSm = occ;
+    const uint64_t capacity = (uint64_t)occ * (uint64_t)b->numSms;
+    b->gridMax = (uint32_t)(capacity < nWorlds ? capacity : nWorlds);
+    const size_t scratchBytes = (size_t)PX_REGIONS * b->gridMax * b->L.maxManifolds * 3 * sizeof(float4);
     if ((e = cudaMalloc(&b->dScratch, scratchBytes)) != cudaSuccess) return fail("cudaMalloc(scratch)", e);
-    if ((e = cudaMalloc(&b->dSlotMask, PX_SCRATCH_SMIDS * sizeof(uint32_t))) != cudaSuccess) return fail("cudaMalloc(slotMask)", e);
-    if ((e = cudaMemsetAsync(b->dSlotMask, 0, PX_SCRATCH_SMIDS * sizeof(uint32_t), b->stream)) != cudaSuccess) return fail("cudaMemset", e);
+    if ((e = cudaMalloc(&b->dCounters, PX_COUNTER_RING * sizeof(uint32_t))) != cudaSuccess) return fail("cudaMalloc(counters)", e);
   }
   if ((e = cudaMallocHost(&b->hMut, mutBytes)) != cudaSuccess) return fail("cudaMallocHost(mutable)", e);
   if ((e = cudaMallocHost(&b->hImm, immBytes)) != cudaSuccess) return fail("cudaMallocHost(immutable)", e);
@@ -174,13 +194,6 @@ extern "C" PxBatch *pxBatchCreate(uint32_t nWorlds, const PxBatchDesc *desc) {
   if ((e = cudaMemcpyAsync(b->dSin, b->sinTable, sizeof(b->sinTable), cudaMemcpyHostToDevice, b->stream)) != cudaSuccess)
     return fail("cudaMemcpy(sin)", e);
 
-  PxStepParams P;
-  memset(&P, 0, sizeof(P));
-  P.L = b->L;
-  P.S = b->plan;
-  b->ctasPerSm = 0;
-  int occ = 0;
-  if (pxStepOccupancy(&P, b->threads, &occ) == 0) b->ctasPerSm = occ;
   if ((e = cudaStreamSynchronize(b->stream)) != cudaSuccess) return fail("cudaStreamSynchronize", e);
   return b;
 }
@@ -218,7 +231,7 @@ extern "C" void pxBatchFree(PxBatch *b) {
     }
     cudaEventDestroy(b->evFork);
   }
-  cudaFree(b->dSlotMask);
+  cudaFree(b->dCounters);
   cudaFree(b->dCmds);
   cudaFree(b->dGlobal);
   cudaFree(b->dWorldStart);
@@ -391,8 +404,9 @@ static int flushCommands(PxBatch *b) {
 }
 
 /* --------------------------------------------------------------------------- stepping */
-/* K substeps for worlds [first, first + n) on `stream` */
-static int launchRange(PxBatch *b, uint32_t kSubsteps, uint32_t first, uint32_t n, cudaStream_t stream) {
+/* K substeps for worlds [first, first + n) on `stream`; launches that may overlap in time use
+ * different scratch regions */
+static int launchRange(PxBatch *b, uint32_t kSubsteps, uint32_t first, uint32_t n, cudaStream_t stream, uint32_t region) {
   PxStepParams P;
   P.L = b->L;
   P.L.nWorlds = n;
@@ -401,16 +415,18 @@ static int launchRange(PxBatch *b, uint32_t kSubsteps, uint32_t first, uint32_t 
   P.imm = b->dImm + (size_t)first * b->L.immStride;
   P.trace = b->dTrace ? b->dTrace + (size_t)first * b->L.traceStride : nullptr;
   P.sinTable = b->dSin;
-  P.prof = b->dProf ? b->dProf + (size_t)first * 8 : nullptr;
-  P.scratch = b->dScratch;
-  P.slotMask = b->dSlotMask;
+  P.prof = b->dProf ? b->dProf + (size_t)first * PX_PROF_SLOTS : nullptr;
+  P.scratch = b->dScratch + (size_t)region * b->gridMax * b->L.maxManifolds * 3;
+  P.worldCounter = b->dCounters + (b->launches % PX_COUNTER_RING);
   P.kSubsteps = kSubsteps;
   P.flags = b->flags;
   {
     static const char *ns = getenv("PX_LAG_SLEEP_NS"); /* tuning switch (500 ns: throughput is flat from 64 to 2000) */
     P.lagSleepNs = ns ? (uint32_t)atoi(ns) : 500u;
   }
-  int rc = pxLaunchStep(&P, b->threads, stream);
+  CU(cudaMemsetAsync(P.worldCounter, 0, sizeof(uint32_t), stream));
+  const uint32_t grid = n < b->gridMax ? n : b->gridMax;
+  int rc = pxLaunchStep(&P, b->threads, grid, stream);
   if (rc != 0) return pxSetError(-rc - 1000, "step kernel launch: %s", cudaGetErrorString((cudaError_t)rc));
   b->launches++;
   return 0;
@@ -421,7 +437,7 @@ extern "C" int pxBatchStep(PxBatch *b, uint32_t kSubsteps) {
   if (useDevice(b)) return -1;
   if (flushCommands(b)) return -1;
   if (kSubsteps == 0) return 0;
-  return launchRange(b, kSubsteps, 0, b->L.nWorlds, b->stream);
+  return launchRange(b, kSubsteps, 0, b->L.nWorlds, b->stream, 0);
 }
 
 extern "C" int pxBatchStepHost(PxBatch *b, uint32_t kSubsteps, void *hostMut, uint32_t chunks) {
@@ -450,7 +466,7 @@ extern "C" int pxBatchStepHost(PxBatch *b, uint32_t kSubsteps, void *hostMut, ui
     if (!n) continue;
     cudaStream_t st = b->aux[c & 1];
     CU(cudaMemcpyAsync(b->dMut + first * stride, host + first * stride, n * stride, cudaMemcpyHostToDevice, st));
-    if (kSubsteps && launchRange(b, kSubsteps, first, n, st)) return -1;
+    if (kSubsteps && launchRange(b, kSubsteps, first, n, st, 1u + (c & 1u))) return -1;
     CU(cudaMemcpyAsync(host + first * stride, b->dMut + first * stride, n * stride, cudaMemcpyDeviceToHost, st));
   }
   /* join: later work on the batch's stream (and pxBatchSync) waits for both helpers */
@@ -486,7 +502,7 @@ extern "C" int pxBatchProfileD2H(PxBatch *b, uint64_t *host) {
   if (!b || !host) return pxSetError(-1, "pxBatchProfileD2H: NULL argument");
   if (!b->dProf) return pxSetError(-1, "pxBatchProfileD2H: the batch was created without PX_BATCH_FLAG_PROFILE");
   if (useDevice(b)) return -1;
-  CU(cudaMemcpyAsync(host, b->dProf, (size_t)b->L.nWorlds * 64, cudaMemcpyDeviceToHost, b->stream));
+  CU(cudaMemcpyAsync(host, b->dProf, (size_t)b->L.nWorlds * PX_PROF_SLOTS * 8, cudaMemcpyDeviceToHost, b->stream));
   CU(cudaStreamSynchronize(b->stream));
   return 0;
 }

@@ -210,8 +210,18 @@ __device__ __forceinline__ float3 materialOf(const Sm &s, uint32_t id, uint32_t 
 }
 
 /* misc[] slots */
-enum { MI_MCOUNT = 0, MI_QTAIL, MI_OVERFLOW, MI_UNSORTED, MI_SLEEPING, MI_VISITS, MI_MATHROUND, MI_SLOT, MI_RDESC = 16 };
+enum { MI_MCOUNT = 0, MI_QTAIL, MI_OVERFLOW, MI_SURVIVORS, MI_SLEEPING, MI_VISITS, MI_MATHROUND, MI_SLOT, MI_WORLD, MI_FED0, MI_FED1, MI_RDESC = 16 };
 #define PX_RING 16u /* round descriptors in flight (misc[MI_RDESC..]) */
+/* round descriptor: (round + 1) mod 2^15 << 17 | first queue index of the round << 6 | visits (PX_DESC_END = no more rounds) */
+#define PX_DESC(round, head, n) (((((round) + 1u) & 0x7fffu) << 17) | (((head) & 0x7ffu) << 6) | (n))
+#define PX_DESC_TAG(d) ((d) >> 17)
+#define PX_DESC_HEAD(d) (((d) >> 6) & 0x7ffu)
+#define PX_DESC_N(d) ((d) & 63u)
+#define PX_DESC_END 63u
+/* fed ring: rounds whose operands the feeder warps have staged for the math warp */
+#define PX_FEDRING 2u
+#define PX_FED_SLOT_BYTES (32u * 68u) /* per round: float4[4][32] operands + u32[32] decoded words */
+#define PX_FED_END 0x80000000u
 #ifndef PX_LAG
 #define PX_LAG 8u
 #endif
@@ -402,21 +412,51 @@ __device__ __forceinline__ float leastPenetrationGroup(uint32_t &faceIndex, cons
   return bestD;
 }
 
-/* pxClipSegmentToLine, px_collision.c:261-290 (IEEE division) */
-__device__ __forceinline__ int clipSegment(V2 out[2], const V2 in0, const V2 in1, V2 normal, float offset) {
-  /* at most two points come out: opposite signs give the intersection plus one endpoint,
-   * equal signs give both endpoints or none */
-  int sp = 0;
-  float d1 = dot(normal, in0) - offset;
-  float d2 = dot(normal, in1) - offset;
-  if (d1 * d2 < 0.0f) {
-    float alpha = d1 / (d1 - d2);
-    out[sp] = in0 + (in1 - in0) * alpha;
-    sp++;
+/* The face of A whose normal points most towards `dWorld` (a heuristic pick: any index is valid). */
+__device__ __forceinline__ uint32_t facingFace(const DBody &A, V2 dWorld) {
+  const V2 dl = mulT(A.rot, dWorld);
+  float best = -FLT_MAX;
+  uint32_t face = 0;
+  for (uint32_t i = 0; i < A.nverts; i++) {
+    const float4 v = A.v[i];
+    const float p = v.z * dl.x + v.w * dl.y;
+    if (p > best) {
+      best = p;
+      face = i;
+    }
   }
-  if (d2 <= 0.0f) out[sp++] = in1;
-  if (d1 <= 0.0f && sp < 2) out[sp++] = in0;
-  return sp;
+  return face;
+}
+
+/* Exact early rejection of a polygon pair.  pxCollidePolygons (px_collision.c:299-337) returns
+ * without contacts as soon as the LARGEST face separation of either polygon is >= 0; one face
+ * whose separation -- evaluated with the reference's own arithmetic (faceSeparation) -- is
+ * >= 0 therefore proves the same outcome without looking at the other faces.  The face tried
+ * is the one pointing most towards the other body; pairs it cannot reject go on to the full
+ * two-pass SAT. */
+__device__ __forceinline__ bool polygonsSeparatedQuick(const DBody &A, const DBody &B, float epsSq) {
+  const V2 d = B.pos - A.pos;
+  if (faceSeparation(A, B, facingFace(A, d), epsSq) >= 0.0f) return true;
+  return faceSeparation(B, A, facingFace(B, -d), epsSq) >= 0.0f;
+}
+
+/* pxClipSegmentToLine, px_collision.c:261-290 (IEEE division).  The reference appends, in this
+ * order, the intersection point (signs differ), in[1] (d2 <= 0) and in[0] (d1 <= 0, if room).
+ * Written as selects so that nothing is indexed dynamically (no local-memory stack frame). */
+__device__ __forceinline__ int clipSegment(V2 &o0, V2 &o1, const V2 in0, const V2 in1, V2 normal, float offset) {
+  const float d1 = dot(normal, in0) - offset;
+  const float d2 = dot(normal, in1) - offset;
+  const bool crossing = d1 * d2 < 0.0f, keep1 = d2 <= 0.0f, keep0 = d1 <= 0.0f;
+  if (crossing) {
+    /* strictly opposite signs: exactly one endpoint is kept, after the intersection */
+    const float alpha = d1 / (d1 - d2);
+    o0 = in0 + (in1 - in0) * alpha;
+    o1 = keep1 ? in1 : in0;
+    return 2;
+  }
+  o0 = keep1 ? in1 : in0;
+  o1 = in0;
+  return (keep1 ? 1 : 0) + (keep0 ? 1 : 0);
 }
 
 /* pxCollidePolygons after the two SAT passes, px_collision.c:312-435 (pxFindIncidentFace
@@ -455,36 +495,25 @@ __device__ void clipPolygons(const DBody &A, const DBody &B, bool flip, uint32_t
 
   float refC = dot(refNormal, ref0);
   float negSide = -dot(side, ref0);
-  V2 clip1[2], clip2[2];
-  int cp = clipSegment(clip1, inc0, inc1, -side, negSide);
+  V2 clip1a, clip1b, clip2[2];
+  int cp = clipSegment(clip1a, clip1b, inc0, inc1, -side, negSide);
   if (cp < 2) return;
   float posSide = dot(side, ref1);
-  cp = clipSegment(clip2, clip1[0], clip1[1], side, posSide);
+  cp = clipSegment(clip2[0], clip2[1], clip1a, clip1b, side, posSide);
   if (cp < 2) return;
 
   m.normal = flip ? -refNormal : refNormal;
-  uint32_t n = 0;
-  float pen = 0.0f;
-  V2 c[2];
-  c[0] = c[1] = v2(0.0f, 0.0f);
-#pragma unroll
-  for (int i = 0; i < 2; i++) {
-    float separation = dot(refNormal, clip2[i]) - refC;
-    if (separation <= 0.0f) {
-      c[n] = clip2[i];
-      if (n == 0) {
-        pen = -separation;
-      } else {
-        pen += -separation;
-      }
-      n++;
-    }
-  }
-  if (n > 1) pen = fDiv(pen, (float)n);
+  /* px_collision.c:407-432: keep the clipped points behind the reference face, in order */
+  const float sep0 = dot(refNormal, clip2[0]) - refC, sep1 = dot(refNormal, clip2[1]) - refC;
+  const bool k0 = sep0 <= 0.0f, k1 = sep1 <= 0.0f;
+  const V2 zero = v2(0.0f, 0.0f);
+  float pen = k0 ? -sep0 : 0.0f;
+  if (k1) pen = k0 ? pen + -sep1 : -sep1;
+  if (k0 && k1) pen = fDiv(pen, 2.0f);
   m.pen = pen;
-  m.c0 = c[0];
-  m.c1 = c[1];
-  m.count = n;
+  m.c0 = k0 ? clip2[0] : (k1 ? clip2[1] : zero);
+  m.c1 = (k0 && k1) ? clip2[1] : zero;
+  m.count = (k0 ? 1u : 0u) + (k1 ? 1u : 0u);
 }
 
 
@@ -669,7 +698,7 @@ __device__ __forceinline__ void copyRows(float *dst, const float *src, uint32_t 
  * is then independent of the rest of the kernel, whose pressure (narrowphase, sweep) would
  * otherwise spill into these latency-critical chains. */
 struct SolverCtx {
-  uint32_t aQueue, aNext, aMids, aSig, aDesc, aMathRound, aBodyP, aBodyV;
+  uint32_t aQueue, aNext, aMids, aSig, aDesc, aMathRound, aBodyP, aBodyV, aFed, aRing;
   uint32_t qmask, qcap, iterations, tail0, lagSleepNs;
   const float4 *man;
   float eps;
@@ -691,7 +720,7 @@ __device__ __noinline__ uint32_t solverSchedule(const SolverCtx c, uint32_t *vis
       mr = ldsVolatile(aMathRound);
     }
     asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(aDesc + 4u * (rounds & (PX_RING - 1u))),
-                 "r"(((rounds + 1u) << 16) | n)
+                 "r"(PX_DESC(rounds, head & QMASK, n))
                  : "memory");
     const bool active = lane < n;
     const uint32_t qw = lds32(aQueue + 4u * ((head + lane) & QMASK));
@@ -727,97 +756,169 @@ __device__ __noinline__ uint32_t solverSchedule(const SolverCtx c, uint32_t *vis
     mr = ldsVolatile(aMathRound);
     __syncwarp();
   }
+  /* end of schedule, once for each of the two feeder warps (they take alternate rounds) */
   asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(aDesc + 4u * (rounds & (PX_RING - 1u))),
-               "r"(((rounds + 1u) << 16) | 0xffffu) /* end of schedule */
+               "r"(PX_DESC(rounds, 0u, PX_DESC_END))
+               : "memory");
+  asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(aDesc + 4u * ((rounds + 1u) & (PX_RING - 1u))),
+               "r"(PX_DESC(rounds + 1u, 0u, PX_DESC_END))
                : "memory");
   *visitsOut = visits;
   return rounds;
 }
 
-__device__ __noinline__ void solverMath(const SolverCtx c) {
+/* Feeder warps (two, alternating rounds).  Everything a contact visit needs that does NOT depend
+ * on a velocity is gathered here, off the math warp's chain: the queue word is decoded, the three
+ * manifold records come from L1/L2, the contact is selected and its lever arms ra = c - posA,
+ * rb = c - posB are formed (positions and masses are frozen during the solver; the subtraction is
+ * the reference's own, px_manifold.c:113-114, merely executed by another warp).  The result goes
+ * to slot round % PX_FEDRING of a small shared-memory ring, one lane-contiguous record per visit:
+ *   [0] {normal.x, normal.y, restitution, staticFriction}   [1] {dynamicFriction, rcpDenom, ra.x, ra.y}
+ *   [2] {rb.x, rb.y, iMassA, iInertiaA}                     [3] {iMassB, iInertiaB, -, -}
+ *   word: slotA << 4 | bodyIdB << 20 | bIsDynamic << 30 | active << 31 */
+__device__ __noinline__ void solverFeed(const SolverCtx c, const uint32_t parity) {
   const uint32_t lane = threadIdx.x & 31u, QMASK = c.qmask;
-  const uint32_t aQueue = c.aQueue, aDesc = c.aDesc, aMathRound = c.aMathRound, aBodyP = c.aBodyP, aBodyV = c.aBodyV;
+  const uint32_t aQueue = c.aQueue, aDesc = c.aDesc, aMathRound = c.aMathRound, aBodyP = c.aBodyP;
+  const uint32_t aFed = c.aFed + 4u * parity, aRing = c.aRing + 16u * lane;
   const float4 *man = c.man;
-  const float eps = c.eps;
-  /* software pipeline: while round r runs, the queue word and the three manifold records of
-   * round r + 1 are already in flight from L2 (the scheduler is rounds ahead, so its
-   * descriptor is normally there); only velocities and the frozen body rows are read at the
-   * last moment, from shared memory */
-  uint32_t head = 0, r = 0, d = ldsAcquire(aDesc);
-  uint32_t w = 0, n = 0;
-  float4 mA, mB, mC;
-  bool have = false; /* w / n / m* hold round r */
-  for (;; r++) {
-    if (!have) {
-      const uint32_t expect = ((r + 1u) & 0xffffu) << 16;
-      while ((d ^ expect) > 0xffffu) d = ldsAcquire(aDesc + 4u * (r & (PX_RING - 1u)));
-      n = d & 0xffffu;
-      if (n == 0xffffu) break;
-      const uint32_t qw = lds32(aQueue + 4u * ((head + lane) & QMASK));
-      w = lane < n ? qw : 0u;
-      mA = ldgPinned(man + 3u * MID_SLOT(w));
-      mB = ldgPinned(man + 3u * MID_SLOT(w) + 1u);
-      mC = ldgPinned(man + 3u * MID_SLOT(w) + 2u);
+  for (uint32_t r = parity;; r += 2u) {
+    const uint32_t expect = (r + 1u) & 0x7fffu;
+    uint32_t d = ldsAcquire(aDesc + 4u * (r & (PX_RING - 1u)));
+    while (PX_DESC_TAG(d) != expect) {
+      __nanosleep(64);
+      d = ldsAcquire(aDesc + 4u * (r & (PX_RING - 1u)));
     }
+    const uint32_t n = PX_DESC_N(d);
+    if (n == PX_DESC_END) {
+      if (lane == 0) asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(aFed), "r"((r + 1u) | PX_FED_END) : "memory");
+      return;
+    }
+    const uint32_t qw = lds32(aQueue + 4u * ((PX_DESC_HEAD(d) + lane) & QMASK));
     const bool active = lane < n;
-    const uint32_t a16 = MID_A(w) * 16u, b16 = MID_B(w) * 16u;
-    ContactIn in;
-    in.mA = mA;
-    in.mB = mB;
-    in.mC = mC;
-    in.pA = lds128(aBodyP + a16);
-    in.pB = lds128(aBodyP + b16);
-    in.vA = lds128(aBodyV + a16);
-    in.vB = lds128(aBodyV + b16);
-    /* next round: descriptor, queue word, records */
-    const uint32_t headNext = head + n;
-    const uint32_t dn = ldsAcquire(aDesc + 4u * ((r + 1u) & (PX_RING - 1u)));
-    const uint32_t expectN = ((r + 2u) & 0xffffu) << 16;
-    const bool haveNext = (dn ^ expectN) <= 32u;
-    const uint32_t nNext = dn & 0xffffu;
-    /* issued unconditionally (an unpublished round reads manifold 0 and is redone above) and
-     * pinned ahead of the arithmetic, so the L2 round trip runs under this round's chain */
-    const uint32_t qwN = lds32(aQueue + 4u * ((headNext + lane) & QMASK));
-    const uint32_t wNext = (haveNext && lane < nNext) ? qwN : 0u;
-    const float4 nA = ldgPinned(man + 3u * MID_SLOT(wNext));
-    const float4 nB = ldgPinned(man + 3u * MID_SLOT(wNext) + 1u);
-    const float4 nC = ldgPinned(man + 3u * MID_SLOT(wNext) + 2u);
-    asm volatile("" : "+f"(in.vA.x), "+f"(in.vB.x), "+f"(in.pA.x), "+f"(in.pB.x));
-    contactImpulse(w, in, eps);
-    sts128If(aBodyV + a16, in.vA, active);
-    sts128If(aBodyV + b16, in.vB, active && MID_BDYN(w));
-    head = headNext;
+    const uint32_t w = active ? qw : 0u; /* idle lanes: manifold 0, every index in range, nothing stored later */
+    const uint32_t ms = MID_SLOT(w), a = MID_A(w), b = MID_B(w);
+    const float4 mA = ldgPinned(man + 3u * ms), mB = ldgPinned(man + 3u * ms + 1u), mC = ldgPinned(man + 3u * ms + 2u);
+    const float4 pA = lds128(aBodyP + 16u * a), pB = lds128(aBodyP + 16u * b);
+    const bool second = MID_CI(w) != 0;
+    const V2 cpt = second ? v2(mC.x, mC.y) : v2(mB.z, mB.w);
+    const float rcpDenom = second ? mC.w : mC.z;
+    const V2 ra = cpt - v2(pA.x, pA.y), rb = cpt - v2(pB.x, pB.y);
+    /* the slot is free once the math warp is done with round r - PX_FEDRING */
+    while ((int32_t)(r - ldsAcquire(aMathRound)) >= (int32_t)PX_FEDRING) __nanosleep(32);
+    const uint32_t slot = aRing + (r % PX_FEDRING) * PX_FED_SLOT_BYTES;
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(slot), "f"(mA.x), "f"(mA.y), "f"(mA.z), "f"(mA.w) : "memory");
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(slot + 512u), "f"(mB.x), "f"(rcpDenom), "f"(ra.x), "f"(ra.y) : "memory");
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(slot + 1024u), "f"(rb.x), "f"(rb.y), "f"(pA.z), "f"(pA.w) : "memory");
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(slot + 1536u), "f"(pB.z), "f"(pB.w), "f"(0.0f), "f"(0.0f) : "memory");
+    sts32(c.aRing + (r % PX_FEDRING) * PX_FED_SLOT_BYTES + 2048u + 4u * lane,
+          (a << 4) | (b << 20) | (MID_BDYN(w) << 30) | (active ? 0x80000000u : 0u));
     __syncwarp();
-    stsVolatile(aMathRound, r + 1u);
-    have = haveNext;
-    d = dn;
-    w = wNext;
-    n = nNext;
-    mA = nA;
-    mB = nB;
-    mC = nC;
+    if (lane == 0) asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(aFed), "r"(r + 1u) : "memory");
   }
 }
 
+/* Math warp: one contact visit per lane and round (px_manifold.c:98-215, see contactImpulse --
+ * same expressions, with the lever arms and masses read from the fed ring).  Its loop holds
+ * nothing but the dependent arithmetic: operands of round r were staged by a feeder warp, only
+ * the two velocity rows are read at the last moment. */
+__device__ __noinline__ void solverMath(const SolverCtx c) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t aMathRound = c.aMathRound, aBodyV = c.aBodyV, aFed = c.aFed;
+  const uint32_t aRing = c.aRing + 16u * lane, aWord = c.aRing + 2048u + 4u * lane;
+  const float eps = c.eps;
+  uint32_t slotOff = 0;
+  for (uint32_t r = 0;; r++) {
+    const uint32_t aF = aFed + 4u * (r & 1u);
+    uint32_t f = ldsAcquire(aF);
+    while ((f & ~PX_FED_END) < r + 1u) f = ldsAcquire(aF);
+    if (f == ((r + 1u) | PX_FED_END)) break;
+    const uint32_t word = lds32(aWord + slotOff);
+    const float4 q0 = lds128(aRing + slotOff), q1 = lds128(aRing + slotOff + 512u), q2 = lds128(aRing + slotOff + 1024u),
+                 q3 = lds128(aRing + slotOff + 1536u);
+    const uint32_t a16 = word & 0xff0u, b16 = (word >> 16) & 0x1ff0u;
+    const bool active = (word >> 31) != 0, bdyn = ((word >> 30) & 1u) != 0;
+    float4 vA = lds128(aBodyV + a16), vB = lds128(aBodyV + b16);
+
+    const V2 n = v2(q0.x, q0.y);
+    const float e = q0.z, sf = q0.w, df = q1.x, rcpDenom = q1.y;
+    const V2 ra = v2(q1.z, q1.w), rb = v2(q2.x, q2.y);
+    const float iMA = q2.z, iIA = q2.w, iMB = q3.x, iIB = q3.y; /* statics: 0 */
+    const V2 va = v2(vA.x, vA.y), vb = v2(vB.x, vB.y);
+    const float wa = vA.z, wb = vB.z;
+    const V2 raPerp = v2(-ra.y, ra.x), rbPerp = v2(-rb.y, rb.x);
+    V2 rv = (vb + rbPerp * wb) - (va + raPerp * wa);
+    const float vn = dot(rv, n);
+    const bool approaching = !(vn > 0);
+    const float normalMag = -(1.0f + e) * vn;
+    const float j = normalMag * rcpDenom;
+    const V2 impulse = n * j;
+    const V2 ni = -impulse;
+    const V2 va1 = v2(va.x + ni.x * iMA, va.y + ni.y * iMA);
+    const float wa1 = wa + cross(ra, ni) * iIA;
+    const V2 vb1 = bdyn ? v2(vb.x + impulse.x * iMB, vb.y + impulse.y * iMB) : vb;
+    const float wb1 = bdyn ? wb + cross(rb, impulse) * iIB : wb;
+    rv = (vb1 + rbPerp * wb1) - (va1 + raPerp * wa1);
+    V2 tangent = rv - n * dot(rv, n);
+    const float tlen = fSqrt(lensq(tangent));
+    const bool slides = tlen > eps;
+    tangent = tangent * fRcp(tlen);
+    const float tmag = -dot(rv, tangent);
+    const float jt = tmag * rcpDenom;
+    const float fmag = (fabsf(jt) < j * sf) ? jt : (-j * df);
+    const V2 friction = tangent * fmag;
+    const V2 nf = -friction;
+    const V2 va2 = v2(va1.x + nf.x * iMA, va1.y + nf.y * iMA);
+    const float wa2 = wa1 + cross(ra, nf) * iIA;
+    const V2 vb2 = bdyn ? v2(vb1.x + friction.x * iMB, vb1.y + friction.y * iMB) : vb1;
+    const float wb2 = bdyn ? wb1 + cross(rb, friction) * iIB : wb1;
+    vA.x = approaching ? (slides ? va2.x : va1.x) : va.x;
+    vA.y = approaching ? (slides ? va2.y : va1.y) : va.y;
+    vA.z = approaching ? (slides ? wa2 : wa1) : wa;
+    vB.x = approaching ? (slides ? vb2.x : vb1.x) : vb.x;
+    vB.y = approaching ? (slides ? vb2.y : vb1.y) : vb.y;
+    vB.z = approaching ? (slides ? wb2 : wb1) : wb;
+
+    sts128If(aBodyV + a16, vA, active);
+    sts128If(aBodyV + b16, vB, active && bdyn);
+    __syncwarp();
+    asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(aMathRound), "r"(r + 1u) : "memory");
+    slotOff = slotOff == (PX_FEDRING - 1u) * PX_FED_SLOT_BYTES ? 0u : slotOff + PX_FED_SLOT_BYTES;
+  }
+}
+
+#ifndef PX_MINB128
+#define PX_MINB128 5
+#endif
 #define PX_DMAX 256 /* dynamic slots per world (PX_MAX_BODIES rounded up to the copy granule) */
 
 /* ============================================================================ kernel ==== */
 template <int NT>
-__global__ void __launch_bounds__(NT, NT == 64 ? 6 : (NT == 128 ? 5 : 3)) pxStepKernel(const PxStepParams P) {
+__global__ void __launch_bounds__(NT, NT == 128 ? PX_MINB128 : 3) pxStepKernel(const PxStepParams P) {
   constexpr int R = PX_DMAX / NT; /* body slots (and sorted positions) owned per thread */
   extern __shared__ __align__(16) uint8_t smemRaw[];
   const PxBatchLayout &L = P.L;
   const uint32_t D = L.maxDynamic, S = L.maxStatic, MM = L.maxManifolds, MP = L.maxPairs;
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-  const uint32_t world = blockIdx.x;
-  uint8_t *gmut = P.mut + (size_t)world * L.mutStride;
-  const uint8_t *gimm = P.imm + (size_t)world * L.immStride;
   Sm s;
-  bindSmem(s, smemRaw, P.S, (const float4 *)(gimm + L.offVerts));
-  s.dynMat = (const float *)(gimm + L.offDynConst);
-  s.statMat = (const float *)(gimm + L.offStat);
+  bindSmem(s, smemRaw, P.S, nullptr);
   const float eps = L.epsilon, epsSq = L.epsilonSq, allowedPen = L.allowedPenetration;
   const uint32_t QMASK = P.S.qcap - 1;
+  /* manifold records of whatever world this CTA is working on: scratch slot blockIdx.x of this
+   * launch's region.  Only this CTA ever touches it, through the L1 of the SM it lives on. */
+  s.man = P.scratch + (size_t)blockIdx.x * MM * 3u;
+
+  /* Persistent CTA: the grid is one wave of resident CTAs; each takes the next world off a
+   * counter until the batch is done (no ragged last wave, and a slow world delays nobody). */
+  for (;;) {
+  if (tid == 0) s.misc[MI_WORLD] = atomicAdd(P.worldCounter, 1u);
+  __syncthreads();
+  const uint32_t world = s.misc[MI_WORLD];
+  if (world >= L.nWorlds) break;
+  uint8_t *gmut = P.mut + (size_t)world * L.mutStride;
+  const uint8_t *gimm = P.imm + (size_t)world * L.immStride;
+  s.verts = P.S.vertsInSmem ? (const float4 *)(smemRaw + P.S.verts) : (const float4 *)(gimm + L.offVerts);
+  s.dynMat = (const float *)(gimm + L.offDynConst);
+  s.statMat = (const float *)(gimm + L.offStat);
   const float *gdynC = (const float *)(gmut + L.offDyn);
   float *gdyn = (float *)(gmut + L.offDyn);
 
@@ -848,26 +949,7 @@ __global__ void __launch_bounds__(NT, NT == 64 ? 6 : (NT == 128 ? 5 : 3)) pxStep
     copyRows<NT>((float *)s.flags, (const float *)(gmut + L.offDynFlags), D / 4);
     copyRows<NT>((float *)s.order, (const float *)(gmut + L.offDynOrder), D / 4);
     copyRows<NT>((float *)s.hdr, (const float *)(gmut + L.offHeader), sizeof(PxWorldHeader) / 4);
-    if (tid < 32 && tid != MI_SLOT) s.misc[tid] = 0;
-    if (tid == 0) {
-      /* claim a manifold scratch slot of this SM: lowest free bit of slotMask[smid] */
-      uint32_t smid;
-      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-      smid &= PX_SCRATCH_SMIDS - 1u;
-      uint32_t bit = 0, old = 0xffffffffu;
-      for (uint32_t tries = 0; tries < (1u << 22); tries++) { /* bounded: never hang the GPU on a bookkeeping bug */
-        bit = __ffs(~*(volatile uint32_t *)(P.slotMask + smid)) - 1u;
-        if (bit >= PX_SCRATCH_SLOTS) continue;
-        old = atomicOr(P.slotMask + smid, 1u << bit);
-        if (!(old & (1u << bit))) break;
-        old = 0xffffffffu;
-      }
-      if (old == 0xffffffffu) { /* no slot: results of this world are unspecified, and flagged */
-        bit = PX_SCRATCH_SLOTS - 1u;
-        s.misc[MI_OVERFLOW] = PX_OVERFLOW_INTERNAL;
-      }
-      s.misc[MI_SLOT] = smid * PX_SCRATCH_SLOTS + bit;
-    }
+    if (tid < 32 && tid != MI_WORLD) s.misc[tid] = 0;
   }
   /* thread-private body state: slot x = tid + r * NT lives in this thread's registers */
   float rAngle[R], rFx[R], rFy[R], rTq[R], rSlp[R];
@@ -883,7 +965,6 @@ __global__ void __launch_bounds__(NT, NT == 64 ? 6 : (NT == 128 ? 5 : 3)) pxStep
   }
   __syncthreads();
 
-  s.man = P.scratch + (size_t)s.misc[MI_SLOT] * MM * 3u;
   const uint32_t nDyn = min(s.hdr->nDynamic, D), nStat = min(s.hdr->nStatic, S);
   const float dt = s.hdr->dt;
   const V2 g = v2(s.hdr->gravityX, s.hdr->gravityY);
@@ -894,7 +975,7 @@ __global__ void __launch_bounds__(NT, NT == 64 ? 6 : (NT == 128 ? 5 : 3)) pxStep
   uint32_t statPairs = 0, statManifolds = 0;
 
   long long profT = 0;
-  unsigned long long *prof = P.prof ? P.prof + (size_t)world * 8 : nullptr;
+  unsigned long long *prof = P.prof ? P.prof + (size_t)world * PX_PROF_SLOTS : nullptr;
 #define PROF_MARK(slot)                              \
   if (prof && tid == 0) {                            \
     long long now = clock64();                       \
@@ -902,6 +983,14 @@ __global__ void __launch_bounds__(NT, NT == 64 ? 6 : (NT == 128 ? 5 : 3)) pxStep
     profT = now;                                     \
   }
   if (prof && tid == 0) profT = clock64();
+  /* finer marks inside a phase: thread 0's arrival time, accumulated next to (not instead of) the phase total */
+  long long profS = 0;
+#define PROF_SUB(slot)                               \
+  if (prof && tid == 0) {                            \
+    long long now = clock64();                       \
+    prof[slot] += (unsigned long long)(now - (profS > profT ? profS : profT)); \
+    profS = now;                                     \
+  }
 
   for (uint32_t step = 0; step < P.kSubsteps; step++) {
     const bool traceNow = P.trace != nullptr && step + 1 == P.kSubsteps;
@@ -909,7 +998,7 @@ __global__ void __launch_bounds__(NT, NT == 64 ? 6 : (NT == 128 ? 5 : 3)) pxStep
 
     /* ====================== phase A: AABB keys, stable order by aabb.min.x ============ */
     /* the order persists across substeps, so it is almost always already sorted */
-    if (tid < 32 && tid != MI_OVERFLOW && tid != MI_SLOT) s.misc[tid] = 0;
+    if (tid < 32 && tid != MI_OVERFLOW && tid != MI_WORLD) s.misc[tid] = 0;
     for (uint32_t i = tid; i < D; i += NT) {
       s.restFlag[i] = 0;
       s.wakeFlag[i] = 0;
@@ -1128,59 +1217,23 @@ __global__ void __launch_bounds__(NT, NT == 64 ? 6 : (NT == 128 ? 5 : 3)) pxStep
     PROF_MARK(1)
 
     /* ====================== phase C: narrowphase ===================================== */
+    /* C1 circle pairs -> C2a exact quick rejection of polygon pairs, survivors compacted ->
+     * C2b two-pass SAT on the survivors -> C3 clipping -> C4 manifold init, one thread per
+     * manifold.  C1 and C3 only stage the contact geometry of a hit. */
+    uint32_t statSurvivors = 0, statPoly = 0;
     {
-      const uint32_t nAll = min(nCC + nCP + nPP, MP), nCircle = min(nCC + nCP, nAll);
-      const V2 gstep = g * dt;
-      const float gsq = lensq(gstep);
-      /* manifold slot + pxManifoldInit + resting contact + sleep flags for a pair with contacts */
-      auto keep = [&](uint32_t word, uint32_t a, uint32_t b, const Contact &m) {
-        const uint32_t bdyn = b < D;
+      const uint32_t nAll = min(nCC + nCP + nPP, MP), nCircle = min(nCC + nCP, nAll), nPoly = nAll - nCircle;
+      /* a pair with contacts takes the next manifold slot and parks {normal, penetration | c0, c1} there */
+      auto stage = [&](uint32_t word, uint32_t a, uint32_t b, const Contact &m) {
         const uint32_t ms = atomicAdd(&s.misc[MI_MCOUNT], 1u);
         if (ms >= MM) { /* manifold overflow, flagged below */
           s.validSlot[BIN_SEQ(word)] = 0;
           return;
         }
-        const float3 mtA = materialOf(s, a, D, S), mtB = materialOf(s, b, D, S);
-        const float4 pA = s.bodyP[a], pB = s.bodyP[b], vA = s.bodyV[a], vB = s.bodyV[b];
-        /* pxManifoldInit, px_manifold.c:12-31: geometric-mean friction via pxFastSqrt */
-        const float sfm = fSqrt(mtA.y * mtB.y), dfm = fSqrt(mtA.z * mtB.z);
-        /* pxManifoldDetectRestingContact, px_manifold.c:46-92, on the velocities as they are
-         * before force integration (a static's are exact zeros) */
-        float minE = mtA.x < mtB.x ? mtA.x : mtB.x;
-        const V2 pa = v2(pA.x, pA.y), pb = v2(pB.x, pB.y);
-        const V2 va = v2(vA.x, vA.y), vb = v2(vB.x, vB.y);
-        const float wa = vA.z, wb = vB.z;
-        const float fcount = (float)m.count;
-        float rcp[2] = {0.0f, 0.0f};
-        bool restingHit = false;
-#pragma unroll
-        for (uint32_t i = 0; i < 2; i++) {
-          if (i < m.count) {
-            const V2 c = i == 0 ? m.c0 : m.c1;
-            const V2 ra = c - pa, rb = c - pb;
-            const V2 rv = (vb + v2(-rb.y, rb.x) * wb) - (va + v2(-ra.y, ra.x) * wa);
-            /* the reference stops at the first hit; later contacts cannot un-hit it */
-            restingHit = restingHit || (lensq(rv) < gsq + eps);
-            /* per-contact solver denominator, px_manifold.c:142-156 */
-            const float raCrossN = cross(ra, m.normal), rbCrossN = cross(rb, m.normal);
-            const float invMassSum = pA.z + pB.z + raCrossN * raCrossN * pA.w + rbCrossN * rbCrossN * pB.w;
-            rcp[i] = fRcp(invMassSum * fcount);
-          }
-        }
-        if (restingHit) minE = 0.0f;
-        manStore(s, ms, make_float4(m.normal.x, m.normal.y, minE, sfm), make_float4(dfm, m.pen, m.c0.x, m.c0.y),
-                 make_float4(m.c1.x, m.c1.y, rcp[0], rcp[1]));
-        s.mids[ms] = a | (b << 8) | (bdyn << 17) | (m.count << 18) | (ms << 20);
+        s.man[3u * ms + 0u] = make_float4(m.normal.x, m.normal.y, m.pen, 0.0f);
+        s.man[3u * ms + 1u] = make_float4(m.c0.x, m.c0.y, m.c1.x, m.c1.y);
+        s.mids[ms] = a | (b << 8) | ((b < D ? 1u : 0u) << 17) | (m.count << 18) | (ms << 20);
         s.validSlot[BIN_SEQ(word)] = (uint16_t)(ms + 1);
-        /* manifold pass of pxUpdateSleepStates, px_world.c:147-177: flags set by SLOT */
-        const bool resting = (minE == 0.0f);
-        if (!bdyn && resting) {
-          s.restFlag[a] = 1;
-        } else if (bdyn && !resting) {
-          if (s.flags[a] & PX_FLAG_SLEEPING) s.wakeFlag[b] = 1;
-          if (s.flags[b] & PX_FLAG_SLEEPING) s.wakeFlag[a] = 1;
-        }
-        if (bdyn) atomicAdd(&s.fillB[b], 1u); /* bodyB-role manifold count of b */
       };
 
       /* C1: circle-circle and circle-polygon pairs, one pair per thread */
@@ -1204,22 +1257,47 @@ __global__ void __launch_bounds__(NT, NT == 64 ? 6 : (NT == 128 ? 5 : 3)) pxStep
             m.normal = -m.normal;
           }
         }
-        if (m.count) keep(word, a, b, m);
+        if (m.count) stage(word, a, b, m);
       }
 
-      /* C2: polygon-polygon SAT, PX_SAT_LANES lanes per pair (the faces of a polygon are spread
-       * over the lanes of its group, so a triangle-box pair and an octagon-octagon pair keep a
-       * warp about equally busy).  Survivors leave {1 << 15 | flip << 8 | reference face} in
-       * validSlot[seq] for the clip pass; separated pairs leave 0. */
+      PROF_SUB(8)
+      /* C2a: polygon pairs, one pair per thread: most AABB-pass pairs do not touch, and one
+       * well-chosen face proves it.  Survivors (bin indices) are compacted with a warp ballot
+       * into the sweep's dead AABB array; their order does not matter -- a manifold's place in
+       * the pool comes from its pair's sequence number. */
+      uint16_t *surv = (uint16_t *)s.sBox;
+      for (uint32_t base = 0; base < nPoly; base += NT) {
+        const uint32_t k = base + tid;
+        uint32_t word = 0xffffffffu;
+        if (k < nPoly) word = s.bins[nCircle + k];
+        bool alive = word != 0xffffffffu;
+        if (alive) {
+          const DBody A = loadBody(s, BIN_A(word)), B = loadBody(s, BIN_B(word));
+          alive = !polygonsSeparatedQuick(A, B, epsSq);
+        }
+        const uint32_t mask = __ballot_sync(0xffffffffu, alive);
+        uint32_t at = 0;
+        if (lane == 0 && mask) at = atomicAdd(&s.misc[MI_SURVIVORS], __popc(mask));
+        at = __shfl_sync(0xffffffffu, at, 0);
+        if (alive) surv[at + __popc(mask & ((1u << lane) - 1u))] = (uint16_t)(nCircle + k);
+      }
+      __syncthreads();
+      PROF_SUB(9)
+      const uint32_t nSurv = s.misc[MI_SURVIVORS];
+      statSurvivors = nSurv;
+      statPoly = nPoly;
+
+      /* C2b: polygon-polygon SAT, PX_SAT_LANES lanes per surviving pair (the faces of a polygon
+       * are spread over the lanes of its group).  Colliding pairs leave
+       * {1 << 15 | flip << 8 | reference face} in validSlot[seq] for the clip pass; separated pairs
+       * keep the 0 the sweep wrote. */
       {
         const uint32_t q = tid & (PX_SAT_LANES - 1u), grp = tid / PX_SAT_LANES;
-        const uint32_t nPoly = nAll - nCircle;
-        for (uint32_t base = 0; base < nPoly; base += NT / PX_SAT_LANES) {
+        for (uint32_t base = 0; base < nSurv; base += NT / PX_SAT_LANES) {
           const uint32_t k = base + grp;
-          uint32_t word = 0xffffffffu;
-          if (k < nPoly) word = s.bins[nCircle + k];
-          const bool valid = word != 0xffffffffu;
-          const uint32_t a = valid ? BIN_A(word) : 0u, b = valid ? BIN_B(word) : 0u;
+          const bool valid = k < nSurv;
+          const uint32_t word = valid ? s.bins[surv[k]] : 0u;
+          const uint32_t a = BIN_A(word), b = BIN_B(word);
           const DBody A = loadBody(s, a), B = loadBody(s, b);
           uint32_t faceA, faceB = 0;
           const float penA = leastPenetrationGroup(faceA, A, B, q, valid, epsSq);
@@ -1234,11 +1312,11 @@ __global__ void __launch_bounds__(NT, NT == 64 ? 6 : (NT == 128 ? 5 : 3)) pxStep
         }
       }
       __syncthreads();
+      PROF_SUB(10)
 
       /* C3: reference-face clipping for the SAT survivors, one pair per thread */
-      for (uint32_t idx = nCircle + tid; idx < nAll; idx += NT) {
-        const uint32_t word = s.bins[idx];
-        if (word == 0xffffffffu) continue;
+      for (uint32_t k = tid; k < nSurv; k += NT) {
+        const uint32_t word = s.bins[surv[k]];
         const uint32_t sat = s.validSlot[BIN_SEQ(word)];
         if (!sat) continue;
         const uint32_t a = BIN_A(word), b = BIN_B(word);
@@ -1249,14 +1327,68 @@ __global__ void __launch_bounds__(NT, NT == 64 ? 6 : (NT == 128 ? 5 : 3)) pxStep
           clipPolygons(A, B, (sat & 0x100u) != 0, sat & 0xffu, eps, m);
         }
         if (m.count) {
-          keep(word, a, b, m);
+          stage(word, a, b, m);
         } else {
           s.validSlot[BIN_SEQ(word)] = 0;
         }
       }
+      __syncthreads();
+      PROF_SUB(11)
+
+      /* C4: pxManifoldInit + resting contact + solver denominators + sleep flags, one manifold
+       * per thread (every lane busy) */
+      const uint32_t nStaged = min(s.misc[MI_MCOUNT], MM);
+      const V2 gstep = g * dt;
+      const float gsq = lensq(gstep);
+      for (uint32_t ms = tid; ms < nStaged; ms += NT) {
+        const uint32_t w = s.mids[ms];
+        const uint32_t a = MID_A(w), b = MID_B(w), bdyn = MID_BDYN(w), count = MID_COUNT(w);
+        const float4 g0 = s.man[3u * ms + 0u], g1 = s.man[3u * ms + 1u];
+        const V2 normal = v2(g0.x, g0.y);
+        const float3 mtA = materialOf(s, a, D, S), mtB = materialOf(s, b, D, S);
+        const float4 pA = s.bodyP[a], pB = s.bodyP[b], vA = s.bodyV[a], vB = s.bodyV[b];
+        /* pxManifoldInit, px_manifold.c:12-31: geometric-mean friction via pxFastSqrt */
+        const float sfm = fSqrt(mtA.y * mtB.y), dfm = fSqrt(mtA.z * mtB.z);
+        /* pxManifoldDetectRestingContact, px_manifold.c:46-92, on the velocities as they are
+         * before force integration (a static's are exact zeros) */
+        float minE = mtA.x < mtB.x ? mtA.x : mtB.x;
+        const V2 pa = v2(pA.x, pA.y), pb = v2(pB.x, pB.y);
+        const V2 va = v2(vA.x, vA.y), vb = v2(vB.x, vB.y);
+        const float wa = vA.z, wb = vB.z;
+        const float fcount = (float)count;
+        float rcp[2] = {0.0f, 0.0f};
+        bool restingHit = false;
+#pragma unroll
+        for (uint32_t i = 0; i < 2; i++) {
+          if (i < count) {
+            const V2 c = i == 0 ? v2(g1.x, g1.y) : v2(g1.z, g1.w);
+            const V2 ra = c - pa, rb = c - pb;
+            const V2 rv = (vb + v2(-rb.y, rb.x) * wb) - (va + v2(-ra.y, ra.x) * wa);
+            /* the reference stops at the first hit; later contacts cannot un-hit it */
+            restingHit = restingHit || (lensq(rv) < gsq + eps);
+            /* per-contact solver denominator, px_manifold.c:142-156 */
+            const float raCrossN = cross(ra, normal), rbCrossN = cross(rb, normal);
+            const float invMassSum = pA.z + pB.z + raCrossN * raCrossN * pA.w + rbCrossN * rbCrossN * pB.w;
+            rcp[i] = fRcp(invMassSum * fcount);
+          }
+        }
+        if (restingHit) minE = 0.0f;
+        manStore(s, ms, make_float4(normal.x, normal.y, minE, sfm), make_float4(dfm, g0.z, g1.x, g1.y),
+                 make_float4(g1.z, g1.w, rcp[0], rcp[1]));
+        /* manifold pass of pxUpdateSleepStates, px_world.c:147-177: flags set by SLOT */
+        const bool resting = (minE == 0.0f);
+        if (!bdyn && resting) {
+          s.restFlag[a] = 1;
+        } else if (bdyn && !resting) {
+          if (s.flags[a] & PX_FLAG_SLEEPING) s.wakeFlag[b] = 1;
+          if (s.flags[b] & PX_FLAG_SLEEPING) s.wakeFlag[a] = 1;
+        }
+        if (bdyn) atomicAdd(&s.fillB[b], 1u); /* bodyB-role manifold count of b */
+      }
     }
     __syncthreads();
     PROF_MARK(2)
+    if (prof && tid == 0) prof[7] += ((unsigned long long)statPoly << 32) + statSurvivors;
     const uint32_t mRaw = s.misc[MI_MCOUNT];
     const uint32_t M = min(mRaw, MM);
     if (tid == 0 && mRaw > MM) overflow |= PX_BATCH_OVERFLOW_MANIFOLDS;
@@ -1402,15 +1534,19 @@ __global__ void __launch_bounds__(NT, NT == 64 ? 6 : (NT == 128 ? 5 : 3)) pxStep
           }
         }
       }
-    } else if (warp == 0 && iterations) {
+    } else if (warp < 4 && iterations) {
       /*
-       * Scheduler warp.  The ORDER in which contact visits may run depends only on the
-       * manifold lists, never on a velocity, so scheduling is split from the arithmetic:
-       * this warp runs the dataflow bookkeeping and publishes rounds of up to 32 mutually
-       * independent visits; warp 1 (below) executes them.  The solver is bound by its
-       * dependency chain (about 21 rounds per iteration in a 252-body pile whatever the round
-       * width), so what matters is the latency of one round; the two chains -- ready
-       * queue/signals here, load/impulse/store there -- run side by side instead of adding up.
+       * Four specialised warps.  The ORDER in which contact visits may run depends only on the
+       * manifold lists, never on a velocity, so everything but the arithmetic is taken off the
+       * arithmetic's chain:
+       *   warp 0  scheduler: runs the dataflow bookkeeping and publishes rounds of up to 32
+       *           mutually independent visits (solverSchedule);
+       *   warps 2, 3  feeders: decode the visits of alternate rounds and stage their operands
+       *           in a shared-memory ring (solverFeed);
+       *   warp 1  math: executes the rounds in order, one contact visit per lane (solverMath).
+       * The solver is bound by its dependency chain -- about 300 rounds per substep in a settled
+       * 252-body pile at 10 iterations whatever the round width (profiles/sched_sim.py) -- so
+       * what matters is the latency of one round of the math warp.
        *
        * sig[m] counts the signals manifold m has received from its A body (low half) and its
        * B body (high half).  Visit v of a manifold may run once each of its dynamic bodies has
@@ -1420,37 +1556,32 @@ __global__ void __launch_bounds__(NT, NT == 64 ? 6 : (NT == 128 ? 5 : 3)) pxStep
        * as they were, so exactly one of the (at most two) signalers sees the other side
        * already complete and enqueues the visit.
        *
-       * Round r is the queue segment [head_r, head_r + n_r); rdesc[r % PX_RING] = (r + 1) << 16
-       * | n_r publishes it (release store; the segment's words were stored in earlier rounds).
-       * Everything signalled in round r is pushed behind the segments of rounds <= r, so a
-       * visit is always published in a later round than the visits it depends on.  The
-       * scheduler stays at most PX_LAG rounds ahead, which bounds the descriptor ring and keeps
-       * unexecuted segments from being overwritten (qcap >= MM + 32 * (PX_LAG + 1)).
-       * The loop body is branch-free: idle lanes and absent pushes go to a dummy slot.
+       * Round r is the queue segment [head_r, head_r + n_r); rdesc[r % PX_RING] = PX_DESC(r,
+       * head_r, n_r) publishes it (release store; the segment's words were stored in earlier
+       * rounds).  Everything signalled in round r is pushed behind the segments of rounds <= r,
+       * so a visit is always published in a later round than the visits it depends on.  The
+       * scheduler stays at most PX_LAG rounds ahead of the math warp, which bounds the
+       * descriptor ring and keeps unexecuted segments from being overwritten (qcap >= MM + 32 *
+       * (PX_LAG + 1)); the feeders stay at most PX_FEDRING rounds ahead of it.
        */
       SolverCtx c;
       c.aQueue = sAddr(s.queue); c.aNext = sAddr(s.nextw); c.aMids = sAddr(s.mids); c.aSig = sAddr(s.sig);
       c.aDesc = sAddr(s.misc + MI_RDESC); c.aMathRound = sAddr(s.misc + MI_MATHROUND);
       c.aBodyP = sAddr(s.bodyP); c.aBodyV = sAddr(s.bodyV);
+      c.aFed = sAddr(s.misc + MI_FED0); c.aRing = sAddr(smemRaw + P.S.fedRing);
       c.qmask = QMASK; c.qcap = P.S.qcap; c.iterations = iterations; c.tail0 = s.misc[MI_QTAIL]; c.lagSleepNs = P.lagSleepNs;
       c.man = s.man; c.eps = eps;
-      uint32_t visits = 0;
-      const uint32_t rounds = solverSchedule(c, &visits);
-      visits = __reduce_add_sync(0xffffffffu, visits);
-      if (lane == 0) s.misc[MI_VISITS] = visits;
-      if (prof && lane == 0) prof[6] += rounds;
-    } else if (warp == 1 && iterations) {
-      /* Math warp: executes the published rounds in order, one contact visit per lane.  The
-       * next round's descriptor is fetched before this round's arithmetic, so in the steady
-       * state (scheduler ahead) a round starts with its queue word already on the way.  Idle
-       * lanes run the arithmetic on manifold 0 and store nothing. */
-      SolverCtx c;
-      c.aQueue = sAddr(s.queue); c.aNext = sAddr(s.nextw); c.aMids = sAddr(s.mids); c.aSig = sAddr(s.sig);
-      c.aDesc = sAddr(s.misc + MI_RDESC); c.aMathRound = sAddr(s.misc + MI_MATHROUND);
-      c.aBodyP = sAddr(s.bodyP); c.aBodyV = sAddr(s.bodyV);
-      c.qmask = QMASK; c.qcap = P.S.qcap; c.iterations = iterations; c.tail0 = 0; c.lagSleepNs = P.lagSleepNs;
-      c.man = s.man; c.eps = eps;
-      solverMath(c);
+      if (warp == 0) {
+        uint32_t visits = 0;
+        const uint32_t rounds = solverSchedule(c, &visits);
+        visits = __reduce_add_sync(0xffffffffu, visits);
+        if (lane == 0) s.misc[MI_VISITS] = visits;
+        if (prof && lane == 0) prof[6] += rounds;
+      } else if (warp == 1) {
+        solverMath(c);
+      } else {
+        solverFeed(c, warp - 2u);
+      }
     }
     __syncthreads();
     if (tid == 0 && iterations && !(P.flags & PX_BATCH_FLAG_SERIAL_SOLVER) && s.misc[MI_VISITS] != M * iterations)
@@ -1586,11 +1717,10 @@ __global__ void __launch_bounds__(NT, NT == 64 ? 6 : (NT == 128 ? 5 : 3)) pxStep
       gh->statSleeping = s.misc[MI_SLEEPING];
       gh->statOverflow = s.hdr->statOverflow | overflow | s.misc[MI_OVERFLOW];
       gh->substeps = s.hdr->substeps + P.kSubsteps;
-      /* every read of the scratch slot is behind the last barrier of the substep loop */
-      const uint32_t slot = s.misc[MI_SLOT];
-      atomicAnd(P.slotMask + slot / PX_SCRATCH_SLOTS, ~(1u << (slot % PX_SCRATCH_SLOTS)));
     }
   }
+  __syncthreads(); /* the next world's load overwrites what the store above still reads */
+  } /* world loop */
 }
 
 /* ------------------------------------------------------------------- control commands */
@@ -1713,17 +1843,23 @@ extern "C" void pxPlanSmem(const PxBatchLayout *L, int vertsInSmem, PxSmemPlan *
   S->misc = take(32 * 4);
   S->scan = take(8 * 8);
   S->mids = take(MM * 4);
-  S->validSlot = take(MP * 2);
-  S->base = take((D + 1) * 2);
   S->listStart = take((D + 1) * 2);
   S->cnt = take(D * 2); S->cntB = take(D * 2);
+  /* validSlot, base and fillB are dead once the lists are built (only the debug serial solver walks
+   * them later): the solver's fed ring lives on top of them */
+  const uint32_t deadAfterLists = o;
+  S->validSlot = take(MP * 2);
+  S->base = take((D + 1) * 2);
   S->fillB = take(D * 4);
+  if (o - deadAfterLists < PX_FEDRING * PX_FED_SLOT_BYTES) o = deadAfterLists + PX_FEDRING * PX_FED_SLOT_BYTES;
+  S->fedRing = deadAfterLists;
   uint32_t qcap = 32;
   while (qcap < MM + 32 * (PX_LAG + 1)) qcap <<= 1; /* ready visits + published, unexecuted rounds */
   S->qcap = qcap;
   /* region X (sweep + narrowphase) overlaid by region Y (solver) */
   const uint32_t rx = o;
-  S->sBox = take(D * 16); S->sInfo = take(D * 4); S->stBox = take(St * 16);
+  S->sBox = take(D * 16 > MP * 2 ? D * 16 : MP * 2); /* AABBs by sorted position; after the sweep, u16[MP] SAT survivors */
+  S->sInfo = take(D * 4); S->stBox = take(St * 16);
   S->bins = take((MP > D ? MP : D) * 4);
   S->vertsInSmem = vertsInSmem ? 1u : 0u;
   S->verts = vertsInSmem ? take(V * 16) : 0;
@@ -1734,39 +1870,52 @@ extern "C" void pxPlanSmem(const PxBatchLayout *L, int vertsInSmem, PxSmemPlan *
   S->total = o;
 }
 
+/* The kernel may use any dynamic shared-memory size up to the device's opt-in maximum: the
+ * attribute is raised to that maximum once per device and never lowered, so batches of different
+ * sizes (and devices) cannot invalidate each other's launches. */
 template <int NT>
-static cudaError_t launchT(const PxStepParams *P, cudaStream_t stream) {
-  static int configured = -1;
-  cudaError_t err = cudaSuccess;
-  if (configured < (int)P->S.total) {
-    err = cudaFuncSetAttribute(pxStepKernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->S.total);
-    if (err != cudaSuccess) return err;
-    configured = (int)P->S.total;
-  }
-  pxStepKernel<NT><<<P->L.nWorlds, NT, P->S.total, stream>>>(*P);
+static cudaError_t configureT() {
+  static bool done[64] = {};
+  int dev = 0;
+  cudaError_t err = cudaGetDevice(&dev);
+  if (err != cudaSuccess) return err;
+  if (dev >= 0 && dev < 64 && done[dev]) return cudaSuccess;
+  int optin = 0;
+  err = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  if (err != cudaSuccess) return err;
+  err = cudaFuncSetAttribute(pxStepKernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+  if (err != cudaSuccess) return err;
+  if (dev >= 0 && dev < 64) done[dev] = true;
+  return cudaSuccess;
+}
+
+template <int NT>
+static cudaError_t launchT(const PxStepParams *P, uint32_t grid, cudaStream_t stream) {
+  cudaError_t err = configureT<NT>();
+  if (err != cudaSuccess) return err;
+  pxStepKernel<NT><<<grid, NT, P->S.total, stream>>>(*P);
   return cudaGetLastError();
 }
 
-extern "C" int pxLaunchStep(const PxStepParams *P, uint32_t threads, void *stream) {
+extern "C" int pxLaunchStep(const PxStepParams *P, uint32_t threads, uint32_t grid, void *stream) {
   cudaStream_t st = (cudaStream_t)stream;
+  if (grid == 0) return (int)cudaErrorInvalidValue;
   switch (threads) {
-  case 64: return (int)launchT<64>(P, st);
-  case 128: return (int)launchT<128>(P, st);
-  case 256: return (int)launchT<256>(P, st);
+  case 128: return (int)launchT<128>(P, grid, st);
+  case 256: return (int)launchT<256>(P, grid, st);
   default: return (int)cudaErrorInvalidValue;
   }
 }
 
 template <int NT>
 static cudaError_t occupancyT(const PxStepParams *P, int *ctasPerSm) {
-  cudaError_t err = cudaFuncSetAttribute(pxStepKernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->S.total);
+  cudaError_t err = configureT<NT>();
   if (err != cudaSuccess) return err;
   return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctasPerSm, pxStepKernel<NT>, NT, P->S.total);
 }
 
 extern "C" int pxStepOccupancy(const PxStepParams *P, uint32_t threads, int *ctasPerSm) {
   switch (threads) {
-  case 64: return (int)occupancyT<64>(P, ctasPerSm);
   case 128: return (int)occupancyT<128>(P, ctasPerSm);
   case 256: return (int)occupancyT<256>(P, ctasPerSm);
   default: return (int)cudaErrorInvalidValue;

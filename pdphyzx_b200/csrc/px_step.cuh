@@ -40,10 +40,13 @@ struct PxSmemPlan {
   uint32_t nextw; /* u16[2*MM] successor of manifold ms on side s: slot | successor has a dynamic B << 14 | side << 15 */
   uint32_t sig;   /* u32[MM]   signals received: A side low half, B side high half */
   uint32_t queue; /* u32[QCAP] ready ring of rich manifold words */
+  uint32_t fedRing; /* PX_FEDRING rounds of staged contact operands for the math warp (px_step.cu: solverFeed) */
   uint32_t total; /* bytes */
   uint32_t qcap;  /* ring capacity (power of two >= MM) */
   uint32_t vertsInSmem;
 };
+
+#define PX_PROF_SLOTS 16 /* 0-5 phases A-F, 6 solver rounds, 7 polygon pairs << 32 | after quick reject, 8-11 narrowphase stages */
 
 struct PxStepParams {
   PxBatchLayout L;
@@ -52,27 +55,27 @@ struct PxStepParams {
   const uint8_t *imm;
   uint8_t *trace; /* NULL unless PX_BATCH_FLAG_TRACE */
   const float *sinTable;
-  unsigned long long *prof; /* NULL, or u64[nWorlds][8] SM-clock cycles per phase (PX_BATCH_FLAG_PROFILE) */
+  unsigned long long *prof; /* NULL, or u64[nWorlds][PX_PROF_SLOTS] SM-clock cycles per phase (PX_BATCH_FLAG_PROFILE) */
   /* manifold records {normal, e, sf | df, pen, c0 | c1, rcpDenom0, rcpDenom1}: float4[3] per manifold,
-   * maxManifolds per slot, PX_SCRATCH_SLOTS slots per SM id.  A CTA claims a free slot of its SM in
-   * slotMask[smid] for its lifetime, so the same few MB are rewritten every substep and stay in L2. */
+   * maxManifolds per slot, one slot per CTA of the (persistent, one-wave) grid: CTA i owns slot i of
+   * this launch's region for its lifetime, so the same few MB are rewritten every substep and stay
+   * in L2.  Launches that may run concurrently get different regions. */
   float4 *scratch;
-  uint32_t *slotMask;
+  uint32_t *worldCounter; /* zeroed before the launch: the CTAs take worlds off it */
   uint32_t kSubsteps;
   uint32_t flags;
   uint32_t lagSleepNs; /* scheduler warp: nanosleep while it is PX_LAG rounds ahead of the math warp */
 };
 
-#define PX_SCRATCH_SLOTS 16u  /* >= resident CTAs per SM */
-#define PX_SCRATCH_SMIDS 256u /* >= %nsmid */
 
 #ifdef __cplusplus
 extern "C" {
 #endif
 /* vertsInSmem: 1 keeps the polygon vertex pool in shared memory, 0 reads it through L1 */
 void pxPlanSmem(const PxBatchLayout *L, int vertsInSmem, PxSmemPlan *S);
-/* launches the step kernel for all worlds of the layout; returns cudaError_t as int */
-int pxLaunchStep(const PxStepParams *P, uint32_t threads, void *stream);
+/* launches the step kernel: `grid` persistent CTAs (<= resident capacity, <= scratch slots) work
+ * through all worlds of the layout; returns cudaError_t as int */
+int pxLaunchStep(const PxStepParams *P, uint32_t threads, uint32_t grid, void *stream);
 /* occupancy query: resident CTAs per SM for this plan */
 int pxStepOccupancy(const PxStepParams *P, uint32_t threads, int *ctasPerSm);
 
