@@ -829,26 +829,16 @@ void pxWorldSetIterations(PxWorld *world, uint8_t iterations) {
   world->iterations = iterations;
 }
 
-static void pxWorldDropBatch(PxWorld *world) {
-  /* the body set changed: the device copy is rebuilt on the next step */
-  if (world->batch) {
-    pxBatchFree((PxBatch *)world->batch);
-    world->batch = NULL;
-  }
-}
-
 PxBody *pxWorldNewStaticBody(PxWorld *world, PxShape shape, PxVec2 position) {
   PxBody body = pxBodyNew(shape, PX_BODY_STATIC, 0, position);
   PxBody *stored = pxBodyArrayAdd(&world->staticBodies, &body);
   pxBodyArraySortByAxis(&world->staticBodies); /* px_world.c:98 */
-  pxWorldDropBatch(world);
-  return stored;
+  return stored; /* the device copy follows at the next step: the facade's batch has headroom */
 }
 
 PxBody *pxWorldNewDynamicBody(PxWorld *world, PxShape shape, float density, PxVec2 position) {
   PxBody body = pxBodyNew(shape, PX_BODY_DYNAMIC, density, position);
   PxBody *stored = pxBodyArrayAdd(&world->dynamicBodies, &body);
-  pxWorldDropBatch(world);
   return stored;
 }
 
@@ -856,7 +846,6 @@ void pxWorldFreeBody(PxWorld *world, PxBody *body) {
   if (!world || !body) return;
   PxBodyArray *arr = body->density > 0 ? &world->dynamicBodies : &world->staticBodies;
   pxBodyArrayRemove(arr, body->worldIndex);
-  pxWorldDropBatch(world);
 }
 
 float pxWorldSubstepDt(const PxWorld *world) {
@@ -881,16 +870,29 @@ bool pxWorldStep(PxWorld *world) {
     return false;
   }
   PxWorld *const one[1] = {world};
+  if (world->batch && pxBatchUpload((PxBatch *)world->batch, one, 0, 1) != 0) {
+    /* the world outgrew the batch's capacities (it was made with generous headroom): make a bigger one */
+    pxBatchFree((PxBatch *)world->batch);
+    world->batch = NULL;
+  }
   if (!world->batch) {
+    /* One batch for the life of the world: bodies come and go (examples/draw spawns and frees
+     * circles while running), so the capacities leave room -- every dynamic slot, twice the
+     * statics and vertices present now -- and add/free never re-creates device buffers. */
     PxBatchDesc desc = pxBatchDescDefault(PDPHYZX_UNIT);
+    if (pxBatchFitDesc(one, 1, &desc) != 0) {
+      fprintf(stderr, "pdphyzx: %s\n", pxBatchLastError());
+      abort();
+    }
+    desc.maxDynamic = PX_MAX_BODIES;
+    desc.maxStatic = desc.maxStatic * 2 > 16 ? desc.maxStatic * 2 : 16;
+    if (desc.maxStatic > 64) desc.maxStatic = 64 > world->staticBodies.length ? 64 : world->staticBodies.length;
+    desc.maxVertices = desc.maxVertices * 2 > 2048 ? desc.maxVertices * 2 : 2048;
     world->batch = pxBatchNew(one, 1, &desc);
     if (!world->batch) {
       fprintf(stderr, "pdphyzx: px->world->step needs the CUDA batch back end: %s\n", pxBatchLastError());
       abort();
     }
-  } else if (pxBatchUpload((PxBatch *)world->batch, one, 0, 1) != 0) {
-    fprintf(stderr, "pdphyzx: upload failed: %s\n", pxBatchLastError());
-    abort();
   }
   int rc = pxBatchStep((PxBatch *)world->batch, (uint32_t)fired * PX_SUBSTEPS_PER_STEP);
   if (rc == 0) {

@@ -103,12 +103,14 @@ enum {
 };
 /* rows of the immutable dynamic matrix f32[PX_DYNC_ROWS][maxDynamic] */
 enum { PX_DYNC_IMASS = 0, PX_DYNC_IINERTIA, PX_DYNC_E, PX_DYNC_SF, PX_DYNC_DF, PX_DYNC_RADIUS, PX_DYNC_ROWS };
-/* rows of the static matrix f32[PX_STAT_ROWS][maxStatic], indexed by POSITION in the static
- * iteration order (staticBodies.activeIndices), not by slot */
-enum {
-  PX_STAT_PX = 0, PX_STAT_PY, PX_STAT_M00, PX_STAT_M01, PX_STAT_M10, PX_STAT_M11, PX_STAT_E, PX_STAT_SF,
-  PX_STAT_DF, PX_STAT_RADIUS, PX_STAT_ROWS
-};
+/* Static bodies are indexed by POSITION in the static iteration order
+ * (staticBodies.activeIndices), not by slot.  Their pose is mutable -- px->body->setPosition /
+ * setOrientation / moveBy / rotate work on static bodies too (reference examples/sprites/main.c:91-95
+ * turns the ground every frame) -- and lives in the mutable block: f32[PX_STATM_ROWS][maxStatic];
+ * the step itself never writes it.  Materials and the AABB radius are immutable:
+ * f32[PX_STAT_ROWS][maxStatic]. */
+enum { PX_STATM_PX = 0, PX_STATM_PY, PX_STATM_ANGLE, PX_STATM_M00, PX_STATM_M01, PX_STATM_M10, PX_STATM_M11, PX_STATM_ROWS };
+enum { PX_STAT_E = 0, PX_STAT_SF, PX_STAT_DF, PX_STAT_RADIUS, PX_STAT_ROWS };
 
 /*
  * Where things are inside the two per-world blocks (all offsets in bytes from the start of
@@ -124,6 +126,7 @@ typedef struct PxBatchLayout {
   uint32_t offDyn;       /* f32[PX_DYN_ROWS][maxDynamic] */
   uint32_t offDynFlags;  /* u8[maxDynamic]   PxBody.flags by slot */
   uint32_t offDynOrder;  /* u8[maxDynamic]   dynamicBodies.activeIndices */
+  uint32_t offStatMut;   /* f32[PX_STATM_ROWS][maxStatic] static poses, by position */
   /* immutable block */
   uint32_t offDynConst;  /* f32[PX_DYNC_ROWS][maxDynamic] */
   uint32_t offDynShape;  /* u32[maxDynamic]  (vertexOffset << 8) | vertexCount, count 0 = circle; see PX_SHAPE_* */
@@ -199,7 +202,8 @@ PX_API int pxBatchSync(PxBatch *b);
 PX_API int pxBatchReadback(PxBatch *b, struct PxWorld *const *worlds, uint32_t first, uint32_t n, uint32_t flags);
 
 /* ------------------------------------------------------------- control path (queued, K=1..) */
-/* Applied in call order at the start of the next pxBatchStep, before its first substep.
+/* Applied in call order at the start of the next pxBatchStep, before its first substep (and
+ * before any device -> host copy: pxBatchReadback / pxBatchMutableD2H see their effect).
  * body = slot (PxBody.worldIndex) of a dynamic body; world = index in the batch or
  * PX_ALL_WORLDS for the setters. */
 #define PX_ALL_WORLDS 0xffffffffu
@@ -213,10 +217,42 @@ PX_API int pxBatchApplyImpulses(PxBatch *b, uint32_t n, const uint32_t *worlds, 
                                 const float *contactXY);
 /* px->body->applyForce (src/px_body_api.c:20-26, src/px_body.c:158-165) */
 PX_API int pxBatchApplyForce(PxBatch *b, uint32_t world, uint32_t body, float fx, float fy, float cx, float cy);
+/* px->body->setPosition / moveBy / setOrientation / rotate (src/px_body_api.c:57-60,
+ * src/px_body.c:85-124): plain pose edits, no wake-up; the orientation matrix comes from the same
+ * sine table as the step's.  `body` is the slot of a dynamic body, or PX_BATCH_STATIC | slot for
+ * a static one (examples/sprites/main.c:91-95 turns its static ground every frame). */
+#define PX_BATCH_STATIC 0x10000u
+PX_API int pxBatchSetPosition(PxBatch *b, uint32_t world, uint32_t body, float x, float y);
+PX_API int pxBatchMoveBy(PxBatch *b, uint32_t world, uint32_t body, float dx, float dy);
+PX_API int pxBatchSetOrientation(PxBatch *b, uint32_t world, uint32_t body, float radians);
+PX_API int pxBatchRotate(PxBatch *b, uint32_t world, uint32_t body, float radians);
 /* px->world->setGravity: stores (x, y) * unit (src/px_world.c:57-63) */
 PX_API int pxBatchSetGravity(PxBatch *b, uint32_t world, float x, float y);
 /* px->world->setIterations (src/px_world.c:65-71) */
 PX_API int pxBatchSetIterations(PxBatch *b, uint32_t world, uint32_t iterations);
+
+/* ------------------------------------------------------ body lifecycle on a resident batch */
+/* The host keeps the reference's PxBodyArray bookkeeping (slot reuse from the freed stack, swap-remove
+ * from activeIndices, src/px_body_array.c:7-79); these calls mirror one host-side
+ * px->world->newDynamicBody / newStaticBody / freeBody onto the resident world without re-creating
+ * or re-uploading it.  Queued like the control commands; no device allocation.
+ *
+ * pxBatchAddBody: `body` is what the host call returned (it lives in hostWorld, its worldIndex is
+ * the slot the reference's rule chose).  Dynamic: constants, shape and vertices go to the world's
+ * immutable block, the mutable rows are written on the device and the slot is appended to the
+ * device's iteration order (which, not the host's stale copy, is the order the reference would
+ * have).  Static: the world's static list is re-packed from hostWorld (the host re-sorts it on
+ * every add, src/px_world.c:94-101; host static poses are authoritative at that moment).
+ * pxBatchFreeBody: dynamic = slot, swap-removed from the device's order with the reference's own
+ * `index >= length` no-op rule (src/px_body_array.c:64); static = PX_BATCH_STATIC | slot, re-packs
+ * the static list from hostWorld (after the host-side freeBody). */
+/* (PxBody is an untagged typedef in the reference, src/includes/px_body.h:82-120, hence the void pointer) */
+PX_API int pxBatchAddBody(PxBatch *b, uint32_t world, const struct PxWorld *hostWorld, const void *body /* const PxBody * */);
+PX_API int pxBatchFreeBody(PxBatch *b, uint32_t world, uint32_t body, const struct PxWorld *hostWorld);
+PX_API int pxBatchSyncStatics(PxBatch *b, uint32_t world, const struct PxWorld *hostWorld);
+/* device + pinned allocations the batch has made since creation (0 unless a command burst outgrew
+ * the buffers sized at creation) */
+PX_API uint64_t pxBatchAllocCount(const PxBatch *b);
 
 /* ------------------------------------------------------------------ raw blocks (SoA level) */
 

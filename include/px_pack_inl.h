@@ -114,6 +114,7 @@ static inline int pxPackOneWorld(const PxBatchLayout *L, const PxWorld *world, u
   float *dynC = (float *)(imm + L->offDynConst);
   uint32_t *dynShape = (uint32_t *)(imm + L->offDynShape);
   float *statF = (float *)(imm + L->offStat);
+  float *statM = (float *)(mut + L->offStatMut);
   uint32_t *statShape = (uint32_t *)(imm + L->offStatShape);
   uint8_t *statSlot = imm + L->offStatSlot;
   float *verts4 = (float *)(imm + L->offVerts);
@@ -154,12 +155,13 @@ static inline int pxPackOneWorld(const PxBatchLayout *L, const PxWorld *world, u
     uint32_t slot = stat->activeIndices[i];
     const PxBody *b = &stat->items[slot];
     statSlot[i] = (uint8_t)slot;
-    statF[PX_STAT_PX * S + i] = b->position.x;
-    statF[PX_STAT_PY * S + i] = b->position.y;
-    statF[PX_STAT_M00 * S + i] = b->orientation.m00;
-    statF[PX_STAT_M01 * S + i] = b->orientation.m01;
-    statF[PX_STAT_M10 * S + i] = b->orientation.m10;
-    statF[PX_STAT_M11 * S + i] = b->orientation.m11;
+    statM[PX_STATM_PX * S + i] = b->position.x;
+    statM[PX_STATM_PY * S + i] = b->position.y;
+    statM[PX_STATM_ANGLE * S + i] = b->orientationAngle;
+    statM[PX_STATM_M00 * S + i] = b->orientation.m00;
+    statM[PX_STATM_M01 * S + i] = b->orientation.m01;
+    statM[PX_STATM_M10 * S + i] = b->orientation.m10;
+    statM[PX_STATM_M11 * S + i] = b->orientation.m11;
     statF[PX_STAT_E * S + i] = b->restitution;
     statF[PX_STAT_SF * S + i] = b->staticFriction;
     statF[PX_STAT_DF * S + i] = b->dynamicFriction;
@@ -218,7 +220,181 @@ static inline int pxUnpackOneWorld(const PxBatchLayout *L, PxWorld *world, uint3
     b->aabb.min = pxVec2Subf(b->position, r);
     b->aabb.max = pxVec2Addf(b->position, r);
   }
+  /* static poses change only through pose commands (pxBatchSetPosition ... pxBatchRotate); the
+   * step never writes them */
+  PxBodyArray *stat = &world->staticBodies;
+  const uint32_t S = L->maxStatic;
+  const float *statM = (const float *)(mut + L->offStatMut);
+  for (uint32_t i = 0; i < stat->length && i < h->nStatic && i < S; i++) {
+    PxBody *b = &stat->items[stat->activeIndices[i]];
+    b->position.x = statM[PX_STATM_PX * S + i];
+    b->position.y = statM[PX_STATM_PY * S + i];
+    b->orientationAngle = statM[PX_STATM_ANGLE * S + i];
+    b->orientation.m00 = statM[PX_STATM_M00 * S + i];
+    b->orientation.m01 = statM[PX_STATM_M01 * S + i];
+    b->orientation.m10 = statM[PX_STATM_M10 * S + i];
+    b->orientation.m11 = statM[PX_STATM_M11 * S + i];
+    float r = pxPackRadius(b);
+    b->aabb.min = pxVec2Subf(b->position, r);
+    b->aabb.max = pxVec2Addf(b->position, r);
+  }
   return overflowed;
+}
+
+/* ---- body lifecycle on a resident world (pxBatchAddBody / pxBatchFreeBody) -------------------
+ * The immutable block has a host mirror; a body added to a live world gets its constants, shape
+ * word and vertices written there.  Vertex ranges are not reference-counted: at every add the
+ * occupied ranges are those of the bodies that are live in the host world, so the ranges of freed
+ * bodies are reclaimed implicitly. */
+static inline void pxPackMarkRange(uint8_t *used, uint32_t cap, uint32_t shapeWord) {
+  const uint32_t n = PX_SHAPE_COUNT(shapeWord), off = PX_SHAPE_OFFSET(shapeWord);
+  for (uint32_t k = 0; k < n && off + k < cap; k++) used[off + k] = 1;
+}
+
+/* first fit of `count` vertices in the pool; returns the offset or UINT32_MAX */
+static inline uint32_t pxPackFirstFit(const uint8_t *used, uint32_t cap, uint32_t count) {
+  uint32_t run = 0;
+  for (uint32_t i = 0; i < cap; i++) {
+    run = used[i] ? 0 : run + 1;
+    if (run == count) return i + 1 - count;
+  }
+  return UINT32_MAX;
+}
+
+static inline void pxPackWriteVerts(const PxBody *b, float *verts4, uint32_t off) {
+  const PxPolygonData *p = &b->collider.shape.polygon;
+  const uint32_t count = pxPackVertexCount(b);
+  for (uint32_t i = 0; i < count; i++) {
+    float *v = verts4 + (size_t)(off + i) * 4;
+    v[0] = p->vertices.items[i].x;
+    v[1] = p->vertices.items[i].y;
+    v[2] = p->normals.items[i].x;
+    v[3] = p->normals.items[i].y;
+  }
+}
+
+/* vertex-pool occupancy of the live bodies of `world` as the mirror `imm` describes them;
+ * `skip` (may be NULL) is left out, statics are included on request.  `used` has maxVertices bytes. */
+static inline void pxPackOccupancy(const PxBatchLayout *L, const PxWorld *world, const uint8_t *imm, const PxBody *skip,
+                                   int withStatics, uint8_t *used) {
+  memset(used, 0, L->maxVertices);
+  const uint32_t *dynShape = (const uint32_t *)(imm + L->offDynShape);
+  const uint32_t *statShape = (const uint32_t *)(imm + L->offStatShape);
+  const uint8_t *statSlot = imm + L->offStatSlot;
+  for (uint32_t i = 0; i < world->dynamicBodies.length; i++) {
+    const uint32_t slot = world->dynamicBodies.activeIndices[i];
+    if (&world->dynamicBodies.items[slot] == skip || slot >= L->maxDynamic) continue;
+    pxPackMarkRange(used, L->maxVertices, dynShape[slot]);
+  }
+  if (withStatics) {
+    /* the mirror's static rows are by position; mark those whose slot is still live on the host */
+    for (uint32_t q = 0; q < L->maxStatic; q++) {
+      if (!PX_SHAPE_COUNT(statShape[q])) continue;
+      for (uint32_t i = 0; i < world->staticBodies.length; i++) {
+        if (world->staticBodies.activeIndices[i] == statSlot[q] && &world->staticBodies.items[statSlot[q]] != skip) {
+          pxPackMarkRange(used, L->maxVertices, statShape[q]);
+          break;
+        }
+      }
+    }
+  }
+}
+
+/* A dynamic body the host has just added to `world` (px->world->newDynamicBody: the reference's
+ * slot-reuse rule already chose body->worldIndex, src/px_body_array.c:32-42): write its
+ * constants, shape and vertices into the mirror `imm` and its mutable rows into `dynRows`
+ * (PX_DYN_ROWS floats) / `flagsOut`.  `used` is scratch of maxVertices bytes. */
+static inline int pxPackAddDynamicBody(const PxBatchLayout *L, const PxWorld *world, const PxBody *b, uint8_t *imm, float *dynRows,
+                                       uint32_t *flagsOut, uint8_t *used) {
+  const uint32_t D = L->maxDynamic, slot = b->worldIndex;
+  if (slot >= D) {
+    PX_PACK_FAIL(-1, "added body: slot %u exceeds maxDynamic %u", slot, D);
+  }
+  float *dynC = (float *)(imm + L->offDynConst);
+  uint32_t *dynShape = (uint32_t *)(imm + L->offDynShape);
+  const uint32_t count = pxPackVertexCount(b);
+  uint32_t shape = PX_SHAPE_PACK(0, 0);
+  if (count) {
+    pxPackOccupancy(L, world, imm, b, 1, used);
+    const uint32_t off = pxPackFirstFit(used, L->maxVertices, count);
+    if (off == UINT32_MAX) {
+      PX_PACK_FAIL(-1, "added body: no room for %u vertices in the world's pool of %u (raise PxBatchDesc.maxVertices)", count,
+                   L->maxVertices);
+    }
+    pxPackWriteVerts(b, (float *)(imm + L->offVerts), off);
+    shape = PX_SHAPE_PACK(off, count);
+  }
+  dynShape[slot] = shape;
+  dynC[PX_DYNC_IMASS * D + slot] = b->iMass;
+  dynC[PX_DYNC_IINERTIA * D + slot] = b->iMomentOfInertia;
+  dynC[PX_DYNC_E * D + slot] = b->restitution;
+  dynC[PX_DYNC_SF * D + slot] = b->staticFriction;
+  dynC[PX_DYNC_DF * D + slot] = b->dynamicFriction;
+  dynC[PX_DYNC_RADIUS * D + slot] = pxPackRadius(b);
+  dynRows[PX_DYN_PX] = b->position.x;
+  dynRows[PX_DYN_PY] = b->position.y;
+  dynRows[PX_DYN_VX] = b->velocity.x;
+  dynRows[PX_DYN_VY] = b->velocity.y;
+  dynRows[PX_DYN_AV] = b->angularVelocity;
+  dynRows[PX_DYN_ANGLE] = b->orientationAngle;
+  dynRows[PX_DYN_FX] = b->force.x;
+  dynRows[PX_DYN_FY] = b->force.y;
+  dynRows[PX_DYN_TORQUE] = b->torque;
+  dynRows[PX_DYN_SLEEP] = b->sleepTime;
+  dynRows[PX_DYN_M00] = b->orientation.m00;
+  dynRows[PX_DYN_M01] = b->orientation.m01;
+  dynRows[PX_DYN_M10] = b->orientation.m10;
+  dynRows[PX_DYN_M11] = b->orientation.m11;
+  *flagsOut = b->flags;
+  return 0;
+}
+
+/* The static bodies of `world` as they are on the host now (after px->world->newStaticBody,
+ * which re-sorts them, src/px_world.c:94-101, or freeBody): rewrites the static rows of the
+ * mirror `imm` and of the mutable image `mut` (header.nStatic and the pose rows only). */
+static inline int pxPackStaticBodies(const PxBatchLayout *L, const PxWorld *world, uint8_t *mut, uint8_t *imm, uint8_t *used) {
+  const uint32_t S = L->maxStatic;
+  const PxBodyArray *stat = &world->staticBodies;
+  if (stat->length > S) {
+    PX_PACK_FAIL(-1, "%u static bodies exceed maxStatic %u", (unsigned)stat->length, S);
+  }
+  pxPackOccupancy(L, world, imm, NULL, 0, used); /* live dynamic polygons keep their ranges */
+  float *statF = (float *)(imm + L->offStat);
+  float *statM = (float *)(mut + L->offStatMut);
+  uint32_t *statShape = (uint32_t *)(imm + L->offStatShape);
+  uint8_t *statSlot = imm + L->offStatSlot;
+  memset(statF, 0, PX_STAT_ROWS * S * 4);
+  memset(statM, 0, PX_STATM_ROWS * S * 4);
+  memset(statShape, 0, S * 4);
+  memset(statSlot, 0, S);
+  for (uint32_t i = 0; i < stat->length; i++) {
+    const uint32_t slot = stat->activeIndices[i];
+    const PxBody *b = &stat->items[slot];
+    statSlot[i] = (uint8_t)slot;
+    statM[PX_STATM_PX * S + i] = b->position.x;
+    statM[PX_STATM_PY * S + i] = b->position.y;
+    statM[PX_STATM_ANGLE * S + i] = b->orientationAngle;
+    statM[PX_STATM_M00 * S + i] = b->orientation.m00;
+    statM[PX_STATM_M01 * S + i] = b->orientation.m01;
+    statM[PX_STATM_M10 * S + i] = b->orientation.m10;
+    statM[PX_STATM_M11 * S + i] = b->orientation.m11;
+    statF[PX_STAT_E * S + i] = b->restitution;
+    statF[PX_STAT_SF * S + i] = b->staticFriction;
+    statF[PX_STAT_DF * S + i] = b->dynamicFriction;
+    statF[PX_STAT_RADIUS * S + i] = pxPackRadius(b);
+    const uint32_t count = pxPackVertexCount(b);
+    if (count) {
+      const uint32_t off = pxPackFirstFit(used, L->maxVertices, count);
+      if (off == UINT32_MAX) {
+        PX_PACK_FAIL(-1, "static body: no room for %u vertices in the world's pool of %u", count, L->maxVertices);
+      }
+      pxPackWriteVerts(b, (float *)(imm + L->offVerts), off);
+      for (uint32_t k = 0; k < count; k++) used[off + k] = 1;
+      statShape[i] = PX_SHAPE_PACK(off, count);
+    }
+  }
+  ((PxWorldHeader *)(mut + L->offHeader))->nStatic = stat->length;
+  return 0;
 }
 
 #endif /* PX_PACK_INL_H */

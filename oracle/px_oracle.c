@@ -89,7 +89,8 @@ typedef struct {
   uint8_t *order;       /* [D] */
   const float *dync;    /* [PX_DYNC_ROWS][D] */
   const uint32_t *dshape;
-  const float *stat;    /* [PX_STAT_ROWS][S] */
+  const float *stat;    /* [PX_STAT_ROWS][S] materials + radius (immutable block) */
+  const float *statm;   /* [PX_STATM_ROWS][S] static poses (mutable block) */
   const uint32_t *sshape;
   const uint8_t *sslot;
   const float *verts;   /* float4 per vertex */
@@ -100,6 +101,7 @@ typedef struct {
 #define DYN(w, row, slot) ((w)->dyn[(row) * (w)->D + (slot)])
 #define DYNC(w, row, slot) ((w)->dync[(row) * (w)->D + (slot)])
 #define STAT(w, row, pos) ((w)->stat[(row) * (w)->S + (pos)])
+#define STATM(w, row, pos) ((w)->statm[(row) * (w)->S + (pos)])
 
 #define FLAG_SLEEPING 8u /* PX_BODY_FLAG_SLEEPING, px_body.h:67 */
 
@@ -125,8 +127,8 @@ static Body loadBody(const World *w, int dynamic, uint32_t id) {
     b.nverts = PX_SHAPE_COUNT(w->dshape[id]);
     b.voff = PX_SHAPE_OFFSET(w->dshape[id]);
   } else {
-    b.pos = v2(STAT(w, PX_STAT_PX, id), STAT(w, PX_STAT_PY, id));
-    b.rot = (M2){STAT(w, PX_STAT_M00, id), STAT(w, PX_STAT_M01, id), STAT(w, PX_STAT_M10, id), STAT(w, PX_STAT_M11, id)};
+    b.pos = v2(STATM(w, PX_STATM_PX, id), STATM(w, PX_STATM_PY, id));
+    b.rot = (M2){STATM(w, PX_STATM_M00, id), STATM(w, PX_STATM_M01, id), STATM(w, PX_STATM_M10, id), STATM(w, PX_STATM_M11, id)};
     b.radius = STAT(w, PX_STAT_RADIUS, id);
     b.nverts = PX_SHAPE_COUNT(w->sshape[id]);
     b.voff = PX_SHAPE_OFFSET(w->sshape[id]);
@@ -505,7 +507,7 @@ static void generateCollisionInfo(World *w, Scratch *s) {
     s->dynBox[slot] = bodyBox(v2(DYN(w, PX_DYN_PX, slot), DYN(w, PX_DYN_PY, slot)), DYNC(w, PX_DYNC_RADIUS, slot));
   }
   for (uint32_t i = 0; i < ns; i++) {
-    s->statBox[i] = bodyBox(v2(STAT(w, PX_STAT_PX, i), STAT(w, PX_STAT_PY, i)), STAT(w, PX_STAT_RADIUS, i));
+    s->statBox[i] = bodyBox(v2(STATM(w, PX_STATM_PX, i), STATM(w, PX_STATM_PY, i)), STAT(w, PX_STAT_RADIUS, i));
   }
   sortByMinX(w, s);
   for (uint32_t i = 0; i < nd; i++) {
@@ -543,7 +545,7 @@ static Mover loadMover(const World *w, int dynamic, uint32_t id) {
   } else { /* statics: zero velocity and zero inverse mass (px_body.c:30-44) */
     m.vel = v2(0, 0);
     m.av = 0;
-    m.pos = v2(STAT(w, PX_STAT_PX, id), STAT(w, PX_STAT_PY, id));
+    m.pos = v2(STATM(w, PX_STATM_PX, id), STATM(w, PX_STATM_PY, id));
     m.iM = 0;
     m.iI = 0;
   }
@@ -803,6 +805,7 @@ static void bindWorld(World *w, const PxBatchLayout *L, void *mut, const void *i
   w->dync = (const float *)(c + L->offDynConst);
   w->dshape = (const uint32_t *)(c + L->offDynShape);
   w->stat = (const float *)(c + L->offStat);
+  w->statm = (const float *)(m + L->offStatMut);
   w->sshape = (const uint32_t *)(c + L->offStatShape);
   w->sslot = c + L->offStatSlot;
   w->verts = (const float *)(c + L->offVerts);

@@ -190,6 +190,12 @@ REF_EXPORT void ref_body_set_position(PxWorld *w, int dynamic, int slot, float x
 REF_EXPORT void ref_body_set_orientation(PxWorld *w, int dynamic, int slot, float rad) {
   g_px->body->setOrientation(&refArray(w, dynamic)->items[slot], rad);
 }
+REF_EXPORT void ref_body_move_by(PxWorld *w, int dynamic, int slot, float dx, float dy) {
+  g_px->body->moveBy(&refArray(w, dynamic)->items[slot], pxVec2(dx, dy));
+}
+REF_EXPORT void ref_body_rotate(PxWorld *w, int dynamic, int slot, float rad) {
+  g_px->body->rotate(&refArray(w, dynamic)->items[slot], rad);
+}
 REF_EXPORT void ref_free_body(PxWorld *w, int dynamic, int slot) {
   g_px->world->freeBody(w, &refArray(w, dynamic)->items[slot]);
 }

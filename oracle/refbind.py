@@ -56,6 +56,8 @@ def load(variant: str = "wide", unit: float = 1.0):
         "ref_body_apply_force": (None, [vp, i, f, f, f, f]),
         "ref_body_set_position": (None, [vp, i, i, f, f]),
         "ref_body_set_orientation": (None, [vp, i, i, f]),
+        "ref_body_move_by": (None, [vp, i, i, f, f]),
+        "ref_body_rotate": (None, [vp, i, i, f]),
         "ref_free_body": (None, [vp, i, i]),
         "ref_substep": (None, [vp, f, i]),
         "ref_step": (i, [vp]),

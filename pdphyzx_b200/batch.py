@@ -23,10 +23,12 @@ FLAG_SERIAL_SOLVER = 2
 FLAG_PROFILE = 4
 OVERFLOW_PAIRS = 1
 OVERFLOW_MANIFOLDS = 2
+STATIC = 0x10000  # PX_BATCH_STATIC: OR into a body slot to address a static body
 
 DYN_ROWS = ("px", "py", "vx", "vy", "av", "angle", "fx", "fy", "torque", "sleep", "m00", "m01", "m10", "m11")
 DYNC_ROWS = ("imass", "iinertia", "e", "sf", "df", "radius")
-STAT_ROWS = ("px", "py", "m00", "m01", "m10", "m11", "e", "sf", "df", "radius")
+STAT_ROWS = ("e", "sf", "df", "radius")  # immutable block
+STATM_ROWS = ("px", "py", "angle", "m00", "m01", "m10", "m11")  # mutable block: static poses
 TRACE_M_F32 = 10
 
 
@@ -54,7 +56,7 @@ HEADER_DTYPE = np.dtype([(n, np.float32 if t is C.c_float else np.uint32) for n,
 class PxBatchLayout(C.Structure):
     _fields_ = [(n, C.c_uint32) for n in (
         "nWorlds", "maxDynamic", "maxStatic", "maxVertices", "maxManifolds", "maxPairs", "mutStride", "immStride",
-        "offHeader", "offDyn", "offDynFlags", "offDynOrder", "offDynConst", "offDynShape", "offStat", "offStatShape",
+        "offHeader", "offDyn", "offDynFlags", "offDynOrder", "offStatMut", "offDynConst", "offDynShape", "offStat", "offStatShape",
         "offStatSlot", "offVerts", "traceStride", "offTracePairs", "offTraceManifolds")] + [
         ("unit", C.c_float), ("epsilon", C.c_float), ("epsilonSq", C.c_float), ("allowedPenetration", C.c_float)]
 
@@ -85,6 +87,14 @@ def core():
         "pxBatchApplyImpulse": (i32, [vp, u32, u32, f, f, f, f]),
         "pxBatchApplyImpulses": (i32, [vp, u32, vp, vp, vp, vp]),
         "pxBatchApplyForce": (i32, [vp, u32, u32, f, f, f, f]),
+        "pxBatchSetPosition": (i32, [vp, u32, u32, f, f]),
+        "pxBatchMoveBy": (i32, [vp, u32, u32, f, f]),
+        "pxBatchSetOrientation": (i32, [vp, u32, u32, f]),
+        "pxBatchRotate": (i32, [vp, u32, u32, f]),
+        "pxBatchAddBody": (i32, [vp, u32, vp, vp]),
+        "pxBatchFreeBody": (i32, [vp, u32, u32, vp]),
+        "pxBatchSyncStatics": (i32, [vp, u32, vp]),
+        "pxBatchAllocCount": (C.c_uint64, [vp]),
         "pxBatchSetGravity": (i32, [vp, u32, f, f]),
         "pxBatchSetIterations": (i32, [vp, u32, u32]),
         "pxBatchGetLayout": (i32, [vp, C.POINTER(PxBatchLayout)]),
@@ -172,6 +182,7 @@ def host(unit: float = 1.0):
         "pxh_body_rotate": (None, [vp, i, i, f]),
         "pxh_body_is_valid": (i, [vp, i, i]),
         "pxh_free_body": (None, [vp, i, i]),
+        "pxh_body_ptr": (vp, [vp, i, i]),
         "pxh_body_row_floats": (i, []),
         "pxh_get_bodies": (i, [vp, i, f32p, u8p, u8p, i]),
         "pxh_get_polygon": (i, [vp, i, i, f32p, f32p, i]),
@@ -291,6 +302,7 @@ class Blocks:
         self.dyn = np.ndarray((n, len(DYN_ROWS), D), np.float32, buffer=mut, offset=L.offDyn, strides=(L.mutStride, 4 * D, 4))
         self.flags = np.ndarray((n, D), np.uint8, buffer=mut, offset=L.offDynFlags, strides=(L.mutStride, 1))
         self.order = np.ndarray((n, D), np.uint8, buffer=mut, offset=L.offDynOrder, strides=(L.mutStride, 1))
+        self.statm = np.ndarray((n, len(STATM_ROWS), S), np.float32, buffer=mut, offset=L.offStatMut, strides=(L.mutStride, 4 * S, 4))
         if imm is not None:
             self.dync = np.ndarray((n, len(DYNC_ROWS), D), np.float32, buffer=imm, offset=L.offDynConst, strides=(L.immStride, 4 * D, 4))
             self.dshape = np.ndarray((n, D), np.uint32, buffer=imm, offset=L.offDynShape, strides=(L.immStride, 4))
@@ -422,6 +434,34 @@ class Batch:
 
     def apply_force(self, world, body, fx, fy, cx, cy):
         _check(self.lib.pxBatchApplyForce(self.h, world, body, fx, fy, cx, cy), "pxBatchApplyForce")
+
+    def set_position(self, world, body, x, y):
+        _check(self.lib.pxBatchSetPosition(self.h, world, body, x, y), "pxBatchSetPosition")
+
+    def move_by(self, world, body, dx, dy):
+        _check(self.lib.pxBatchMoveBy(self.h, world, body, dx, dy), "pxBatchMoveBy")
+
+    def set_orientation(self, world, body, radians):
+        _check(self.lib.pxBatchSetOrientation(self.h, world, body, radians), "pxBatchSetOrientation")
+
+    def rotate(self, world, body, radians):
+        _check(self.lib.pxBatchRotate(self.h, world, body, radians), "pxBatchRotate")
+
+    # -- body lifecycle on the resident batch ----------------------------------------------
+    def add_body(self, world: int, host_worlds: "HostWorlds", w: int, dynamic: bool, slot: int):
+        """Mirror a body just added to host world `w` (px->world->newDynamicBody / newStaticBody) onto batch world `world`."""
+        ptr = host_worlds.lib.pxh_body_ptr(host_worlds.ptrs[w], int(dynamic), int(slot))
+        _check(self.lib.pxBatchAddBody(self.h, world, host_worlds.ptrs[w], ptr), "pxBatchAddBody")
+
+    def free_body(self, world: int, slot: int, dynamic: bool = True, host_worlds: "HostWorlds | None" = None, w: int = 0):
+        """Mirror px->world->freeBody (already done on the host world for statics) onto batch world `world`."""
+        body = int(slot) | (0 if dynamic else STATIC)
+        hw = host_worlds.ptrs[w] if host_worlds is not None else None
+        _check(self.lib.pxBatchFreeBody(self.h, world, body, hw), "pxBatchFreeBody")
+
+    @property
+    def alloc_count(self) -> int:
+        return int(self.lib.pxBatchAllocCount(self.h))
 
     def set_gravity(self, world, x, y):
         _check(self.lib.pxBatchSetGravity(self.h, world, x, y), "pxBatchSetGravity")

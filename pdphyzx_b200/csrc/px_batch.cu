@@ -40,6 +40,10 @@ struct PxBatch {
   float sinTable[256];
   /* control path */
   std::vector<PxCommand> cmds, globalCmds;
+  std::vector<PxBodyPayload> payloads; /* mutable rows of bodies added since the last flush */
+  PxBodyPayload *dPayloads;
+  size_t dPayloadCap;
+  uint64_t allocs; /* device / pinned allocations made so far (pxBatchAllocCount) */
   uint32_t cmdSeq;
   PxCommand *dCmds, *dGlobal;
   uint32_t *dWorldStart;
@@ -86,6 +90,9 @@ extern "C" PxBatch *pxBatchCreate(uint32_t nWorlds, const PxBatchDesc *desc) {
   b->hCmds = nullptr;
   b->hWorldStart = nullptr;
   b->dCmdCap = b->dGlobalCap = b->hCmdCap = 0;
+  b->dPayloads = nullptr;
+  b->dPayloadCap = 0;
+  b->allocs = 0;
   b->cmdSeq = 0;
   b->launches = 0;
   b->stream = nullptr;
@@ -179,6 +186,19 @@ extern "C" PxBatch *pxBatchCreate(uint32_t nWorlds, const PxBatchDesc *desc) {
     if ((e = cudaMalloc(&b->dScratch, scratchBytes)) != cudaSuccess) return fail("cudaMalloc(scratch)", e);
     if ((e = cudaMalloc(&b->dCounters, PX_COUNTER_RING * sizeof(uint32_t))) != cudaSuccess) return fail("cudaMalloc(counters)", e);
   }
+  {
+    /* the control path's buffers, sized so that ordinary per-step control (a few commands per
+     * world) never allocates after creation */
+    b->hCmdCap = b->dCmdCap = std::max<size_t>(4096, (size_t)nWorlds * 4);
+    b->dGlobalCap = 256;
+    b->dPayloadCap = std::max<size_t>(256, (size_t)nWorlds / 4);
+    if ((e = cudaMallocHost(&b->hCmds, b->hCmdCap * sizeof(PxCommand))) != cudaSuccess) return fail("cudaMallocHost(commands)", e);
+    if ((e = cudaMallocHost(&b->hWorldStart, (size_t)(nWorlds + 1) * sizeof(uint32_t))) != cudaSuccess) return fail("cudaMallocHost(worldStart)", e);
+    if ((e = cudaMalloc(&b->dCmds, b->dCmdCap * sizeof(PxCommand))) != cudaSuccess) return fail("cudaMalloc(commands)", e);
+    if ((e = cudaMalloc(&b->dWorldStart, (size_t)(nWorlds + 1) * sizeof(uint32_t))) != cudaSuccess) return fail("cudaMalloc(worldStart)", e);
+    if ((e = cudaMalloc(&b->dGlobal, b->dGlobalCap * sizeof(PxCommand))) != cudaSuccess) return fail("cudaMalloc(global commands)", e);
+    if ((e = cudaMalloc(&b->dPayloads, b->dPayloadCap * sizeof(PxBodyPayload))) != cudaSuccess) return fail("cudaMalloc(payloads)", e);
+  }
   if ((e = cudaMallocHost(&b->hMut, mutBytes)) != cudaSuccess) return fail("cudaMallocHost(mutable)", e);
   if ((e = cudaMallocHost(&b->hImm, immBytes)) != cudaSuccess) return fail("cudaMallocHost(immutable)", e);
   memset(b->hMut, 0, mutBytes);
@@ -233,6 +253,7 @@ extern "C" void pxBatchFree(PxBatch *b) {
   }
   cudaFree(b->dCounters);
   cudaFree(b->dCmds);
+  cudaFree(b->dPayloads);
   cudaFree(b->dGlobal);
   cudaFree(b->dWorldStart);
   cudaFreeHost(b->hMut);
@@ -242,6 +263,8 @@ extern "C" void pxBatchFree(PxBatch *b) {
   if (b->ownStream && b->stream) cudaStreamDestroy(b->stream);
   delete b;
 }
+
+static int flushCommands(PxBatch *b);
 
 static int checkRange(const PxBatch *b, uint32_t first, uint32_t n, const char *who) {
   if (!b) return pxSetError(-1, "%s: NULL batch", who);
@@ -260,6 +283,7 @@ extern "C" int pxBatchMutableH2D(PxBatch *b, const void *host, uint32_t first, u
 extern "C" int pxBatchMutableD2H(PxBatch *b, void *host, uint32_t first, uint32_t n) {
   if (checkRange(b, first, n, "pxBatchMutableD2H")) return -1;
   if (useDevice(b)) return -1;
+  if (flushCommands(b)) return -1; /* what the host reads reflects every call made so far */
   uint8_t *dst = host ? (uint8_t *)host : b->hMut + (size_t)first * b->L.mutStride;
   CU(cudaMemcpyAsync(dst, b->dMut + (size_t)first * b->L.mutStride, (size_t)n * b->L.mutStride, cudaMemcpyDeviceToHost, b->stream));
   return 0;
@@ -312,10 +336,13 @@ extern "C" int pxBatchReadback(PxBatch *b, struct PxWorld *const *worlds, uint32
 static int pushCommand(PxBatch *b, uint32_t world, uint32_t op, uint32_t body, float a, float c0, float c1, float c2, const char *who) {
   if (!b) return pxSetError(-1, "%s: NULL batch", who);
   if (world != PX_ALL_WORLDS && world >= b->L.nWorlds) return pxSetError(-1, "%s: world %u out of range", who, world);
-  if (body >= b->L.maxDynamic) return pxSetError(-1, "%s: body slot %u out of range", who, body);
+  const bool isStatic = (body & PX_BATCH_STATIC) != 0;
+  body &= ~PX_BATCH_STATIC;
+  if (body > 255u || (!isStatic && body >= b->L.maxDynamic)) return pxSetError(-1, "%s: body slot %u out of range", who, body);
+  if (isStatic && (op < PX_CMD_SET_POSITION || op > PX_CMD_ROTATE)) return pxSetError(-1, "%s: static bodies only take pose commands", who);
   PxCommand c;
   c.world = world;
-  c.op = op | (body << 8);
+  c.op = op | (body << 8) | (isStatic ? PX_CMD_STATIC_BIT : 0u);
   c.seq = b->cmdSeq++;
   c.a = a;
   c.b = c0;
@@ -348,6 +375,77 @@ extern "C" int pxBatchApplyImpulses(PxBatch *b, uint32_t n, const uint32_t *worl
   }
   return 0;
 }
+extern "C" int pxBatchSetPosition(PxBatch *b, uint32_t world, uint32_t body, float x, float y) {
+  if (world == PX_ALL_WORLDS) return pxSetError(-1, "pxBatchSetPosition: needs a world index");
+  return pushCommand(b, world, PX_CMD_SET_POSITION, body, x, y, 0, 0, "pxBatchSetPosition");
+}
+extern "C" int pxBatchMoveBy(PxBatch *b, uint32_t world, uint32_t body, float dx, float dy) {
+  if (world == PX_ALL_WORLDS) return pxSetError(-1, "pxBatchMoveBy: needs a world index");
+  return pushCommand(b, world, PX_CMD_MOVE_BY, body, dx, dy, 0, 0, "pxBatchMoveBy");
+}
+extern "C" int pxBatchSetOrientation(PxBatch *b, uint32_t world, uint32_t body, float radians) {
+  return pushCommand(b, world, PX_CMD_SET_ORIENTATION, body, radians, 0, 0, 0, "pxBatchSetOrientation");
+}
+extern "C" int pxBatchRotate(PxBatch *b, uint32_t world, uint32_t body, float radians) {
+  return pushCommand(b, world, PX_CMD_ROTATE, body, radians, 0, 0, 0, "pxBatchRotate");
+}
+
+/* ---- body lifecycle on a resident batch ---- */
+static int copyImmWorld(PxBatch *b, uint32_t world) {
+  const size_t off = (size_t)world * b->L.immStride;
+  CU(cudaMemcpyAsync(b->dImm + off, b->hImm + off, b->L.immStride, cudaMemcpyHostToDevice, b->stream));
+  return 0;
+}
+
+extern "C" int pxBatchAddBody(PxBatch *b, uint32_t world, const struct PxWorld *hostWorld, const void *body) {
+  if (!b || !hostWorld || !body) return pxSetError(-1, "pxBatchAddBody: NULL argument");
+  if (world >= b->L.nWorlds) return pxSetError(-1, "pxBatchAddBody: world %u out of range", world);
+  if (useDevice(b)) return -1;
+  uint8_t *immW = b->hImm + (size_t)world * b->L.immStride;
+  if (pxPackBodyIsDynamic(body)) {
+    /* earlier copies out of the mirror must have left before it is edited */
+    CU(cudaStreamSynchronize(b->stream));
+    PxBodyPayload pl;
+    uint32_t slot = 0;
+    int rc = pxPackAddDynamic(&b->L, hostWorld, body, immW, pl.dyn, &pl.flags, &slot);
+    if (rc != 0) return rc;
+    if (copyImmWorld(b, world)) return -1;
+    b->payloads.push_back(pl);
+    return pushCommand(b, world, PX_CMD_ADD_DYNAMIC, slot, (float)(b->payloads.size() - 1), 0, 0, 0, "pxBatchAddBody");
+  }
+  return pxBatchSyncStatics(b, world, hostWorld);
+}
+
+extern "C" int pxBatchFreeBody(PxBatch *b, uint32_t world, uint32_t body, const struct PxWorld *hostWorld) {
+  if (!b) return pxSetError(-1, "pxBatchFreeBody: NULL batch");
+  if (world >= b->L.nWorlds) return pxSetError(-1, "pxBatchFreeBody: world %u out of range", world);
+  if (body & PX_BATCH_STATIC) {
+    if (!hostWorld) return pxSetError(-1, "pxBatchFreeBody: freeing a static body needs the host world (its static list is authoritative)");
+    return pxBatchSyncStatics(b, world, hostWorld);
+  }
+  return pushCommand(b, world, PX_CMD_FREE_DYNAMIC, body, 0, 0, 0, 0, "pxBatchFreeBody");
+}
+
+extern "C" int pxBatchSyncStatics(PxBatch *b, uint32_t world, const struct PxWorld *hostWorld) {
+  if (!b || !hostWorld) return pxSetError(-1, "pxBatchSyncStatics: NULL argument");
+  if (world >= b->L.nWorlds) return pxSetError(-1, "pxBatchSyncStatics: world %u out of range", world);
+  if (useDevice(b)) return -1;
+  if (flushCommands(b)) return -1; /* queued pose commands address statics by their old positions */
+  CU(cudaStreamSynchronize(b->stream));
+  const PxBatchLayout &L = b->L;
+  uint8_t *mutW = b->hMut + (size_t)world * L.mutStride, *immW = b->hImm + (size_t)world * L.immStride;
+  int rc = pxPackStatics(&L, hostWorld, mutW, immW);
+  if (rc != 0) return rc;
+  if (copyImmWorld(b, world)) return -1;
+  uint8_t *dMutW = b->dMut + (size_t)world * L.mutStride;
+  CU(cudaMemcpyAsync(dMutW + L.offStatMut, mutW + L.offStatMut, (size_t)PX_STATM_ROWS * L.maxStatic * 4, cudaMemcpyHostToDevice, b->stream));
+  const size_t offN = L.offHeader + offsetof(PxWorldHeader, nStatic);
+  CU(cudaMemcpyAsync(dMutW + offN, mutW + offN, sizeof(uint32_t), cudaMemcpyHostToDevice, b->stream));
+  return 0;
+}
+
+extern "C" uint64_t pxBatchAllocCount(const PxBatch *b) { return b ? b->allocs : 0; }
+
 extern "C" int pxBatchSetGravity(PxBatch *b, uint32_t world, float x, float y) {
   return pushCommand(b, world, PX_CMD_GRAVITY, 0, x, y, 0, 0, "pxBatchSetGravity");
 }
@@ -361,14 +459,14 @@ static int flushCommands(PxBatch *b) {
   const uint32_t W = b->L.nWorlds;
   if (n > 0) {
     /* counting sort by world keeps submission order inside a world */
+    CU(cudaStreamSynchronize(b->stream)); /* pinned buffers may be in flight */
     if (b->hCmdCap < n) {
       cudaFreeHost(b->hCmds);
       b->hCmds = nullptr;
       b->hCmdCap = std::max(n, b->hCmdCap * 2);
       CU(cudaMallocHost(&b->hCmds, b->hCmdCap * sizeof(PxCommand)));
+      b->allocs++;
     }
-    if (!b->hWorldStart) CU(cudaMallocHost(&b->hWorldStart, (size_t)(W + 1) * sizeof(uint32_t)));
-    CU(cudaStreamSynchronize(b->stream)); /* pinned buffers may be in flight */
     memset(b->hWorldStart, 0, (size_t)(W + 1) * sizeof(uint32_t));
     for (const PxCommand &c : b->cmds) b->hWorldStart[c.world + 1]++;
     for (uint32_t w = 0; w < W; w++) b->hWorldStart[w + 1] += b->hWorldStart[w];
@@ -379,8 +477,8 @@ static int flushCommands(PxBatch *b) {
       b->dCmds = nullptr;
       b->dCmdCap = b->hCmdCap;
       CU(cudaMalloc(&b->dCmds, b->dCmdCap * sizeof(PxCommand)));
+      b->allocs++;
     }
-    if (!b->dWorldStart) CU(cudaMalloc(&b->dWorldStart, (size_t)(W + 1) * sizeof(uint32_t)));
     CU(cudaMemcpyAsync(b->dCmds, b->hCmds, n * sizeof(PxCommand), cudaMemcpyHostToDevice, b->stream));
     CU(cudaMemcpyAsync(b->dWorldStart, b->hWorldStart, (size_t)(W + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, b->stream));
   }
@@ -390,16 +488,31 @@ static int flushCommands(PxBatch *b) {
       b->dGlobal = nullptr;
       b->dGlobalCap = std::max(ng, b->dGlobalCap * 2);
       CU(cudaMalloc(&b->dGlobal, b->dGlobalCap * sizeof(PxCommand)));
+      b->allocs++;
     }
     /* pageable source: the copy is staged by the runtime before the call returns */
     CU(cudaMemcpyAsync(b->dGlobal, b->globalCmds.data(), ng * sizeof(PxCommand), cudaMemcpyHostToDevice, b->stream));
   }
+  const size_t np = b->payloads.size();
+  if (np > 0) {
+    if (b->dPayloadCap < np) {
+      CU(cudaStreamSynchronize(b->stream));
+      cudaFree(b->dPayloads);
+      b->dPayloads = nullptr;
+      b->dPayloadCap = std::max(np, b->dPayloadCap * 2);
+      CU(cudaMalloc(&b->dPayloads, b->dPayloadCap * sizeof(PxBodyPayload)));
+      b->allocs++;
+    }
+    /* pageable source: staged by the runtime before the call returns */
+    CU(cudaMemcpyAsync(b->dPayloads, b->payloads.data(), np * sizeof(PxBodyPayload), cudaMemcpyHostToDevice, b->stream));
+  }
   int rc = pxLaunchCommands(&b->L, b->dMut, b->dImm, n ? b->dCmds : nullptr, n ? b->dWorldStart : nullptr,
-                            ng ? b->dGlobal : nullptr, (uint32_t)ng, b->stream);
+                            ng ? b->dGlobal : nullptr, (uint32_t)ng, b->dPayloads, b->dSin, b->stream);
   if (rc != 0) return pxSetError(-rc - 1000, "command kernel: %s", cudaGetErrorString((cudaError_t)rc));
   b->launches++;
   b->cmds.clear();
   b->globalCmds.clear();
+  b->payloads.clear();
   return 0;
 }
 

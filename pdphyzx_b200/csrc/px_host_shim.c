@@ -146,6 +146,7 @@ PXH void pxh_body_rotate(PxWorld *w, int dynamic, int slot, float rad) {
 PXH int pxh_body_is_valid(PxWorld *w, int dynamic, int slot) {
   return g_px->body->isValid(&pxhArray(w, dynamic)->items[slot]) ? 1 : 0;
 }
+PXH void *pxh_body_ptr(PxWorld *w, int dynamic, int slot) { return &pxhArray(w, dynamic)->items[slot]; }
 PXH void pxh_free_body(PxWorld *w, int dynamic, int slot) {
   g_px->world->freeBody(w, &pxhArray(w, dynamic)->items[slot]);
 }

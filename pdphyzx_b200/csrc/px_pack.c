@@ -65,6 +65,8 @@ int pxBatchComputeLayout(uint32_t nWorlds, const PxBatchDesc *desc, PxBatchLayou
   o += alignUp(D, 16);
   L->offDynOrder = o;
   o += alignUp(D, 16);
+  L->offStatMut = o;
+  o += PX_STATM_ROWS * S * 4;
   L->mutStride = alignUp(o, 128);
 
   o = 0;
@@ -121,6 +123,80 @@ int pxBatchFitDesc(struct PxWorld *const *worlds, uint32_t n, PxBatchDesc *desc)
   return 0;
 }
 
+/* ---- pxPackWorlds / pxUnpackWorlds: worlds are independent, so large batches are converted by
+ * several host threads (PX_PACK_THREADS, default = online cores, at most one per 64 worlds) */
+#include <pthread.h>
+#include <stdlib.h>
+#include <unistd.h>
+
+typedef struct {
+  const PxBatchLayout *L;
+  struct PxWorld *const *worlds;
+  uint32_t first, last;
+  uint8_t *mut, *imm;
+  const uint8_t *mutIn;
+  uint32_t flags;
+  int rc, overflowed;
+} PxPackJob;
+
+static void *packJob(void *arg) {
+  PxPackJob *j = (PxPackJob *)arg;
+  for (uint32_t w = j->first; w < j->last && j->rc == 0; w++) {
+    j->rc = pxPackOneWorld(j->L, j->worlds[w], w, j->mut + (size_t)w * j->L->mutStride, j->imm + (size_t)w * j->L->immStride);
+  }
+  return NULL;
+}
+
+static void *unpackJob(void *arg) {
+  PxPackJob *j = (PxPackJob *)arg;
+  for (uint32_t w = j->first; w < j->last; w++) {
+    int rc = pxUnpackOneWorld(j->L, j->worlds[w], w, j->mutIn + (size_t)w * j->L->mutStride, j->flags);
+    if (rc < 0) {
+      j->rc = rc;
+      return NULL;
+    }
+    j->overflowed += rc;
+  }
+  return NULL;
+}
+
+static uint32_t packThreads(uint32_t n) {
+  const char *env = getenv("PX_PACK_THREADS");
+  long t = env ? atol(env) : sysconf(_SC_NPROCESSORS_ONLN);
+  if (t < 1) t = 1;
+  if (t > 64) t = 64;
+  if ((uint32_t)t > (n + 63) / 64) t = (long)((n + 63) / 64);
+  return (uint32_t)(t < 1 ? 1 : t);
+}
+
+static int runJobs(PxPackJob *proto, uint32_t n, void *(*fn)(void *), int *overflowed) {
+  const uint32_t T = packThreads(n);
+  PxPackJob jobs[64];
+  pthread_t tid[64];
+  for (uint32_t t = 0; t < T; t++) {
+    jobs[t] = *proto;
+    jobs[t].first = (uint32_t)((uint64_t)n * t / T);
+    jobs[t].last = (uint32_t)((uint64_t)n * (t + 1) / T);
+    jobs[t].rc = 0;
+    jobs[t].overflowed = 0;
+  }
+  uint32_t started = 0;
+  for (uint32_t t = 1; t < T; t++) {
+    if (pthread_create(&tid[t], NULL, fn, &jobs[t]) != 0) break;
+    started = t;
+  }
+  fn(&jobs[0]);
+  for (uint32_t t = started + 1; t < T; t++) fn(&jobs[t]); /* threads that could not be started run here */
+  for (uint32_t t = 1; t <= started; t++) pthread_join(tid[t], NULL);
+  int total = 0;
+  for (uint32_t t = 0; t < T; t++) {
+    if (jobs[t].rc != 0) return jobs[t].rc;
+    total += jobs[t].overflowed;
+  }
+  if (overflowed) *overflowed = total;
+  return 0;
+}
+
 int pxPackWorlds(const PxBatchLayout *L, struct PxWorld *const *worlds, uint32_t n, void *mutBase, void *immBase) {
   if (!L || !worlds || !mutBase || !immBase) {
     return pxSetError(-1, "pxPackWorlds: NULL argument");
@@ -129,29 +205,60 @@ int pxPackWorlds(const PxBatchLayout *L, struct PxWorld *const *worlds, uint32_t
     if (!worlds[w]) {
       return pxSetError(-1, "pxPackWorlds: world %u is NULL", w);
     }
-    int rc = pxPackOneWorld(L, worlds[w], w, (uint8_t *)mutBase + (size_t)w * L->mutStride,
-                            (uint8_t *)immBase + (size_t)w * L->immStride);
-    if (rc != 0) {
-      return rc;
-    }
   }
-  return 0;
+  PxPackJob proto;
+  memset(&proto, 0, sizeof(proto));
+  proto.L = L;
+  proto.worlds = worlds;
+  proto.mut = (uint8_t *)mutBase;
+  proto.imm = (uint8_t *)immBase;
+  return runJobs(&proto, n, packJob, NULL);
 }
 
 int pxUnpackWorlds(const PxBatchLayout *L, struct PxWorld *const *worlds, uint32_t n, const void *mutBase, uint32_t flags) {
   if (!L || !worlds || !mutBase) {
     return pxSetError(-1, "pxUnpackWorlds: NULL argument");
   }
-  int overflowed = 0;
   for (uint32_t w = 0; w < n; w++) {
     if (!worlds[w]) {
       return pxSetError(-1, "pxUnpackWorlds: world %u is NULL", w);
     }
-    int rc = pxUnpackOneWorld(L, worlds[w], w, (const uint8_t *)mutBase + (size_t)w * L->mutStride, flags);
-    if (rc < 0) {
-      return rc;
-    }
-    overflowed += rc;
   }
-  return overflowed;
+  PxPackJob proto;
+  memset(&proto, 0, sizeof(proto));
+  proto.L = L;
+  proto.worlds = worlds;
+  proto.mutIn = (const uint8_t *)mutBase;
+  proto.flags = flags;
+  int overflowed = 0;
+  int rc = runJobs(&proto, n, unpackJob, &overflowed);
+  return rc != 0 ? rc : overflowed;
+}
+
+/* ---- body lifecycle on a resident world: host half (see px_pack_inl.h) */
+int pxPackBodyIsDynamic(const void *body) { return body && ((const PxBody *)body)->density > 0; /* the reference's own test, px_world.c:116-117 */ }
+
+int pxPackAddDynamic(const PxBatchLayout *L, const struct PxWorld *world, const void *bodyPtr, void *immWorld, float *dynRows,
+                     uint32_t *flags, uint32_t *slot) {
+  const PxBody *body = (const PxBody *)bodyPtr;
+  if (!L || !world || !body || !immWorld || !dynRows || !flags || !slot) {
+    return pxSetError(-1, "pxPackAddDynamic: NULL argument");
+  }
+  uint8_t *used = (uint8_t *)malloc(L->maxVertices ? L->maxVertices : 1);
+  if (!used) return pxSetError(-1, "pxPackAddDynamic: out of memory");
+  *slot = body->worldIndex;
+  int rc = pxPackAddDynamicBody(L, world, body, (uint8_t *)immWorld, dynRows, flags, used);
+  free(used);
+  return rc;
+}
+
+int pxPackStatics(const PxBatchLayout *L, const struct PxWorld *world, void *mutWorld, void *immWorld) {
+  if (!L || !world || !mutWorld || !immWorld) {
+    return pxSetError(-1, "pxPackStatics: NULL argument");
+  }
+  uint8_t *used = (uint8_t *)malloc(L->maxVertices ? L->maxVertices : 1);
+  if (!used) return pxSetError(-1, "pxPackStatics: out of memory");
+  int rc = pxPackStaticBodies(L, world, (uint8_t *)mutWorld, (uint8_t *)immWorld, used);
+  free(used);
+  return rc;
 }

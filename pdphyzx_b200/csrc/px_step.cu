@@ -938,12 +938,13 @@ __global__ void __launch_bounds__(NT, NT == 128 ? PX_MINB128 : 3) pxStepKernel(c
       s.shape[x] = gshape[x];
     }
     const float *gs = (const float *)(gimm + L.offStat);
+    const float *gsm = (const float *)(gmut + L.offStatMut); /* static poses: mutable by command, never by the step */
     const uint32_t *gsshape = (const uint32_t *)(gimm + L.offStatShape);
     for (uint32_t q = tid; q < S; q += NT) {
-      s.bodyP[D + q] = make_float4(gs[PX_STAT_PX * S + q], gs[PX_STAT_PY * S + q], 0.0f, 0.0f);
+      s.bodyP[D + q] = make_float4(gsm[PX_STATM_PX * S + q], gsm[PX_STATM_PY * S + q], 0.0f, 0.0f);
       s.bodyV[D + q] = make_float4(0.0f, 0.0f, 0.0f, gs[PX_STAT_RADIUS * S + q]);
-      s.bodyR[D + q] = make_float4(gs[PX_STAT_M00 * S + q], gs[PX_STAT_M01 * S + q], gs[PX_STAT_M10 * S + q],
-                                   gs[PX_STAT_M11 * S + q]);
+      s.bodyR[D + q] = make_float4(gsm[PX_STATM_M00 * S + q], gsm[PX_STATM_M01 * S + q], gsm[PX_STATM_M10 * S + q],
+                                   gsm[PX_STATM_M11 * S + q]);
       s.shape[D + q] = gsshape[q];
     }
     copyRows<NT>((float *)s.flags, (const float *)(gmut + L.offDynFlags), D / 4);
@@ -1727,16 +1728,20 @@ __global__ void __launch_bounds__(NT, NT == 128 ? PX_MINB128 : 3) pxStepKernel(c
 /* One thread per world applies that world's queued API calls in submission order, merged
  * with the batch-wide (PX_ALL_WORLDS) calls by sequence number. */
 __global__ void pxCommandKernel(const PxBatchLayout L, uint8_t *mut, const uint8_t *imm, const PxCommand *cmds,
-                                const uint32_t *worldStart, const PxCommand *global, uint32_t nGlobal) {
+                                const uint32_t *worldStart, const PxCommand *global, uint32_t nGlobal,
+                                const PxBodyPayload *payloads, const float *sinTable) {
   const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
   if (w >= L.nWorlds) return;
   uint8_t *gmut = mut + (size_t)w * L.mutStride;
   const uint8_t *gimm = imm + (size_t)w * L.immStride;
   PxWorldHeader *h = (PxWorldHeader *)(gmut + L.offHeader);
   float *dyn = (float *)(gmut + L.offDyn);
+  float *statm = (float *)(gmut + L.offStatMut);
   uint8_t *flags = gmut + L.offDynFlags;
+  uint8_t *order = gmut + L.offDynOrder;
   const float *dc = (const float *)(gimm + L.offDynConst);
-  const uint32_t D = L.maxDynamic;
+  const uint8_t *statSlot = gimm + L.offStatSlot;
+  const uint32_t D = L.maxDynamic, S = L.maxStatic;
   uint32_t i = worldStart ? worldStart[w] : 0, iEnd = worldStart ? worldStart[w + 1] : 0, gi = 0;
   while (i < iEnd || gi < nGlobal) {
     const PxCommand *c;
@@ -1745,13 +1750,75 @@ __global__ void pxCommandKernel(const PxBatchLayout L, uint8_t *mut, const uint8
     } else {
       c = &cmds[i++];
     }
-    const uint32_t op = c->op & 0xffu, body = c->op >> 8;
+    const uint32_t op = c->op & 0xffu, body = (c->op >> 8) & 0xffu;
+    const bool isStatic = (c->op & PX_CMD_STATIC_BIT) != 0;
     if (op == PX_CMD_GRAVITY) { /* pxWorldSetGravity, px_world.c:57-63 */
       h->gravityX = c->a * L.unit;
       h->gravityY = c->b * L.unit;
     } else if (op == PX_CMD_ITERATIONS) {
       h->iterations = (uint32_t)c->a & 255u;
-    } else if (body < D) {
+    } else if (op >= PX_CMD_SET_POSITION && op <= PX_CMD_ROTATE) {
+      /* pxBodySetPosition / MoveBy / SetOrientation / Rotate, px_body.c:85-124: plain pose edits
+       * of a dynamic OR static body; none of them wakes the body, the AABB follows the position
+       * (it is derived on the device) */
+      float *px, *py, *angle, *m00, *m01, *m10, *m11;
+      if (!isStatic) {
+        if (body >= D) continue;
+        px = dyn + PX_DYN_PX * D + body; py = dyn + PX_DYN_PY * D + body; angle = dyn + PX_DYN_ANGLE * D + body;
+        m00 = dyn + PX_DYN_M00 * D + body; m01 = dyn + PX_DYN_M01 * D + body;
+        m10 = dyn + PX_DYN_M10 * D + body; m11 = dyn + PX_DYN_M11 * D + body;
+      } else {
+        /* statics are stored by position in the static iteration order */
+        uint32_t q = 0;
+        const uint32_t nS = min(h->nStatic, S);
+        while (q < nS && statSlot[q] != body) q++;
+        if (q >= nS) continue;
+        px = statm + PX_STATM_PX * S + q; py = statm + PX_STATM_PY * S + q; angle = statm + PX_STATM_ANGLE * S + q;
+        m00 = statm + PX_STATM_M00 * S + q; m01 = statm + PX_STATM_M01 * S + q;
+        m10 = statm + PX_STATM_M10 * S + q; m11 = statm + PX_STATM_M11 * S + q;
+      }
+      if (op == PX_CMD_SET_POSITION) {
+        *px = c->a;
+        *py = c->b;
+      } else if (op == PX_CMD_MOVE_BY) { /* pxVec2AddAssign */
+        *px = *px + c->a;
+        *py = *py + c->b;
+      } else {
+        float radians = op == PX_CMD_ROTATE ? *angle + c->a : c->a;
+        radians = fmodf(radians, D_2PI); /* px_body.c:110-112 */
+        if (radians < 0) radians += D_2PI;
+        *angle = radians;
+        const float cs = fSin(sinTable, radians + D_PI * 0.5f), sn = fSin(sinTable, radians); /* pxMat2Orientation */
+        *m00 = cs;
+        *m01 = -sn;
+        *m10 = sn;
+        *m11 = cs;
+      }
+    } else if (op == PX_CMD_ADD_DYNAMIC) {
+      /* device half of pxBodyArrayAdd, px_body_array.c:7-59: the host chose the slot by the
+       * reference's rule (freed stack first, else `length`); here the body's mutable rows are
+       * written and the slot is appended to the iteration order */
+      const uint32_t n = h->nDynamic;
+      if (body >= D || n >= D) continue;
+      const PxBodyPayload *pl = payloads + (uint32_t)c->a;
+      for (uint32_t r = 0; r < PX_DYN_ROWS; r++) dyn[r * D + body] = pl->dyn[r];
+      flags[body] = (uint8_t)pl->flags;
+      order[n] = (uint8_t)body;
+      h->nDynamic = n + 1;
+    } else if (op == PX_CMD_FREE_DYNAMIC) {
+      /* pxBodyArrayRemove, px_body_array.c:61-79: a no-op when the SLOT index is >= the body
+       * COUNT (the reference's own check), else swap-remove from the iteration order */
+      const uint32_t n = h->nDynamic;
+      if (body >= n) continue;
+      for (uint32_t k = 0; k < n; k++) {
+        if (order[k] == body) {
+          order[k] = order[n - 1];
+          h->nDynamic = n - 1;
+          flags[body] = 0; /* device-side only: the slot no longer holds a valid body for the per-slot phases */
+          break;
+        }
+      }
+    } else if (body < D && !isStatic) {
       /* pxBodyApiApplyImpulse / pxBodyApiApplyForce, px_body_api.c:20-42: scale by the unit,
        * accumulate, wake */
       const float sx = c->a * L.unit, sy = c->b * L.unit;
@@ -1769,8 +1836,6 @@ __global__ void pxCommandKernel(const PxBatchLayout L, uint8_t *mut, const uint8
     }
   }
 }
-
-
 
 /* ------------------------------------------------------------------- arithmetic self-test */
 /* T0 parity tier: the device's restatement of the reference's inline math (px_math.h:50-114,
@@ -1923,8 +1988,9 @@ extern "C" int pxStepOccupancy(const PxStepParams *P, uint32_t threads, int *cta
 }
 
 extern "C" int pxLaunchCommands(const PxBatchLayout *L, uint8_t *mut, const uint8_t *imm, const PxCommand *cmds,
-                                const uint32_t *worldStart, const PxCommand *global, uint32_t nGlobal, void *stream) {
+                                const uint32_t *worldStart, const PxCommand *global, uint32_t nGlobal,
+                                const PxBodyPayload *payloads, const float *sinTable, void *stream) {
   const uint32_t threads = 128, blocks = (L->nWorlds + threads - 1) / threads;
-  pxCommandKernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(*L, mut, imm, cmds, worldStart, global, nGlobal);
+  pxCommandKernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(*L, mut, imm, cmds, worldStart, global, nGlobal, payloads, sinTable);
   return (int)cudaGetLastError();
 }

@@ -86,11 +86,23 @@ struct PxCommand {
   uint32_t seq;   /* submission order */
   float a, b, c, d;
 };
-enum { PX_CMD_IMPULSE = 1, PX_CMD_FORCE = 2, PX_CMD_GRAVITY = 3, PX_CMD_ITERATIONS = 4 };
+enum {
+  PX_CMD_IMPULSE = 1, PX_CMD_FORCE = 2, PX_CMD_GRAVITY = 3, PX_CMD_ITERATIONS = 4,
+  PX_CMD_SET_POSITION = 5, PX_CMD_MOVE_BY = 6, PX_CMD_SET_ORIENTATION = 7, PX_CMD_ROTATE = 8, /* body may be static */
+  PX_CMD_ADD_DYNAMIC = 9,  /* a = index into the payload array; the slot is the body field */
+  PX_CMD_FREE_DYNAMIC = 10
+};
+#define PX_CMD_STATIC_BIT 0x10000u /* op word: PX_CMD_* | slot << 8 | PX_CMD_STATIC_BIT if the slot is a static body's */
+/* mutable state of a body added to a resident world (PX_CMD_ADD_DYNAMIC) */
+struct PxBodyPayload {
+  float dyn[PX_DYN_ROWS];
+  uint32_t flags;
+};
 /* cmds sorted by (world, seq); worldStart[w]..worldStart[w+1] is world w's range; the
  * `global` list (PX_ALL_WORLDS, in seq order) is merged in by sequence number */
 int pxLaunchCommands(const PxBatchLayout *L, uint8_t *mut, const uint8_t *imm, const struct PxCommand *cmds,
-                     const uint32_t *worldStart, const struct PxCommand *global, uint32_t nGlobal, void *stream);
+                     const uint32_t *worldStart, const struct PxCommand *global, uint32_t nGlobal,
+                     const struct PxBodyPayload *payloads, const float *sinTable, void *stream);
 /* arithmetic self-tests (device pointers) */
 int pxLaunchMath(int op, const float *a, const float *b, const float *sinTable, float *out, uint32_t n, void *stream);
 int pxLaunchRsqrtSweep(unsigned long long *sums4096, void *stream);
