@@ -59,10 +59,31 @@ def parse_args():
     ap.add_argument("--control", action="store_true",
                     help="BASELINE config 5: polygon stacks, PDPHYZX_UNIT_MM, every step the host queues one applyImpulse per "
                          "world and a setGravity before stepping --fused substeps (compare --fused 1 with --fused 8)")
+    ap.add_argument("--config", type=int, default=0, choices=[0, 2, 3, 4, 5],
+                    help="BASELINE.json configs as stated: 2 = 4,096 circle-pile worlds; 3 = 16,384 mixed worlds, 10 it.; "
+                         "4 = 65,536 mixed worlds IN TOTAL, 20 it., sharded over --gpus (strong scaling); 5 = 32,768 polygon-stack "
+                         "worlds, UNIT_MM, host control every step (use --fused 1 and --fused 8); 0 = the default line")
+    ap.add_argument("--sharded", action="store_true",
+                    help="single process: one PxBatchGroup (C ABI) over --gpus devices instead of one process per GPU")
+    ap.add_argument("--no-aos", action="store_true", help="skip the e2e_aos leg (PxWorld structs in, PxWorld structs out)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--profile", action="store_true", help="per-phase SM-cycle breakdown (adds clock reads)")
-    return ap.parse_args()
+    args = ap.parse_args()
+    args.scaling = "weak"
+    if args.config == 2:
+        args.worlds, args.mix, args.iterations = 4096, "circles", 10
+    elif args.config == 3:
+        args.worlds, args.mix, args.iterations = 16384, "mixed", 10
+    elif args.config == 4:
+        world_size = int(os.environ.get("WORLD_SIZE", "1")) if not args.sharded else 1
+        n = world_size if not args.sharded else 1
+        args.total_worlds = 65536
+        args.worlds = 65536 // max(n, 1) if not args.sharded else 65536
+        args.mix, args.iterations, args.scaling = "mixed", 20, "strong"
+    elif args.config == 5:
+        args.worlds, args.control = 32768, True
+    return args
 
 
 class ClockSampler:
@@ -135,9 +156,9 @@ def kernel_facts(args):
     return facts
 
 
-def build_scenes(args, rank: int, n_worlds: int):
+def build_scenes(args, rank: int, n_worlds: int, first: int = 0):
     from pdphyzx_b200 import scenes
-    base = rank * args.worlds
+    base = rank * args.worlds + first
     if args.control:
         return [scenes.stack_scene(base + w, seed=args.seed, n_dynamic=N_DYNAMIC, iterations=args.iterations, cols=21)
                 for w in range(n_worlds)]
@@ -145,7 +166,60 @@ def build_scenes(args, rank: int, n_worlds: int):
             for w in range(n_worlds)]
 
 
+def bind_to_gpu_numa_node(index: int):
+    """Pin this process to the CPUs NVML reports as local to GPU `index`, BEFORE the pinned staging
+    buffers are allocated and first touched: with one process per GPU the host <-> device copies of
+    pxBatchStepHost then stay on the GPU's own NUMA node.  Returns the CPU count, or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        ncpu = os.cpu_count() or 1
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = [i for i in range(ncpu) if (mask[i // 64] >> (i % 64)) & 1]
+        if cpus and len(cpus) < ncpu:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
+CHUNK = 2048  # worlds built on the host at a time when the AoS form of the whole batch would be large
+
+
+def make_batch(pxb, args, rank, device, stream):
+    """The batch of args.worlds worlds on `device`.  Up to 8192 worlds are built in one go and the
+    host PxWorld structs are kept (e2e_aos needs them); larger batches (configs 3-5) are created
+    empty and uploaded chunk by chunk (pxBatchCreate + pxBatchUpload), 340 KB of AoS per world."""
+    flags = pxb.FLAG_PROFILE if args.profile else 0
+    if args.worlds <= 8192:
+        worlds = pxb.HostWorlds(build_scenes(args, rank, args.worlds))
+        b = pxb.Batch(worlds, device=device, stream=stream, threads=args.threads, flags=flags,
+                      max_manifolds=args.max_manifolds, max_pairs=args.max_pairs)
+        return b, worlds
+    b = None
+    for first in range(0, args.worlds, CHUNK):
+        n = min(CHUNK, args.worlds - first)
+        hw = pxb.HostWorlds(build_scenes(args, rank, n, first))
+        if b is None:
+            d = pxb.make_desc(hw.unit)
+            pxb._check(pxb.core().pxBatchFitDesc(hw.pointer_array(), n, pxb.C.byref(d)), "pxBatchFitDesc")
+            b = pxb.Batch(None, n_worlds=args.worlds, unit=hw.unit, device=device, stream=stream, threads=args.threads,
+                          flags=flags, max_dynamic=d.maxDynamic, max_static=d.maxStatic,
+                          max_vertices=max(d.maxVertices + 256, N_DYNAMIC * 6), max_manifolds=args.max_manifolds,
+                          max_pairs=args.max_pairs)
+        b.upload(hw, first=first)
+        b.sync()
+        hw.close()
+    return b, None
+
+
 def workload_name(args, n_gpus):
+    if args.config == 4:
+        return (f"BASELINE config 4: 65,536 worlds in total x {BODIES_PER_WORLD} mixed bodies ({N_DYNAMIC} dynamic + 4 static), "
+                f"20 iterations, PDPHYZX_UNIT_M, sharded over {n_gpus} GPU(s) = {args.worlds} worlds/GPU, penned piles settled "
+                f"{args.settle} substeps")
     if args.control:
         return (f"{args.worlds} worlds/GPU x polygon stacks ({N_DYNAMIC} dynamic bodies), {args.iterations} iterations, "
                 f"PDPHYZX_UNIT_MM, host-driven applyImpulse per world + setGravity before every step of "
@@ -241,19 +315,16 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the product has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
+    numa_cpus = None
     if world_size > 1:
+        numa_cpus = bind_to_gpu_numa_node(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    scenes = build_scenes(args, rank, args.worlds)
-    worlds = pxb.HostWorlds(scenes)
     # a real (non-default) torch stream, made current, so torch.cuda.Event times the stream
     # the kernels are launched on
     tstream = torch.cuda.Stream()
     torch.cuda.set_stream(tstream)
-    b = pxb.Batch(worlds, device=local_rank, stream=tstream.cuda_stream, threads=args.threads,
-                  flags=pxb.FLAG_PROFILE if args.profile else 0, max_manifolds=args.max_manifolds,
-                  max_pairs=args.max_pairs)
-    del scenes
+    b, worlds = make_batch(pxb, args, rank, local_rank, tstream.cuda_stream)
     info = b.kernel_info()
 
     # settle the piles (untimed), in chunks so a hung kernel cannot run for minutes
@@ -333,11 +404,31 @@ def run_ours(args):
         barrier()
         e2e_ms = max(e0.elapsed_time(e1), 1e3 * (time.perf_counter() - t0))
 
+    # ---- end to end through PxWorld structs: what a px->world->step over N host worlds costs ----
+    # pxBatchUpload (AoS -> SoA on the host threads, both blocks host -> HBM) -> pxBatchStep ->
+    # pxBatchReadback (HBM -> host, SoA -> AoS into the same PxWorld structs), waited for every step
+    aos_ms = None
+    if worlds is not None and not args.no_e2e and not args.no_aos and not args.control:
+        for _ in range(2):
+            b.upload(worlds)
+            b.step(args.fused)
+            b.readback(worlds)
+        barrier()
+        n_aos = max(3, min(args.steps, 10))
+        t0 = time.perf_counter()
+        for _ in range(n_aos):
+            b.upload(worlds)
+            b.step(args.fused)
+            b.readback(worlds)
+        aos_ms = 1e3 * (time.perf_counter() - t0) / n_aos
+        barrier()
+
     if world_size > 1:
-        t = torch.tensor([ms, e2e_ms or 0.0], device="cuda", dtype=torch.float64)
+        t = torch.tensor([ms, e2e_ms or 0.0, aos_ms or 0.0], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, e2e_max = float(t[0]), float(t[1])
+        ms, e2e_max, aos_max = float(t[0]), float(t[1]), float(t[2])
         e2e_ms = e2e_max if e2e_ms is not None else None
+        aos_ms = aos_max if aos_ms is not None else None
 
     blocks = b.download_blocks()
     stats = np.array([blocks.header["statManifolds"].mean(), blocks.header["statPairs"].mean(),
@@ -362,9 +453,11 @@ def run_ours(args):
         out = {
             "metric": "body_steps_per_sec", "value": value, "unit": "body-substeps/s", "n_gpus": world_size,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {
                 "workload": workload_name(args, world_size), "substeps_per_step": args.fused,
+                **({"baseline_config": args.config} if args.config else {}),
+                **({"host_cpus_per_rank_numa_local": numa_cpus} if numa_cpus else {}),
                 "body_frame_steps_per_sec": value / 5.0, "l2": "inputs larger than L2 (state > 126 MB per GPU)"
                 if args.worlds * (b.L.mutStride + b.L.immStride) > 126e6 else "inputs smaller than L2",
                 "threads_per_world_cta": info["threads"], "ctas_per_sm": info["ctas_per_sm"],
@@ -417,6 +510,13 @@ def run_ours(args):
             out["e2e"] = {"value": body_substeps / (e2e_ms * 1e-3), "unit": "body-substeps/s",
                           "h2d_bytes_per_step": int(mut_bytes), "d2h_bytes_per_step": int(mut_bytes),
                           "ms_per_step": e2e_ms / args.steps}
+        if aos_ms is not None:
+            aos_bytes = int(b.n * (b.L.mutStride + b.L.immStride))
+            out["e2e_aos"] = {"value": args.worlds * world_size * BODIES_PER_WORLD * args.fused / (aos_ms * 1e-3),
+                              "unit": "body-substeps/s", "ms_per_step": aos_ms, "h2d_bytes_per_step": aos_bytes,
+                              "d2h_bytes_per_step": int(mut_bytes), "host_threads": min(os.cpu_count() or 1, (b.n + 63) // 64, 64),
+                              "note": "pxBatchUpload -> pxBatchStep -> pxBatchReadback over host PxWorld structs (AoS, 664-byte "
+                                      "bodies): the host-side AoS <-> SoA conversion dominates; e2e above moves pre-packed SoA blocks"}
         if world_size == 1 and not args.no_cpu:
             try:
                 cb = cpu_baseline(args, b, blocks)
@@ -427,9 +527,85 @@ def run_ours(args):
                 out["cpu_baseline"] = cb
         print(json.dumps(out))
     b.close()
-    worlds.close()
+    if worlds is not None:
+        worlds.close()
     if world_size > 1:
         dist.destroy_process_group()
+    return 0
+
+
+def run_sharded(args):
+    """--sharded: ONE process, one PxBatchGroup (C ABI) over --gpus devices; the calling thread fans
+    every step out, the devices run side by side.  Device-timed with CUDA events per device, the
+    slowest device counts.  The comparison line for the one-process-per-GPU mode."""
+    import torch
+    from pdphyzx_b200 import batch as pxb
+    n_gpus = args.gpus
+    if torch.cuda.device_count() < n_gpus:
+        raise SystemExit(f"bench.py --sharded: {n_gpus} GPUs asked for, {torch.cuda.device_count()} visible")
+    total = args.worlds if args.config == 4 else args.worlds * n_gpus
+    devices = list(range(n_gpus))
+    g = None
+    for first in range(0, total, CHUNK):
+        n = min(CHUNK, total - first)
+        hw = pxb.HostWorlds(build_scenes(args, 0, n, first))
+        if g is None:
+            d = pxb.make_desc(hw.unit)
+            pxb._check(pxb.core().pxBatchFitDesc(hw.pointer_array(), n, pxb.C.byref(d)), "pxBatchFitDesc")
+            g = pxb.BatchGroup(None, devices, threads=args.threads, n_worlds=total, unit=hw.unit, max_dynamic=d.maxDynamic,
+                               max_static=d.maxStatic, max_vertices=max(d.maxVertices + 256, N_DYNAMIC * 6),
+                               max_manifolds=args.max_manifolds, max_pairs=args.max_pairs)
+        g.upload(hw, first)
+        g.sync()
+        hw.close()
+    done = 0
+    while done < args.settle:
+        k = min(50, args.settle - done)
+        g.step(k)
+        done += k
+    for _ in range(max(args.warmup, 3)):
+        g.step(args.fused)
+    g.sync()
+    samplers = [ClockSampler(i) for i in devices[:1]]
+    for s_ in samplers:
+        s_.start()
+    shards = [g.shard(s)[0] for s in range(g.n_shards)]
+    launches0 = g.launches()
+    for h in shards:
+        pxb._check(g.lib.pxBatchTimerStart(h), "pxBatchTimerStart")
+    for _ in range(args.steps):
+        g.step(args.fused)
+    ms = 0.0
+    for h in shards:
+        t = pxb.C.c_float(0)
+        pxb._check(g.lib.pxBatchTimerStop(h, pxb.C.byref(t)), "pxBatchTimerStop")
+        ms = max(ms, float(t.value))
+    gpu_launches = g.launches() - launches0
+    clocks = samplers[0].stop()
+    for _ in range(2):
+        g.step_host(args.fused, args.e2e_chunks)
+        g.sync()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        g.step_host(args.fused, args.e2e_chunks)
+        g.sync()
+    e2e_ms = 1e3 * (time.perf_counter() - t0)
+    L = g.shard_layout(0)
+    body_substeps = total * BODIES_PER_WORLD * args.fused * args.steps
+    out = {
+        "metric": "body_steps_per_sec", "value": body_substeps / (ms * 1e-3), "unit": "body-substeps/s", "n_gpus": n_gpus,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args, n_gpus), "substeps_per_step": args.fused,
+                   "mode": f"single process, PxBatchGroup over {n_gpus} devices ({g.n_shards} shards)",
+                   "l2": "inputs larger than L2 (state > 126 MB per GPU)"},
+        "clocks": clocks, "gpu_launches": int(gpu_launches),
+        "e2e": {"value": body_substeps / (e2e_ms * 1e-3), "unit": "body-substeps/s",
+                "h2d_bytes_per_step": int(total * L.mutStride), "d2h_bytes_per_step": int(total * L.mutStride),
+                "ms_per_step": e2e_ms / args.steps},
+    }
+    print(json.dumps(out))
+    g.close()
     return 0
 
 
@@ -439,6 +615,8 @@ def main():
         args.no_cpu = args.no_e2e = True
     if args.impl == "reference":
         return run_reference(args)
+    if args.sharded:
+        return run_sharded(args)
     return run_ours(args)
 
 

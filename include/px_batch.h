@@ -188,6 +188,11 @@ PX_API int pxBatchStep(PxBatch *b, uint32_t kSubsteps);
  * what a px->world->step over N host-resident worlds costs end to end. */
 PX_API int pxBatchStepHost(PxBatch *b, uint32_t kSubsteps, void *hostMut, uint32_t chunks);
 
+/* CUDA events on the batch's stream around whatever is queued between the two calls; Stop blocks
+ * until the work is done; *ms = device time.  (Start/Stop of several batches on several devices
+ * can be interleaved: pxBatchGroupStepTimed.) */
+PX_API int pxBatchTimerStart(PxBatch *b);
+PX_API int pxBatchTimerStop(PxBatch *b, float *ms);
 /* Same, bracketed by CUDA events on the launching stream; blocks; *ms = device time. */
 PX_API int pxBatchStepTimed(PxBatch *b, uint32_t kSubsteps, float *ms);
 
@@ -296,6 +301,36 @@ PX_API int pxBatchFitDesc(struct PxWorld *const *worlds, uint32_t n, PxBatchDesc
  * result bit patterns (block i covers patterns [i << 20, (i + 1) << 20)). */
 PX_API int pxSelfTestMath(int op, const float *a, const float *b, const float *sinTable256, float *out, uint32_t n);
 PX_API int pxSelfTestRsqrtSweep(uint64_t *sums4096);
+
+/* --------------------------------------------------------------- several GPUs, one caller */
+/*
+ * Worlds are independent, so a batch shards over the GPUs of a box with no collective and no peer
+ * traffic: a PxBatchGroup owns one PxBatch -- slab, stream, staging -- per device and
+ * fans every call out from the calling host thread; the per-device work is asynchronous, so the
+ * devices run side by side.  World w of the group lives in shard w / ceil(nWorlds / nDevices)
+ * (contiguous ranges, the same rule as pdphyzx_b200/sharding.py).  devices == NULL: devices
+ * 0 .. nDevices-1.  The control and lifecycle calls of a single world go to its shard:
+ * pxBatchGroupLocate gives the shard's PxBatch and the world's index in it.
+ */
+typedef struct PxBatchGroup PxBatchGroup;
+PX_API PxBatchGroup *pxBatchGroupNew(struct PxWorld *const *worlds, uint32_t nWorlds, const PxBatchDesc *desc,
+                                     const int32_t *devices, uint32_t nDevices);
+PX_API PxBatchGroup *pxBatchGroupCreate(uint32_t nWorlds, const PxBatchDesc *desc, const int32_t *devices, uint32_t nDevices);
+PX_API void pxBatchGroupFree(PxBatchGroup *g);
+PX_API uint32_t pxBatchGroupShards(const PxBatchGroup *g);
+PX_API PxBatch *pxBatchGroupShard(const PxBatchGroup *g, uint32_t shard, uint32_t *firstWorld, uint32_t *nWorlds);
+PX_API PxBatch *pxBatchGroupLocate(const PxBatchGroup *g, uint32_t world, uint32_t *localWorld);
+PX_API int pxBatchGroupUpload(PxBatchGroup *g, struct PxWorld *const *worlds, uint32_t first, uint32_t n);
+PX_API int pxBatchGroupStep(PxBatchGroup *g, uint32_t kSubsteps);
+PX_API int pxBatchGroupStepHost(PxBatchGroup *g, uint32_t kSubsteps, uint32_t chunks);
+/* one step on every device, device-timed: *ms = the slowest device's time */
+PX_API int pxBatchGroupStepTimed(PxBatchGroup *g, uint32_t kSubsteps, float *ms);
+PX_API int pxBatchGroupSync(PxBatchGroup *g);
+PX_API int pxBatchGroupReadback(PxBatchGroup *g, struct PxWorld *const *worlds, uint32_t first, uint32_t n, uint32_t flags);
+/* setters for one world or PX_ALL_WORLDS, routed to the owning shard(s) */
+PX_API int pxBatchGroupSetGravity(PxBatchGroup *g, uint32_t world, float x, float y);
+PX_API int pxBatchGroupSetIterations(PxBatchGroup *g, uint32_t world, uint32_t iterations);
+PX_API int pxBatchGroupApplyImpulse(PxBatchGroup *g, uint32_t world, uint32_t body, float ix, float iy, float cx, float cy);
 
 PX_API const char *pxBatchLastError(void);
 PX_API const char *pxBatchVersion(void);

@@ -115,6 +115,23 @@ def core():
         "pxBatchFitDesc": (i32, [pp, u32, C.POINTER(PxBatchDesc)]),
         "pxSelfTestMath": (i32, [C.c_int, vp, vp, vp, vp, u32]),
         "pxSelfTestRsqrtSweep": (i32, [vp]),
+        "pxBatchTimerStart": (i32, [vp]),
+        "pxBatchTimerStop": (i32, [vp, C.POINTER(C.c_float)]),
+        "pxBatchGroupNew": (vp, [pp, u32, C.POINTER(PxBatchDesc), C.POINTER(C.c_int32), u32]),
+        "pxBatchGroupCreate": (vp, [u32, C.POINTER(PxBatchDesc), C.POINTER(C.c_int32), u32]),
+        "pxBatchGroupFree": (None, [vp]),
+        "pxBatchGroupShards": (u32, [vp]),
+        "pxBatchGroupShard": (vp, [vp, u32, C.POINTER(u32), C.POINTER(u32)]),
+        "pxBatchGroupLocate": (vp, [vp, u32, C.POINTER(u32)]),
+        "pxBatchGroupUpload": (i32, [vp, pp, u32, u32]),
+        "pxBatchGroupStep": (i32, [vp, u32]),
+        "pxBatchGroupStepHost": (i32, [vp, u32, u32]),
+        "pxBatchGroupStepTimed": (i32, [vp, u32, C.POINTER(C.c_float)]),
+        "pxBatchGroupSync": (i32, [vp]),
+        "pxBatchGroupReadback": (i32, [vp, pp, u32, u32, u32]),
+        "pxBatchGroupSetGravity": (i32, [vp, u32, f, f]),
+        "pxBatchGroupSetIterations": (i32, [vp, u32, u32]),
+        "pxBatchGroupApplyImpulse": (i32, [vp, u32, u32, f, f, f, f]),
         "pxBatchLastError": (C.c_char_p, []),
         "pxBatchVersion": (C.c_char_p, []),
     }
@@ -519,6 +536,86 @@ class Batch:
         a, b, c, d = C.c_int(0), C.c_int(0), C.c_int(0), C.c_int(0)
         _check(self.lib.pxBatchKernelInfo(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(d)), "pxBatchKernelInfo")
         return dict(ctas_per_sm=a.value, smem_bytes=b.value, threads=c.value, num_sms=d.value)
+
+
+class BatchGroup:
+    """A PxBatchGroup: one batch of worlds sharded over several GPUs, driven from this thread
+    (include/px_batch.h).  `devices` may name a device twice (two shards on one GPU)."""
+
+    def __init__(self, worlds: HostWorlds | None, devices, flags: int = 0, threads: int = 0, n_worlds: int | None = None,
+                 unit: float | None = None, **caps):
+        lib = core()
+        self.lib = lib
+        self.worlds = worlds
+        u = worlds.unit if worlds is not None else float(unit)
+        self.desc = make_desc(u, flags=flags, threads=threads,
+                              **{{"max_dynamic": "maxDynamic", "max_static": "maxStatic", "max_vertices": "maxVertices",
+                                  "max_manifolds": "maxManifolds", "max_pairs": "maxPairs"}[k]: v for k, v in caps.items()})
+        dev = (C.c_int32 * len(devices))(*devices)
+        if worlds is not None and n_worlds is None:
+            self.desc.sinTable = worlds.lib.pxh_sin_table()
+            self.h = lib.pxBatchGroupNew(worlds.pointer_array(), worlds.n, C.byref(self.desc), dev, len(devices))
+            self.n = worlds.n
+        else:  # empty group with explicit capacities, filled by upload() in chunks
+            self.h = lib.pxBatchGroupCreate(int(n_worlds), C.byref(self.desc), dev, len(devices))
+            self.n = int(n_worlds)
+        if not self.h:
+            raise PxError(f"pxBatchGroupNew/Create failed: {last_error()}")
+        self.n_shards = int(lib.pxBatchGroupShards(self.h))
+
+    def upload(self, worlds: HostWorlds, first: int = 0):
+        _check(self.lib.pxBatchGroupUpload(self.h, worlds.pointer_array(), first, worlds.n), "pxBatchGroupUpload")
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.pxBatchGroupFree(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def shard(self, s: int):
+        first, count = C.c_uint32(0), C.c_uint32(0)
+        h = self.lib.pxBatchGroupShard(self.h, s, C.byref(first), C.byref(count))
+        return h, int(first.value), int(count.value)
+
+    def shard_layout(self, s: int) -> PxBatchLayout:
+        L = PxBatchLayout()
+        _check(self.lib.pxBatchGetLayout(self.shard(s)[0], C.byref(L)), "pxBatchGetLayout")
+        return L
+
+    def step(self, k: int = 1):
+        _check(self.lib.pxBatchGroupStep(self.h, int(k)), "pxBatchGroupStep")
+
+    def step_host(self, k: int = 1, chunks: int = 0):
+        _check(self.lib.pxBatchGroupStepHost(self.h, int(k), int(chunks)), "pxBatchGroupStepHost")
+
+    def step_timed(self, k: int = 1) -> float:
+        ms = C.c_float(0)
+        _check(self.lib.pxBatchGroupStepTimed(self.h, int(k), C.byref(ms)), "pxBatchGroupStepTimed")
+        return float(ms.value)
+
+    def sync(self):
+        _check(self.lib.pxBatchGroupSync(self.h), "pxBatchGroupSync")
+
+    def readback(self, worlds: HostWorlds | None = None, flags: int = 0) -> int:
+        worlds = worlds or self.worlds
+        return _check(self.lib.pxBatchGroupReadback(self.h, worlds.pointer_array(), 0, worlds.n, flags), "pxBatchGroupReadback")
+
+    def set_gravity(self, world, x, y):
+        _check(self.lib.pxBatchGroupSetGravity(self.h, world, x, y), "pxBatchGroupSetGravity")
+
+    def set_iterations(self, world, it):
+        _check(self.lib.pxBatchGroupSetIterations(self.h, world, it), "pxBatchGroupSetIterations")
+
+    def apply_impulse(self, world, body, ix, iy, cx, cy):
+        _check(self.lib.pxBatchGroupApplyImpulse(self.h, world, body, ix, iy, cx, cy), "pxBatchGroupApplyImpulse")
+
+    def launches(self) -> int:
+        return sum(int(self.lib.pxBatchLaunchCount(self.shard(s)[0])) for s in range(self.n_shards))
 
 
 def device_math(op: int, a: np.ndarray, b: np.ndarray | None = None, sin_table: np.ndarray | None = None) -> np.ndarray:

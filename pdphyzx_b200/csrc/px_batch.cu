@@ -57,6 +57,8 @@ struct PxBatch {
   cudaStream_t aux[2];
   cudaEvent_t evFork, evJoin[2];
   bool auxReady;
+  cudaEvent_t evTimer[2]; /* pxBatchTimerStart / pxBatchTimerStop */
+  bool timerReady;
 };
 
 #define CU(call)                                                                                        \
@@ -82,6 +84,7 @@ extern "C" PxBatch *pxBatchCreate(uint32_t nWorlds, const PxBatchDesc *desc) {
   b->dProf = nullptr;
   b->dScratch = nullptr;
   b->auxReady = false;
+  b->timerReady = false;
   b->dCounters = nullptr;
   b->gridMax = 0;
   b->hMut = b->hImm = nullptr;
@@ -250,6 +253,10 @@ extern "C" void pxBatchFree(PxBatch *b) {
       cudaEventDestroy(b->evJoin[i]);
     }
     cudaEventDestroy(b->evFork);
+  }
+  if (b->timerReady) {
+    cudaEventDestroy(b->evTimer[0]);
+    cudaEventDestroy(b->evTimer[1]);
   }
   cudaFree(b->dCounters);
   cudaFree(b->dCmds);
@@ -607,6 +614,29 @@ extern "C" int pxBatchStepTimed(PxBatch *b, uint32_t kSubsteps, float *ms) {
   cudaEventDestroy(e1);
   if (rc != 0) return rc;
   if (err != cudaSuccess) return pxSetError(-(int)err - 1000, "pxBatchStepTimed: %s", cudaGetErrorString(err));
+  if (ms) *ms = t;
+  return 0;
+}
+
+/* device time of whatever is queued on the batch's stream between the two calls */
+extern "C" int pxBatchTimerStart(PxBatch *b) {
+  if (!b) return pxSetError(-1, "pxBatchTimerStart: NULL batch");
+  if (useDevice(b)) return -1;
+  if (!b->timerReady) {
+    CU(cudaEventCreate(&b->evTimer[0]));
+    CU(cudaEventCreate(&b->evTimer[1]));
+    b->timerReady = true;
+  }
+  CU(cudaEventRecord(b->evTimer[0], b->stream));
+  return 0;
+}
+extern "C" int pxBatchTimerStop(PxBatch *b, float *ms) {
+  if (!b || !b->timerReady) return pxSetError(-1, "pxBatchTimerStop: no timer was started");
+  if (useDevice(b)) return -1;
+  CU(cudaEventRecord(b->evTimer[1], b->stream));
+  CU(cudaEventSynchronize(b->evTimer[1]));
+  float t = 0;
+  CU(cudaEventElapsedTime(&t, b->evTimer[0], b->evTimer[1]));
   if (ms) *ms = t;
   return 0;
 }

@@ -115,3 +115,30 @@ def run_side_by_side(scenes, substeps: int, k: int = 1, flags: int = 0, threads:
     finally:
         b.close()
         worlds.close()
+
+
+def oracle_substeps_threaded(L, mut: np.ndarray, imm: np.ndarray, table: np.ndarray, k: int, trace: np.ndarray | None = None,
+                             threads: int | None = None):
+    """pxOracleSubsteps over every world of a block pair, disjoint world ranges on `threads` host
+    threads (worlds are independent; ctypes releases the GIL while the C oracle runs)."""
+    import threading
+    n = L.nWorlds
+    threads = max(1, min(threads or (os.cpu_count() or 1), n))
+    bounds = [n * t // threads for t in range(threads + 1)]
+    errs = []
+
+    def run(a, b):
+        try:
+            if b > a:
+                tr = None if trace is None else trace[a * L.traceStride:]  # the oracle indexes its trace from `first`
+                oraclebind.substeps(L, mut, imm, table, k, first=a, n=b - a, trace=tr)
+        except Exception as exc:  # pragma: no cover
+            errs.append(exc)
+
+    ts = [threading.Thread(target=run, args=(bounds[t], bounds[t + 1])) for t in range(threads)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    if errs:
+        raise errs[0]

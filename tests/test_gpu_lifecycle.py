@@ -189,3 +189,64 @@ def test_a_small_batch_does_not_break_a_large_ones_launch():
     np.testing.assert_array_equal(np.asarray(a.download_blocks().mut), np.asarray(ref.download_blocks().mut))
     for x in (a, small, ref):
         x.close()
+
+
+def _state(worlds, n):
+    out = []
+    for w in range(n):
+        rows, flags, order = worlds.bodies(w, True)
+        out.append((bits(rows[order][:, :18]).copy(), flags[order].copy(), order.copy()))
+    return out
+
+
+@pytest.mark.parametrize("devices", [[0, 0, 0], "all"])
+def test_batch_group_shards_one_batch_over_devices(devices):
+    """PxBatchGroup: contiguous world ranges per device, every call fanned out from one
+    host thread, no collective.  A sharded run equals the single-batch run world for world -- with
+    three shards on one GPU, and with one shard per GPU when the box has several."""
+    import torch
+    if devices == "all":
+        if torch.cuda.device_count() < 2:
+            pytest.skip("needs two GPUs")
+        devices = list(range(torch.cuda.device_count()))
+    n = 11  # not a multiple of the shard count: the last shard is short
+    sc = [scenes.pile_scene(w, mix="mixed", n_dynamic=40, cols=6) for w in range(n)]
+    wa, wb = pxb.HostWorlds(sc), pxb.HostWorlds(sc)
+    a = pxb.Batch(wa)
+    g = pxb.BatchGroup(wb, devices)
+    assert g.n_shards == min(len(devices), n)
+    covered = []
+    for s in range(g.n_shards):
+        _, first, count = g.shard(s)
+        covered += list(range(first, first + count))
+    assert covered == list(range(n))
+    for it in range(6):
+        for x in (a, g):
+            x.set_gravity(pxb.ALL_WORLDS, 0.1 * it, 9.8)
+            x.set_gravity(7, -0.3, 9.0)
+            x.apply_impulse(10, 3, 0.5, -1.0, 0.0, 0.0)
+            x.set_iterations(2, 6)
+        a.step(25)
+        ms = g.step_timed(25) if it % 2 else (g.step(25), 0.0)[1]
+        assert ms >= 0.0
+    assert a.readback(wa) == 0
+    assert g.readback(wb) == 0
+    for (ra, fa, oa), (rb, fb, ob) in zip(_state(wa, n), _state(wb, n)):
+        np.testing.assert_array_equal(oa, ob)
+        np.testing.assert_array_equal(ra, rb)
+        np.testing.assert_array_equal(fa, fb)
+    # host-buffer stepping through the group: every shard's pinned staging in, stepped, out
+    g.step_host(5, 2)
+    g.sync()
+    a.step(5)
+    for s in range(g.n_shards):
+        h, first, count = g.shard(s)
+        L = g.shard_layout(s)
+        buf = (pxb.C.c_uint8 * (count * L.mutStride)).from_address(g.lib.pxBatchHostMutable(h))
+        got = pxb.Blocks(L, np.frombuffer(buf, np.uint8), None)
+        want = a.download_blocks()
+        np.testing.assert_array_equal(np.asarray(got.dyn).view(np.uint32), np.asarray(want.dyn[first:first + count]).view(np.uint32))
+    a.close()
+    g.close()
+    wa.close()
+    wb.close()
