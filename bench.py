@@ -409,6 +409,7 @@ def run_ours(args):
     # pxBatchReadback (HBM -> host, SoA -> AoS into the same PxWorld structs), waited for every step
     aos_ms = None
     if worlds is not None and not args.no_e2e and not args.no_aos and not args.control:
+        b.readback(worlds)  # the host structs still hold the initial scene: bring the settled piles over first
         for _ in range(2):
             b.upload(worlds)
             b.step(args.fused)

@@ -54,7 +54,7 @@ typedef struct PxBatchDesc {
   uint32_t maxDynamic;   /* per-world capacities; 0 = take from the worlds given to pxBatchNew */
   uint32_t maxStatic;
   uint32_t maxVertices;  /* polygon vertices per world (sum over bodies) */
-  uint32_t maxManifolds; /* 0 = 2.75 * maxDynamic (<= 1024) */
+  uint32_t maxManifolds; /* 0 = 2.875 * maxDynamic (<= 1024) */
   uint32_t maxPairs;     /* 0 = 7 * maxDynamic */
   int32_t device;        /* CUDA device ordinal, -1 = current device */
   void *stream;          /* cudaStream_t to launch on; NULL = a stream owned by the batch */

@@ -40,9 +40,11 @@ int pxBatchComputeLayout(uint32_t nWorlds, const PxBatchDesc *desc, PxBatchLayou
   L->maxDynamic = alignUp(desc->maxDynamic, 16); /* byte rows are copied 16 bytes at a time */
   L->maxStatic = alignUp(desc->maxStatic ? desc->maxStatic : 1, 4);
   L->maxVertices = alignUp(desc->maxVertices ? desc->maxVertices : 4, 4);
-  /* defaults sized from dense piles (about 2.5 manifolds and 5.5 AABB-pass pairs per body);
+  /* defaults sized from dense piles: a settled 252-circle pile peaks at 705 manifolds (SURVEY 0.2,
+   * 6), a mixed one at about 660, so 23/8 = 2.875 per body slot (736 at 256 slots; the ready queue
+   * of the solver stays at 1024 entries up to exactly that) and 7 AABB-pass pairs per slot;
    * a world that needs more sets its PX_BATCH_OVERFLOW_* flag and the caller raises these */
-  L->maxManifolds = desc->maxManifolds ? desc->maxManifolds : (11 * L->maxDynamic) / 4;
+  L->maxManifolds = desc->maxManifolds ? desc->maxManifolds : (23 * L->maxDynamic) / 8;
   L->maxPairs = desc->maxPairs ? desc->maxPairs : 7 * L->maxDynamic;
   L->maxManifolds = alignUp(L->maxManifolds, 32);
   L->maxPairs = alignUp(L->maxPairs, 32);

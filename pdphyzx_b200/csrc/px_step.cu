@@ -1041,12 +1041,23 @@ __global__ void __launch_bounds__(NT, NT == 128 ? PX_MINB128 : 3) pxStepKernel(c
         dirty = __syncthreads_or(unsorted);
       }
       if (dirty) {
+        /* keys compared as order-preserving integers: a total order even if a diverged world
+         * holds NaN positions, so the ranks are always a permutation (no out-of-range slot) */
+        auto ordered = [](float f) {
+          const uint32_t u = __float_as_uint(f);
+          return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+        };
         for (uint32_t p = tid; p < nDyn; p += NT) {
           const float key = keys[p];
+          const uint32_t ukey = ordered(key);
           uint32_t rank = 0;
           for (uint32_t q = 0; q < nDyn; q++) {
             const float kq = keys[q];
-            rank += (kq < key || (kq == key && q < p)) ? 1u : 0u;
+            const uint32_t uq = ordered(kq);
+            /* -0.0f == 0.0f in the reference's float comparison: equal keys keep their order */
+            const bool less = (kq == kq && key == key) ? kq < key : uq < ukey;
+            const bool same = (kq == kq && key == key) ? kq == key : uq == ukey;
+            rank += (less || (same && q < p)) ? 1u : 0u;
           }
           s.order2[rank] = s.order[p];
         }

@@ -46,7 +46,7 @@ def test_struct_sizes_match_c():
     assert L.maxDynamic == 256 and L.maxStatic == 4 and L.nWorlds == 16
     assert L.mutStride % 128 == 0 and L.immStride % 128 == 0
     assert L.offDyn % 16 == 0 and L.offVerts % 16 == 0
-    assert L.maxManifolds == 704 and L.maxPairs == 1792
+    assert L.maxManifolds == 736 and L.maxPairs == 1792  # 23/8 and 7 per body slot
     # unit-derived constants use the reference's association (px_math.h:23, px_polygon.c:329)
     for unit in (1.0, 100.0, 1000.0):
         Lu = pxb.compute_layout(1, pxb.make_desc(unit, maxDynamic=8))
@@ -118,3 +118,17 @@ def test_reference_side_binding_builds_and_loads():
     lib.ref_is_b200.restype = C.c_int
     assert lib.ref_is_b200() == 1
     assert refbind.load("wide", 1.0).ref_is_b200() == 0
+
+
+def test_amalgamated_header_builds_on_its_own(tmp_path):
+    """the host side ships as ONE header, the way the reference ships dist/pdphyzx.h
+    (reference .nob/nob.c:936-984); tools/amalgamate.py generates it and it compiles alone."""
+    import subprocess
+    import sys
+    out = tmp_path / "pdphyzx_b200.h"
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "amalgamate.py"), "--out", str(out), "--check"],
+                         stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert res.returncode == 0, res.stdout
+    text = out.read_text()
+    assert "pxBatchGroupStep" in text and "registerPdPhyzx" in text and "pxPackOneWorld" in text
+    assert '#include "px_batch.h"' not in text
