@@ -66,6 +66,8 @@ def parse_args():
     ap.add_argument("--sharded", action="store_true",
                     help="single process: one PxBatchGroup (C ABI) over --gpus devices instead of one process per GPU")
     ap.add_argument("--no-aos", action="store_true", help="skip the e2e_aos leg (PxWorld structs in, PxWorld structs out)")
+    ap.add_argument("--timed-iterations", type=int, default=-1,
+                    help="experiment: switch every world to this many solver iterations after settling (0 = time phases A-D+F alone)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--profile", action="store_true", help="per-phase SM-cycle breakdown (adds clock reads)")
@@ -334,6 +336,8 @@ def run_ours(args):
         b.step(k)
         done += k
     b.sync()
+    if args.timed_iterations >= 0:
+        b.set_iterations(0xFFFFFFFF, args.timed_iterations)
     for _ in range(max(args.warmup, 3)):
         b.step(args.fused)
     b.sync()

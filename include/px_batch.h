@@ -38,6 +38,8 @@ struct PxWorld; /* include/pdphyzx.h */
 #define PX_BATCH_FLAG_TRACE 1u        /* keep the last substep's ordered pair + manifold lists */
 #define PX_BATCH_FLAG_SERIAL_SOLVER 2u /* debug: one thread walks the manifolds in pool order */
 #define PX_BATCH_FLAG_PROFILE 4u       /* accumulate SM-clock cycles per kernel phase per world */
+#define PX_BATCH_FLAG_SPLIT 8u         /* force the split pipeline (sweep kernel + solver kernel per substep) */
+#define PX_BATCH_FLAG_FUSED 16u        /* force the fused pipeline (one kernel, K substeps); default: by batch size */
 
 /* PxWorldHeader.statOverflow bits */
 #define PX_BATCH_OVERFLOW_PAIRS 1u     /* more AABB-pass pairs than maxPairs: extra pairs dropped */

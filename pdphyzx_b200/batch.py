@@ -21,6 +21,8 @@ ALL_WORLDS = 0xFFFFFFFF
 FLAG_TRACE = 1
 FLAG_SERIAL_SOLVER = 2
 FLAG_PROFILE = 4
+FLAG_SPLIT = 8
+FLAG_FUSED = 16
 OVERFLOW_PAIRS = 1
 OVERFLOW_MANIFOLDS = 2
 STATIC = 0x10000  # PX_BATCH_STATIC: OR into a body slot to address a static body

@@ -20,7 +20,7 @@
 #include "px_step.cuh"
 
 #define PX_REGIONS 3u       /* scratch regions: the batch's stream and the two helper streams of pxBatchStepHost */
-#define PX_COUNTER_RING 64u /* >= launches that can be in flight at once */
+#define PX_COUNTER_RING 1024u /* >= launches that can be in flight at once (a host-buffer step queues (2K + 1) x chunks) */
 
 struct PxBatch {
   PxBatchLayout L;
@@ -36,6 +36,14 @@ struct PxBatch {
   float4 *dScratch;   /* manifold records of the resident CTAs (px_step.cuh): PX_REGIONS regions of gridMax slots */
   uint32_t *dCounters; /* world counters of the persistent grids, one per launch in flight (ring) */
   uint32_t gridMax;    /* CTAs of a full launch: resident capacity of the device, at most nWorlds */
+  /* split pipeline (sweep kernel + solver kernel per substep, px_step.cu) */
+  bool split;
+  PxHandLayout hand;
+  PxSmemPlan solvePlan;
+  uint8_t *dHand;      /* hand-over records, one per world */
+  uint32_t gridSolve, solveWarps;
+  int solveCtasPerSm;
+
   uint8_t *hMut, *hImm; /* pinned staging, same layout */
   float sinTable[256];
   /* control path */
@@ -87,6 +95,11 @@ extern "C" PxBatch *pxBatchCreate(uint32_t nWorlds, const PxBatchDesc *desc) {
   b->timerReady = false;
   b->dCounters = nullptr;
   b->gridMax = 0;
+  b->split = false;
+  b->dHand = nullptr;
+  b->gridSolve = 0;
+  b->solveCtasPerSm = 0;
+
   b->hMut = b->hImm = nullptr;
   b->dCmds = b->dGlobal = nullptr;
   b->dWorldStart = nullptr;
@@ -128,9 +141,21 @@ extern "C" PxBatch *pxBatchCreate(uint32_t nWorlds, const PxBatchDesc *desc) {
     if ((e = cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
     b->ownStream = true;
   }
-  /* 128 threads: 5 CTAs/SM (37.6 KB of shared memory and <= 102 registers each) keep the SM's
-   * issue slots busier than 3 CTAs of 256 threads */
-  b->threads = desc->threads ? desc->threads : 128;
+  /* Pipeline: fused (one kernel, K substeps, state never leaves the SM) for small batches and
+   * single worlds; split (a sweep kernel and a solver kernel per substep) once the batch is a few
+   * waves deep -- the solver's latency-bound chains then run at more than twice the residency and
+   * without throughput warps stealing their issue slots.  PX_BATCH_FLAG_SPLIT / _FUSED force one. */
+  {
+    const char *env = getenv("PX_PIPELINE"); /* tuning switch: "split" or "fused" */
+    if (desc->flags & PX_BATCH_FLAG_SERIAL_SOLVER) b->split = false; /* the debug walk lives in the fused kernel */
+    else if (desc->flags & PX_BATCH_FLAG_SPLIT) b->split = true;
+    else if (desc->flags & PX_BATCH_FLAG_FUSED) b->split = false;
+    else if (env) b->split = env[0] == 's';
+    else b->split = nWorlds >= 4u * (uint32_t)b->numSms;
+  }
+  /* fused: 128 threads, 5 CTAs/SM keep the SM's issue slots busier than 3 CTAs of 256 threads;
+   * split: the sweep kernel alone is throughput work, 256 threads x 3 CTAs leave it a larger L1 */
+  b->threads = desc->threads ? desc->threads : (b->split ? 256 : 128);
   if (b->threads != 128 && b->threads != 256) { /* the solver alone occupies four specialised warps */
     pxSetError(-1, "PxBatchDesc.threads must be 128 or 256");
     pxBatchFree(b);
@@ -143,7 +168,23 @@ extern "C" PxBatch *pxBatchCreate(uint32_t nWorlds, const PxBatchDesc *desc) {
     PxSmemPlan slim;
     pxPlanSmem(&b->L, 0, &slim);
     const size_t perSm = (size_t)prop.sharedMemPerMultiprocessor, reserve = (size_t)prop.reservedSharedMemPerBlock;
-    const size_t fat = perSm / (b->plan.total + reserve), thin = perSm / (slim.total + reserve);
+    size_t fat = perSm / (b->plan.total + reserve), thin = perSm / (slim.total + reserve);
+    if (b->plan.total <= (uint32_t)prop.sharedMemPerBlockOptin) {
+      /* what counts is the occupancy the kernel really gets (registers may bind before shared memory) */
+      PxStepParams Q;
+      memset(&Q, 0, sizeof(Q));
+      Q.L = b->L;
+      Q.mode = b->split ? PX_MODE_SWEEP : PX_MODE_FUSED;
+      int of = 0, ot = 0;
+      Q.S = b->plan;
+      const int r1 = pxStepOccupancy(&Q, b->threads, &of);
+      Q.S = slim;
+      const int r2 = pxStepOccupancy(&Q, b->threads, &ot);
+      if (r1 == 0 && r2 == 0) {
+        fat = (size_t)of;
+        thin = (size_t)ot;
+      }
+    }
     const char *force = getenv("PX_VERTS_SMEM"); /* tuning switch, undocumented on purpose: 1 = keep them in shared memory, 0 = never */
     if (b->plan.total > (uint32_t)prop.sharedMemPerBlockOptin || (force ? force[0] == '0' : thin > fat)) b->plan = slim;
   }
@@ -174,6 +215,7 @@ extern "C" PxBatch *pxBatchCreate(uint32_t nWorlds, const PxBatchDesc *desc) {
     memset(&P, 0, sizeof(P));
     P.L = b->L;
     P.S = b->plan;
+    P.mode = b->split ? PX_MODE_SWEEP : PX_MODE_FUSED;
     int occ = 0;
     int rc = pxStepOccupancy(&P, b->threads, &occ);
     if (rc != 0) return fail("occupancy query of the step kernel", (cudaError_t)rc);
@@ -185,8 +227,27 @@ extern "C" PxBatch *pxBatchCreate(uint32_t nWorlds, const PxBatchDesc *desc) {
     b->ctasPerSm = occ;
     const uint64_t capacity = (uint64_t)occ * (uint64_t)b->numSms;
     b->gridMax = (uint32_t)(capacity < nWorlds ? capacity : nWorlds);
-    const size_t scratchBytes = (size_t)PX_REGIONS * b->gridMax * b->L.maxManifolds * 3 * sizeof(float4);
-    if ((e = cudaMalloc(&b->dScratch, scratchBytes)) != cudaSuccess) return fail("cudaMalloc(scratch)", e);
+    if (!b->split) {
+      const size_t scratchBytes = (size_t)PX_REGIONS * b->gridMax * b->L.maxManifolds * 3 * sizeof(float4);
+      if ((e = cudaMalloc(&b->dScratch, scratchBytes)) != cudaSuccess) return fail("cudaMalloc(scratch)", e);
+    } else {
+      pxPlanHandover(&b->L, &b->plan, &b->hand);
+      {
+        const char *env = getenv("PX_SOLVE_WARPS"); /* tuning switch: 4 (fed math warp) or 2 (self-feeding) */
+        b->solveWarps = env && env[0] == '4' ? 4u : 2u;
+      }
+      pxPlanSolveSmem(&b->L, &b->plan, b->solveWarps, &b->solvePlan);
+      P.solveS = b->solvePlan;
+      int socc = 0;
+      rc = pxSolveOccupancy(&P, b->solveWarps, &socc);
+      if (rc != 0 || socc < 1) return fail("occupancy query of the solver kernel", (cudaError_t)(rc ? rc : (int)cudaErrorLaunchOutOfResources));
+      b->solveCtasPerSm = socc;
+      const uint64_t scap = (uint64_t)socc * (uint64_t)b->numSms;
+      b->gridSolve = (uint32_t)(scap < nWorlds ? scap : nWorlds);
+      const size_t handBytes = (size_t)nWorlds * b->hand.stride;
+      if ((e = cudaMalloc(&b->dHand, handBytes)) != cudaSuccess) return fail("cudaMalloc(hand-over records)", e);
+      if ((e = cudaMemsetAsync(b->dHand, 0, handBytes, b->stream)) != cudaSuccess) return fail("cudaMemset", e);
+    }
     if ((e = cudaMalloc(&b->dCounters, PX_COUNTER_RING * sizeof(uint32_t))) != cudaSuccess) return fail("cudaMalloc(counters)", e);
   }
   {
@@ -247,6 +308,7 @@ extern "C" void pxBatchFree(PxBatch *b) {
   cudaFree(b->dSin);
   cudaFree(b->dProf);
   cudaFree(b->dScratch);
+  cudaFree(b->dHand);
   if (b->auxReady) {
     for (int i = 0; i < 2; i++) {
       cudaStreamDestroy(b->aux[i]);
@@ -524,31 +586,76 @@ static int flushCommands(PxBatch *b) {
 }
 
 /* --------------------------------------------------------------------------- stepping */
+static void baseParams(PxBatch *b, uint32_t kSubsteps, uint32_t first, uint32_t n, PxStepParams *P) {
+  memset(P, 0, sizeof(*P));
+  P->L = b->L;
+  P->L.nWorlds = n;
+  P->S = b->plan;
+  P->mut = b->dMut + (size_t)first * b->L.mutStride;
+  P->imm = b->dImm + (size_t)first * b->L.immStride;
+  P->trace = b->dTrace ? b->dTrace + (size_t)first * b->L.traceStride : nullptr;
+  P->sinTable = b->dSin;
+  P->prof = b->dProf ? b->dProf + (size_t)first * PX_PROF_SLOTS : nullptr;
+  P->kSubsteps = kSubsteps;
+  P->flags = b->flags;
+  P->mode = PX_MODE_FUSED;
+  static const char *ns = getenv("PX_LAG_SLEEP_NS"); /* tuning switch (500 ns: throughput is flat from 64 to 2000) */
+  P->lagSleepNs = ns ? (uint32_t)atoi(ns) : 500u;
+}
+
+static void splitParams(PxBatch *b, uint32_t first, PxStepParams *P) {
+  P->mode = PX_MODE_SWEEP;
+  P->scratch = nullptr;
+  P->hand = b->dHand + (size_t)first * b->hand.stride;
+  P->H = b->hand;
+  P->solveS = b->solvePlan;
+}
+
+/* launch s of the split pipeline's sweep kernel: phase F of substep s - 1 (s > 0), phases A-D of substep s (s < K) */
+static int launchSweep(PxBatch *b, PxStepParams *P, uint32_t s, uint32_t kSubsteps, uint32_t grid, cudaStream_t stream) {
+  P->doFinish = s > 0 ? 1u : 0u;
+  P->doSweep = s < kSubsteps ? 1u : 0u;
+  P->traceNow = (s + 1 == kSubsteps) ? 1u : 0u;
+  P->worldCounter = b->dCounters + (b->launches % PX_COUNTER_RING);
+  CU(cudaMemsetAsync(P->worldCounter, 0, sizeof(uint32_t), stream));
+  int rc = pxLaunchStep(P, b->threads, grid, stream);
+  if (rc != 0) return pxSetError(-rc - 1000, "sweep kernel launch: %s", cudaGetErrorString((cudaError_t)rc));
+  b->launches++;
+  return 0;
+}
+
+static int launchSolve(PxBatch *b, PxStepParams *P, uint32_t grid, cudaStream_t stream) {
+  P->worldCounter = b->dCounters + (b->launches % PX_COUNTER_RING);
+  CU(cudaMemsetAsync(P->worldCounter, 0, sizeof(uint32_t), stream));
+  int rc = pxLaunchSolve(P, b->solveWarps, grid, stream);
+  if (rc != 0) return pxSetError(-rc - 1000, "solver kernel launch: %s", cudaGetErrorString((cudaError_t)rc));
+  b->launches++;
+  return 0;
+}
+
 /* K substeps for worlds [first, first + n) on `stream`; launches that may overlap in time use
  * different scratch regions */
 static int launchRange(PxBatch *b, uint32_t kSubsteps, uint32_t first, uint32_t n, cudaStream_t stream, uint32_t region) {
   PxStepParams P;
-  P.L = b->L;
-  P.L.nWorlds = n;
-  P.S = b->plan;
-  P.mut = b->dMut + (size_t)first * b->L.mutStride;
-  P.imm = b->dImm + (size_t)first * b->L.immStride;
-  P.trace = b->dTrace ? b->dTrace + (size_t)first * b->L.traceStride : nullptr;
-  P.sinTable = b->dSin;
-  P.prof = b->dProf ? b->dProf + (size_t)first * PX_PROF_SLOTS : nullptr;
-  P.scratch = b->dScratch + (size_t)region * b->gridMax * b->L.maxManifolds * 3;
+  baseParams(b, kSubsteps, first, n, &P);
+  P.scratch = b->dScratch ? b->dScratch + (size_t)region * b->gridMax * b->L.maxManifolds * 3 : nullptr;
   P.worldCounter = b->dCounters + (b->launches % PX_COUNTER_RING);
-  P.kSubsteps = kSubsteps;
-  P.flags = b->flags;
-  {
-    static const char *ns = getenv("PX_LAG_SLEEP_NS"); /* tuning switch (500 ns: throughput is flat from 64 to 2000) */
-    P.lagSleepNs = ns ? (uint32_t)atoi(ns) : 500u;
+  if (!b->split) {
+    P.mode = PX_MODE_FUSED;
+    CU(cudaMemsetAsync(P.worldCounter, 0, sizeof(uint32_t), stream));
+    const uint32_t grid = n < b->gridMax ? n : b->gridMax;
+    int rc = pxLaunchStep(&P, b->threads, grid, stream);
+    if (rc != 0) return pxSetError(-rc - 1000, "step kernel launch: %s", cudaGetErrorString((cudaError_t)rc));
+    b->launches++;
+    return 0;
   }
-  CU(cudaMemsetAsync(P.worldCounter, 0, sizeof(uint32_t), stream));
-  const uint32_t grid = n < b->gridMax ? n : b->gridMax;
-  int rc = pxLaunchStep(&P, b->threads, grid, stream);
-  if (rc != 0) return pxSetError(-rc - 1000, "step kernel launch: %s", cudaGetErrorString((cudaError_t)rc));
-  b->launches++;
+  /* split pipeline: sweep(A-D) | solve | sweep(F, A-D) | solve | ... | sweep(F) */
+  splitParams(b, first, &P);
+  const uint32_t gridSweep = n < b->gridMax ? n : b->gridMax, gridSolve = n < b->gridSolve ? n : b->gridSolve;
+  for (uint32_t s = 0; s <= kSubsteps; s++) {
+    if (launchSweep(b, &P, s, kSubsteps, gridSweep, stream)) return -1;
+    if (s < kSubsteps && launchSolve(b, &P, gridSolve, stream)) return -1;
+  }
   return 0;
 }
 

@@ -38,6 +38,7 @@
 #include <cuda_runtime.h>
 #include <float.h>
 #include <stdint.h>
+#include <string.h>
 
 #include "px_step.cuh"
 
@@ -693,6 +694,15 @@ __device__ __forceinline__ void copyRows(float *dst, const float *src, uint32_t 
   for (uint32_t i = threadIdx.x; i < nFloats / 4; i += NT) d4[i] = s4[i];
 }
 
+/* bytes between shared memory and a world's hand-over record (either direction), 16 at a time;
+ * both sides are 16-byte aligned and padded, `bytes` is rounded up */
+template <int NT>
+__device__ __forceinline__ void handCopy(void *dst, const void *src, uint32_t bytes) {
+  const uint4 *s4 = reinterpret_cast<const uint4 *>(src);
+  uint4 *d4 = reinterpret_cast<uint4 *>(dst);
+  for (uint32_t i = threadIdx.x; i < (bytes + 15u) / 16u; i += NT) d4[i] = s4[i];
+}
+
 /* ------------------------------------------------------------------ solver warps */
 /* The two solver loops are functions of their own (never inlined): their register allocation
  * is then independent of the rest of the kernel, whose pressure (narrowphase, sweep) would
@@ -886,13 +896,74 @@ __device__ __noinline__ void solverMath(const SolverCtx c) {
   }
 }
 
+/* Math warp that fetches its own operands (no feeder warps): the solver kernel's two-warp form.
+ * While round r runs, the queue word and the three manifold records of round r + 1 are already in
+ * flight.  Fewer shared-memory wavefronts per round than the fed form (no operand ring), a longer
+ * chain per round: the better trade when many worlds share an SM and the L1/shared data pipe, not
+ * latency, is what binds. */
+__device__ __noinline__ void solverMathDirect(const SolverCtx c) {
+  const uint32_t lane = threadIdx.x & 31u, QMASK = c.qmask;
+  const uint32_t aQueue = c.aQueue, aDesc = c.aDesc, aMathRound = c.aMathRound, aBodyP = c.aBodyP, aBodyV = c.aBodyV;
+  const float4 *man = c.man;
+  const float eps = c.eps;
+  uint32_t r = 0, d = ldsAcquire(aDesc);
+  uint32_t w = 0, n = 0;
+  float4 mA, mB, mC;
+  bool have = false; /* w / n / m* hold round r */
+  for (;; r++) {
+    if (!have) {
+      const uint32_t expect = (r + 1u) & 0x7fffu;
+      while (PX_DESC_TAG(d) != expect) d = ldsAcquire(aDesc + 4u * (r & (PX_RING - 1u)));
+      n = PX_DESC_N(d);
+      if (n == PX_DESC_END) break;
+      const uint32_t qw = lds32(aQueue + 4u * ((PX_DESC_HEAD(d) + lane) & QMASK));
+      w = lane < n ? qw : 0u;
+      mA = ldgPinned(man + 3u * MID_SLOT(w));
+      mB = ldgPinned(man + 3u * MID_SLOT(w) + 1u);
+      mC = ldgPinned(man + 3u * MID_SLOT(w) + 2u);
+    }
+    const bool active = lane < n;
+    const uint32_t a16 = MID_A(w) * 16u, b16 = MID_B(w) * 16u;
+    ContactIn in;
+    in.mA = mA;
+    in.mB = mB;
+    in.mC = mC;
+    in.pA = lds128(aBodyP + a16);
+    in.pB = lds128(aBodyP + b16);
+    in.vA = lds128(aBodyV + a16);
+    in.vB = lds128(aBodyV + b16);
+    /* next round: descriptor, queue word, records */
+    const uint32_t dn = ldsAcquire(aDesc + 4u * ((r + 1u) & (PX_RING - 1u)));
+    const uint32_t nNext = PX_DESC_N(dn);
+    const bool haveNext = PX_DESC_TAG(dn) == ((r + 2u) & 0x7fffu) && nNext != PX_DESC_END;
+    const uint32_t qwN = lds32(aQueue + 4u * ((PX_DESC_HEAD(dn) + lane) & QMASK));
+    const uint32_t wNext = (haveNext && lane < nNext) ? qwN : 0u;
+    const float4 nA = ldgPinned(man + 3u * MID_SLOT(wNext));
+    const float4 nB = ldgPinned(man + 3u * MID_SLOT(wNext) + 1u);
+    const float4 nC = ldgPinned(man + 3u * MID_SLOT(wNext) + 2u);
+    asm volatile("" : "+f"(in.vA.x), "+f"(in.vB.x), "+f"(in.pA.x), "+f"(in.pB.x));
+    contactImpulse(w, in, eps);
+    sts128If(aBodyV + a16, in.vA, active);
+    sts128If(aBodyV + b16, in.vB, active && MID_BDYN(w));
+    __syncwarp();
+    asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(aMathRound), "r"(r + 1u) : "memory");
+    have = haveNext;
+    d = dn;
+    w = wNext;
+    n = nNext;
+    mA = nA;
+    mB = nB;
+    mC = nC;
+  }
+}
+
 #ifndef PX_MINB128
 #define PX_MINB128 5
 #endif
 #define PX_DMAX 256 /* dynamic slots per world (PX_MAX_BODIES rounded up to the copy granule) */
 
 /* ============================================================================ kernel ==== */
-template <int NT>
+template <int NT, int MODE>
 __global__ void __launch_bounds__(NT, NT == 128 ? PX_MINB128 : 3) pxStepKernel(const PxStepParams P) {
   constexpr int R = PX_DMAX / NT; /* body slots (and sorted positions) owned per thread */
   extern __shared__ __align__(16) uint8_t smemRaw[];
@@ -993,13 +1064,29 @@ __global__ void __launch_bounds__(NT, NT == 128 ? PX_MINB128 : 3) pxStepKernel(c
     profS = now;                                     \
   }
 
-  for (uint32_t step = 0; step < P.kSubsteps; step++) {
-    const bool traceNow = P.trace != nullptr && step + 1 == P.kSubsteps;
+  /* Split pipeline (PX_MODE_SWEEP): this launch runs phase F of the substep whose solver has
+   * just finished (pxSolveKernel) and then phases A-D of the next one; everything the two
+   * kernels and phase F exchange beyond the mutable block lives in the world's hand-over
+   * record in global memory.  Fused (PX_MODE_FUSED): K whole substeps, nothing leaves the SM. */
+  constexpr bool sweepMode = MODE == PX_MODE_SWEEP; /* compile-time: each pipeline carries only its own code */
+  uint8_t *hand = sweepMode ? P.hand + (size_t)world * P.H.stride : nullptr;
+  if (sweepMode) {
+    s.man = (float4 *)(hand + P.H.records);
+    statPairs = s.hdr->statPairs;
+    statManifolds = s.hdr->statManifolds;
+  }
+  uint32_t nPairs = 0, M = 0;
+  const uint32_t nLoop = sweepMode ? 2u : P.kSubsteps;
+  for (uint32_t step = 0; step < nLoop; step++) {
+    const bool runSweep = sweepMode ? (step == 1u && P.doSweep) : true;
+    const bool runFinish = sweepMode ? (step == 0u && P.doFinish) : true;
+    const bool traceNow = P.trace != nullptr && (sweepMode ? P.traceNow != 0u : step + 1 == P.kSubsteps);
     uint8_t *gtrace = traceNow ? P.trace + (size_t)world * L.traceStride : nullptr;
+    if (runSweep) {
 
     /* ====================== phase A: AABB keys, stable order by aabb.min.x ============ */
     /* the order persists across substeps, so it is almost always already sorted */
-    if (tid < 32 && tid != MI_OVERFLOW && tid != MI_WORLD) s.misc[tid] = 0;
+    if (tid < 32 && tid != MI_OVERFLOW && tid != MI_WORLD && !(sweepMode && tid == MI_SLEEPING)) s.misc[tid] = 0;
     for (uint32_t i = tid; i < D; i += NT) {
       s.restFlag[i] = 0;
       s.wakeFlag[i] = 0;
@@ -1139,7 +1226,7 @@ __global__ void __launch_bounds__(NT, NT == 128 ? PX_MINB128 : 3) pxStepKernel(c
       if (p < nDyn) s.base[p] = (uint16_t)min((uint32_t)(exr[r] & 0xffffu), MP);
     }
     const uint32_t totalPairsRaw = (uint32_t)(carry & 0xffffu);
-    const uint32_t nPairs = min(totalPairsRaw, MP);
+    nPairs = min(totalPairsRaw, MP);
     const uint32_t nCC = (uint32_t)((carry >> 16) & 0xffffu), nCP = (uint32_t)((carry >> 32) & 0xffffu);
     const uint32_t nPP = (uint32_t)((carry >> 48) & 0x7fffu);
     if (tid == 0) {
@@ -1278,20 +1365,35 @@ __global__ void __launch_bounds__(NT, NT == 128 ? PX_MINB128 : 3) pxStepKernel(c
        * into the sweep's dead AABB array; their order does not matter -- a manifold's place in
        * the pool comes from its pair's sequence number. */
       uint16_t *surv = (uint16_t *)s.sBox;
+      /* pass 1: reject; a survivor leaves its size class (1: both polygons <= 4 vertices, 2: <= 6,
+       * 3: larger) in validSlot[seq], which the sweep zeroed */
       for (uint32_t base = 0; base < nPoly; base += NT) {
         const uint32_t k = base + tid;
-        uint32_t word = 0xffffffffu;
-        if (k < nPoly) word = s.bins[nCircle + k];
-        bool alive = word != 0xffffffffu;
-        if (alive) {
-          const DBody A = loadBody(s, BIN_A(word)), B = loadBody(s, BIN_B(word));
-          alive = !polygonsSeparatedQuick(A, B, epsSq);
+        if (k >= nPoly) continue;
+        const uint32_t word = s.bins[nCircle + k];
+        if (word == 0xffffffffu) continue;
+        const DBody A = loadBody(s, BIN_A(word)), B = loadBody(s, BIN_B(word));
+        if (polygonsSeparatedQuick(A, B, epsSq)) continue;
+        const uint32_t big = max(A.nverts, B.nverts);
+        s.validSlot[BIN_SEQ(word)] = (uint16_t)(1u + (big > 4u ? 1u : 0u) + (big > 6u ? 1u : 0u));
+      }
+      __syncthreads();
+      /* pass 2: survivors compacted class by class, so that the lanes of a warp of the SAT pass
+       * below run loops of similar length */
+      for (uint32_t cls = 1; cls <= 3; cls++) {
+        for (uint32_t base = 0; base < nPoly; base += NT) {
+          const uint32_t k = base + tid;
+          bool mine = false;
+          if (k < nPoly) {
+            const uint32_t word = s.bins[nCircle + k];
+            mine = word != 0xffffffffu && s.validSlot[BIN_SEQ(word)] == cls;
+          }
+          const uint32_t mask = __ballot_sync(0xffffffffu, mine);
+          uint32_t at = 0;
+          if (lane == 0 && mask) at = atomicAdd(&s.misc[MI_SURVIVORS], __popc(mask));
+          at = __shfl_sync(0xffffffffu, at, 0);
+          if (mine) surv[at + __popc(mask & ((1u << lane) - 1u))] = (uint16_t)(nCircle + k);
         }
-        const uint32_t mask = __ballot_sync(0xffffffffu, alive);
-        uint32_t at = 0;
-        if (lane == 0 && mask) at = atomicAdd(&s.misc[MI_SURVIVORS], __popc(mask));
-        at = __shfl_sync(0xffffffffu, at, 0);
-        if (alive) surv[at + __popc(mask & ((1u << lane) - 1u))] = (uint16_t)(nCircle + k);
       }
       __syncthreads();
       PROF_SUB(9)
@@ -1302,7 +1404,7 @@ __global__ void __launch_bounds__(NT, NT == 128 ? PX_MINB128 : 3) pxStepKernel(c
       /* C2b: polygon-polygon SAT, PX_SAT_LANES lanes per surviving pair (the faces of a polygon
        * are spread over the lanes of its group).  Colliding pairs leave
        * {1 << 15 | flip << 8 | reference face} in validSlot[seq] for the clip pass; separated pairs
-       * keep the 0 the sweep wrote. */
+       * get 0 back. */
       {
         const uint32_t q = tid & (PX_SAT_LANES - 1u), grp = tid / PX_SAT_LANES;
         for (uint32_t base = 0; base < nSurv; base += NT / PX_SAT_LANES) {
@@ -1317,9 +1419,10 @@ __global__ void __launch_bounds__(NT, NT == 128 ? PX_MINB128 : 3) pxStepKernel(c
           /* the second pass is skipped only when no pair of the warp needs it */
           float penB = 0.0f;
           if (__any_sync(0xffffffffu, alive)) penB = leastPenetrationGroup(faceB, B, A, q, alive, epsSq);
-          if (alive && !(penB >= 0.0f) && q == 0) {
+          if (valid && q == 0) { /* the size class written by C2a is replaced by the verdict */
+            const bool hit = alive && !(penB >= 0.0f);
             const bool flip = !(penA >= penB * 0.95f + penA * 0.01f); /* pxBiasGt */
-            s.validSlot[BIN_SEQ(word)] = (uint16_t)(0x8000u | (flip ? 0x100u : 0u) | (flip ? faceB : faceA));
+            s.validSlot[BIN_SEQ(word)] = hit ? (uint16_t)(0x8000u | (flip ? 0x100u : 0u) | (flip ? faceB : faceA)) : (uint16_t)0;
           }
         }
       }
@@ -1402,7 +1505,7 @@ __global__ void __launch_bounds__(NT, NT == 128 ? PX_MINB128 : 3) pxStepKernel(c
     PROF_MARK(2)
     if (prof && tid == 0) prof[7] += ((unsigned long long)statPoly << 32) + statSurvivors;
     const uint32_t mRaw = s.misc[MI_MCOUNT];
-    const uint32_t M = min(mRaw, MM);
+    M = min(mRaw, MM);
     if (tid == 0 && mRaw > MM) overflow |= PX_BATCH_OVERFLOW_MANIFOLDS;
 
     /* ====================== phase D: per-body manifold lists, integrate forces ======== */
@@ -1529,9 +1632,34 @@ __global__ void __launch_bounds__(NT, NT == 128 ? PX_MINB128 : 3) pxStepKernel(c
     }
     __syncthreads();
     PROF_MARK(3)
+    if (sweepMode) {
+      /* hand the substep over: what the solver kernel needs (manifold ids, successor words, initial
+       * signals, the first ready visits) and what phase F needs after it (the per-body lists) */
+      handCopy<NT>(hand + P.H.mids, s.mids, M * 4u);
+      handCopy<NT>(hand + P.H.nextw, s.nextw, M * 4u);
+      handCopy<NT>(hand + P.H.sig, s.sig, M * 4u);
+      handCopy<NT>(hand + P.H.queue, s.queue, min(s.misc[MI_QTAIL], P.S.qcap) * 4u);
+      handCopy<NT>(hand + P.H.list, s.list, 2u * M * 2u);
+      handCopy<NT>(hand + P.H.listStart, s.listStart, (D + 1u) * 2u);
+      handCopy<NT>(hand + P.H.cnt, s.cnt, D * 2u);
+      handCopy<NT>(hand + P.H.cntB, s.cntB, D * 2u);
+      handCopy<NT>(hand + P.H.posOf, s.posOf, D);
+      handCopy<NT>(hand + P.H.restFlag, s.restFlag, D);
+      handCopy<NT>(hand + P.H.wakeFlag, s.wakeFlag, D);
+      if (tid == 0) {
+        uint32_t *sc = (uint32_t *)(hand + P.H.scalars);
+        sc[0] = M;
+        sc[1] = s.misc[MI_QTAIL];
+      }
+      statPairs = nPairs;
+      statManifolds = M;
+    }
+    } /* runSweep */
 
     /* ====================== phase E: sequential impulses, dataflow order ============== */
-    if (P.flags & PX_BATCH_FLAG_SERIAL_SOLVER) {
+    if (sweepMode) {
+      /* the solver is a kernel of its own (pxSolveKernel) */
+    } else if (P.flags & PX_BATCH_FLAG_SERIAL_SOLVER) {
       /* debug: literal pool-order walk by one thread */
       if (tid == 0) {
         for (uint32_t it = 0; it < iterations; it++) {
@@ -1596,10 +1724,25 @@ __global__ void __launch_bounds__(NT, NT == 128 ? PX_MINB128 : 3) pxStepKernel(c
       }
     }
     __syncthreads();
-    if (tid == 0 && iterations && !(P.flags & PX_BATCH_FLAG_SERIAL_SOLVER) && s.misc[MI_VISITS] != M * iterations)
+    if (!sweepMode && tid == 0 && iterations && !(P.flags & PX_BATCH_FLAG_SERIAL_SOLVER) && s.misc[MI_VISITS] != M * iterations)
       overflow |= PX_OVERFLOW_INTERNAL;
     PROF_MARK(4)
 
+    if (runFinish) {
+    if (sweepMode) {
+      /* the lists of the substep being finished come back from its hand-over record */
+      const uint32_t Mh = min(((const uint32_t *)(hand + P.H.scalars))[0], MM);
+      handCopy<NT>(s.mids, hand + P.H.mids, Mh * 4u);
+      handCopy<NT>(s.list, hand + P.H.list, 2u * Mh * 2u);
+      handCopy<NT>(s.listStart, hand + P.H.listStart, (D + 1u) * 2u);
+      handCopy<NT>(s.cnt, hand + P.H.cnt, D * 2u);
+      handCopy<NT>(s.cntB, hand + P.H.cntB, D * 2u);
+      handCopy<NT>(s.posOf, hand + P.H.posOf, D);
+      handCopy<NT>(s.restFlag, hand + P.H.restFlag, D);
+      handCopy<NT>(s.wakeFlag, hand + P.H.wakeFlag, D);
+      if (tid == 0) s.misc[MI_SLEEPING] = 0;
+      __syncthreads();
+    }
     /* ====================== phase F: integrate velocities, correct positions, sleep ==== */
     uint32_t sleepingLocal = 0;
 #pragma unroll
@@ -1688,13 +1831,16 @@ __global__ void __launch_bounds__(NT, NT == 128 ? PX_MINB128 : 3) pxStepKernel(c
       s.bodyV[x] = bv;
       s.flags[x] = (uint8_t)fl;
     }
-    if (step + 1 == P.kSubsteps) {
+    if (sweepMode || step + 1 == P.kSubsteps) {
       if (sleepingLocal) atomicAdd(&s.misc[MI_SLEEPING], sleepingLocal);
-      statPairs = nPairs;
-      statManifolds = M;
+      if (!sweepMode) {
+        statPairs = nPairs;
+        statManifolds = M;
+      }
     }
     __syncthreads();
     PROF_MARK(5)
+    } /* runFinish */
   }
 
   /* ------------------------------------------- store (smem records -> HBM SoA rows) */
@@ -1726,13 +1872,105 @@ __global__ void __launch_bounds__(NT, NT == 128 ? PX_MINB128 : 3) pxStepKernel(c
       PxWorldHeader *gh = (PxWorldHeader *)(gmut + L.offHeader);
       gh->statManifolds = statManifolds;
       gh->statPairs = statPairs;
-      gh->statSleeping = s.misc[MI_SLEEPING];
+      gh->statSleeping = (sweepMode && !P.doFinish) ? s.hdr->statSleeping : s.misc[MI_SLEEPING];
       gh->statOverflow = s.hdr->statOverflow | overflow | s.misc[MI_OVERFLOW];
-      gh->substeps = s.hdr->substeps + P.kSubsteps;
+      gh->substeps = s.hdr->substeps + (sweepMode ? (P.doFinish ? 1u : 0u) : P.kSubsteps);
     }
   }
   __syncthreads(); /* the next world's load overwrites what the store above still reads */
   } /* world loop */
+}
+
+/* ======================================================================= solver kernel ==== */
+/*
+ * Split pipeline, phase E: one CTA of four specialised warps (scheduler, math, two feeders -- see
+ * pxStepKernel) per world.  It needs a fraction of the sweep kernel's shared memory and registers
+ * (bodies' position/mass and velocity rows, manifold ids, successor words, signals, ready queue),
+ * so more than twice as many worlds are resident per SM while their dependency chains run, and
+ * no throughput-oriented warp competes with them.  Reads the velocity rows the sweep kernel left in
+ * the mutable block (after force integration), writes them back solved.
+ */
+#ifndef PX_SOLVE_MINB
+#define PX_SOLVE_MINB 7
+#endif
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, WARPS == 4 ? PX_SOLVE_MINB : 8) pxSolveKernel(const PxStepParams P) {
+  constexpr uint32_t NT = WARPS * 32;
+  extern __shared__ __align__(16) uint8_t smemRaw[];
+  const PxBatchLayout &L = P.L;
+  const uint32_t D = L.maxDynamic, S = L.maxStatic, MM = L.maxManifolds;
+  const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  Sm s;
+  bindSmem(s, smemRaw, P.solveS, nullptr);
+  const uint32_t QMASK = P.solveS.qcap - 1;
+  for (;;) {
+    if (tid == 0) s.misc[MI_WORLD] = atomicAdd(P.worldCounter, 1u);
+    __syncthreads();
+    const uint32_t world = s.misc[MI_WORLD];
+    if (world >= L.nWorlds) break;
+    uint8_t *gmut = P.mut + (size_t)world * L.mutStride;
+    const uint8_t *gimm = P.imm + (size_t)world * L.immStride;
+    const uint8_t *hand = P.hand + (size_t)world * P.H.stride;
+    float *gdyn = (float *)(gmut + L.offDyn);
+    const PxWorldHeader *gh = (const PxWorldHeader *)(gmut + L.offHeader);
+    const uint32_t iterations = gh->iterations & 255u;
+    const uint32_t M = min(((const uint32_t *)(hand + P.H.scalars))[0], MM);
+    const uint32_t qtail = min(((const uint32_t *)(hand + P.H.scalars))[1], P.solveS.qcap);
+    if (M && iterations) { /* uniform: nothing to solve otherwise */
+      const float *gc = (const float *)(gimm + L.offDynConst);
+      for (uint32_t x = tid; x < D; x += NT) {
+        s.bodyP[x] = make_float4(gdyn[PX_DYN_PX * D + x], gdyn[PX_DYN_PY * D + x], gc[PX_DYNC_IMASS * D + x],
+                                 gc[PX_DYNC_IINERTIA * D + x]);
+        s.bodyV[x] = make_float4(gdyn[PX_DYN_VX * D + x], gdyn[PX_DYN_VY * D + x], gdyn[PX_DYN_AV * D + x], 0.0f);
+      }
+      const float *gsm = (const float *)(gmut + L.offStatMut);
+      for (uint32_t q = tid; q < S; q += NT) {
+        s.bodyP[D + q] = make_float4(gsm[PX_STATM_PX * S + q], gsm[PX_STATM_PY * S + q], 0.0f, 0.0f);
+        s.bodyV[D + q] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+      }
+      handCopy<NT>(s.mids, hand + P.H.mids, M * 4u);
+      handCopy<NT>(s.nextw, hand + P.H.nextw, M * 4u);
+      handCopy<NT>(s.sig, hand + P.H.sig, M * 4u);
+      handCopy<NT>(s.queue, hand + P.H.queue, qtail * 4u);
+      if (tid < 32 && tid != MI_WORLD) s.misc[tid] = 0;
+      __syncthreads();
+      s.man = (float4 *)(const_cast<uint8_t *>(hand) + P.H.records);
+      SolverCtx c;
+      c.aQueue = sAddr(s.queue); c.aNext = sAddr(s.nextw); c.aMids = sAddr(s.mids); c.aSig = sAddr(s.sig);
+      c.aDesc = sAddr(s.misc + MI_RDESC); c.aMathRound = sAddr(s.misc + MI_MATHROUND);
+      c.aBodyP = sAddr(s.bodyP); c.aBodyV = sAddr(s.bodyV);
+      c.aFed = sAddr(s.misc + MI_FED0); c.aRing = sAddr(smemRaw + P.solveS.fedRing);
+      c.qmask = QMASK; c.qcap = P.solveS.qcap; c.iterations = iterations; c.tail0 = qtail; c.lagSleepNs = P.lagSleepNs;
+      c.man = s.man; c.eps = L.epsilon;
+      long long t0 = 0;
+      unsigned long long *prof = P.prof ? P.prof + (size_t)world * PX_PROF_SLOTS : nullptr;
+      if (prof && tid == 0) t0 = clock64();
+      if (warp == 0) {
+        uint32_t visits = 0;
+        const uint32_t rounds = solverSchedule(c, &visits);
+        visits = __reduce_add_sync(0xffffffffu, visits);
+        if (lane == 0) s.misc[MI_VISITS] = visits;
+        if (prof && lane == 0) prof[6] += rounds;
+      } else if (warp == 1) {
+        if (WARPS == 4) solverMath(c); else solverMathDirect(c);
+      } else {
+        solverFeed(c, warp - 2u);
+      }
+      __syncthreads();
+      if (prof && tid == 0) prof[4] += (unsigned long long)(clock64() - t0);
+      for (uint32_t x = tid; x < D; x += NT) {
+        const float4 bv = s.bodyV[x];
+        gdyn[PX_DYN_VX * D + x] = bv.x;
+        gdyn[PX_DYN_VY * D + x] = bv.y;
+        gdyn[PX_DYN_AV * D + x] = bv.z;
+      }
+      if (tid == 0 && s.misc[MI_VISITS] != M * iterations) {
+        PxWorldHeader *wh = (PxWorldHeader *)(gmut + L.offHeader);
+        wh->statOverflow |= PX_OVERFLOW_INTERNAL;
+      }
+    }
+    __syncthreads(); /* the next world's load overwrites what the store above still reads */
+  }
 }
 
 /* ------------------------------------------------------------------- control commands */
@@ -1949,7 +2187,7 @@ extern "C" void pxPlanSmem(const PxBatchLayout *L, int vertsInSmem, PxSmemPlan *
 /* The kernel may use any dynamic shared-memory size up to the device's opt-in maximum: the
  * attribute is raised to that maximum once per device and never lowered, so batches of different
  * sizes (and devices) cannot invalidate each other's launches. */
-template <int NT>
+template <int NT, int MODE>
 static cudaError_t configureT() {
   static bool done[64] = {};
   int dev = 0;
@@ -1959,18 +2197,22 @@ static cudaError_t configureT() {
   int optin = 0;
   err = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
   if (err != cudaSuccess) return err;
-  err = cudaFuncSetAttribute(pxStepKernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+  err = cudaFuncSetAttribute(pxStepKernel<NT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
   if (err != cudaSuccess) return err;
   if (dev >= 0 && dev < 64) done[dev] = true;
   return cudaSuccess;
 }
 
+template <int NT, int MODE>
+static cudaError_t launchTM(const PxStepParams *P, uint32_t grid, cudaStream_t stream) {
+  cudaError_t err = configureT<NT, MODE>();
+  if (err != cudaSuccess) return err;
+  pxStepKernel<NT, MODE><<<grid, NT, P->S.total, stream>>>(*P);
+  return cudaGetLastError();
+}
 template <int NT>
 static cudaError_t launchT(const PxStepParams *P, uint32_t grid, cudaStream_t stream) {
-  cudaError_t err = configureT<NT>();
-  if (err != cudaSuccess) return err;
-  pxStepKernel<NT><<<grid, NT, P->S.total, stream>>>(*P);
-  return cudaGetLastError();
+  return P->mode == PX_MODE_SWEEP ? launchTM<NT, PX_MODE_SWEEP>(P, grid, stream) : launchTM<NT, PX_MODE_FUSED>(P, grid, stream);
 }
 
 extern "C" int pxLaunchStep(const PxStepParams *P, uint32_t threads, uint32_t grid, void *stream) {
@@ -1985,9 +2227,14 @@ extern "C" int pxLaunchStep(const PxStepParams *P, uint32_t threads, uint32_t gr
 
 template <int NT>
 static cudaError_t occupancyT(const PxStepParams *P, int *ctasPerSm) {
-  cudaError_t err = configureT<NT>();
+  if (P->mode == PX_MODE_SWEEP) {
+    cudaError_t err = configureT<NT, PX_MODE_SWEEP>();
+    if (err != cudaSuccess) return err;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctasPerSm, pxStepKernel<NT, PX_MODE_SWEEP>, NT, P->S.total);
+  }
+  cudaError_t err = configureT<NT, PX_MODE_FUSED>();
   if (err != cudaSuccess) return err;
-  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctasPerSm, pxStepKernel<NT>, NT, P->S.total);
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctasPerSm, pxStepKernel<NT, PX_MODE_FUSED>, NT, P->S.total);
 }
 
 extern "C" int pxStepOccupancy(const PxStepParams *P, uint32_t threads, int *ctasPerSm) {
@@ -2004,4 +2251,71 @@ extern "C" int pxLaunchCommands(const PxBatchLayout *L, uint8_t *mut, const uint
   const uint32_t threads = 128, blocks = (L->nWorlds + threads - 1) / threads;
   pxCommandKernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(*L, mut, imm, cmds, worldStart, global, nGlobal, payloads, sinTable);
   return (int)cudaGetLastError();
+}
+
+/* ---------------------------------------------------------------- split pipeline, host side */
+extern "C" void pxPlanHandover(const PxBatchLayout *L, const PxSmemPlan *S, PxHandLayout *H) {
+  const uint32_t D = L->maxDynamic, MM = L->maxManifolds;
+  uint32_t o = 0;
+  auto take = [&](uint32_t bytes) {
+    uint32_t at = o;
+    o += alignUp(bytes, 16) + 16; /* + one granule: copies are rounded up to 16 bytes */
+    return at;
+  };
+  H->mids = take(MM * 4); H->nextw = take(2 * MM * 2); H->sig = take(MM * 4); H->queue = take((S->qcap + 4) * 4);
+  H->list = take(2 * MM * 2); H->listStart = take((D + 1) * 2); H->cnt = take(D * 2); H->cntB = take(D * 2);
+  H->posOf = take(D); H->restFlag = take(D); H->wakeFlag = take(D);
+  H->scalars = take(16);
+  H->records = take(MM * 3 * 16);
+  H->stride = alignUp(o, 128);
+}
+
+extern "C" void pxPlanSolveSmem(const PxBatchLayout *L, const PxSmemPlan *S, uint32_t warps, PxSmemPlan *out) {
+  const uint32_t NB = L->maxDynamic + L->maxStatic, MM = L->maxManifolds;
+  memset(out, 0, sizeof(*out));
+  uint32_t o = 0;
+  auto take = [&](uint32_t bytes) {
+    uint32_t at = o;
+    o += alignUp(bytes, 16);
+    return at;
+  };
+  out->bodyP = take(NB * 16); out->bodyV = take(NB * 16);
+  out->hdr = take(sizeof(PxWorldHeader)); out->misc = take(32 * 4);
+  out->mids = take(MM * 4 + 16); out->nextw = take(2 * MM * 2 + 16); out->sig = take(MM * 4 + 16);
+  out->qcap = S->qcap;
+  out->queue = take((S->qcap + 4) * 4 + 16);
+  out->fedRing = warps == 4 ? take(PX_FEDRING * PX_FED_SLOT_BYTES) : 0;
+  out->total = o;
+}
+
+template <int WARPS>
+static cudaError_t configureSolve() {
+  static bool done[64] = {};
+  int dev = 0;
+  cudaError_t err = cudaGetDevice(&dev);
+  if (err != cudaSuccess) return err;
+  if (dev >= 0 && dev < 64 && done[dev]) return cudaSuccess;
+  int optin = 0;
+  err = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  if (err != cudaSuccess) return err;
+  err = cudaFuncSetAttribute(pxSolveKernel<WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+  if (err != cudaSuccess) return err;
+  if (dev >= 0 && dev < 64) done[dev] = true;
+  return cudaSuccess;
+}
+
+extern "C" int pxLaunchSolve(const PxStepParams *P, uint32_t warps, uint32_t grid, void *stream) {
+  if (grid == 0 || (warps != 2 && warps != 4)) return (int)cudaErrorInvalidValue;
+  cudaError_t err = warps == 4 ? configureSolve<4>() : configureSolve<2>();
+  if (err != cudaSuccess) return (int)err;
+  if (warps == 4) pxSolveKernel<4><<<grid, 128, P->solveS.total, (cudaStream_t)stream>>>(*P);
+  else pxSolveKernel<2><<<grid, 64, P->solveS.total, (cudaStream_t)stream>>>(*P);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int pxSolveOccupancy(const PxStepParams *P, uint32_t warps, int *ctasPerSm) {
+  cudaError_t err = warps == 4 ? configureSolve<4>() : configureSolve<2>();
+  if (err != cudaSuccess) return (int)err;
+  if (warps == 4) return (int)cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctasPerSm, pxSolveKernel<4>, 128, P->solveS.total);
+  return (int)cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctasPerSm, pxSolveKernel<2>, 64, P->solveS.total);
 }

@@ -46,6 +46,18 @@ struct PxSmemPlan {
   uint32_t vertsInSmem;
 };
 
+/* A world's hand-over record in global memory (split pipeline): byte offsets of what the sweep
+ * kernel leaves for the solver kernel and for the phase F that follows it.  Laid out by
+ * pxPlanHandover. */
+struct PxHandLayout {
+  uint32_t mids, nextw, sig, queue;                              /* solver inputs */
+  uint32_t list, listStart, cnt, cntB, posOf, restFlag, wakeFlag; /* phase F inputs */
+  uint32_t scalars;                                               /* u32[4]: manifolds, ready visits */
+  uint32_t records;                                               /* float4[3][maxManifolds] manifold records */
+  uint32_t stride;
+};
+enum { PX_MODE_FUSED = 0, PX_MODE_SWEEP = 1 };
+
 #define PX_PROF_SLOTS 16 /* 0-5 phases A-F, 6 solver rounds, 7 polygon pairs << 32 | after quick reject, 8-11 narrowphase stages */
 
 struct PxStepParams {
@@ -65,6 +77,13 @@ struct PxStepParams {
   uint32_t kSubsteps;
   uint32_t flags;
   uint32_t lagSleepNs; /* scheduler warp: nanosleep while it is PX_LAG rounds ahead of the math warp */
+  /* split pipeline: pxStepKernel in PX_MODE_SWEEP does [phase F of the previous substep] + [phases
+   * A-D of the next], pxSolveKernel does phase E in between */
+  uint32_t mode;
+  uint32_t doFinish, doSweep, traceNow;
+  uint8_t *hand; /* hand-over records, one per world, H.stride apart */
+  PxHandLayout H;
+  PxSmemPlan solveS; /* shared memory of pxSolveKernel (bodyP, bodyV, mids, nextw, sig, queue, fedRing, misc, hdr) */
 };
 
 
@@ -78,6 +97,12 @@ void pxPlanSmem(const PxBatchLayout *L, int vertsInSmem, PxSmemPlan *S);
 int pxLaunchStep(const PxStepParams *P, uint32_t threads, uint32_t grid, void *stream);
 /* occupancy query: resident CTAs per SM for this plan */
 int pxStepOccupancy(const PxStepParams *P, uint32_t threads, int *ctasPerSm);
+/* split pipeline: hand-over layout, the solver kernel's shared-memory plan, its launch and occupancy */
+void pxPlanHandover(const PxBatchLayout *L, const PxSmemPlan *S, PxHandLayout *H);
+void pxPlanSolveSmem(const PxBatchLayout *L, const PxSmemPlan *S, uint32_t warps, PxSmemPlan *out);
+/* warps: 4 = scheduler + math + two feeders, 2 = scheduler + self-feeding math */
+int pxLaunchSolve(const PxStepParams *P, uint32_t warps, uint32_t grid, void *stream);
+int pxSolveOccupancy(const PxStepParams *P, uint32_t warps, int *ctasPerSm);
 
 /* control path: one command = one API call (px_batch.h "control path") */
 struct PxCommand {
