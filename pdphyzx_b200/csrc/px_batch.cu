@@ -41,7 +41,7 @@ struct PxBatch {
   PxHandLayout hand;
   PxSmemPlan solvePlan;
   uint8_t *dHand;      /* hand-over records, one per world */
-  uint32_t gridSolve, solveWarps;
+  uint32_t gridSolve;
   int solveCtasPerSm;
 
   uint8_t *hMut, *hImm; /* pinned staging, same layout */
@@ -156,7 +156,7 @@ extern "C" PxBatch *pxBatchCreate(uint32_t nWorlds, const PxBatchDesc *desc) {
   /* fused: 128 threads, 5 CTAs/SM keep the SM's issue slots busier than 3 CTAs of 256 threads;
    * split: the sweep kernel alone is throughput work, 256 threads x 3 CTAs leave it a larger L1 */
   b->threads = desc->threads ? desc->threads : (b->split ? 256 : 128);
-  if (b->threads != 128 && b->threads != 256) { /* the solver alone occupies four specialised warps */
+  if (b->threads != 128 && b->threads != 256) {
     pxSetError(-1, "PxBatchDesc.threads must be 128 or 256");
     pxBatchFree(b);
     return nullptr;
@@ -232,14 +232,10 @@ extern "C" PxBatch *pxBatchCreate(uint32_t nWorlds, const PxBatchDesc *desc) {
       if ((e = cudaMalloc(&b->dScratch, scratchBytes)) != cudaSuccess) return fail("cudaMalloc(scratch)", e);
     } else {
       pxPlanHandover(&b->L, &b->plan, &b->hand);
-      {
-        const char *env = getenv("PX_SOLVE_WARPS"); /* tuning switch: 4 (fed math warp) or 2 (self-feeding) */
-        b->solveWarps = env && env[0] == '4' ? 4u : 2u;
-      }
-      pxPlanSolveSmem(&b->L, &b->plan, b->solveWarps, &b->solvePlan);
+      pxPlanSolveSmem(&b->L, &b->plan, &b->solvePlan);
       P.solveS = b->solvePlan;
       int socc = 0;
-      rc = pxSolveOccupancy(&P, b->solveWarps, &socc);
+      rc = pxSolveOccupancy(&P, &socc);
       if (rc != 0 || socc < 1) return fail("occupancy query of the solver kernel", (cudaError_t)(rc ? rc : (int)cudaErrorLaunchOutOfResources));
       b->solveCtasPerSm = socc;
       const uint64_t scap = (uint64_t)socc * (uint64_t)b->numSms;
@@ -627,7 +623,7 @@ static int launchSweep(PxBatch *b, PxStepParams *P, uint32_t s, uint32_t kSubste
 static int launchSolve(PxBatch *b, PxStepParams *P, uint32_t grid, cudaStream_t stream) {
   P->worldCounter = b->dCounters + (b->launches % PX_COUNTER_RING);
   CU(cudaMemsetAsync(P->worldCounter, 0, sizeof(uint32_t), stream));
-  int rc = pxLaunchSolve(P, b->solveWarps, grid, stream);
+  int rc = pxLaunchSolve(P, grid, stream);
   if (rc != 0) return pxSetError(-rc - 1000, "solver kernel launch: %s", cudaGetErrorString((cudaError_t)rc));
   b->launches++;
   return 0;

@@ -211,7 +211,7 @@ __device__ __forceinline__ float3 materialOf(const Sm &s, uint32_t id, uint32_t 
 }
 
 /* misc[] slots */
-enum { MI_MCOUNT = 0, MI_QTAIL, MI_OVERFLOW, MI_SURVIVORS, MI_SLEEPING, MI_VISITS, MI_MATHROUND, MI_SLOT, MI_WORLD, MI_FED0, MI_FED1, MI_RDESC = 16 };
+enum { MI_MCOUNT = 0, MI_QTAIL, MI_OVERFLOW, MI_SURVIVORS, MI_SLEEPING, MI_VISITS, MI_MATHROUND, MI_SLOT, MI_WORLD, MI_RDESC = 16 };
 #define PX_RING 16u /* round descriptors in flight (misc[MI_RDESC..]) */
 /* round descriptor: (round + 1) mod 2^15 << 17 | first queue index of the round << 6 | visits (PX_DESC_END = no more rounds) */
 #define PX_DESC(round, head, n) (((((round) + 1u) & 0x7fffu) << 17) | (((head) & 0x7ffu) << 6) | (n))
@@ -219,15 +219,9 @@ enum { MI_MCOUNT = 0, MI_QTAIL, MI_OVERFLOW, MI_SURVIVORS, MI_SLEEPING, MI_VISIT
 #define PX_DESC_HEAD(d) (((d) >> 6) & 0x7ffu)
 #define PX_DESC_N(d) ((d) & 63u)
 #define PX_DESC_END 63u
-/* fed ring: rounds whose operands the feeder warps have staged for the math warp */
-#define PX_FEDRING 2u
-#define PX_FED_SLOT_BYTES (32u * 68u) /* per round: float4[4][32] operands + u32[32] decoded words */
-#define PX_FED_END 0x80000000u
 #ifndef PX_LAG
-#define PX_LAG 8u
+#define PX_LAG 8u /* rounds the scheduler warp may run ahead of the math warp */
 #endif
-//   /* rounds the scheduler warp may run ahead of the math warp */
-
 /*
  * Rich manifold word (mids[] and ready-queue entries):
  *   slotA | bodyIdB << 8 | bIsDynamic << 17 | contactCount << 18 | manifoldSlot << 20 | contactIndex << 30
@@ -708,7 +702,7 @@ __device__ __forceinline__ void handCopy(void *dst, const void *src, uint32_t by
  * is then independent of the rest of the kernel, whose pressure (narrowphase, sweep) would
  * otherwise spill into these latency-critical chains. */
 struct SolverCtx {
-  uint32_t aQueue, aNext, aMids, aSig, aDesc, aMathRound, aBodyP, aBodyV, aFed, aRing;
+  uint32_t aQueue, aNext, aMids, aSig, aDesc, aMathRound, aBodyP, aBodyV;
   uint32_t qmask, qcap, iterations, tail0, lagSleepNs;
   const float4 *man;
   float eps;
@@ -766,142 +760,20 @@ __device__ __noinline__ uint32_t solverSchedule(const SolverCtx c, uint32_t *vis
     mr = ldsVolatile(aMathRound);
     __syncwarp();
   }
-  /* end of schedule, once for each of the two feeder warps (they take alternate rounds) */
   asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(aDesc + 4u * (rounds & (PX_RING - 1u))),
-               "r"(PX_DESC(rounds, 0u, PX_DESC_END))
-               : "memory");
-  asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(aDesc + 4u * ((rounds + 1u) & (PX_RING - 1u))),
-               "r"(PX_DESC(rounds + 1u, 0u, PX_DESC_END))
+               "r"(PX_DESC(rounds, 0u, PX_DESC_END)) /* end of schedule */
                : "memory");
   *visitsOut = visits;
   return rounds;
 }
 
-/* Feeder warps (two, alternating rounds).  Everything a contact visit needs that does NOT depend
- * on a velocity is gathered here, off the math warp's chain: the queue word is decoded, the three
- * manifold records come from L1/L2, the contact is selected and its lever arms ra = c - posA,
- * rb = c - posB are formed (positions and masses are frozen during the solver; the subtraction is
- * the reference's own, px_manifold.c:113-114, merely executed by another warp).  The result goes
- * to slot round % PX_FEDRING of a small shared-memory ring, one lane-contiguous record per visit:
- *   [0] {normal.x, normal.y, restitution, staticFriction}   [1] {dynamicFriction, rcpDenom, ra.x, ra.y}
- *   [2] {rb.x, rb.y, iMassA, iInertiaA}                     [3] {iMassB, iInertiaB, -, -}
- *   word: slotA << 4 | bodyIdB << 20 | bIsDynamic << 30 | active << 31 */
-__device__ __noinline__ void solverFeed(const SolverCtx c, const uint32_t parity) {
-  const uint32_t lane = threadIdx.x & 31u, QMASK = c.qmask;
-  const uint32_t aQueue = c.aQueue, aDesc = c.aDesc, aMathRound = c.aMathRound, aBodyP = c.aBodyP;
-  const uint32_t aFed = c.aFed + 4u * parity, aRing = c.aRing + 16u * lane;
-  const float4 *man = c.man;
-  for (uint32_t r = parity;; r += 2u) {
-    const uint32_t expect = (r + 1u) & 0x7fffu;
-    uint32_t d = ldsAcquire(aDesc + 4u * (r & (PX_RING - 1u)));
-    while (PX_DESC_TAG(d) != expect) {
-      __nanosleep(64);
-      d = ldsAcquire(aDesc + 4u * (r & (PX_RING - 1u)));
-    }
-    const uint32_t n = PX_DESC_N(d);
-    if (n == PX_DESC_END) {
-      if (lane == 0) asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(aFed), "r"((r + 1u) | PX_FED_END) : "memory");
-      return;
-    }
-    const uint32_t qw = lds32(aQueue + 4u * ((PX_DESC_HEAD(d) + lane) & QMASK));
-    const bool active = lane < n;
-    const uint32_t w = active ? qw : 0u; /* idle lanes: manifold 0, every index in range, nothing stored later */
-    const uint32_t ms = MID_SLOT(w), a = MID_A(w), b = MID_B(w);
-    const float4 mA = ldgPinned(man + 3u * ms), mB = ldgPinned(man + 3u * ms + 1u), mC = ldgPinned(man + 3u * ms + 2u);
-    const float4 pA = lds128(aBodyP + 16u * a), pB = lds128(aBodyP + 16u * b);
-    const bool second = MID_CI(w) != 0;
-    const V2 cpt = second ? v2(mC.x, mC.y) : v2(mB.z, mB.w);
-    const float rcpDenom = second ? mC.w : mC.z;
-    const V2 ra = cpt - v2(pA.x, pA.y), rb = cpt - v2(pB.x, pB.y);
-    /* the slot is free once the math warp is done with round r - PX_FEDRING */
-    while ((int32_t)(r - ldsAcquire(aMathRound)) >= (int32_t)PX_FEDRING) __nanosleep(32);
-    const uint32_t slot = aRing + (r % PX_FEDRING) * PX_FED_SLOT_BYTES;
-    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(slot), "f"(mA.x), "f"(mA.y), "f"(mA.z), "f"(mA.w) : "memory");
-    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(slot + 512u), "f"(mB.x), "f"(rcpDenom), "f"(ra.x), "f"(ra.y) : "memory");
-    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(slot + 1024u), "f"(rb.x), "f"(rb.y), "f"(pA.z), "f"(pA.w) : "memory");
-    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(slot + 1536u), "f"(pB.z), "f"(pB.w), "f"(0.0f), "f"(0.0f) : "memory");
-    sts32(c.aRing + (r % PX_FEDRING) * PX_FED_SLOT_BYTES + 2048u + 4u * lane,
-          (a << 4) | (b << 20) | (MID_BDYN(w) << 30) | (active ? 0x80000000u : 0u));
-    __syncwarp();
-    if (lane == 0) asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(aFed), "r"(r + 1u) : "memory");
-  }
-}
-
-/* Math warp: one contact visit per lane and round (px_manifold.c:98-215, see contactImpulse --
- * same expressions, with the lever arms and masses read from the fed ring).  Its loop holds
- * nothing but the dependent arithmetic: operands of round r were staged by a feeder warp, only
- * the two velocity rows are read at the last moment. */
+/* Math warp: executes the published rounds in order, one contact visit per lane (the two contacts
+ * of a manifold are two consecutive visits: handling both in one visit was measured, twice -- 27 %
+ * fewer rounds, each 48 % longer).  While round r runs, the queue word and the three manifold
+ * records of round r + 1 are already in flight; only the velocities and the frozen body rows are
+ * read at the last moment, from shared memory.  Idle lanes run the arithmetic on manifold 0 and
+ * store nothing. */
 __device__ __noinline__ void solverMath(const SolverCtx c) {
-  const uint32_t lane = threadIdx.x & 31u;
-  const uint32_t aMathRound = c.aMathRound, aBodyV = c.aBodyV, aFed = c.aFed;
-  const uint32_t aRing = c.aRing + 16u * lane, aWord = c.aRing + 2048u + 4u * lane;
-  const float eps = c.eps;
-  uint32_t slotOff = 0;
-  for (uint32_t r = 0;; r++) {
-    const uint32_t aF = aFed + 4u * (r & 1u);
-    uint32_t f = ldsAcquire(aF);
-    while ((f & ~PX_FED_END) < r + 1u) f = ldsAcquire(aF);
-    if (f == ((r + 1u) | PX_FED_END)) break;
-    const uint32_t word = lds32(aWord + slotOff);
-    const float4 q0 = lds128(aRing + slotOff), q1 = lds128(aRing + slotOff + 512u), q2 = lds128(aRing + slotOff + 1024u),
-                 q3 = lds128(aRing + slotOff + 1536u);
-    const uint32_t a16 = word & 0xff0u, b16 = (word >> 16) & 0x1ff0u;
-    const bool active = (word >> 31) != 0, bdyn = ((word >> 30) & 1u) != 0;
-    float4 vA = lds128(aBodyV + a16), vB = lds128(aBodyV + b16);
-
-    const V2 n = v2(q0.x, q0.y);
-    const float e = q0.z, sf = q0.w, df = q1.x, rcpDenom = q1.y;
-    const V2 ra = v2(q1.z, q1.w), rb = v2(q2.x, q2.y);
-    const float iMA = q2.z, iIA = q2.w, iMB = q3.x, iIB = q3.y; /* statics: 0 */
-    const V2 va = v2(vA.x, vA.y), vb = v2(vB.x, vB.y);
-    const float wa = vA.z, wb = vB.z;
-    const V2 raPerp = v2(-ra.y, ra.x), rbPerp = v2(-rb.y, rb.x);
-    V2 rv = (vb + rbPerp * wb) - (va + raPerp * wa);
-    const float vn = dot(rv, n);
-    const bool approaching = !(vn > 0);
-    const float normalMag = -(1.0f + e) * vn;
-    const float j = normalMag * rcpDenom;
-    const V2 impulse = n * j;
-    const V2 ni = -impulse;
-    const V2 va1 = v2(va.x + ni.x * iMA, va.y + ni.y * iMA);
-    const float wa1 = wa + cross(ra, ni) * iIA;
-    const V2 vb1 = bdyn ? v2(vb.x + impulse.x * iMB, vb.y + impulse.y * iMB) : vb;
-    const float wb1 = bdyn ? wb + cross(rb, impulse) * iIB : wb;
-    rv = (vb1 + rbPerp * wb1) - (va1 + raPerp * wa1);
-    V2 tangent = rv - n * dot(rv, n);
-    const float tlen = fSqrt(lensq(tangent));
-    const bool slides = tlen > eps;
-    tangent = tangent * fRcp(tlen);
-    const float tmag = -dot(rv, tangent);
-    const float jt = tmag * rcpDenom;
-    const float fmag = (fabsf(jt) < j * sf) ? jt : (-j * df);
-    const V2 friction = tangent * fmag;
-    const V2 nf = -friction;
-    const V2 va2 = v2(va1.x + nf.x * iMA, va1.y + nf.y * iMA);
-    const float wa2 = wa1 + cross(ra, nf) * iIA;
-    const V2 vb2 = bdyn ? v2(vb1.x + friction.x * iMB, vb1.y + friction.y * iMB) : vb1;
-    const float wb2 = bdyn ? wb1 + cross(rb, friction) * iIB : wb1;
-    vA.x = approaching ? (slides ? va2.x : va1.x) : va.x;
-    vA.y = approaching ? (slides ? va2.y : va1.y) : va.y;
-    vA.z = approaching ? (slides ? wa2 : wa1) : wa;
-    vB.x = approaching ? (slides ? vb2.x : vb1.x) : vb.x;
-    vB.y = approaching ? (slides ? vb2.y : vb1.y) : vb.y;
-    vB.z = approaching ? (slides ? wb2 : wb1) : wb;
-
-    sts128If(aBodyV + a16, vA, active);
-    sts128If(aBodyV + b16, vB, active && bdyn);
-    __syncwarp();
-    asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(aMathRound), "r"(r + 1u) : "memory");
-    slotOff = slotOff == (PX_FEDRING - 1u) * PX_FED_SLOT_BYTES ? 0u : slotOff + PX_FED_SLOT_BYTES;
-  }
-}
-
-/* Math warp that fetches its own operands (no feeder warps): the solver kernel's two-warp form.
- * While round r runs, the queue word and the three manifold records of round r + 1 are already in
- * flight.  Fewer shared-memory wavefronts per round than the fed form (no operand ring), a longer
- * chain per round: the better trade when many worlds share an SM and the L1/shared data pipe, not
- * latency, is what binds. */
-__device__ __noinline__ void solverMathDirect(const SolverCtx c) {
   const uint32_t lane = threadIdx.x & 31u, QMASK = c.qmask;
   const uint32_t aQueue = c.aQueue, aDesc = c.aDesc, aMathRound = c.aMathRound, aBodyP = c.aBodyP, aBodyV = c.aBodyV;
   const float4 *man = c.man;
@@ -1674,19 +1546,17 @@ __global__ void __launch_bounds__(NT, NT == 128 ? PX_MINB128 : 3) pxStepKernel(c
           }
         }
       }
-    } else if (warp < 4 && iterations) {
+    } else if (warp < 2 && iterations) {
       /*
-       * Four specialised warps.  The ORDER in which contact visits may run depends only on the
-       * manifold lists, never on a velocity, so everything but the arithmetic is taken off the
-       * arithmetic's chain:
+       * Two specialised warps.  The ORDER in which manifold visits may run depends only on the
+       * manifold lists, never on a velocity, so scheduling is split from the arithmetic:
        *   warp 0  scheduler: runs the dataflow bookkeeping and publishes rounds of up to 32
        *           mutually independent visits (solverSchedule);
-       *   warps 2, 3  feeders: decode the visits of alternate rounds and stage their operands
-       *           in a shared-memory ring (solverFeed);
        *   warp 1  math: executes the rounds in order, one contact visit per lane (solverMath).
-       * The solver is bound by its dependency chain -- about 300 rounds per substep in a settled
-       * 252-body pile at 10 iterations whatever the round width (profiles/sched_sim.py) -- so
-       * what matters is the latency of one round of the math warp.
+       * The solver is bound by its dependency chain -- more than 200 rounds per substep in a
+       * settled 252-body pile at 10 iterations whatever the round width (profiles/sched_sim.py) --
+       * so the two chains (ready queue / signals here, load / impulse / store there) run side by
+       * side instead of adding up.
        *
        * sig[m] counts the signals manifold m has received from its A body (low half) and its
        * B body (high half).  Visit v of a manifold may run once each of its dynamic bodies has
@@ -1702,13 +1572,12 @@ __global__ void __launch_bounds__(NT, NT == 128 ? PX_MINB128 : 3) pxStepKernel(c
        * so a visit is always published in a later round than the visits it depends on.  The
        * scheduler stays at most PX_LAG rounds ahead of the math warp, which bounds the
        * descriptor ring and keeps unexecuted segments from being overwritten (qcap >= MM + 32 *
-       * (PX_LAG + 1)); the feeders stay at most PX_FEDRING rounds ahead of it.
+       * (PX_LAG + 1)).
        */
       SolverCtx c;
       c.aQueue = sAddr(s.queue); c.aNext = sAddr(s.nextw); c.aMids = sAddr(s.mids); c.aSig = sAddr(s.sig);
       c.aDesc = sAddr(s.misc + MI_RDESC); c.aMathRound = sAddr(s.misc + MI_MATHROUND);
       c.aBodyP = sAddr(s.bodyP); c.aBodyV = sAddr(s.bodyV);
-      c.aFed = sAddr(s.misc + MI_FED0); c.aRing = sAddr(smemRaw + P.S.fedRing);
       c.qmask = QMASK; c.qcap = P.S.qcap; c.iterations = iterations; c.tail0 = s.misc[MI_QTAIL]; c.lagSleepNs = P.lagSleepNs;
       c.man = s.man; c.eps = eps;
       if (warp == 0) {
@@ -1717,10 +1586,8 @@ __global__ void __launch_bounds__(NT, NT == 128 ? PX_MINB128 : 3) pxStepKernel(c
         visits = __reduce_add_sync(0xffffffffu, visits);
         if (lane == 0) s.misc[MI_VISITS] = visits;
         if (prof && lane == 0) prof[6] += rounds;
-      } else if (warp == 1) {
-        solverMath(c);
       } else {
-        solverFeed(c, warp - 2u);
+        solverMath(c);
       }
     }
     __syncthreads();
@@ -1883,19 +1750,18 @@ __global__ void __launch_bounds__(NT, NT == 128 ? PX_MINB128 : 3) pxStepKernel(c
 
 /* ======================================================================= solver kernel ==== */
 /*
- * Split pipeline, phase E: one CTA of four specialised warps (scheduler, math, two feeders -- see
- * pxStepKernel) per world.  It needs a fraction of the sweep kernel's shared memory and registers
+ * Split pipeline, phase E: one CTA of two specialised warps (scheduler, math -- see pxStepKernel)
+ * per world.  It needs a fraction of the sweep kernel's shared memory and registers
  * (bodies' position/mass and velocity rows, manifold ids, successor words, signals, ready queue),
  * so more than twice as many worlds are resident per SM while their dependency chains run, and
  * no throughput-oriented warp competes with them.  Reads the velocity rows the sweep kernel left in
  * the mutable block (after force integration), writes them back solved.
  */
 #ifndef PX_SOLVE_MINB
-#define PX_SOLVE_MINB 7
+#define PX_SOLVE_MINB 8
 #endif
-template <int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, WARPS == 4 ? PX_SOLVE_MINB : 8) pxSolveKernel(const PxStepParams P) {
-  constexpr uint32_t NT = WARPS * 32;
+__global__ void __launch_bounds__(PX_SOLVE_THREADS, PX_SOLVE_MINB) pxSolveKernel(const PxStepParams P) {
+  constexpr uint32_t NT = PX_SOLVE_THREADS;
   extern __shared__ __align__(16) uint8_t smemRaw[];
   const PxBatchLayout &L = P.L;
   const uint32_t D = L.maxDynamic, S = L.maxStatic, MM = L.maxManifolds;
@@ -1939,7 +1805,6 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 4 ? PX_SOLVE_MINB : 8) px
       c.aQueue = sAddr(s.queue); c.aNext = sAddr(s.nextw); c.aMids = sAddr(s.mids); c.aSig = sAddr(s.sig);
       c.aDesc = sAddr(s.misc + MI_RDESC); c.aMathRound = sAddr(s.misc + MI_MATHROUND);
       c.aBodyP = sAddr(s.bodyP); c.aBodyV = sAddr(s.bodyV);
-      c.aFed = sAddr(s.misc + MI_FED0); c.aRing = sAddr(smemRaw + P.solveS.fedRing);
       c.qmask = QMASK; c.qcap = P.solveS.qcap; c.iterations = iterations; c.tail0 = qtail; c.lagSleepNs = P.lagSleepNs;
       c.man = s.man; c.eps = L.epsilon;
       long long t0 = 0;
@@ -1951,10 +1816,8 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 4 ? PX_SOLVE_MINB : 8) px
         visits = __reduce_add_sync(0xffffffffu, visits);
         if (lane == 0) s.misc[MI_VISITS] = visits;
         if (prof && lane == 0) prof[6] += rounds;
-      } else if (warp == 1) {
-        if (WARPS == 4) solverMath(c); else solverMathDirect(c);
       } else {
-        solverFeed(c, warp - 2u);
+        solverMath(c);
       }
       __syncthreads();
       if (prof && tid == 0) prof[4] += (unsigned long long)(clock64() - t0);
@@ -2159,14 +2022,9 @@ extern "C" void pxPlanSmem(const PxBatchLayout *L, int vertsInSmem, PxSmemPlan *
   S->mids = take(MM * 4);
   S->listStart = take((D + 1) * 2);
   S->cnt = take(D * 2); S->cntB = take(D * 2);
-  /* validSlot, base and fillB are dead once the lists are built (only the debug serial solver walks
-   * them later): the solver's fed ring lives on top of them */
-  const uint32_t deadAfterLists = o;
   S->validSlot = take(MP * 2);
   S->base = take((D + 1) * 2);
   S->fillB = take(D * 4);
-  if (o - deadAfterLists < PX_FEDRING * PX_FED_SLOT_BYTES) o = deadAfterLists + PX_FEDRING * PX_FED_SLOT_BYTES;
-  S->fedRing = deadAfterLists;
   uint32_t qcap = 32;
   while (qcap < MM + 32 * (PX_LAG + 1)) qcap <<= 1; /* ready visits + published, unexecuted rounds */
   S->qcap = qcap;
@@ -2270,7 +2128,7 @@ extern "C" void pxPlanHandover(const PxBatchLayout *L, const PxSmemPlan *S, PxHa
   H->stride = alignUp(o, 128);
 }
 
-extern "C" void pxPlanSolveSmem(const PxBatchLayout *L, const PxSmemPlan *S, uint32_t warps, PxSmemPlan *out) {
+extern "C" void pxPlanSolveSmem(const PxBatchLayout *L, const PxSmemPlan *S, PxSmemPlan *out) {
   const uint32_t NB = L->maxDynamic + L->maxStatic, MM = L->maxManifolds;
   memset(out, 0, sizeof(*out));
   uint32_t o = 0;
@@ -2284,11 +2142,9 @@ extern "C" void pxPlanSolveSmem(const PxBatchLayout *L, const PxSmemPlan *S, uin
   out->mids = take(MM * 4 + 16); out->nextw = take(2 * MM * 2 + 16); out->sig = take(MM * 4 + 16);
   out->qcap = S->qcap;
   out->queue = take((S->qcap + 4) * 4 + 16);
-  out->fedRing = warps == 4 ? take(PX_FEDRING * PX_FED_SLOT_BYTES) : 0;
   out->total = o;
 }
 
-template <int WARPS>
 static cudaError_t configureSolve() {
   static bool done[64] = {};
   int dev = 0;
@@ -2298,24 +2154,22 @@ static cudaError_t configureSolve() {
   int optin = 0;
   err = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
   if (err != cudaSuccess) return err;
-  err = cudaFuncSetAttribute(pxSolveKernel<WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+  err = cudaFuncSetAttribute(pxSolveKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
   if (err != cudaSuccess) return err;
   if (dev >= 0 && dev < 64) done[dev] = true;
   return cudaSuccess;
 }
 
-extern "C" int pxLaunchSolve(const PxStepParams *P, uint32_t warps, uint32_t grid, void *stream) {
-  if (grid == 0 || (warps != 2 && warps != 4)) return (int)cudaErrorInvalidValue;
-  cudaError_t err = warps == 4 ? configureSolve<4>() : configureSolve<2>();
+extern "C" int pxLaunchSolve(const PxStepParams *P, uint32_t grid, void *stream) {
+  if (grid == 0) return (int)cudaErrorInvalidValue;
+  cudaError_t err = configureSolve();
   if (err != cudaSuccess) return (int)err;
-  if (warps == 4) pxSolveKernel<4><<<grid, 128, P->solveS.total, (cudaStream_t)stream>>>(*P);
-  else pxSolveKernel<2><<<grid, 64, P->solveS.total, (cudaStream_t)stream>>>(*P);
+  pxSolveKernel<<<grid, PX_SOLVE_THREADS, P->solveS.total, (cudaStream_t)stream>>>(*P);
   return (int)cudaGetLastError();
 }
 
-extern "C" int pxSolveOccupancy(const PxStepParams *P, uint32_t warps, int *ctasPerSm) {
-  cudaError_t err = warps == 4 ? configureSolve<4>() : configureSolve<2>();
+extern "C" int pxSolveOccupancy(const PxStepParams *P, int *ctasPerSm) {
+  cudaError_t err = configureSolve();
   if (err != cudaSuccess) return (int)err;
-  if (warps == 4) return (int)cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctasPerSm, pxSolveKernel<4>, 128, P->solveS.total);
-  return (int)cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctasPerSm, pxSolveKernel<2>, 64, P->solveS.total);
+  return (int)cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctasPerSm, pxSolveKernel, PX_SOLVE_THREADS, P->solveS.total);
 }

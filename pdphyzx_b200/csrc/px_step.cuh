@@ -40,7 +40,6 @@ struct PxSmemPlan {
   uint32_t nextw; /* u16[2*MM] successor of manifold ms on side s: slot | successor has a dynamic B << 14 | side << 15 */
   uint32_t sig;   /* u32[MM]   signals received: A side low half, B side high half */
   uint32_t queue; /* u32[QCAP] ready ring of rich manifold words */
-  uint32_t fedRing; /* PX_FEDRING rounds of staged contact operands for the math warp (px_step.cu: solverFeed) */
   uint32_t total; /* bytes */
   uint32_t qcap;  /* ring capacity (power of two >= MM) */
   uint32_t vertsInSmem;
@@ -83,7 +82,7 @@ struct PxStepParams {
   uint32_t doFinish, doSweep, traceNow;
   uint8_t *hand; /* hand-over records, one per world, H.stride apart */
   PxHandLayout H;
-  PxSmemPlan solveS; /* shared memory of pxSolveKernel (bodyP, bodyV, mids, nextw, sig, queue, fedRing, misc, hdr) */
+  PxSmemPlan solveS; /* shared memory of pxSolveKernel (bodyP, bodyV, mids, nextw, sig, queue, misc, hdr) */
 };
 
 
@@ -99,10 +98,10 @@ int pxLaunchStep(const PxStepParams *P, uint32_t threads, uint32_t grid, void *s
 int pxStepOccupancy(const PxStepParams *P, uint32_t threads, int *ctasPerSm);
 /* split pipeline: hand-over layout, the solver kernel's shared-memory plan, its launch and occupancy */
 void pxPlanHandover(const PxBatchLayout *L, const PxSmemPlan *S, PxHandLayout *H);
-void pxPlanSolveSmem(const PxBatchLayout *L, const PxSmemPlan *S, uint32_t warps, PxSmemPlan *out);
-/* warps: 4 = scheduler + math + two feeders, 2 = scheduler + self-feeding math */
-int pxLaunchSolve(const PxStepParams *P, uint32_t warps, uint32_t grid, void *stream);
-int pxSolveOccupancy(const PxStepParams *P, uint32_t warps, int *ctasPerSm);
+void pxPlanSolveSmem(const PxBatchLayout *L, const PxSmemPlan *S, PxSmemPlan *out);
+int pxLaunchSolve(const PxStepParams *P, uint32_t grid, void *stream);
+int pxSolveOccupancy(const PxStepParams *P, int *ctasPerSm);
+#define PX_SOLVE_THREADS 64u /* scheduler warp + math warp */
 
 /* control path: one command = one API call (px_batch.h "control path") */
 struct PxCommand {
