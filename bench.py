@@ -385,6 +385,15 @@ def run_ours(args):
     ms = e0.elapsed_time(e1)
     gpu_launches = b.launches - launches0
     clocks = sampler.stop()
+    # per-kernel device time, live: CUDA events around EVERY launch of a few extra steps
+    # (pxBatchStepTimedKernels); feeds the roofline of the dominant kernel below
+    pipe = b.pipeline_info()
+    kt = {"sweep_ms": 0.0, "sweep_launches": 0, "solve_ms": 0.0, "solve_launches": 0}
+    for _ in range(3):
+        control(0)
+        r = b.step_timed_kernels(args.fused)
+        for k_ in kt:
+            kt[k_] += r[k_]
 
     # ---- end to end through the C ABI with host buffers -------------------------------
     # pxBatchStepHost: pinned host blocks -> HBM -> FUSED substeps -> pinned host blocks, per world
@@ -451,10 +460,15 @@ def run_ours(args):
         value = body_substeps / (ms * 1e-3)
         peak, peak_src = measured_peak_hbm()
         alg = ALG_BYTES[args.mix]
-        # dominant (only) kernel: algorithmic bytes of one launch = bodies x B_alg (state is
-        # streamed once per launch whatever K is) / average launch duration
-        launch_ms = ms / max(gpu_launches, 1)
-        achieved = args.worlds * BODIES_PER_WORLD * alg / (launch_ms * 1e-3) / 1e9
+        # Roofline of the dominant kernel.  Fused pipeline: the one kernel, which streams the state once
+        # per launch whatever K is.  Split pipeline: the sweep kernel (phases F + A-D: the one that streams
+        # the state; the solver kernel takes about as long and is bound by the shared-memory data pipe,
+        # see roofline_lsu) -- one launch advances every body by ONE substep, so its algorithmic bytes are
+        # bodies x B_alg(K = 1).  Launch durations: CUDA events around every launch, measured live above.
+        sweep_ms = kt["sweep_ms"] / max(kt["sweep_launches"], 1)
+        solve_ms = kt["solve_ms"] / max(kt["solve_launches"], 1)
+        alg_bytes = args.worlds * BODIES_PER_WORLD * alg
+        achieved = alg_bytes / (sweep_ms * 1e-3) / 1e9
         out = {
             "metric": "body_steps_per_sec", "value": value, "unit": "body-substeps/s", "n_gpus": world_size,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
@@ -465,37 +479,58 @@ def run_ours(args):
                 **({"host_cpus_per_rank_numa_local": numa_cpus} if numa_cpus else {}),
                 "body_frame_steps_per_sec": value / 5.0, "l2": "inputs larger than L2 (state > 126 MB per GPU)"
                 if args.worlds * (b.L.mutStride + b.L.immStride) > 126e6 else "inputs smaller than L2",
+                "pipeline": ("split: sweep kernel (phase F of the previous substep + phases A-D) and solver kernel per substep"
+                             if pipe["split"] else "fused: one kernel, K substeps"),
                 "threads_per_world_cta": info["threads"], "ctas_per_sm": info["ctas_per_sm"],
-                "smem_bytes_per_cta": info["smem_bytes"], "seed": args.seed,
+                "smem_bytes_per_cta": info["smem_bytes"], "solver_ctas_per_sm": pipe["solve_ctas_per_sm"], "seed": args.seed,
                 "avg_manifolds_per_world": stats[0], "avg_pairs_per_world": stats[1],
                 "avg_sleeping_per_world": stats[2], "worlds_overflowed": int(stats[3]),
                 **({"host_wall_ms_per_step": host_ms / args.steps} if args.control else {}),
             },
             "clocks": clocks, "gpu_launches": int(gpu_launches),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "kernels": {"sweep_ms_per_launch": sweep_ms, "sweep_launches_per_step": kt["sweep_launches"] // 3,
+                        "solve_ms_per_launch": solve_ms, "solve_launches_per_step": kt["solve_launches"] // 3,
+                        "timed_with": "CUDA events around every launch (pxBatchStepTimedKernels), 3 steps"},
+            "roofline": {"bound": "hbm", "kernel": "pxStepKernel (sweep)" if pipe["split"] else "pxStepKernel (fused)",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": args.worlds * BODIES_PER_WORLD * alg,
-                         "note": "HBM is the nominal bound of this path (SURVEY 8d) but not the binding one: the "
-                                 "solver's dependency chain and non-FMA fp32 issue are; see roofline_issue, "
-                                 "DESIGN.md and profiles/"},
+                         "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": sweep_ms,
+                         "note": "HBM is the nominal bound of this path (SURVEY 8d) but not the binding one: the L1 / "
+                                 "shared-memory data pipe (random float4 gathers of the solver, bank conflicts) and "
+                                 "non-FMA fp32 issue are; see roofline_lsu, roofline_issue, DESIGN.md and profiles/"},
         }
         facts = kernel_facts(args)
-        if facts:
-            # ncu of this very command line (profiles/summarize.py): DRAM bytes of one launch, and
-            # the warp instructions one world-substep costs -> issue-slot utilisation at the
-            # rate measured live above
-            out["roofline"]["traffic"] = facts["dram_bytes_per_launch"]
+        if facts and pipe["split"] == ("sweep" in facts.get("kernels", {})):
+            # ncu of this very command line (profiles/summarize.py): DRAM bytes of one launch of the dominant
+            # kernel, the data-pipe utilisation of both kernels, and the warp instructions one world-substep
+            # costs -> issue-slot utilisation at the rate measured live above
+            ks = facts["kernels"]
+            dom = ks["sweep"] if pipe["split"] else ks["fused"]
+            out["roofline"]["traffic"] = dom["dram_bytes_per_launch"]
             out["roofline"]["traffic_source"] = "profiles/" + facts["_file"]
             sm_hz = (clocks.get("sm_mhz") or 1965.0) * 1e6
             n_sms = info.get("num_sms", 148)
             issue_peak = n_sms * 4 * sm_hz  # one warp instruction per scheduler per cycle
-            issue_rate = facts["warp_instructions_per_world_substep"] * (value / world_size) / BODIES_PER_WORLD
+            instr = sum(k_["warp_instructions_per_world_substep"] for k_ in ks.values())
+            issue_rate = instr * (value / world_size) / BODIES_PER_WORLD
             out["roofline_issue"] = {
                 "bound": "issue", "achieved": issue_rate / 1e12, "peak": issue_peak / 1e12, "unit": "T warp-instr/s",
-                "frac": issue_rate / issue_peak,
-                "warp_instructions_per_world_substep": facts["warp_instructions_per_world_substep"],
-                "lanes_per_instruction": facts["lanes_per_instruction"],
-                "note": "per GPU; instruction count from ncu (smsp__inst_executed.sum), rate from this run"}
+                "frac": issue_rate / issue_peak, "warp_instructions_per_world_substep": instr,
+                "per_kernel": {n_: {"warp_instructions_per_world_substep": k_["warp_instructions_per_world_substep"],
+                                    "lanes_per_instruction": k_["lanes_per_instruction"], "issue_active_pct": k_["issue_active_pct"]}
+                               for n_, k_ in ks.items()},
+                "note": "per GPU; instruction counts from ncu (smsp__inst_executed.sum), rate from this run"}
+            # the binding unit: wavefronts through the L1 / shared-memory data pipe, one per cycle per SM
+            wf = sum((k_["shared_wavefronts"] + k_["global_load_wavefronts"]) / facts["worlds"] / k_["substeps_per_launch"]
+                     for k_ in ks.values())
+            wf_rate = wf * (value / world_size) / BODIES_PER_WORLD
+            out["roofline_lsu"] = {
+                "bound": "l1-shared-data-pipe", "achieved": wf_rate / 1e12, "peak": n_sms * sm_hz / 1e12, "unit": "T wavefronts/s",
+                "frac": wf_rate / (n_sms * sm_hz), "wavefronts_per_world_substep": wf,
+                "per_kernel_pct_of_peak_under_ncu": {n_: k_["l1_data_pipe_wavefronts_pct"] for n_, k_ in ks.items()},
+                "note": "shared-memory + global-load wavefronts per world-substep from ncu "
+                        "(l1tex__data_pipe_lsu_wavefronts_mem_shared, l1tex__t_output_wavefronts_pipe_lsu_mem_global_op_ld) x the "
+                        "rate measured live; peak = one wavefront per cycle per SM"}
         if args.profile:
             pr = b.profile().astype(np.float64) - prof0
             nsub = float(blocks.header["substeps"].mean()) - nsub0

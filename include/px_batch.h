@@ -195,6 +195,13 @@ PX_API int pxBatchStepHost(PxBatch *b, uint32_t kSubsteps, void *hostMut, uint32
  * can be interleaved: pxBatchGroupStepTimed.) */
 PX_API int pxBatchTimerStart(PxBatch *b);
 PX_API int pxBatchTimerStop(PxBatch *b, float *ms);
+/* One step with EVERY kernel launch bracketed by CUDA events; blocks.  msSweep / nSweep: summed device
+ * time and number of the sweep-kernel launches (or of the one fused launch), msSolve / nSolve: of the
+ * solver-kernel launches (0 for the fused pipeline).  The roofline numbers of bench.py come from here. */
+PX_API int pxBatchStepTimedKernels(PxBatch *b, uint32_t kSubsteps, float *msSweep, uint32_t *nSweep, float *msSolve, uint32_t *nSolve);
+/* which pipeline the batch runs: *split = 1 for sweep + solver kernels per substep (large batches),
+ * 0 for the fused kernel; *solveCtasPerSm = resident solver CTAs per SM */
+PX_API int pxBatchPipelineInfo(const PxBatch *b, int *split, int *solveCtasPerSm);
 /* Same, bracketed by CUDA events on the launching stream; blocks; *ms = device time. */
 PX_API int pxBatchStepTimed(PxBatch *b, uint32_t kSubsteps, float *ms);
 

@@ -117,6 +117,8 @@ def core():
         "pxBatchFitDesc": (i32, [pp, u32, C.POINTER(PxBatchDesc)]),
         "pxSelfTestMath": (i32, [C.c_int, vp, vp, vp, vp, u32]),
         "pxSelfTestRsqrtSweep": (i32, [vp]),
+        "pxBatchStepTimedKernels": (i32, [vp, u32, C.POINTER(C.c_float), C.POINTER(u32), C.POINTER(C.c_float), C.POINTER(u32)]),
+        "pxBatchPipelineInfo": (i32, [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
         "pxBatchTimerStart": (i32, [vp]),
         "pxBatchTimerStop": (i32, [vp, C.POINTER(C.c_float)]),
         "pxBatchGroupNew": (vp, [pp, u32, C.POINTER(PxBatchDesc), C.POINTER(C.c_int32), u32]),
@@ -433,6 +435,17 @@ class Batch:
         ms = C.c_float(0)
         _check(self.lib.pxBatchStepTimed(self.h, int(k), C.byref(ms)), "pxBatchStepTimed")
         return float(ms.value)
+
+    def step_timed_kernels(self, k: int = 1):
+        """One step with every launch timed: dict(sweep_ms, sweep_launches, solve_ms, solve_launches)."""
+        ts, tv, ns, nv = C.c_float(0), C.c_float(0), C.c_uint32(0), C.c_uint32(0)
+        _check(self.lib.pxBatchStepTimedKernels(self.h, int(k), C.byref(ts), C.byref(ns), C.byref(tv), C.byref(nv)), "pxBatchStepTimedKernels")
+        return dict(sweep_ms=float(ts.value), sweep_launches=int(ns.value), solve_ms=float(tv.value), solve_launches=int(nv.value))
+
+    def pipeline_info(self):
+        a, c = C.c_int(0), C.c_int(0)
+        _check(self.lib.pxBatchPipelineInfo(self.h, C.byref(a), C.byref(c)), "pxBatchPipelineInfo")
+        return dict(split=bool(a.value), solve_ctas_per_sm=int(c.value))
 
     def sync(self):
         _check(self.lib.pxBatchSync(self.h), "pxBatchSync")

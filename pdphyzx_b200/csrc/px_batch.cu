@@ -744,6 +744,70 @@ extern "C" int pxBatchTimerStop(PxBatch *b, float *ms) {
   return 0;
 }
 
+/* One step with every kernel launch bracketed by CUDA events: device time per kernel class.
+ * msSweep / msSolve = summed durations of the sweep (or fused) and solver launches, nSweep / nSolve
+ * how many there were.  Blocks. */
+extern "C" int pxBatchStepTimedKernels(PxBatch *b, uint32_t kSubsteps, float *msSweep, uint32_t *nSweep, float *msSolve, uint32_t *nSolve) {
+  if (!b) return pxSetError(-1, "pxBatchStepTimedKernels: NULL batch");
+  if (useDevice(b)) return -1;
+  if (flushCommands(b)) return -1;
+  float tSweep = 0, tSolve = 0;
+  uint32_t cSweep = 0, cSolve = 0;
+  if (kSubsteps) {
+    const uint32_t W = b->L.nWorlds;
+    const uint32_t nLaunch = b->split ? 2 * kSubsteps + 1 : 1;
+    std::vector<cudaEvent_t> ev(nLaunch + 1);
+    for (auto &e : ev) CU(cudaEventCreate(&e));
+    PxStepParams P;
+    baseParams(b, kSubsteps, 0, W, &P);
+    CU(cudaStreamSynchronize(b->stream));
+    CU(cudaEventRecord(ev[0], b->stream));
+    if (!b->split) {
+      if (launchRange(b, kSubsteps, 0, W, b->stream, 0)) return -1;
+      CU(cudaEventRecord(ev[1], b->stream));
+    } else {
+      splitParams(b, 0, &P);
+      const uint32_t gridSweep = W < b->gridMax ? W : b->gridMax, gridSolve = W < b->gridSolve ? W : b->gridSolve;
+      uint32_t k = 1;
+      for (uint32_t s = 0; s <= kSubsteps; s++) {
+        if (launchSweep(b, &P, s, kSubsteps, gridSweep, b->stream)) return -1;
+        CU(cudaEventRecord(ev[k++], b->stream));
+        if (s < kSubsteps) {
+          if (launchSolve(b, &P, gridSolve, b->stream)) return -1;
+          CU(cudaEventRecord(ev[k++], b->stream));
+        }
+      }
+    }
+    CU(cudaEventSynchronize(ev[nLaunch]));
+    for (uint32_t k = 0; k < nLaunch; k++) {
+      float t = 0;
+      CU(cudaEventElapsedTime(&t, ev[k], ev[k + 1]));
+      if (b->split && (k & 1u)) {
+        tSolve += t;
+        cSolve++;
+      } else {
+        tSweep += t;
+        cSweep++;
+      }
+    }
+    for (auto &e : ev) cudaEventDestroy(e);
+  }
+  if (msSweep) *msSweep = tSweep;
+  if (nSweep) *nSweep = cSweep;
+  if (msSolve) *msSolve = tSolve;
+  if (nSolve) *nSolve = cSolve;
+  return 0;
+}
+
+/* 1 if the batch runs the split pipeline (sweep kernel + solver kernel per substep), 0 if fused;
+ * *solveCtasPerSm = residency of the solver kernel */
+extern "C" int pxBatchPipelineInfo(const PxBatch *b, int *split, int *solveCtasPerSm) {
+  if (!b) return pxSetError(-1, "pxBatchPipelineInfo: NULL batch");
+  if (split) *split = b->split ? 1 : 0;
+  if (solveCtasPerSm) *solveCtasPerSm = b->solveCtasPerSm;
+  return 0;
+}
+
 extern "C" int pxBatchProfileD2H(PxBatch *b, uint64_t *host) {
   if (!b || !host) return pxSetError(-1, "pxBatchProfileD2H: NULL argument");
   if (!b->dProf) return pxSetError(-1, "pxBatchProfileD2H: the batch was created without PX_BATCH_FLAG_PROFILE");

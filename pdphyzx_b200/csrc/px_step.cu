@@ -1758,7 +1758,7 @@ __global__ void __launch_bounds__(NT, NT == 128 ? PX_MINB128 : 3) pxStepKernel(c
  * the mutable block (after force integration), writes them back solved.
  */
 #ifndef PX_SOLVE_MINB
-#define PX_SOLVE_MINB 8
+#define PX_SOLVE_MINB 10
 #endif
 __global__ void __launch_bounds__(PX_SOLVE_THREADS, PX_SOLVE_MINB) pxSolveKernel(const PxStepParams P) {
   constexpr uint32_t NT = PX_SOLVE_THREADS;
