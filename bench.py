@@ -388,7 +388,7 @@ def run_ours(args):
     # per-kernel device time, live: CUDA events around EVERY launch of a few extra steps
     # (pxBatchStepTimedKernels); feeds the roofline of the dominant kernel below
     pipe = b.pipeline_info()
-    kt = {"sweep_ms": 0.0, "sweep_launches": 0, "solve_ms": 0.0, "solve_launches": 0}
+    kt = {"sweep_ms": 0.0, "sweep_launches": 0, "sched_ms": 0.0, "sched_launches": 0, "solve_ms": 0.0, "solve_launches": 0}
     for _ in range(3):
         control(0)
         r = b.step_timed_kernels(args.fused)
@@ -467,6 +467,7 @@ def run_ours(args):
         # bodies x B_alg(K = 1).  Launch durations: CUDA events around every launch, measured live above.
         sweep_ms = kt["sweep_ms"] / max(kt["sweep_launches"], 1)
         solve_ms = kt["solve_ms"] / max(kt["solve_launches"], 1)
+        sched_ms = kt["sched_ms"] / max(kt["sched_launches"], 1)
         alg_bytes = args.worlds * BODIES_PER_WORLD * alg
         achieved = alg_bytes / (sweep_ms * 1e-3) / 1e9
         out = {
@@ -479,16 +480,20 @@ def run_ours(args):
                 **({"host_cpus_per_rank_numa_local": numa_cpus} if numa_cpus else {}),
                 "body_frame_steps_per_sec": value / 5.0, "l2": "inputs larger than L2 (state > 126 MB per GPU)"
                 if args.worlds * (b.L.mutStride + b.L.immStride) > 126e6 else "inputs smaller than L2",
-                "pipeline": ("split: sweep kernel (phase F of the previous substep + phases A-D) and solver kernel per substep"
+                "pipeline": (("split: sweep kernel (phase F of the previous substep + phases A-D), schedule kernel (the substep's "
+                              "periodic visit schedule) and replay kernel per substep" if pipe.get("static_schedule") else
+                              "split: sweep kernel (phase F of the previous substep + phases A-D) and dataflow-solver kernel per substep")
                              if pipe["split"] else "fused: one kernel, K substeps"),
                 "threads_per_world_cta": info["threads"], "ctas_per_sm": info["ctas_per_sm"],
-                "smem_bytes_per_cta": info["smem_bytes"], "solver_ctas_per_sm": pipe["solve_ctas_per_sm"], "seed": args.seed,
+                "smem_bytes_per_cta": info["smem_bytes"], "solver_ctas_per_sm": pipe["solve_ctas_per_sm"],
+                "schedule_ctas_per_sm": pipe["sched_ctas_per_sm"], "seed": args.seed,
                 "avg_manifolds_per_world": stats[0], "avg_pairs_per_world": stats[1],
                 "avg_sleeping_per_world": stats[2], "worlds_overflowed": int(stats[3]),
                 **({"host_wall_ms_per_step": host_ms / args.steps} if args.control else {}),
             },
             "clocks": clocks, "gpu_launches": int(gpu_launches),
             "kernels": {"sweep_ms_per_launch": sweep_ms, "sweep_launches_per_step": kt["sweep_launches"] // 3,
+                        "sched_ms_per_launch": sched_ms, "sched_launches_per_step": kt["sched_launches"] // 3,
                         "solve_ms_per_launch": solve_ms, "solve_launches_per_step": kt["solve_launches"] // 3,
                         "timed_with": "CUDA events around every launch (pxBatchStepTimedKernels), 3 steps"},
             "roofline": {"bound": "hbm", "kernel": "pxStepKernel (sweep)" if pipe["split"] else "pxStepKernel (fused)",
@@ -534,7 +539,7 @@ def run_ours(args):
         if args.profile:
             pr = b.profile().astype(np.float64) - prof0
             nsub = float(blocks.header["substeps"].mean()) - nsub0
-            tot = pr[:, :6].sum()
+            tot = pr[:, :6].sum() + pr[:, 12].sum()
             out["phase_share"] = {n: float(pr[:, i].sum() / tot) for i, n in enumerate(
                 ("A_sort", "B_sweep", "C_narrowphase", "D_lists", "E_solver", "F_integrate"))}
             out["solver_rounds_per_substep"] = float(pr[:, 6].mean() / nsub)
@@ -543,6 +548,17 @@ def run_ours(args):
             c = pr[:, 8:12].sum(axis=0) / pr[:, 2].sum()
             out["narrowphase_stage_share"] = {"C1_circle_pairs": float(c[0]), "C2a_quick_reject": float(c[1]), "C2b_sat": float(c[2]),
                                               "C3_clip": float(c[3]), "C4_manifold_init": float(1.0 - c.sum())}
+            if pipe.get("static_schedule"):
+                # static schedule: relaxation + sort/stream-build cycles of phase D (slots 12, 14; included in D_lists'
+                # neighbour slot 12 of the phase clock), relaxation votes and period (slot 13)
+                raw13 = b.profile()[:, 13] - prof0_raw[:, 13]
+                out["schedule"] = {
+                    "sweep_kernel_hand_over_share_of_cycles": float(pr[:, 12].sum() / tot),
+                    "relaxation_cycles_per_substep": float(pr[:, 15].mean() / nsub),
+                    "schedule_kernel_cycles_per_substep": float(pr[:, 14].mean() / nsub),
+                    "relaxation_passes_per_substep": float((raw13 >> np.uint64(32)).mean() / nsub),
+                    "period_rounds": float((raw13 & np.uint64(0xFFFFFFFF)).mean() / nsub),
+                    "replay_chunks_per_substep": float(pr[:, 6].mean() / nsub)}
             raw7 = b.profile()[:, 7] - prof0_raw[:, 7]
             out["polygon_pairs_per_substep"] = float((raw7 >> np.uint64(32)).mean() / nsub)
             out["polygon_pairs_after_quick_reject_per_substep"] = float((raw7 & np.uint64(0xFFFFFFFF)).mean() / nsub)

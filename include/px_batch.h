@@ -40,6 +40,8 @@ struct PxWorld; /* include/pdphyzx.h */
 #define PX_BATCH_FLAG_PROFILE 4u       /* accumulate SM-clock cycles per kernel phase per world */
 #define PX_BATCH_FLAG_SPLIT 8u         /* force the split pipeline (sweep kernel + solver kernel per substep) */
 #define PX_BATCH_FLAG_FUSED 16u        /* force the fused pipeline (one kernel, K substeps); default: by batch size */
+#define PX_BATCH_FLAG_DYNAMIC_SOLVER 32u /* split pipeline: solve with the dataflow scheduler kernel instead of replaying the
+                                            periodic schedule the sweep kernel derives (the default) */
 
 /* PxWorldHeader.statOverflow bits */
 #define PX_BATCH_OVERFLOW_PAIRS 1u     /* more AABB-pass pairs than maxPairs: extra pairs dropped */
@@ -195,13 +197,14 @@ PX_API int pxBatchStepHost(PxBatch *b, uint32_t kSubsteps, void *hostMut, uint32
  * can be interleaved: pxBatchGroupStepTimed.) */
 PX_API int pxBatchTimerStart(PxBatch *b);
 PX_API int pxBatchTimerStop(PxBatch *b, float *ms);
-/* One step with EVERY kernel launch bracketed by CUDA events; blocks.  msSweep / nSweep: summed device
- * time and number of the sweep-kernel launches (or of the one fused launch), msSolve / nSolve: of the
- * solver-kernel launches (0 for the fused pipeline).  The roofline numbers of bench.py come from here. */
-PX_API int pxBatchStepTimedKernels(PxBatch *b, uint32_t kSubsteps, float *msSweep, uint32_t *nSweep, float *msSolve, uint32_t *nSolve);
-/* which pipeline the batch runs: *split = 1 for sweep + solver kernels per substep (large batches),
- * 0 for the fused kernel; *solveCtasPerSm = resident solver CTAs per SM */
-PX_API int pxBatchPipelineInfo(const PxBatch *b, int *split, int *solveCtasPerSm);
+/* One step with EVERY kernel launch bracketed by CUDA events; blocks.  ms[c] / n[c]: summed device time and number of
+ * the launches of class c -- 0 the sweep kernel (or the one fused launch), 1 the schedule kernel (static solver
+ * only), 2 the solver kernel (dataflow or replay).  The roofline numbers of bench.py come from here. */
+PX_API int pxBatchStepTimedKernels(PxBatch *b, uint32_t kSubsteps, float ms[3], uint32_t n[3]);
+/* which pipeline the batch runs: *split = 0 for the fused kernel, 1 for sweep + dataflow-solver kernels per substep,
+ * 2 for sweep + schedule + replay kernels per substep (large batches); resident CTAs per SM of the solver (dataflow
+ * or replay) kernel and of the schedule kernel (0 if there is none) */
+PX_API int pxBatchPipelineInfo(const PxBatch *b, int *split, int *solveCtasPerSm, int *schedCtasPerSm);
 /* Same, bracketed by CUDA events on the launching stream; blocks; *ms = device time. */
 PX_API int pxBatchStepTimed(PxBatch *b, uint32_t kSubsteps, float *ms);
 

@@ -23,6 +23,7 @@ FLAG_SERIAL_SOLVER = 2
 FLAG_PROFILE = 4
 FLAG_SPLIT = 8
 FLAG_FUSED = 16
+FLAG_DYNAMIC_SOLVER = 32
 OVERFLOW_PAIRS = 1
 OVERFLOW_MANIFOLDS = 2
 STATIC = 0x10000  # PX_BATCH_STATIC: OR into a body slot to address a static body
@@ -117,8 +118,8 @@ def core():
         "pxBatchFitDesc": (i32, [pp, u32, C.POINTER(PxBatchDesc)]),
         "pxSelfTestMath": (i32, [C.c_int, vp, vp, vp, vp, u32]),
         "pxSelfTestRsqrtSweep": (i32, [vp]),
-        "pxBatchStepTimedKernels": (i32, [vp, u32, C.POINTER(C.c_float), C.POINTER(u32), C.POINTER(C.c_float), C.POINTER(u32)]),
-        "pxBatchPipelineInfo": (i32, [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+        "pxBatchStepTimedKernels": (i32, [vp, u32, C.POINTER(C.c_float), C.POINTER(u32)]),
+        "pxBatchPipelineInfo": (i32, [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
         "pxBatchTimerStart": (i32, [vp]),
         "pxBatchTimerStop": (i32, [vp, C.POINTER(C.c_float)]),
         "pxBatchGroupNew": (vp, [pp, u32, C.POINTER(PxBatchDesc), C.POINTER(C.c_int32), u32]),
@@ -437,15 +438,16 @@ class Batch:
         return float(ms.value)
 
     def step_timed_kernels(self, k: int = 1):
-        """One step with every launch timed: dict(sweep_ms, sweep_launches, solve_ms, solve_launches)."""
-        ts, tv, ns, nv = C.c_float(0), C.c_float(0), C.c_uint32(0), C.c_uint32(0)
-        _check(self.lib.pxBatchStepTimedKernels(self.h, int(k), C.byref(ts), C.byref(ns), C.byref(tv), C.byref(nv)), "pxBatchStepTimedKernels")
-        return dict(sweep_ms=float(ts.value), sweep_launches=int(ns.value), solve_ms=float(tv.value), solve_launches=int(nv.value))
+        """One step with every launch timed: dict of summed ms and launch counts per kernel class."""
+        ms, n = (C.c_float * 3)(), (C.c_uint32 * 3)()
+        _check(self.lib.pxBatchStepTimedKernels(self.h, int(k), ms, n), "pxBatchStepTimedKernels")
+        return dict(sweep_ms=float(ms[0]), sweep_launches=int(n[0]), sched_ms=float(ms[1]), sched_launches=int(n[1]),
+                    solve_ms=float(ms[2]), solve_launches=int(n[2]))
 
     def pipeline_info(self):
-        a, c = C.c_int(0), C.c_int(0)
-        _check(self.lib.pxBatchPipelineInfo(self.h, C.byref(a), C.byref(c)), "pxBatchPipelineInfo")
-        return dict(split=bool(a.value), solve_ctas_per_sm=int(c.value))
+        a, c, d = C.c_int(0), C.c_int(0), C.c_int(0)
+        _check(self.lib.pxBatchPipelineInfo(self.h, C.byref(a), C.byref(c), C.byref(d)), "pxBatchPipelineInfo")
+        return dict(split=bool(a.value), static_schedule=a.value == 2, solve_ctas_per_sm=int(c.value), sched_ctas_per_sm=int(d.value))
 
     def sync(self):
         _check(self.lib.pxBatchSync(self.h), "pxBatchSync")

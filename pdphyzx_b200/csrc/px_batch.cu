@@ -38,11 +38,12 @@ struct PxBatch {
   uint32_t gridMax;    /* CTAs of a full launch: resident capacity of the device, at most nWorlds */
   /* split pipeline (sweep kernel + solver kernel per substep, px_step.cu) */
   bool split;
+  bool staticSched;    /* split pipeline: the sweep kernel derives a periodic visit schedule, pxReplayKernel replays it */
   PxHandLayout hand;
-  PxSmemPlan solvePlan;
+  PxSmemPlan solvePlan, schedPlan;
   uint8_t *dHand;      /* hand-over records, one per world */
-  uint32_t gridSolve;
-  int solveCtasPerSm;
+  uint32_t gridSolve, gridSched;
+  int solveCtasPerSm, schedCtasPerSm;
 
   uint8_t *hMut, *hImm; /* pinned staging, same layout */
   float sinTable[256];
@@ -96,9 +97,10 @@ extern "C" PxBatch *pxBatchCreate(uint32_t nWorlds, const PxBatchDesc *desc) {
   b->dCounters = nullptr;
   b->gridMax = 0;
   b->split = false;
+  b->staticSched = false;
   b->dHand = nullptr;
-  b->gridSolve = 0;
-  b->solveCtasPerSm = 0;
+  b->gridSolve = b->gridSched = 0;
+  b->solveCtasPerSm = b->schedCtasPerSm = 0;
 
   b->hMut = b->hImm = nullptr;
   b->dCmds = b->dGlobal = nullptr;
@@ -118,7 +120,6 @@ extern "C" PxBatch *pxBatchCreate(uint32_t nWorlds, const PxBatchDesc *desc) {
     delete b;
     return nullptr;
   }
-  pxPlanSmem(&b->L, 1, &b->plan);
 
   auto fail = [&](const char *what, cudaError_t e) -> PxBatch * {
     pxSetError(-(int)e - 1000, "pxBatchCreate: %s: %s", what, cudaGetErrorString(e));
@@ -152,7 +153,11 @@ extern "C" PxBatch *pxBatchCreate(uint32_t nWorlds, const PxBatchDesc *desc) {
     else if (desc->flags & PX_BATCH_FLAG_FUSED) b->split = false;
     else if (env) b->split = env[0] == 's';
     else b->split = nWorlds >= 4u * (uint32_t)b->numSms;
+    /* the split pipeline's solver: the static (replayed) schedule unless the dataflow solver is asked for */
+    const char *sv = getenv("PX_SOLVER"); /* tuning switch: "dynamic" or "static" */
+    b->staticSched = b->split && !(desc->flags & PX_BATCH_FLAG_DYNAMIC_SOLVER) && !(sv && sv[0] == 'd');
   }
+  pxPlanSmem(&b->L, 1, b->staticSched ? 1 : 0, &b->plan);
   /* fused: 128 threads, 5 CTAs/SM keep the SM's issue slots busier than 3 CTAs of 256 threads;
    * split: the sweep kernel alone is throughput work, 256 threads x 3 CTAs leave it a larger L1 */
   b->threads = desc->threads ? desc->threads : (b->split ? 256 : 128);
@@ -166,7 +171,7 @@ extern "C" PxBatch *pxBatchCreate(uint32_t nWorlds, const PxBatchDesc *desc) {
      * lets one more world be resident per SM (the solver phase is latency-bound: resident
      * worlds are what hides it) */
     PxSmemPlan slim;
-    pxPlanSmem(&b->L, 0, &slim);
+    pxPlanSmem(&b->L, 0, b->staticSched ? 1 : 0, &slim);
     const size_t perSm = (size_t)prop.sharedMemPerMultiprocessor, reserve = (size_t)prop.reservedSharedMemPerBlock;
     size_t fat = perSm / (b->plan.total + reserve), thin = perSm / (slim.total + reserve);
     if (b->plan.total <= (uint32_t)prop.sharedMemPerBlockOptin) {
@@ -232,14 +237,25 @@ extern "C" PxBatch *pxBatchCreate(uint32_t nWorlds, const PxBatchDesc *desc) {
       if ((e = cudaMalloc(&b->dScratch, scratchBytes)) != cudaSuccess) return fail("cudaMalloc(scratch)", e);
     } else {
       pxPlanHandover(&b->L, &b->plan, &b->hand);
-      pxPlanSolveSmem(&b->L, &b->plan, &b->solvePlan);
+      pxPlanSolveSmem(&b->L, &b->plan, b->staticSched ? 1 : 0, &b->solvePlan);
       P.solveS = b->solvePlan;
+      P.solver = b->staticSched ? PX_SOLVER_STATIC : PX_SOLVER_DYNAMIC;
       int socc = 0;
       rc = pxSolveOccupancy(&P, &socc);
       if (rc != 0 || socc < 1) return fail("occupancy query of the solver kernel", (cudaError_t)(rc ? rc : (int)cudaErrorLaunchOutOfResources));
       b->solveCtasPerSm = socc;
       const uint64_t scap = (uint64_t)socc * (uint64_t)b->numSms;
       b->gridSolve = (uint32_t)(scap < nWorlds ? scap : nWorlds);
+      if (b->staticSched) {
+        pxPlanSchedSmem(&b->L, &b->schedPlan);
+        P.schedS = b->schedPlan;
+        int kocc = 0;
+        rc = pxSchedOccupancy(&P, &kocc);
+        if (rc != 0 || kocc < 1) return fail("occupancy query of the schedule kernel", (cudaError_t)(rc ? rc : (int)cudaErrorLaunchOutOfResources));
+        b->schedCtasPerSm = kocc;
+        const uint64_t kcap = (uint64_t)kocc * (uint64_t)b->numSms;
+        b->gridSched = (uint32_t)(kcap < nWorlds ? kcap : nWorlds);
+      }
       const size_t handBytes = (size_t)nWorlds * b->hand.stride;
       if ((e = cudaMalloc(&b->dHand, handBytes)) != cudaSuccess) return fail("cudaMalloc(hand-over records)", e);
       if ((e = cudaMemsetAsync(b->dHand, 0, handBytes, b->stream)) != cudaSuccess) return fail("cudaMemset", e);
@@ -601,10 +617,12 @@ static void baseParams(PxBatch *b, uint32_t kSubsteps, uint32_t first, uint32_t 
 
 static void splitParams(PxBatch *b, uint32_t first, PxStepParams *P) {
   P->mode = PX_MODE_SWEEP;
+  P->solver = b->staticSched ? PX_SOLVER_STATIC : PX_SOLVER_DYNAMIC;
   P->scratch = nullptr;
   P->hand = b->dHand + (size_t)first * b->hand.stride;
   P->H = b->hand;
   P->solveS = b->solvePlan;
+  P->schedS = b->schedPlan;
 }
 
 /* launch s of the split pipeline's sweep kernel: phase F of substep s - 1 (s > 0), phases A-D of substep s (s < K) */
@@ -616,6 +634,16 @@ static int launchSweep(PxBatch *b, PxStepParams *P, uint32_t s, uint32_t kSubste
   CU(cudaMemsetAsync(P->worldCounter, 0, sizeof(uint32_t), stream));
   int rc = pxLaunchStep(P, b->threads, grid, stream);
   if (rc != 0) return pxSetError(-rc - 1000, "sweep kernel launch: %s", cudaGetErrorString((cudaError_t)rc));
+  b->launches++;
+  return 0;
+}
+
+/* static solver: the schedule kernel between the sweep kernel and the replay kernel */
+static int launchSched(PxBatch *b, PxStepParams *P, uint32_t grid, cudaStream_t stream) {
+  P->worldCounter = b->dCounters + (b->launches % PX_COUNTER_RING);
+  CU(cudaMemsetAsync(P->worldCounter, 0, sizeof(uint32_t), stream));
+  int rc = pxLaunchSched(P, grid, stream);
+  if (rc != 0) return pxSetError(-rc - 1000, "schedule kernel launch: %s", cudaGetErrorString((cudaError_t)rc));
   b->launches++;
   return 0;
 }
@@ -648,8 +676,10 @@ static int launchRange(PxBatch *b, uint32_t kSubsteps, uint32_t first, uint32_t 
   /* split pipeline: sweep(A-D) | solve | sweep(F, A-D) | solve | ... | sweep(F) */
   splitParams(b, first, &P);
   const uint32_t gridSweep = n < b->gridMax ? n : b->gridMax, gridSolve = n < b->gridSolve ? n : b->gridSolve;
+  const uint32_t gridSched = n < b->gridSched ? n : b->gridSched;
   for (uint32_t s = 0; s <= kSubsteps; s++) {
     if (launchSweep(b, &P, s, kSubsteps, gridSweep, stream)) return -1;
+    if (s < kSubsteps && b->staticSched && launchSched(b, &P, gridSched, stream)) return -1;
     if (s < kSubsteps && launchSolve(b, &P, gridSolve, stream)) return -1;
   }
   return 0;
@@ -745,66 +775,63 @@ extern "C" int pxBatchTimerStop(PxBatch *b, float *ms) {
 }
 
 /* One step with every kernel launch bracketed by CUDA events: device time per kernel class.
- * msSweep / msSolve = summed durations of the sweep (or fused) and solver launches, nSweep / nSolve
- * how many there were.  Blocks. */
-extern "C" int pxBatchStepTimedKernels(PxBatch *b, uint32_t kSubsteps, float *msSweep, uint32_t *nSweep, float *msSolve, uint32_t *nSolve) {
-  if (!b) return pxSetError(-1, "pxBatchStepTimedKernels: NULL batch");
+ * ms[c] / n[c] = summed durations and number of the launches of class c: 0 sweep (or the one fused launch),
+ * 1 schedule kernel (static solver only), 2 solver (dataflow or replay).  Blocks. */
+extern "C" int pxBatchStepTimedKernels(PxBatch *b, uint32_t kSubsteps, float ms[3], uint32_t n[3]) {
+  if (!b || !ms || !n) return pxSetError(-1, "pxBatchStepTimedKernels: NULL argument");
   if (useDevice(b)) return -1;
   if (flushCommands(b)) return -1;
-  float tSweep = 0, tSolve = 0;
-  uint32_t cSweep = 0, cSolve = 0;
-  if (kSubsteps) {
-    const uint32_t W = b->L.nWorlds;
-    const uint32_t nLaunch = b->split ? 2 * kSubsteps + 1 : 1;
-    std::vector<cudaEvent_t> ev(nLaunch + 1);
-    for (auto &e : ev) CU(cudaEventCreate(&e));
-    PxStepParams P;
-    baseParams(b, kSubsteps, 0, W, &P);
-    CU(cudaStreamSynchronize(b->stream));
-    CU(cudaEventRecord(ev[0], b->stream));
-    if (!b->split) {
-      if (launchRange(b, kSubsteps, 0, W, b->stream, 0)) return -1;
-      CU(cudaEventRecord(ev[1], b->stream));
-    } else {
-      splitParams(b, 0, &P);
-      const uint32_t gridSweep = W < b->gridMax ? W : b->gridMax, gridSolve = W < b->gridSolve ? W : b->gridSolve;
-      uint32_t k = 1;
-      for (uint32_t s = 0; s <= kSubsteps; s++) {
-        if (launchSweep(b, &P, s, kSubsteps, gridSweep, b->stream)) return -1;
-        CU(cudaEventRecord(ev[k++], b->stream));
-        if (s < kSubsteps) {
-          if (launchSolve(b, &P, gridSolve, b->stream)) return -1;
-          CU(cudaEventRecord(ev[k++], b->stream));
-        }
-      }
-    }
-    CU(cudaEventSynchronize(ev[nLaunch]));
-    for (uint32_t k = 0; k < nLaunch; k++) {
-      float t = 0;
-      CU(cudaEventElapsedTime(&t, ev[k], ev[k + 1]));
-      if (b->split && (k & 1u)) {
-        tSolve += t;
-        cSolve++;
-      } else {
-        tSweep += t;
-        cSweep++;
-      }
-    }
-    for (auto &e : ev) cudaEventDestroy(e);
+  for (int c = 0; c < 3; c++) {
+    ms[c] = 0;
+    n[c] = 0;
   }
-  if (msSweep) *msSweep = tSweep;
-  if (nSweep) *nSweep = cSweep;
-  if (msSolve) *msSolve = tSolve;
-  if (nSolve) *nSolve = cSolve;
+  if (!kSubsteps) return 0;
+  const uint32_t W = b->L.nWorlds;
+  std::vector<cudaEvent_t> ev;
+  std::vector<int> cls;
+  auto mark = [&](int c) -> int {
+    cudaEvent_t e;
+    CU(cudaEventCreate(&e));
+    CU(cudaEventRecord(e, b->stream));
+    ev.push_back(e);
+    cls.push_back(c);
+    return 0;
+  };
+  PxStepParams P;
+  baseParams(b, kSubsteps, 0, W, &P);
+  CU(cudaStreamSynchronize(b->stream));
+  if (mark(-1)) return -1;
+  if (!b->split) {
+    if (launchRange(b, kSubsteps, 0, W, b->stream, 0)) return -1;
+    if (mark(0)) return -1;
+  } else {
+    splitParams(b, 0, &P);
+    const uint32_t gridSweep = W < b->gridMax ? W : b->gridMax, gridSolve = W < b->gridSolve ? W : b->gridSolve;
+    const uint32_t gridSched = W < b->gridSched ? W : b->gridSched;
+    for (uint32_t s = 0; s <= kSubsteps; s++) {
+      if (launchSweep(b, &P, s, kSubsteps, gridSweep, b->stream) || mark(0)) return -1;
+      if (s < kSubsteps && b->staticSched && (launchSched(b, &P, gridSched, b->stream) || mark(1))) return -1;
+      if (s < kSubsteps && (launchSolve(b, &P, gridSolve, b->stream) || mark(2))) return -1;
+    }
+  }
+  CU(cudaEventSynchronize(ev.back()));
+  for (size_t k = 1; k < ev.size(); k++) {
+    float t = 0;
+    CU(cudaEventElapsedTime(&t, ev[k - 1], ev[k]));
+    ms[cls[k]] += t;
+    n[cls[k]]++;
+  }
+  for (auto &e : ev) cudaEventDestroy(e);
   return 0;
 }
 
 /* 1 if the batch runs the split pipeline (sweep kernel + solver kernel per substep), 0 if fused;
  * *solveCtasPerSm = residency of the solver kernel */
-extern "C" int pxBatchPipelineInfo(const PxBatch *b, int *split, int *solveCtasPerSm) {
+extern "C" int pxBatchPipelineInfo(const PxBatch *b, int *split, int *solveCtasPerSm, int *schedCtasPerSm) {
   if (!b) return pxSetError(-1, "pxBatchPipelineInfo: NULL batch");
-  if (split) *split = b->split ? 1 : 0;
+  if (split) *split = b->split ? (b->staticSched ? 2 : 1) : 0;
   if (solveCtasPerSm) *solveCtasPerSm = b->solveCtasPerSm;
+  if (schedCtasPerSm) *schedCtasPerSm = b->schedCtasPerSm;
   return 0;
 }
 

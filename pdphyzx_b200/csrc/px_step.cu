@@ -191,6 +191,8 @@ struct Sm {
   uint16_t *list, *nextw;
   uint32_t *sig;
   uint32_t *queue;
+  /* static schedule (region Y'), see PxSmemPlan */
+  uint16_t *predA, *predB, *rankOf;
 };
 
 /* Manifold records use ordinary (L1-allocating) accesses: a slot is only ever touched by CTAs of
@@ -211,7 +213,8 @@ __device__ __forceinline__ float3 materialOf(const Sm &s, uint32_t id, uint32_t 
 }
 
 /* misc[] slots */
-enum { MI_MCOUNT = 0, MI_QTAIL, MI_OVERFLOW, MI_SURVIVORS, MI_SLEEPING, MI_VISITS, MI_MATHROUND, MI_SLOT, MI_WORLD, MI_RDESC = 16 };
+enum { MI_MCOUNT = 0, MI_QTAIL, MI_OVERFLOW, MI_SURVIVORS, MI_SLEEPING, MI_VISITS, MI_MATHROUND, MI_SLOT, MI_WORLD,
+       MI_RING = 9 /* static schedule: longest body ring in contact visits */, MI_RDESC = 16 };
 #define PX_RING 16u /* round descriptors in flight (misc[MI_RDESC..]) */
 /* round descriptor: (round + 1) mod 2^15 << 17 | first queue index of the round << 6 | visits (PX_DESC_END = no more rounds) */
 #define PX_DESC(round, head, n) (((((round) + 1u) & 0x7fffu) << 17) | (((head) & 0x7ffu) << 6) | (n))
@@ -595,22 +598,13 @@ __device__ __forceinline__ ContactIn loadContact(const Sm &s, uint32_t w) {
   return in;
 }
 
-/* the arithmetic of one contact visit: in.vA / in.vB come back updated */
-__device__ __forceinline__ void contactImpulse(uint32_t w, ContactIn &in, float eps) {
-  const bool second = MID_CI(w) != 0, bdyn = MID_BDYN(w) != 0;
-  const float4 mA = in.mA, mB = in.mB, mC = in.mC;
-  const float4 pA = in.pA, pB = in.pB;
-  float4 &vA = in.vA, &vB = in.vB;
-  const V2 n = v2(mA.x, mA.y);
-  const float e = mA.z, sf = mA.w, df = mB.x;
-  const V2 c = second ? v2(mC.x, mC.y) : v2(mB.z, mB.w);
-  const float rcpDenom = second ? mC.w : mC.z;
-  const V2 pa = v2(pA.x, pA.y), pb = v2(pB.x, pB.y);
-  const float iMA = pA.z, iIA = pA.w, iMB = pB.z, iIB = pB.w; /* statics: 0 */
+/* the arithmetic of one contact visit from its frozen operands (normal, lever arms ra = c - posA and rb = c - posB,
+ * materials, the precomputed denominator, inverse masses / inertias): vA / vB come back updated */
+__device__ __forceinline__ void contactImpulseCore(const V2 n, const V2 ra, const V2 rb, const float e, const float sf, const float df,
+                                                   const float rcpDenom, const float iMA, const float iIA, const float iMB,
+                                                   const float iIB, const bool bdyn, float4 &vA, float4 &vB, const float eps) {
   V2 va = v2(vA.x, vA.y), vb = v2(vB.x, vB.y);
   float wa = vA.z, wb = vB.z;
-
-  const V2 ra = c - pa, rb = c - pb;
   const V2 raPerp = v2(-ra.y, ra.x), rbPerp = v2(-rb.y, rb.x);
   V2 rv = (vb + rbPerp * wb) - (va + raPerp * wa);
   const float vn = dot(rv, n);
@@ -653,6 +647,17 @@ __device__ __forceinline__ void contactImpulse(uint32_t w, ContactIn &in, float 
   vB.z = approaching ? (slides ? wb2 : wb1) : wb;
 }
 
+/* one contact visit of the dynamic solver: operands from the manifold record and the two body rows */
+__device__ __forceinline__ void contactImpulse(uint32_t w, ContactIn &in, float eps) {
+  const bool second = MID_CI(w) != 0, bdyn = MID_BDYN(w) != 0;
+  const float4 mA = in.mA, mB = in.mB, mC = in.mC;
+  const float4 pA = in.pA, pB = in.pB;
+  const V2 c = second ? v2(mC.x, mC.y) : v2(mB.z, mB.w);
+  const V2 pa = v2(pA.x, pA.y), pb = v2(pB.x, pB.y);
+  contactImpulseCore(v2(mA.x, mA.y), c - pa, c - pb, mA.z, mA.w, mB.x, second ? mC.w : mC.z, pA.z, pA.w, pB.z, pB.w, bdyn,
+                     in.vA, in.vB, eps);
+}
+
 __device__ __forceinline__ void solveContact(const Sm &s, uint32_t w, ContactIn &in, float eps) {
   contactImpulse(w, in, eps);
   s.bodyV[MID_A(w)] = in.vA;
@@ -676,6 +681,7 @@ __device__ __forceinline__ void bindSmem(Sm &s, uint8_t *base, const PxSmemPlan 
   BIND(sBox, float4); BIND(sInfo, uint32_t); BIND(stBox, float4);
   BIND(bins, uint32_t);
   BIND(list, uint16_t); BIND(nextw, uint16_t); BIND(sig, uint32_t); BIND(queue, uint32_t);
+  BIND(predA, uint16_t); BIND(predB, uint16_t); BIND(rankOf, uint16_t);
 #undef BIND
   s.verts = S.vertsInSmem ? (const float4 *)(base + S.verts) : globalVerts;
 }
@@ -941,6 +947,9 @@ __global__ void __launch_bounds__(NT, NT == 128 ? PX_MINB128 : 3) pxStepKernel(c
    * kernels and phase F exchange beyond the mutable block lives in the world's hand-over
    * record in global memory.  Fused (PX_MODE_FUSED): K whole substeps, nothing leaves the SM. */
   constexpr bool sweepMode = MODE == PX_MODE_SWEEP; /* compile-time: each pipeline carries only its own code */
+  /* split pipeline: the solver kernel either runs the dataflow schedule itself (pxSolveKernel) or replays a periodic
+   * schedule that phase D derives here, once per substep (pxReplayKernel) */
+  const bool staticSched = sweepMode && P.solver == PX_SOLVER_STATIC;
   uint8_t *hand = sweepMode ? P.hand + (size_t)world * P.H.stride : nullptr;
   if (sweepMode) {
     s.man = (float4 *)(hand + P.H.records);
@@ -1407,7 +1416,11 @@ __global__ void __launch_bounds__(NT, NT == 128 ? PX_MINB128 : 3) pxStepKernel(c
         s.fillB[x] = 0;
       }
     }
-    for (uint32_t i = tid; i < M; i += NT) s.sig[i] = 0;
+    if (staticSched) {
+      for (uint32_t i = tid; i < M; i += NT) s.predB[i] = 0xffffu; /* by pool rank; stays so for a static B */
+    } else {
+      for (uint32_t i = tid; i < M; i += NT) s.sig[i] = 0;
+    }
     __syncthreads();
 #pragma unroll
     for (int r = 0; r < R; r++) {
@@ -1422,6 +1435,7 @@ __global__ void __launch_bounds__(NT, NT == 128 ? PX_MINB128 : 3) pxStepKernel(c
         const uint32_t ms = vs - 1;
         const uint32_t ids = s.mids[ms];
         s.list[startX + nBx + k] = (uint16_t)ms;
+        if (staticSched) s.rankOf[ms] = (uint16_t)(rankStartR[r] + k); /* place in the manifold pool (px_world.c:327-345) */
         if (MID_BDYN(ids)) { /* unordered placement in B's bodyB segment, sorted below */
           const uint32_t y = MID_B(ids);
           s.list[s.listStart[y] + atomicAdd(&s.fillB[y], 1u)] = (uint16_t)ms;
@@ -1467,6 +1481,22 @@ __global__ void __launch_bounds__(NT, NT == 128 ? PX_MINB128 : 3) pxStepKernel(c
         }
         s.list[start + jj + 1] = (uint16_t)cur;
       }
+      if (staticSched) {
+        /* the body's ring of visits: every manifold learns its predecessor on this body (the last one closes the
+         * ring: its edge carries the iteration boundary) and how many rounds that predecessor takes */
+        uint32_t ring = 0;
+        for (uint32_t i = 0; i < n; i++) {
+          const uint32_t ms = s.list[start + i];
+          const uint32_t pred = s.list[start + (i ? i - 1 : n - 1)];
+          const uint32_t own = MID_COUNT(s.mids[ms]);
+          /* pool rank of the predecessor | closes the ring << 10 | its contacts << 11 | own contacts << 13 */
+          const uint32_t word = s.rankOf[pred] | (i ? 0u : 0x400u) | (MID_COUNT(s.mids[pred]) << 11) | (own << 13);
+          if (i < nBx) s.predB[s.rankOf[ms]] = (uint16_t)word;
+          else s.predA[s.rankOf[ms]] = (uint16_t)word;
+          ring += own;
+        }
+        if (ring) atomicMax(&s.misc[MI_RING], ring);
+      } else {
       for (uint32_t i = 0; i < n; i++) {
         const uint32_t ms = s.list[start + i];
         const uint32_t side = i < nBx ? 1u : 0u;
@@ -1477,6 +1507,7 @@ __global__ void __launch_bounds__(NT, NT == 128 ? PX_MINB128 : 3) pxStepKernel(c
       if (n) { /* the body's first manifold receives its first signal from the body itself */
         const uint32_t first = s.list[start];
         atomicAdd(&s.sig[first], nBx ? 0x10000u : 1u);
+      }
       }
       /* pxIntegrateForces, px_world.c:231-239 / px_body.c:167-179 (resting-contact detection
        * above already consumed the pre-integration velocities) */
@@ -1493,7 +1524,7 @@ __global__ void __launch_bounds__(NT, NT == 128 ? PX_MINB128 : 3) pxStepKernel(c
     }
     __syncthreads();
     /* manifolds at the head of the lists of all their dynamic bodies start the solver */
-    if (iterations && !(P.flags & PX_BATCH_FLAG_SERIAL_SOLVER)) {
+    if (iterations && !(P.flags & PX_BATCH_FLAG_SERIAL_SOLVER) && !staticSched) {
       for (uint32_t ms = tid; ms < M; ms += NT) {
         const uint32_t w = s.mids[ms];
         const uint32_t sg = s.sig[ms];
@@ -1504,13 +1535,39 @@ __global__ void __launch_bounds__(NT, NT == 128 ? PX_MINB128 : 3) pxStepKernel(c
     }
     __syncthreads();
     PROF_MARK(3)
-    if (sweepMode) {
-      /* hand the substep over: what the solver kernel needs (manifold ids, successor words, initial
-       * signals, the first ready visits) and what phase F needs after it (the per-body lists) */
+    if constexpr (sweepMode) {
+      if (staticSched && iterations) {
+        /* static schedule: the rings in pool-rank space and, by rank, the frozen operands of every contact visit
+         * {n, ra | rb, rcpDenom, e | sf, df, ids} (entry 2 * rank + contact); pxSchedKernel orders them */
+        float4 *pl0 = (float4 *)(hand + P.H.vrec), *pl1 = pl0 + PX_VCAP(MM), *pl2 = pl1 + PX_VCAP(MM);
+        for (uint32_t v = tid; v < 2u * M; v += NT) {
+          const uint32_t m = v >> 1, ci = v & 1u, w = s.mids[m];
+          if (ci < MID_COUNT(w)) {
+            const uint32_t a = MID_A(w), b = MID_B(w), at = 2u * s.rankOf[m] + ci;
+            const float4 mA = manLoad(s, m, 0), mB = manLoad(s, m, 1), mC = manLoad(s, m, 2);
+            const float4 pA = s.bodyP[a], pB = s.bodyP[b];
+            const V2 cpt = ci ? v2(mC.x, mC.y) : v2(mB.z, mB.w);
+            const V2 ra = cpt - v2(pA.x, pA.y), rb = cpt - v2(pB.x, pB.y); /* px_manifold.c:112-113 */
+            pl0[at] = make_float4(mA.x, mA.y, ra.x, ra.y);
+            pl1[at] = make_float4(rb.x, rb.y, ci ? mC.w : mC.z, mA.z);
+            pl2[at] = make_float4(mA.w, mB.x, __uint_as_float(a | (b << 8) | (MID_BDYN(w) << 17)), 0.0f);
+          }
+        }
+        handCopy<NT>(hand + P.H.predA, s.predA, M * 2u);
+        handCopy<NT>(hand + P.H.predB, s.predB, M * 2u);
+      }
+      PROF_MARK(12)
+      /* hand the substep over: what the solver kernel needs (dynamic: manifold ids, successor words, initial
+       * signals, the first ready visits; static: the visit stream written above and its segment table) and what
+       * phase F needs after it (the per-body lists) */
       handCopy<NT>(hand + P.H.mids, s.mids, M * 4u);
-      handCopy<NT>(hand + P.H.nextw, s.nextw, M * 4u);
-      handCopy<NT>(hand + P.H.sig, s.sig, M * 4u);
-      handCopy<NT>(hand + P.H.queue, s.queue, min(s.misc[MI_QTAIL], P.S.qcap) * 4u);
+      if (staticSched) {
+        if (tid == 0) ((uint32_t *)(hand + P.H.scalars))[PX_HS_RING] = s.misc[MI_RING];
+      } else {
+        handCopy<NT>(hand + P.H.nextw, s.nextw, M * 4u);
+        handCopy<NT>(hand + P.H.sig, s.sig, M * 4u);
+        handCopy<NT>(hand + P.H.queue, s.queue, min(s.misc[MI_QTAIL], P.S.qcap) * 4u);
+      }
       handCopy<NT>(hand + P.H.list, s.list, 2u * M * 2u);
       handCopy<NT>(hand + P.H.listStart, s.listStart, (D + 1u) * 2u);
       handCopy<NT>(hand + P.H.cnt, s.cnt, D * 2u);
@@ -1836,6 +1893,321 @@ __global__ void __launch_bounds__(PX_SOLVE_THREADS, PX_SOLVE_MINB) pxSolveKernel
   }
 }
 
+/* ===================================================================== schedule kernel ==== */
+/*
+ * Split pipeline with the static solver: a PERIODIC schedule of the substep's contact visits, derived once per
+ * substep (here) and replayed for every iteration (pxReplayKernel) -- the dataflow solver re-derives the same order
+ * `iterations` times.
+ *
+ * The visits of one body form a ring in pool order (its manifold list; a 2-contact manifold takes two rounds), and
+ * the ring's closing edge carries the iteration boundary.  Give every manifold a start round t(m) inside "its"
+ * iteration and let visit k of manifold m run in round t(m) + k * II.  That is a valid execution of the sequential
+ * Gauss-Seidel loop (px_world.c:249-260) iff
+ *     t(m) >= t(p) + contacts(p)                  for the predecessor p of m in each of its bodies' rings, and
+ *     t(first) + II >= t(last) + contacts(last)   for every body (the closing edge, weight -II),
+ * because two visits that share a dynamic body then never overlap and keep their pool order -- and any such
+ * execution produces the sequential loop's bits.  The least such t is the longest-path solution of those difference
+ * constraints.  Pool rank is a topological order of all but the closing edges, so ONE warp relaxes the manifolds in
+ * rank order, 32 at a time (each block repeated until it is stable: its inner chains are a body's few consecutive
+ * manifolds), and one pass settles everything the closing edges' current values imply; 3-5 passes reach the fixed
+ * point.  It exists iff II is at least the critical cycle ratio of the rings' graph -- on settled piles the longest ring
+ * plus 0..5 rounds (profiles/sched_sim.py).  A period that is too short shows after PX_SCHED_PASSES passes, which is
+ * cheap, so the periods are tried from tight to loose: ring + 2, + 4, + 8, 2 * ring + 8, and finally the closing
+ * edges are dropped and II = the depth of one iteration (iterations back to back: always valid).
+ *
+ * Visits are then sorted by (round mod II, round div II) with a counting sort: round R of the replay is slot
+ * R mod II, and the visits of the iterations alive in it are one contiguous segment of that order (segment starts ->
+ * H.seg).  The visits' frozen operands, which the sweep kernel left by pool rank, are permuted into that order
+ * (H.vrec -> H.stream), so the replay reads them coalesced.  Work per world: about ten thousand warp instructions,
+ * on one warp; twenty-odd worlds per SM hide its latency.
+ */
+#ifndef PX_SCHED_MINB
+#define PX_SCHED_MINB 16
+#endif
+#ifndef PX_SCHED_PASSES
+#define PX_SCHED_PASSES 8u
+#endif
+__device__ __forceinline__ uint32_t lds16(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts16(uint32_t a, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+
+__global__ void __launch_bounds__(PX_SCHED_THREADS, PX_SCHED_MINB) pxSchedKernel(const PxStepParams P) {
+  extern __shared__ __align__(16) uint8_t smemRaw[];
+  const PxBatchLayout &L = P.L;
+  const uint32_t MM = L.maxManifolds, lane = threadIdx.x;
+  uint16_t *tlev = (uint16_t *)(smemRaw + P.schedS.tlev);
+  uint32_t *h32 = (uint32_t *)(smemRaw + P.schedS.khist);
+  uint16_t *h16 = (uint16_t *)h32;
+  const uint32_t aT = sAddr(tlev);
+  for (;;) {
+    uint32_t world = 0;
+    if (lane == 0) world = atomicAdd(P.worldCounter, 1u);
+    world = __shfl_sync(0xffffffffu, world, 0);
+    if (world >= L.nWorlds) break;
+    const uint8_t *gmut = P.mut + (size_t)world * L.mutStride;
+    uint8_t *hand = P.hand + (size_t)world * P.H.stride;
+    uint32_t *sc = (uint32_t *)(hand + P.H.scalars);
+    const uint32_t iterations = ((const PxWorldHeader *)(gmut + L.offHeader))->iterations & 255u;
+    const uint32_t M = min(sc[PX_HS_M], MM), ring = sc[PX_HS_RING];
+    uint32_t II = 0, QN = 0, depth = 0, nVisits = 0;
+    long long t0 = 0;
+    unsigned long long *prof = P.prof ? P.prof + (size_t)world * PX_PROF_SLOTS : nullptr;
+    if (prof && lane == 0) t0 = clock64();
+    if (M && iterations) {
+      const uint16_t *gA = (const uint16_t *)(hand + P.H.predA), *gB = (const uint16_t *)(hand + P.H.predB);
+      uint32_t passes = 0;
+      bool converged = false, sequential = false;
+      for (uint32_t attempt = 0; attempt < 5 && !converged; attempt++) {
+        II = min(attempt < 3 ? ring + (PX_II_MARGIN << attempt) : 2u * ring + 8u, 2u * MM + 8u);
+        sequential = attempt == 4;
+        const int closing = sequential ? 0x8000 : (int)II; /* dropped edges: a cost no start round can reach */
+        for (uint32_t r = lane; r < M; r += 32u) tlev[r] = 0;
+        __syncwarp();
+        for (uint32_t pass = 0; pass < (sequential ? 3u : PX_SCHED_PASSES) && !converged; pass++) {
+          bool moved = false;
+          for (uint32_t base = 0; base < M; base += 32u) {
+            const uint32_t r = base + lane;
+            const bool valid = r < M;
+            /* rank | closes the ring << 10 | predecessor's contacts << 11 | own contacts << 13; 0xffff: static B */
+            const uint32_t pa = valid ? __ldg(gA + r) : 0u, pb = valid ? __ldg(gB + r) : 0xffffu;
+            const uint32_t adA = aT + 2u * (pa & 0x3ffu), adB = aT + 2u * ((pb == 0xffffu ? pa : pb) & 0x3ffu);
+            const int addA = (int)((pa >> 11) & 3u) - ((pa & 0x400u) ? closing : 0);
+            const int addB = pb == 0xffffu ? -0x10000 : (int)((pb >> 11) & 3u) - ((pb & 0x400u) ? closing : 0);
+            int cur = valid ? (int)lds16(aT + 2u * r) : 0x7fffffff;
+            for (uint32_t it = 0; it < 34u; it++) { /* a block's inner chains: at most 31 hops unless the period is infeasible */
+              const int v = max((int)lds16(adA) + addA, (int)lds16(adB) + addB);
+              const bool up = v > cur;
+              if (up) {
+                cur = v;
+                sts16(aT + 2u * r, (uint32_t)v);
+              }
+              __syncwarp();
+              if (!__any_sync(0xffffffffu, up)) break;
+              moved = true;
+            }
+          }
+          passes++;
+          converged = !moved;
+        }
+      }
+      /* depth of one iteration; own contact count: bits 13-14 of the A word */
+      for (uint32_t base = 0; base < M; base += 32u) {
+        const uint32_t r = base + lane;
+        if (r < M) depth = max(depth, (uint32_t)tlev[r] + ((__ldg(gA + r) >> 13) & 3u));
+      }
+      depth = max(__reduce_max_sync(0xffffffffu, depth), 1u);
+      if (sequential) II = depth;
+      if (!converged && lane == 0) /* unreachable: the sequential attempt always converges */
+        ((PxWorldHeader *)(const_cast<uint8_t *>(gmut) + L.offHeader))->statOverflow |= PX_OVERFLOW_INTERNAL;
+      QN = (depth - 1u) / II + 1u;
+      const uint32_t nKeys = II * QN; /* <= depth - 1 + II < PX_KCAP */
+      if (prof && lane == 0) {
+        const long long now = clock64();
+        prof[15] += (unsigned long long)(now - t0);
+        prof[13] += ((unsigned long long)passes << 32) + II;
+      }
+      /* visits per key, two 16-bit counters per word */
+      for (uint32_t i = lane; i < (nKeys + 3u) / 2u; i += 32u) h32[i] = 0;
+      __syncwarp();
+      for (uint32_t base = 0; base < 2u * M; base += 32u) {
+        const uint32_t v = base + lane, r = v >> 1, ci = v & 1u;
+        if (r < M && ci < ((__ldg(gA + r) >> 13) & 3u)) {
+          const uint32_t tau = (uint32_t)tlev[r] + ci, q = tau / II, key = (tau - q * II) * QN + q;
+          atomicAdd(&h32[key >> 1], (key & 1u) ? 0x10000u : 1u);
+        }
+      }
+      __syncwarp();
+      /* exclusive prefix over the keys, in place: segment starts, copied out (entry nKeys = the number of visits),
+       * then used as the cursors of the scatter below */
+      uint16_t *seg = (uint16_t *)(hand + P.H.seg);
+      uint32_t run = 0;
+      for (uint32_t base = 0; base <= nKeys; base += 32u) {
+        const uint32_t k = base + lane;
+        const uint32_t n = (k < nKeys) ? h16[k] : 0u;
+        uint32_t inc = n;
+#pragma unroll
+        for (uint32_t o = 1; o < 32u; o <<= 1) {
+          const uint32_t up = __shfl_up_sync(0xffffffffu, inc, o);
+          if (lane >= o) inc += up;
+        }
+        const uint32_t ex = run + inc - n;
+        __syncwarp();
+        if (k <= nKeys) {
+          h16[k] = (uint16_t)ex;
+          seg[k] = (uint16_t)ex;
+        }
+        run += __shfl_sync(0xffffffffu, inc, 31);
+      }
+      nVisits = run;
+      __syncwarp();
+      /* permute the visit operands from pool-rank order into schedule order */
+      const float4 *in0 = (const float4 *)(hand + P.H.vrec), *in1 = in0 + PX_VCAP(MM), *in2 = in1 + PX_VCAP(MM);
+      float4 *out0 = (float4 *)(hand + P.H.stream), *out1 = out0 + PX_VCAP(MM), *out2 = out1 + PX_VCAP(MM);
+      for (uint32_t base = 0; base < 2u * M; base += 32u) {
+        const uint32_t v = base + lane, r = v >> 1, ci = v & 1u;
+        if (r < M && ci < ((__ldg(gA + r) >> 13) & 3u)) {
+          const uint32_t tau = (uint32_t)tlev[r] + ci, q = tau / II, key = (tau - q * II) * QN + q;
+          const uint32_t old = atomicAdd(&h32[key >> 1], (key & 1u) ? 0x10000u : 1u);
+          const uint32_t pos = (key & 1u) ? old >> 16 : old & 0xffffu;
+          const float4 a = in0[v], b = in1[v], c = in2[v];
+          out0[pos] = a;
+          out1[pos] = b;
+          out2[pos] = c;
+        }
+      }
+      if (prof && lane == 0) prof[14] += (unsigned long long)(clock64() - t0);
+    }
+    if (lane == 0) {
+      sc[PX_HS_PERIOD] = II;
+      sc[PX_HS_PHASES] = QN;
+      sc[PX_HS_DEPTH] = depth;
+      sc[PX_HS_VISITS] = nVisits;
+    }
+    __syncwarp(); /* the next world's tables overwrite this one's */
+  }
+}
+
+/* ======================================================================= replay kernel ==== */
+/*
+ * Split pipeline, phase E with the static schedule (buildStaticSchedule): ONE warp per world replays the periodic
+ * schedule.  Round R is slot R mod II of the period; the visits alive in it -- phases q with 0 <= R div II - q <
+ * iterations -- are one contiguous segment of the visit stream, processed 32 at a time, one contact per lane.
+ * The stream (three coalesced float4 planes in the hand-over record) holds everything frozen during the solve, so
+ * a visit costs three coalesced global loads, two velocity gathers and two mass gathers from shared memory and two
+ * predicated velocity stores; there is no scheduler, no atomics and no second warp.  Shared memory per world is
+ * the velocity and mass rows only (6.2 KB at 260 bodies), so residency is bound by registers and the dependent chains
+ * of twenty-odd worlds per SM interleave.  The next chunk's operands are in flight while the current one computes.
+ */
+#ifndef PX_REPLAY_MINB
+#define PX_REPLAY_MINB 20
+#endif
+__device__ __forceinline__ float2 lds64(uint32_t a) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
+  return v;
+}
+__global__ void __launch_bounds__(PX_REPLAY_THREADS, PX_REPLAY_MINB) pxReplayKernel(const PxStepParams P) {
+  extern __shared__ __align__(16) uint8_t smemRaw[];
+  const PxBatchLayout &L = P.L;
+  const uint32_t D = L.maxDynamic, S = L.maxStatic, MM = L.maxManifolds;
+  const uint32_t lane = threadIdx.x;
+  float4 *bodyV = (float4 *)(smemRaw + P.solveS.bodyV);
+  float2 *bodyM = (float2 *)(smemRaw + P.solveS.bodyM);
+  const uint32_t aBodyV = sAddr(bodyV), aBodyM = sAddr(bodyM);
+  const float eps = L.epsilon;
+  for (;;) {
+    uint32_t world = 0;
+    if (lane == 0) world = atomicAdd(P.worldCounter, 1u);
+    world = __shfl_sync(0xffffffffu, world, 0);
+    if (world >= L.nWorlds) break;
+    uint8_t *gmut = P.mut + (size_t)world * L.mutStride;
+    const uint8_t *gimm = P.imm + (size_t)world * L.immStride;
+    const uint8_t *hand = P.hand + (size_t)world * P.H.stride;
+    float *gdyn = (float *)(gmut + L.offDyn);
+    const uint32_t iterations = ((const PxWorldHeader *)(gmut + L.offHeader))->iterations & 255u;
+    const uint32_t *sc = (const uint32_t *)(hand + P.H.scalars);
+    const uint32_t M = min(sc[PX_HS_M], MM), II = sc[PX_HS_PERIOD], QN = sc[PX_HS_PHASES], depth = sc[PX_HS_DEPTH];
+    const uint32_t nVisits = sc[PX_HS_VISITS];
+    if (M && iterations && II && nVisits) { /* uniform: nothing to solve otherwise */
+      const float *gc = (const float *)(gimm + L.offDynConst);
+      for (uint32_t x = lane; x < D; x += PX_REPLAY_THREADS) {
+        bodyV[x] = make_float4(gdyn[PX_DYN_VX * D + x], gdyn[PX_DYN_VY * D + x], gdyn[PX_DYN_AV * D + x], 0.0f);
+        bodyM[x] = make_float2(gc[PX_DYNC_IMASS * D + x], gc[PX_DYNC_IINERTIA * D + x]);
+      }
+      for (uint32_t q = lane; q < S; q += PX_REPLAY_THREADS) {
+        bodyV[D + q] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        bodyM[D + q] = make_float2(0.0f, 0.0f);
+      }
+      __syncwarp();
+      long long t0 = 0;
+      unsigned long long *prof = P.prof ? P.prof + (size_t)world * PX_PROF_SLOTS : nullptr;
+      if (prof && lane == 0) t0 = clock64();
+
+      const uint16_t *seg = (const uint16_t *)(hand + P.H.seg);
+      const float4 *pl0 = (const float4 *)(hand + P.H.stream), *pl1 = pl0 + PX_VCAP(MM), *pl2 = pl1 + PX_VCAP(MM);
+      const uint32_t nR = depth + (iterations - 1u) * II;
+      /* chunk iterator (warp-uniform): [beg, end) = the unprocessed visits of round R = Q * II + slot */
+      uint32_t R = 0, slot = 0, Q = 0, beg = 0, end = 0;
+      auto loadRound = [&]() {
+        const uint32_t qlo = Q + 1u > iterations ? Q + 1u - iterations : 0u, qhi = min(Q, QN - 1u);
+        if (qlo <= qhi) {
+          beg = __ldg(seg + slot * QN + qlo);
+          end = __ldg(seg + slot * QN + qhi + 1u);
+        } else {
+          beg = end = 0;
+        }
+      };
+      auto nextChunk = [&](uint32_t &base, uint32_t &cnt) {
+        while (beg >= end) {
+          if (++R >= nR) {
+            base = cnt = 0;
+            return;
+          }
+          if (++slot == II) {
+            slot = 0;
+            Q++;
+          }
+          loadRound();
+        }
+        base = beg;
+        cnt = min(32u, end - beg);
+        beg += cnt;
+      };
+      loadRound();
+      uint32_t b0, c0, chunks = 0, visits = 0;
+      nextChunk(b0, c0);
+      float4 r0, r1, r2;
+      {
+        const uint32_t idx = b0 + min(lane, c0 ? c0 - 1u : 0u);
+        r0 = ldgPinned(pl0 + idx);
+        r1 = ldgPinned(pl1 + idx);
+        r2 = ldgPinned(pl2 + idx);
+      }
+      while (c0) {
+        uint32_t b1, c1;
+        nextChunk(b1, c1);
+        /* idle lanes repeat the chunk's last visit and store nothing; past the end: entry 0, discarded */
+        const uint32_t idx = b1 + min(lane, c1 ? c1 - 1u : 0u);
+        const float4 n0 = ldgPinned(pl0 + idx), n1 = ldgPinned(pl1 + idx), n2 = ldgPinned(pl2 + idx);
+        const uint32_t ids = __float_as_uint(r2.z);
+        const uint32_t a16 = (ids & 0xffu) * 16u, b16 = ((ids >> 8) & 0x1ffu) * 16u;
+        const bool bdyn = ((ids >> 17) & 1u) != 0, active = lane < c0;
+        float4 vA = lds128(aBodyV + a16), vB = lds128(aBodyV + b16);
+        const float2 mA = lds64(aBodyM + (a16 >> 1)), mB = lds64(aBodyM + (b16 >> 1));
+        contactImpulseCore(v2(r0.x, r0.y), v2(r0.z, r0.w), v2(r1.x, r1.y), r1.w, r2.x, r2.y, r1.z, mA.x, mA.y, mB.x, mB.y, bdyn, vA,
+                           vB, eps);
+        sts128If(aBodyV + a16, vA, active);
+        sts128If(aBodyV + b16, vB, active && bdyn);
+        __syncwarp();
+        visits += c0;
+        chunks++;
+        r0 = n0;
+        r1 = n1;
+        r2 = n2;
+        c0 = c1;
+      }
+      if (prof && lane == 0) {
+        prof[4] += (unsigned long long)(clock64() - t0);
+        prof[6] += chunks;
+      }
+      for (uint32_t x = lane; x < D; x += PX_REPLAY_THREADS) {
+        const float4 bv = bodyV[x];
+        gdyn[PX_DYN_VX * D + x] = bv.x;
+        gdyn[PX_DYN_VY * D + x] = bv.y;
+        gdyn[PX_DYN_AV * D + x] = bv.z;
+      }
+      if (lane == 0 && visits != nVisits * iterations) {
+        PxWorldHeader *wh = (PxWorldHeader *)(gmut + L.offHeader);
+        wh->statOverflow |= PX_OVERFLOW_INTERNAL;
+      }
+    }
+    __syncwarp(); /* the next world's load overwrites what the store above still reads */
+  }
+}
+
 /* ------------------------------------------------------------------- control commands */
 /* One thread per world applies that world's queued API calls in submission order, merged
  * with the batch-wide (PX_ALL_WORLDS) calls by sequence number. */
@@ -2004,7 +2376,7 @@ extern "C" int pxLaunchRsqrtSweep(unsigned long long *sums, void *stream) {
 /* ---------------------------------------------------------------------- host launchers */
 static uint32_t alignUp(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
 
-extern "C" void pxPlanSmem(const PxBatchLayout *L, int vertsInSmem, PxSmemPlan *S) {
+extern "C" void pxPlanSmem(const PxBatchLayout *L, int vertsInSmem, int staticSolver, PxSmemPlan *S) {
   const uint32_t D = L->maxDynamic, St = L->maxStatic, NB = D + St, V = L->maxVertices;
   const uint32_t MM = L->maxManifolds, MP = L->maxPairs;
   uint32_t o = 0;
@@ -2037,7 +2409,16 @@ extern "C" void pxPlanSmem(const PxBatchLayout *L, int vertsInSmem, PxSmemPlan *
   S->verts = vertsInSmem ? take(V * 16) : 0;
   const uint32_t rxEnd = o;
   o = rx;
-  S->list = take(2 * MM * 2); S->nextw = take(2 * MM * 2); S->sig = take(MM * 4); S->queue = take((qcap + 4) * 4); /* + the dummy sink at [qcap] */
+  S->list = take(2 * MM * 2);
+  const uint32_t ry = o;
+  S->nextw = take(2 * MM * 2); S->sig = take(MM * 4); S->queue = take((qcap + 4) * 4); /* + the dummy sink at [qcap] */
+  const uint32_t ryEnd = o;
+  S->predA = S->predB = S->rankOf = S->tlev = S->khist = S->bodyM = 0;
+  if (staticSolver) { /* region Y': the rings in pool-rank space take the place of the dynamic solver's tables */
+    o = ry;
+    S->predA = take(MM * 2); S->predB = take(MM * 2); S->rankOf = take(MM * 2);
+  }
+  o = o > ryEnd ? o : ryEnd;
   o = o > rxEnd ? o : rxEnd;
   S->total = o;
 }
@@ -2123,12 +2504,20 @@ extern "C" void pxPlanHandover(const PxBatchLayout *L, const PxSmemPlan *S, PxHa
   H->mids = take(MM * 4); H->nextw = take(2 * MM * 2); H->sig = take(MM * 4); H->queue = take((S->qcap + 4) * 4);
   H->list = take(2 * MM * 2); H->listStart = take((D + 1) * 2); H->cnt = take(D * 2); H->cntB = take(D * 2);
   H->posOf = take(D); H->restFlag = take(D); H->wakeFlag = take(D);
-  H->scalars = take(16);
+  H->scalars = take(32);
   H->records = take(MM * 3 * 16);
+  H->stream = H->seg = 0;
+  H->predA = H->predB = H->vrec = 0;
+  if (S->rankOf) { /* static schedule */
+    H->stream = take(3 * PX_VCAP(MM) * 16);
+    H->seg = take((PX_KCAP(MM) + 2) * 2);
+    H->predA = take(MM * 2); H->predB = take(MM * 2);
+    H->vrec = take(3 * PX_VCAP(MM) * 16);
+  }
   H->stride = alignUp(o, 128);
 }
 
-extern "C" void pxPlanSolveSmem(const PxBatchLayout *L, const PxSmemPlan *S, PxSmemPlan *out) {
+extern "C" void pxPlanSolveSmem(const PxBatchLayout *L, const PxSmemPlan *S, int staticSolver, PxSmemPlan *out) {
   const uint32_t NB = L->maxDynamic + L->maxStatic, MM = L->maxManifolds;
   memset(out, 0, sizeof(*out));
   uint32_t o = 0;
@@ -2137,6 +2526,12 @@ extern "C" void pxPlanSolveSmem(const PxBatchLayout *L, const PxSmemPlan *S, PxS
     o += alignUp(bytes, 16);
     return at;
   };
+  if (staticSolver) { /* pxReplayKernel: velocity and mass rows only */
+    out->bodyV = take(NB * 16); out->bodyM = take(NB * 8);
+    out->qcap = S->qcap;
+    out->total = o;
+    return;
+  }
   out->bodyP = take(NB * 16); out->bodyV = take(NB * 16);
   out->hdr = take(sizeof(PxWorldHeader)); out->misc = take(32 * 4);
   out->mids = take(MM * 4 + 16); out->nextw = take(2 * MM * 2 + 16); out->sig = take(MM * 4 + 16);
@@ -2160,8 +2555,71 @@ static cudaError_t configureSolve() {
   return cudaSuccess;
 }
 
+extern "C" void pxPlanSchedSmem(const PxBatchLayout *L, PxSmemPlan *out) {
+  const uint32_t MM = L->maxManifolds;
+  memset(out, 0, sizeof(*out));
+  out->tlev = 0;
+  out->khist = alignUp(MM * 2, 16);
+  out->total = out->khist + alignUp((PX_KCAP(MM) + 2) * 2, 16);
+}
+
+static cudaError_t configureSched() {
+  static bool done[64] = {};
+  int dev = 0;
+  cudaError_t err = cudaGetDevice(&dev);
+  if (err != cudaSuccess) return err;
+  if (dev >= 0 && dev < 64 && done[dev]) return cudaSuccess;
+  int optin = 0;
+  err = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  if (err != cudaSuccess) return err;
+  err = cudaFuncSetAttribute(pxSchedKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+  if (err != cudaSuccess) return err;
+  err = cudaFuncSetAttribute(pxSchedKernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  if (err != cudaSuccess) return err;
+  if (dev >= 0 && dev < 64) done[dev] = true;
+  return cudaSuccess;
+}
+
+extern "C" int pxLaunchSched(const PxStepParams *P, uint32_t grid, void *stream) {
+  if (grid == 0) return (int)cudaErrorInvalidValue;
+  cudaError_t err = configureSched();
+  if (err != cudaSuccess) return (int)err;
+  pxSchedKernel<<<grid, PX_SCHED_THREADS, P->schedS.total, (cudaStream_t)stream>>>(*P);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int pxSchedOccupancy(const PxStepParams *P, int *ctasPerSm) {
+  cudaError_t err = configureSched();
+  if (err != cudaSuccess) return (int)err;
+  return (int)cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctasPerSm, pxSchedKernel, PX_SCHED_THREADS, P->schedS.total);
+}
+
+static cudaError_t configureReplay() {
+  static bool done[64] = {};
+  int dev = 0;
+  cudaError_t err = cudaGetDevice(&dev);
+  if (err != cudaSuccess) return err;
+  if (dev >= 0 && dev < 64 && done[dev]) return cudaSuccess;
+  int optin = 0;
+  err = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  if (err != cudaSuccess) return err;
+  err = cudaFuncSetAttribute(pxReplayKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+  if (err != cudaSuccess) return err;
+  /* many small CTAs: ask for the largest shared-memory carve-out, or the default split caps residency */
+  err = cudaFuncSetAttribute(pxReplayKernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  if (err != cudaSuccess) return err;
+  if (dev >= 0 && dev < 64) done[dev] = true;
+  return cudaSuccess;
+}
+
 extern "C" int pxLaunchSolve(const PxStepParams *P, uint32_t grid, void *stream) {
   if (grid == 0) return (int)cudaErrorInvalidValue;
+  if (P->solver == PX_SOLVER_STATIC) {
+    cudaError_t err = configureReplay();
+    if (err != cudaSuccess) return (int)err;
+    pxReplayKernel<<<grid, PX_REPLAY_THREADS, P->solveS.total, (cudaStream_t)stream>>>(*P);
+    return (int)cudaGetLastError();
+  }
   cudaError_t err = configureSolve();
   if (err != cudaSuccess) return (int)err;
   pxSolveKernel<<<grid, PX_SOLVE_THREADS, P->solveS.total, (cudaStream_t)stream>>>(*P);
@@ -2169,6 +2627,11 @@ extern "C" int pxLaunchSolve(const PxStepParams *P, uint32_t grid, void *stream)
 }
 
 extern "C" int pxSolveOccupancy(const PxStepParams *P, int *ctasPerSm) {
+  if (P->solver == PX_SOLVER_STATIC) {
+    cudaError_t err = configureReplay();
+    if (err != cudaSuccess) return (int)err;
+    return (int)cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctasPerSm, pxReplayKernel, PX_REPLAY_THREADS, P->solveS.total);
+  }
   cudaError_t err = configureSolve();
   if (err != cudaSuccess) return (int)err;
   return (int)cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctasPerSm, pxSolveKernel, PX_SOLVE_THREADS, P->solveS.total);

@@ -40,10 +40,22 @@ struct PxSmemPlan {
   uint32_t nextw; /* u16[2*MM] successor of manifold ms on side s: slot | successor has a dynamic B << 14 | side << 15 */
   uint32_t sig;   /* u32[MM]   signals received: A side low half, B side high half */
   uint32_t queue; /* u32[QCAP] ready ring of rich manifold words */
+  /* region Y' (static schedule, split pipeline): overlays nextw / sig / queue, which only the dynamic solver uses */
+  uint32_t predA, predB; /* u16[MM] BY POOL RANK: predecessor of the manifold in its A / B body's ring: rank | closes the ring << 10 |
+                            contacts of the predecessor << 11 | own contacts << 13 (0xffff: static B) */
+  uint32_t rankOf;       /* u16[MM] pool rank by manifold slot */
+  /* pxSchedKernel only */
+  uint32_t tlev;         /* u16[MM] start round of the manifold's first contact inside one iteration, by rank */
+  uint32_t khist;        /* u16[KCAP + 2] visits per (slot, phase) key, then their exclusive prefix = segment starts / cursors */
+  uint32_t bodyM;        /* replay kernel only: float2[NB] {inverse mass, inverse inertia} */
   uint32_t total; /* bytes */
   uint32_t qcap;  /* ring capacity (power of two >= MM) */
   uint32_t vertsInSmem;
 };
+/* static schedule: contact visits per world <= 2 * maxManifolds; (slot, phase) keys <= depth + period <= 4 * maxManifolds + margin */
+#define PX_VCAP(MM) (2u * (MM))
+#define PX_KCAP(MM) (4u * (MM) + 16u)
+#define PX_II_MARGIN 2u /* period tried first = longest body ring + this (profiles/sched_sim.py: on settled 252-body piles the least feasible period is ring + 0..5, ring + 2 on average; every extra round of period costs iterations - 1 replay rounds, a failed attempt costs a relaxation run to its cap) */
 
 /* A world's hand-over record in global memory (split pipeline): byte offsets of what the sweep
  * kernel leaves for the solver kernel and for the phase F that follows it.  Laid out by
@@ -51,13 +63,22 @@ struct PxSmemPlan {
 struct PxHandLayout {
   uint32_t mids, nextw, sig, queue;                              /* solver inputs */
   uint32_t list, listStart, cnt, cntB, posOf, restFlag, wakeFlag; /* phase F inputs */
-  uint32_t scalars;                                               /* u32[4]: manifolds, ready visits */
+  uint32_t scalars;                                               /* u32[8]: manifolds, ready visits | period, phases, depth, contact visits, longest ring */
   uint32_t records;                                               /* float4[3][maxManifolds] manifold records */
+  /* static schedule: the contact visits of ONE iteration sorted by (round mod period, round div period), as three
+   * float4 planes of PX_VCAP entries {n, ra | rb, rcpDenom, e | sf, df, ids, -}, and the segment starts by key */
+  uint32_t stream, seg;
+  uint32_t predA, predB; /* u16[maxManifolds] rings by pool rank (PxSmemPlan.predA) */
+  uint32_t vrec;         /* the visit operands by pool rank (entry 2 * rank + contact), same three planes as `stream` */
   uint32_t stride;
 };
 enum { PX_MODE_FUSED = 0, PX_MODE_SWEEP = 1 };
+enum { PX_SOLVER_DYNAMIC = 0, PX_SOLVER_STATIC = 1 };
+enum { PX_HS_M = 0, PX_HS_READY = 1, PX_HS_PERIOD = 2, PX_HS_PHASES = 3, PX_HS_DEPTH = 4, PX_HS_VISITS = 5, PX_HS_RING = 6 };
 
-#define PX_PROF_SLOTS 16 /* 0-5 phases A-F, 6 solver rounds, 7 polygon pairs << 32 | after quick reject, 8-11 narrowphase stages */
+#define PX_PROF_SLOTS 16 /* 0-5 phases A-F, 6 solver rounds, 7 polygon pairs << 32 | after quick reject, 8-11 narrowphase stages,
+                            12 static schedule (end of phase D), 13 relaxation votes << 32 | period, 14 sort + stream build cycles,
+                            15 relaxation cycles */
 
 struct PxStepParams {
   PxBatchLayout L;
@@ -79,10 +100,12 @@ struct PxStepParams {
   /* split pipeline: pxStepKernel in PX_MODE_SWEEP does [phase F of the previous substep] + [phases
    * A-D of the next], pxSolveKernel does phase E in between */
   uint32_t mode;
+  uint32_t solver; /* split pipeline: PX_SOLVER_DYNAMIC (pxSolveKernel) or PX_SOLVER_STATIC (schedule built in phase D, pxReplayKernel) */
   uint32_t doFinish, doSweep, traceNow;
   uint8_t *hand; /* hand-over records, one per world, H.stride apart */
   PxHandLayout H;
-  PxSmemPlan solveS; /* shared memory of pxSolveKernel (bodyP, bodyV, mids, nextw, sig, queue, misc, hdr) */
+  PxSmemPlan solveS; /* shared memory of pxSolveKernel (bodyP, bodyV, mids, nextw, sig, queue, misc, hdr) or pxReplayKernel (bodyV, bodyM) */
+  PxSmemPlan schedS; /* shared memory of pxSchedKernel (tlev, khist) */
 };
 
 
@@ -90,7 +113,7 @@ struct PxStepParams {
 extern "C" {
 #endif
 /* vertsInSmem: 1 keeps the polygon vertex pool in shared memory, 0 reads it through L1 */
-void pxPlanSmem(const PxBatchLayout *L, int vertsInSmem, PxSmemPlan *S);
+void pxPlanSmem(const PxBatchLayout *L, int vertsInSmem, int staticSolver, PxSmemPlan *S);
 /* launches the step kernel: `grid` persistent CTAs (<= resident capacity, <= scratch slots) work
  * through all worlds of the layout; returns cudaError_t as int */
 int pxLaunchStep(const PxStepParams *P, uint32_t threads, uint32_t grid, void *stream);
@@ -98,10 +121,15 @@ int pxLaunchStep(const PxStepParams *P, uint32_t threads, uint32_t grid, void *s
 int pxStepOccupancy(const PxStepParams *P, uint32_t threads, int *ctasPerSm);
 /* split pipeline: hand-over layout, the solver kernel's shared-memory plan, its launch and occupancy */
 void pxPlanHandover(const PxBatchLayout *L, const PxSmemPlan *S, PxHandLayout *H);
-void pxPlanSolveSmem(const PxBatchLayout *L, const PxSmemPlan *S, PxSmemPlan *out);
+void pxPlanSolveSmem(const PxBatchLayout *L, const PxSmemPlan *S, int staticSolver, PxSmemPlan *out);
 int pxLaunchSolve(const PxStepParams *P, uint32_t grid, void *stream);
 int pxSolveOccupancy(const PxStepParams *P, int *ctasPerSm);
-#define PX_SOLVE_THREADS 64u /* scheduler warp + math warp */
+#define PX_SOLVE_THREADS 64u  /* dynamic solver: scheduler warp + math warp */
+#define PX_REPLAY_THREADS 32u /* static solver: one warp replays the world's schedule */
+#define PX_SCHED_THREADS 32u  /* static solver: one warp derives the world's schedule */
+void pxPlanSchedSmem(const PxBatchLayout *L, PxSmemPlan *out);
+int pxLaunchSched(const PxStepParams *P, uint32_t grid, void *stream);
+int pxSchedOccupancy(const PxStepParams *P, int *ctasPerSm);
 
 /* control path: one command = one API call (px_batch.h "control path") */
 struct PxCommand {

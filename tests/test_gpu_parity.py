@@ -223,14 +223,45 @@ def test_maximum_body_count():
     side_by_side([scenes.pile_scene(w, mix="mixed", n_dynamic=255) for w in range(2)], substeps=300, check_every=10)
 
 
+@pytest.mark.parametrize("solver", ["static", "dynamic"])
 @pytest.mark.parametrize("mix,unit,fused,threads", [("mixed", 1.0, 1, 256), ("mixed", 1000.0, 5, 128), ("circles", 1.0, 8, 256),
                                                     ("polygons", 100.0, 5, 256)])
-def test_split_pipeline_every_substep(mix, unit, fused, threads):
+def test_split_pipeline_every_substep(mix, unit, fused, threads, solver):
     """The split pipeline (sweep kernel | solver kernel per substep, hand-over records in global
-    memory) forced on small batches: pair lists, manifolds and state against the oracle."""
+    memory) forced on small batches, with both of its solvers -- the replayed periodic schedule
+    (default) and the dataflow scheduler kernel: pair lists, manifolds and state against the oracle."""
+    flags = pxb.FLAG_SPLIT | (pxb.FLAG_DYNAMIC_SOLVER if solver == "dynamic" else 0)
     stats = side_by_side([scenes.pile_scene(w, mix=mix, unit=unit) for w in range(3)], substeps=400, k=fused,
-                         threads=threads, flags=pxb.FLAG_SPLIT, check_every=1 if fused == 1 else 2)
+                         threads=threads, flags=flags, check_every=1 if fused == 1 else 2)
     assert stats["manifolds"].min() > 100
+
+
+@pytest.mark.parametrize("iterations", [0, 1, 2, 8, 20, 255])
+def test_static_schedule_iteration_counts(iterations):
+    """The replayed schedule at every iteration count the API allows (uint8): 0 (no solve), 1 (only the prologue of
+    the period), 255 (254 periods), on full-size 252-body worlds."""
+    sc = [scenes.pile_scene(w, mix="mixed", n_dynamic=252, iterations=iterations) for w in range(2)]
+    side_by_side(sc, substeps=120 if iterations < 255 else 40, k=5, flags=pxb.FLAG_SPLIT, check_every=5)
+
+
+def test_static_schedule_stacks_ragged_worlds_and_overflow():
+    """Worlds the schedule builder must cope with: tall polygon stacks (one long dependency chain: deep
+    iterations, short periods), a ragged batch with an empty world and a single-body world (no manifolds: nothing
+    to schedule), and a world whose manifold capacity overflows (the kept manifolds still form consistent rings:
+    the replay's visit count adds up, bit 31 stays clear)."""
+    sc = [scenes.stack_scene(w, n_dynamic=40 + 30 * w) for w in range(3)]
+    side_by_side(sc, substeps=300, k=1, flags=pxb.FLAG_SPLIT, check_every=3)
+    sc = [scenes.pile_scene(0, mix="mixed", n_dynamic=200, cols=16), scenes.pile_scene(1, mix="circles", n_dynamic=0),
+          scenes.pile_scene(2, mix="circles", n_dynamic=1, cols=1), scenes.pile_scene(3, mix="polygons", n_dynamic=64, cols=8)]
+    side_by_side(sc, substeps=200, k=5, flags=pxb.FLAG_SPLIT, check_every=5)
+    worlds = pxb.HostWorlds([scenes.pile_scene(0, mix="circles", n_dynamic=60, cols=8)])
+    b = pxb.Batch(worlds, flags=pxb.FLAG_SPLIT, max_manifolds=32)
+    for _ in range(8):
+        b.step(50)
+    flags = int(b.download_blocks().header[0]["statOverflow"])
+    assert flags & pxb.OVERFLOW_MANIFOLDS and not flags & 0x80000000
+    b.close()
+    worlds.close()
 
 
 def test_split_and_fused_pipelines_agree_on_a_large_batch():
