@@ -480,8 +480,8 @@ def run_ours(args):
                 **({"host_cpus_per_rank_numa_local": numa_cpus} if numa_cpus else {}),
                 "body_frame_steps_per_sec": value / 5.0, "l2": "inputs larger than L2 (state > 126 MB per GPU)"
                 if args.worlds * (b.L.mutStride + b.L.immStride) > 126e6 else "inputs smaller than L2",
-                "pipeline": (("split: sweep kernel (phase F of the previous substep + phases A-D), schedule kernel (the substep's "
-                              "periodic visit schedule) and replay kernel per substep" if pipe.get("static_schedule") else
+                "pipeline": (("split: sweep kernel (phase F of the previous substep + phases A-D) and solver kernel (derives the "
+                              "substep's periodic visit schedule, then replays it per iteration) per substep" if pipe.get("static_schedule") else
                               "split: sweep kernel (phase F of the previous substep + phases A-D) and dataflow-solver kernel per substep")
                              if pipe["split"] else "fused: one kernel, K substeps"),
                 "threads_per_world_cta": info["threads"], "ctas_per_sm": info["ctas_per_sm"],

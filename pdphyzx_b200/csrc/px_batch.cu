@@ -40,10 +40,10 @@ struct PxBatch {
   bool split;
   bool staticSched;    /* split pipeline: the sweep kernel derives a periodic visit schedule, pxReplayKernel replays it */
   PxHandLayout hand;
-  PxSmemPlan solvePlan, schedPlan;
+  PxSmemPlan solvePlan;
   uint8_t *dHand;      /* hand-over records, one per world */
-  uint32_t gridSolve, gridSched;
-  int solveCtasPerSm, schedCtasPerSm;
+  uint32_t gridSolve;
+  int solveCtasPerSm;
 
   uint8_t *hMut, *hImm; /* pinned staging, same layout */
   float sinTable[256];
@@ -99,8 +99,8 @@ extern "C" PxBatch *pxBatchCreate(uint32_t nWorlds, const PxBatchDesc *desc) {
   b->split = false;
   b->staticSched = false;
   b->dHand = nullptr;
-  b->gridSolve = b->gridSched = 0;
-  b->solveCtasPerSm = b->schedCtasPerSm = 0;
+  b->gridSolve = 0;
+  b->solveCtasPerSm = 0;
 
   b->hMut = b->hImm = nullptr;
   b->dCmds = b->dGlobal = nullptr;
@@ -246,16 +246,6 @@ extern "C" PxBatch *pxBatchCreate(uint32_t nWorlds, const PxBatchDesc *desc) {
       b->solveCtasPerSm = socc;
       const uint64_t scap = (uint64_t)socc * (uint64_t)b->numSms;
       b->gridSolve = (uint32_t)(scap < nWorlds ? scap : nWorlds);
-      if (b->staticSched) {
-        pxPlanSchedSmem(&b->L, &b->schedPlan);
-        P.schedS = b->schedPlan;
-        int kocc = 0;
-        rc = pxSchedOccupancy(&P, &kocc);
-        if (rc != 0 || kocc < 1) return fail("occupancy query of the schedule kernel", (cudaError_t)(rc ? rc : (int)cudaErrorLaunchOutOfResources));
-        b->schedCtasPerSm = kocc;
-        const uint64_t kcap = (uint64_t)kocc * (uint64_t)b->numSms;
-        b->gridSched = (uint32_t)(kcap < nWorlds ? kcap : nWorlds);
-      }
       const size_t handBytes = (size_t)nWorlds * b->hand.stride;
       if ((e = cudaMalloc(&b->dHand, handBytes)) != cudaSuccess) return fail("cudaMalloc(hand-over records)", e);
       if ((e = cudaMemsetAsync(b->dHand, 0, handBytes, b->stream)) != cudaSuccess) return fail("cudaMemset", e);
@@ -622,7 +612,6 @@ static void splitParams(PxBatch *b, uint32_t first, PxStepParams *P) {
   P->hand = b->dHand + (size_t)first * b->hand.stride;
   P->H = b->hand;
   P->solveS = b->solvePlan;
-  P->schedS = b->schedPlan;
 }
 
 /* launch s of the split pipeline's sweep kernel: phase F of substep s - 1 (s > 0), phases A-D of substep s (s < K) */
@@ -634,16 +623,6 @@ static int launchSweep(PxBatch *b, PxStepParams *P, uint32_t s, uint32_t kSubste
   CU(cudaMemsetAsync(P->worldCounter, 0, sizeof(uint32_t), stream));
   int rc = pxLaunchStep(P, b->threads, grid, stream);
   if (rc != 0) return pxSetError(-rc - 1000, "sweep kernel launch: %s", cudaGetErrorString((cudaError_t)rc));
-  b->launches++;
-  return 0;
-}
-
-/* static solver: the schedule kernel between the sweep kernel and the replay kernel */
-static int launchSched(PxBatch *b, PxStepParams *P, uint32_t grid, cudaStream_t stream) {
-  P->worldCounter = b->dCounters + (b->launches % PX_COUNTER_RING);
-  CU(cudaMemsetAsync(P->worldCounter, 0, sizeof(uint32_t), stream));
-  int rc = pxLaunchSched(P, grid, stream);
-  if (rc != 0) return pxSetError(-rc - 1000, "schedule kernel launch: %s", cudaGetErrorString((cudaError_t)rc));
   b->launches++;
   return 0;
 }
@@ -676,10 +655,8 @@ static int launchRange(PxBatch *b, uint32_t kSubsteps, uint32_t first, uint32_t 
   /* split pipeline: sweep(A-D) | solve | sweep(F, A-D) | solve | ... | sweep(F) */
   splitParams(b, first, &P);
   const uint32_t gridSweep = n < b->gridMax ? n : b->gridMax, gridSolve = n < b->gridSolve ? n : b->gridSolve;
-  const uint32_t gridSched = n < b->gridSched ? n : b->gridSched;
   for (uint32_t s = 0; s <= kSubsteps; s++) {
     if (launchSweep(b, &P, s, kSubsteps, gridSweep, stream)) return -1;
-    if (s < kSubsteps && b->staticSched && launchSched(b, &P, gridSched, stream)) return -1;
     if (s < kSubsteps && launchSolve(b, &P, gridSolve, stream)) return -1;
   }
   return 0;
@@ -776,7 +753,7 @@ extern "C" int pxBatchTimerStop(PxBatch *b, float *ms) {
 
 /* One step with every kernel launch bracketed by CUDA events: device time per kernel class.
  * ms[c] / n[c] = summed durations and number of the launches of class c: 0 sweep (or the one fused launch),
- * 1 schedule kernel (static solver only), 2 solver (dataflow or replay).  Blocks. */
+ * 1 reserved (a kernel between the two; none at present), 2 solver (dataflow or schedule + replay).  Blocks. */
 extern "C" int pxBatchStepTimedKernels(PxBatch *b, uint32_t kSubsteps, float ms[3], uint32_t n[3]) {
   if (!b || !ms || !n) return pxSetError(-1, "pxBatchStepTimedKernels: NULL argument");
   if (useDevice(b)) return -1;
@@ -807,10 +784,8 @@ extern "C" int pxBatchStepTimedKernels(PxBatch *b, uint32_t kSubsteps, float ms[
   } else {
     splitParams(b, 0, &P);
     const uint32_t gridSweep = W < b->gridMax ? W : b->gridMax, gridSolve = W < b->gridSolve ? W : b->gridSolve;
-    const uint32_t gridSched = W < b->gridSched ? W : b->gridSched;
     for (uint32_t s = 0; s <= kSubsteps; s++) {
       if (launchSweep(b, &P, s, kSubsteps, gridSweep, b->stream) || mark(0)) return -1;
-      if (s < kSubsteps && b->staticSched && (launchSched(b, &P, gridSched, b->stream) || mark(1))) return -1;
       if (s < kSubsteps && (launchSolve(b, &P, gridSolve, b->stream) || mark(2))) return -1;
     }
   }
@@ -831,7 +806,7 @@ extern "C" int pxBatchPipelineInfo(const PxBatch *b, int *split, int *solveCtasP
   if (!b) return pxSetError(-1, "pxBatchPipelineInfo: NULL batch");
   if (split) *split = b->split ? (b->staticSched ? 2 : 1) : 0;
   if (solveCtasPerSm) *solveCtasPerSm = b->solveCtasPerSm;
-  if (schedCtasPerSm) *schedCtasPerSm = b->schedCtasPerSm;
+  if (schedCtasPerSm) *schedCtasPerSm = 0;
   return 0;
 }
 

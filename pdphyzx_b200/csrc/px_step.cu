@@ -1538,8 +1538,8 @@ __global__ void __launch_bounds__(NT, NT == 128 ? PX_MINB128 : 3) pxStepKernel(c
     if constexpr (sweepMode) {
       if (staticSched && iterations) {
         /* static schedule: the rings in pool-rank space and, by rank, the frozen operands of every contact visit
-         * {n, ra | rb, rcpDenom, e | sf, df, ids} (entry 2 * rank + contact); pxSchedKernel orders them */
-        float4 *pl0 = (float4 *)(hand + P.H.vrec), *pl1 = pl0 + PX_VCAP(MM), *pl2 = pl1 + PX_VCAP(MM);
+         * {n, ra | rb, rcpDenom, e | sf, df, ids} (entry 2 * rank + contact); pxReplayKernel orders them */
+        float4 *pl0 = (float4 *)(hand + P.H.vrec), *pl1 = pl0 + PX_PLANE, *pl2 = pl1 + PX_PLANE;
         for (uint32_t v = tid; v < 2u * M; v += NT) {
           const uint32_t m = v >> 1, ci = v & 1u, w = s.mids[m];
           if (ci < MID_COUNT(w)) {
@@ -1893,7 +1893,7 @@ __global__ void __launch_bounds__(PX_SOLVE_THREADS, PX_SOLVE_MINB) pxSolveKernel
   }
 }
 
-/* ===================================================================== schedule kernel ==== */
+/* ===================================================================== static schedule ==== */
 /*
  * Split pipeline with the static solver: a PERIODIC schedule of the substep's contact visits, derived once per
  * substep (here) and replayed for every iteration (pxReplayKernel) -- the dataflow solver re-derives the same order
@@ -1921,8 +1921,8 @@ __global__ void __launch_bounds__(PX_SOLVE_THREADS, PX_SOLVE_MINB) pxSolveKernel
  * (H.vrec -> H.stream), so the replay reads them coalesced.  Work per world: about ten thousand warp instructions,
  * on one warp; twenty-odd worlds per SM hide its latency.
  */
-#ifndef PX_SCHED_MINB
-#define PX_SCHED_MINB 16
+#ifndef PX_REPLAY_MINB
+#define PX_REPLAY_MINB 20
 #endif
 #ifndef PX_SCHED_PASSES
 #define PX_SCHED_PASSES 8u
@@ -1933,162 +1933,171 @@ __device__ __forceinline__ uint32_t lds16(uint32_t a) {
   return v;
 }
 __device__ __forceinline__ void sts16(uint32_t a, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
-
-__global__ void __launch_bounds__(PX_SCHED_THREADS, PX_SCHED_MINB) pxSchedKernel(const PxStepParams P) {
-  extern __shared__ __align__(16) uint8_t smemRaw[];
-  const PxBatchLayout &L = P.L;
-  const uint32_t MM = L.maxManifolds, lane = threadIdx.x;
-  uint16_t *tlev = (uint16_t *)(smemRaw + P.schedS.tlev);
-  uint32_t *h32 = (uint32_t *)(smemRaw + P.schedS.khist);
-  uint16_t *h16 = (uint16_t *)h32;
-  const uint32_t aT = sAddr(tlev);
-  for (;;) {
-    uint32_t world = 0;
-    if (lane == 0) world = atomicAdd(P.worldCounter, 1u);
-    world = __shfl_sync(0xffffffffu, world, 0);
-    if (world >= L.nWorlds) break;
-    const uint8_t *gmut = P.mut + (size_t)world * L.mutStride;
-    uint8_t *hand = P.hand + (size_t)world * P.H.stride;
-    uint32_t *sc = (uint32_t *)(hand + P.H.scalars);
-    const uint32_t iterations = ((const PxWorldHeader *)(gmut + L.offHeader))->iterations & 255u;
-    const uint32_t M = min(sc[PX_HS_M], MM), ring = sc[PX_HS_RING];
-    uint32_t II = 0, QN = 0, depth = 0, nVisits = 0;
-    long long t0 = 0;
-    unsigned long long *prof = P.prof ? P.prof + (size_t)world * PX_PROF_SLOTS : nullptr;
-    if (prof && lane == 0) t0 = clock64();
-    if (M && iterations) {
-      const uint16_t *gA = (const uint16_t *)(hand + P.H.predA), *gB = (const uint16_t *)(hand + P.H.predB);
-      uint32_t passes = 0;
-      bool converged = false, sequential = false;
-      for (uint32_t attempt = 0; attempt < 5 && !converged; attempt++) {
-        II = min(attempt < 3 ? ring + (PX_II_MARGIN << attempt) : 2u * ring + 8u, 2u * MM + 8u);
-        sequential = attempt == 4;
-        const int closing = sequential ? 0x8000 : (int)II; /* dropped edges: a cost no start round can reach */
-        for (uint32_t r = lane; r < M; r += 32u) tlev[r] = 0;
-        __syncwarp();
-        for (uint32_t pass = 0; pass < (sequential ? 3u : PX_SCHED_PASSES) && !converged; pass++) {
-          bool moved = false;
-          for (uint32_t base = 0; base < M; base += 32u) {
-            const uint32_t r = base + lane;
-            const bool valid = r < M;
-            /* rank | closes the ring << 10 | predecessor's contacts << 11 | own contacts << 13; 0xffff: static B */
-            const uint32_t pa = valid ? __ldg(gA + r) : 0u, pb = valid ? __ldg(gB + r) : 0xffffu;
-            const uint32_t adA = aT + 2u * (pa & 0x3ffu), adB = aT + 2u * ((pb == 0xffffu ? pa : pb) & 0x3ffu);
-            const int addA = (int)((pa >> 11) & 3u) - ((pa & 0x400u) ? closing : 0);
-            const int addB = pb == 0xffffu ? -0x10000 : (int)((pb >> 11) & 3u) - ((pb & 0x400u) ? closing : 0);
-            int cur = valid ? (int)lds16(aT + 2u * r) : 0x7fffffff;
-            for (uint32_t it = 0; it < 34u; it++) { /* a block's inner chains: at most 31 hops unless the period is infeasible */
-              const int v = max((int)lds16(adA) + addA, (int)lds16(adB) + addB);
-              const bool up = v > cur;
-              if (up) {
-                cur = v;
-                sts16(aT + 2u * r, (uint32_t)v);
-              }
-              __syncwarp();
-              if (!__any_sync(0xffffffffu, up)) break;
-              moved = true;
-            }
-          }
-          passes++;
-          converged = !moved;
-        }
-      }
-      /* depth of one iteration; own contact count: bits 13-14 of the A word */
-      for (uint32_t base = 0; base < M; base += 32u) {
-        const uint32_t r = base + lane;
-        if (r < M) depth = max(depth, (uint32_t)tlev[r] + ((__ldg(gA + r) >> 13) & 3u));
-      }
-      depth = max(__reduce_max_sync(0xffffffffu, depth), 1u);
-      if (sequential) II = depth;
-      if (!converged && lane == 0) /* unreachable: the sequential attempt always converges */
-        ((PxWorldHeader *)(const_cast<uint8_t *>(gmut) + L.offHeader))->statOverflow |= PX_OVERFLOW_INTERNAL;
-      QN = (depth - 1u) / II + 1u;
-      const uint32_t nKeys = II * QN; /* <= depth - 1 + II < PX_KCAP */
-      if (prof && lane == 0) {
-        const long long now = clock64();
-        prof[15] += (unsigned long long)(now - t0);
-        prof[13] += ((unsigned long long)passes << 32) + II;
-      }
-      /* visits per key, two 16-bit counters per word */
-      for (uint32_t i = lane; i < (nKeys + 3u) / 2u; i += 32u) h32[i] = 0;
-      __syncwarp();
-      for (uint32_t base = 0; base < 2u * M; base += 32u) {
-        const uint32_t v = base + lane, r = v >> 1, ci = v & 1u;
-        if (r < M && ci < ((__ldg(gA + r) >> 13) & 3u)) {
-          const uint32_t tau = (uint32_t)tlev[r] + ci, q = tau / II, key = (tau - q * II) * QN + q;
-          atomicAdd(&h32[key >> 1], (key & 1u) ? 0x10000u : 1u);
-        }
-      }
-      __syncwarp();
-      /* exclusive prefix over the keys, in place: segment starts, copied out (entry nKeys = the number of visits),
-       * then used as the cursors of the scatter below */
-      uint16_t *seg = (uint16_t *)(hand + P.H.seg);
-      uint32_t run = 0;
-      for (uint32_t base = 0; base <= nKeys; base += 32u) {
-        const uint32_t k = base + lane;
-        const uint32_t n = (k < nKeys) ? h16[k] : 0u;
-        uint32_t inc = n;
-#pragma unroll
-        for (uint32_t o = 1; o < 32u; o <<= 1) {
-          const uint32_t up = __shfl_up_sync(0xffffffffu, inc, o);
-          if (lane >= o) inc += up;
-        }
-        const uint32_t ex = run + inc - n;
-        __syncwarp();
-        if (k <= nKeys) {
-          h16[k] = (uint16_t)ex;
-          seg[k] = (uint16_t)ex;
-        }
-        run += __shfl_sync(0xffffffffu, inc, 31);
-      }
-      nVisits = run;
-      __syncwarp();
-      /* permute the visit operands from pool-rank order into schedule order */
-      const float4 *in0 = (const float4 *)(hand + P.H.vrec), *in1 = in0 + PX_VCAP(MM), *in2 = in1 + PX_VCAP(MM);
-      float4 *out0 = (float4 *)(hand + P.H.stream), *out1 = out0 + PX_VCAP(MM), *out2 = out1 + PX_VCAP(MM);
-      for (uint32_t base = 0; base < 2u * M; base += 32u) {
-        const uint32_t v = base + lane, r = v >> 1, ci = v & 1u;
-        if (r < M && ci < ((__ldg(gA + r) >> 13) & 3u)) {
-          const uint32_t tau = (uint32_t)tlev[r] + ci, q = tau / II, key = (tau - q * II) * QN + q;
-          const uint32_t old = atomicAdd(&h32[key >> 1], (key & 1u) ? 0x10000u : 1u);
-          const uint32_t pos = (key & 1u) ? old >> 16 : old & 0xffffu;
-          const float4 a = in0[v], b = in1[v], c = in2[v];
-          out0[pos] = a;
-          out1[pos] = b;
-          out2[pos] = c;
-        }
-      }
-      if (prof && lane == 0) prof[14] += (unsigned long long)(clock64() - t0);
-    }
-    if (lane == 0) {
-      sc[PX_HS_PERIOD] = II;
-      sc[PX_HS_PHASES] = QN;
-      sc[PX_HS_DEPTH] = depth;
-      sc[PX_HS_VISITS] = nVisits;
-    }
-    __syncwarp(); /* the next world's tables overwrite this one's */
-  }
+/* a global load of data that is read exactly once: evicted first from L2 */
+__device__ __forceinline__ float4 ldgStream(const float4 *p) {
+  float4 v;
+  asm volatile("ld.global.cs.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
 }
-
-/* ======================================================================= replay kernel ==== */
-/*
- * Split pipeline, phase E with the static schedule (buildStaticSchedule): ONE warp per world replays the periodic
- * schedule.  Round R is slot R mod II of the period; the visits alive in it -- phases q with 0 <= R div II - q <
- * iterations -- are one contiguous segment of the visit stream, processed 32 at a time, one contact per lane.
- * The stream (three coalesced float4 planes in the hand-over record) holds everything frozen during the solve, so
- * a visit costs three coalesced global loads, two velocity gathers and two mass gathers from shared memory and two
- * predicated velocity stores; there is no scheduler, no atomics and no second warp.  Shared memory per world is
- * the velocity and mass rows only (6.2 KB at 260 bodies), so residency is bound by registers and the dependent chains
- * of twenty-odd worlds per SM interleave.  The next chunk's operands are in flight while the current one computes.
- */
-#ifndef PX_REPLAY_MINB
-#define PX_REPLAY_MINB 20
-#endif
 __device__ __forceinline__ float2 lds64(uint32_t a) {
   float2 v;
   asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
   return v;
 }
+
+/* Schedule of one world, by one warp (see above).  Shared memory: tlev u16[MM], khist u16[KCAP + 2], pred u32[MM]
+ * (A word | B word << 16).  Leaves the visit stream and the segment table in the world's hand-over record. */
+__device__ __forceinline__ void buildSchedule(const PxStepParams &P, uint8_t *smem, uint8_t *hand, const uint32_t M, const uint32_t ring,
+                                              unsigned long long *prof, uint32_t &IIout, uint32_t &QNout, uint32_t &depthOut,
+                                              uint32_t &visitsOut) {
+  const uint32_t MM = P.L.maxManifolds, lane = threadIdx.x;
+  uint16_t *tlev = (uint16_t *)(smem + P.solveS.tlev);
+  uint32_t *h32 = (uint32_t *)(smem + P.solveS.khist);
+  uint16_t *h16 = (uint16_t *)h32;
+  uint32_t *pred = (uint32_t *)(smem + P.solveS.predA);
+  const uint32_t aT = sAddr(tlev);
+  long long t0 = (prof && lane == 0) ? clock64() : 0;
+  {
+    const uint16_t *gA = (const uint16_t *)(hand + P.H.predA), *gB = (const uint16_t *)(hand + P.H.predB);
+#pragma unroll 4
+    for (uint32_t r = lane; r < M; r += 32u) pred[r] = (uint32_t)gA[r] | ((uint32_t)gB[r] << 16);
+  }
+  uint32_t II = 1, passes = 0, depth = 0;
+  bool converged = false, sequential = false;
+  for (uint32_t attempt = 0; attempt < 5 && !converged; attempt++) {
+    II = min(attempt < 3 ? ring + (PX_II_MARGIN << attempt) : 2u * ring + 8u, 2u * MM + 8u);
+    sequential = attempt == 4;
+    const int closing = sequential ? 0x8000 : (int)II; /* dropped edges: a cost no start round can reach */
+    for (uint32_t r = lane; r < M; r += 32u) tlev[r] = 0;
+    __syncwarp();
+    /* a block of 32 ranks is relaxed again only if a block holding one of its predecessors has moved since: lane b
+     * keeps the set of blocks that block b reads (maxManifolds <= 1024: at most 32 blocks) */
+    uint32_t myDeps = 0, movedPrev = 0xffffffffu;
+    for (uint32_t pass = 0; pass < (sequential ? 3u : PX_SCHED_PASSES) && !converged; pass++) {
+      uint32_t movedNow = 0;
+      for (uint32_t base = 0; base < M; base += 32u) {
+        const uint32_t r = base + lane, blk = base >> 5;
+        const bool valid = r < M;
+        if (pass && !(__shfl_sync(0xffffffffu, myDeps, blk) & (movedPrev | movedNow))) continue;
+        /* rank | closes the ring << 10 | predecessor's contacts << 11 | own contacts << 13; 0xffff: static B */
+        const uint32_t w = valid ? pred[r] : 0xffff0000u, pa = w & 0xffffu, pb = w >> 16;
+        if (!pass) {
+          const uint32_t deps = __reduce_or_sync(0xffffffffu, valid ? (1u << ((pa & 0x3ffu) >> 5)) | (pb == 0xffffu ? 0u : 1u << ((pb & 0x3ffu) >> 5)) : 0u);
+          if (lane == blk) myDeps = deps;
+        }
+        const uint32_t adA = aT + 2u * (pa & 0x3ffu), adB = aT + 2u * ((pb == 0xffffu ? pa : pb) & 0x3ffu);
+        const int addA = (int)((pa >> 11) & 3u) - ((pa & 0x400u) ? closing : 0);
+        const int addB = pb == 0xffffu ? -0x10000 : (int)((pb >> 11) & 3u) - ((pb & 0x400u) ? closing : 0);
+        int cur = valid ? (int)lds16(aT + 2u * r) : 0x7fffffff;
+        for (uint32_t it = 0; it < 34u; it++) { /* a block's inner chains: at most 31 hops unless the period is infeasible */
+          const int v = max((int)lds16(adA) + addA, (int)lds16(adB) + addB);
+          const bool up = v > cur;
+          if (up) {
+            cur = v;
+            sts16(aT + 2u * r, (uint32_t)v);
+          }
+          __syncwarp();
+          if (!__any_sync(0xffffffffu, up)) break;
+          movedNow |= 1u << blk;
+        }
+      }
+      passes++;
+      converged = movedNow == 0;
+      movedPrev = movedNow;
+    }
+  }
+  /* depth of one iteration; own contact count: bits 13-14 of the A word */
+  for (uint32_t r = lane; r < M; r += 32u) depth = max(depth, (uint32_t)tlev[r] + ((pred[r] >> 13) & 3u));
+  depth = max(__reduce_max_sync(0xffffffffu, depth), 1u);
+  if (sequential) II = depth;
+  const uint32_t QN = (depth - 1u) / II + 1u, nKeys = II * QN; /* <= depth - 1 + II < PX_KCAP */
+  if (prof && lane == 0) {
+    const long long now = clock64();
+    prof[15] += (unsigned long long)(now - t0);
+    prof[13] += ((unsigned long long)passes << 32) + II;
+  }
+  /* visits per key, two 16-bit counters per word */
+  for (uint32_t i = lane; i < (nKeys + 3u) / 2u; i += 32u) h32[i] = 0;
+  __syncwarp();
+  for (uint32_t base = 0; base < 2u * M; base += 32u) {
+    const uint32_t v = base + lane, r = v >> 1, ci = v & 1u;
+    if (r < M && ci < ((pred[r] >> 13) & 3u)) {
+      const uint32_t tau = (uint32_t)tlev[r] + ci, q = tau / II, key = (tau - q * II) * QN + q;
+      atomicAdd(&h32[key >> 1], (key & 1u) ? 0x10000u : 1u);
+    }
+  }
+  __syncwarp();
+  /* exclusive prefix over the keys, in place: segment starts, copied out (entry nKeys = the number of visits),
+   * then used as the cursors of the scatter below */
+  uint16_t *seg = (uint16_t *)(hand + P.H.seg);
+  uint32_t run = 0;
+  for (uint32_t base = 0; base <= nKeys; base += 32u) {
+    const uint32_t k = base + lane;
+    const uint32_t n = (k < nKeys) ? h16[k] : 0u;
+    uint32_t inc = n;
+#pragma unroll
+    for (uint32_t o = 1; o < 32u; o <<= 1) {
+      const uint32_t up = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += up;
+    }
+    const uint32_t ex = run + inc - n;
+    __syncwarp();
+    if (k <= nKeys) {
+      h16[k] = (uint16_t)ex;
+      seg[k] = (uint16_t)ex;
+    }
+    run += __shfl_sync(0xffffffffu, inc, 31);
+  }
+  __syncwarp();
+  /* permute the visit operands from pool-rank order into schedule order, two blocks of 32 in flight */
+  const float4 *in0 = (const float4 *)(hand + P.H.vrec), *in1 = in0 + PX_PLANE, *in2 = in1 + PX_PLANE;
+  float4 *out0 = (float4 *)(hand + P.H.stream), *out1 = out0 + PX_PLANE, *out2 = out1 + PX_PLANE;
+  for (uint32_t base = 0; base < 2u * M; base += 64u) {
+    float4 a[2], b[2], c[2];
+    bool on[2];
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+      const uint32_t v = base + 32u * u + lane, r = v >> 1, ci = v & 1u;
+      on[u] = r < M && ci < ((pred[min(r, M - 1u)] >> 13) & 3u);
+      if (on[u]) {
+        a[u] = ldgStream(in0 + v); /* read once: first out of L2, which the visit stream should keep */
+        b[u] = ldgStream(in1 + v);
+        c[u] = ldgStream(in2 + v);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+      if (on[u]) {
+        const uint32_t v = base + 32u * u + lane, r = v >> 1, ci = v & 1u;
+        const uint32_t tau = (uint32_t)tlev[r] + ci, q = tau / II, key = (tau - q * II) * QN + q;
+        const uint32_t old = atomicAdd(&h32[key >> 1], (key & 1u) ? 0x10000u : 1u);
+        const uint32_t pos = (key & 1u) ? old >> 16 : old & 0xffffu;
+        out0[pos] = a[u];
+        out1[pos] = b[u];
+        out2[pos] = c[u];
+      }
+    }
+  }
+  if (prof && lane == 0) prof[14] += (unsigned long long)(clock64() - t0);
+  IIout = II;
+  QNout = QN;
+  depthOut = depth;
+  visitsOut = run;
+  if (!converged && lane == 0) atomicOr((uint32_t *)(hand + P.H.scalars) + PX_HS_READY, 0x80000000u); /* unreachable */
+}
+
+/* ======================================================================= replay kernel ==== */
+/*
+ * Split pipeline, phase E with the static schedule: ONE warp per world first derives the schedule (buildSchedule)
+ * and then replays it.  Round R is slot R mod II of the period; the visits alive in it -- phases q with
+ * 0 <= R div II - q < iterations -- are one contiguous segment of the visit stream, processed 32 at a time, one
+ * contact per lane.  The stream (three coalesced float4 planes in the hand-over record) holds everything frozen
+ * during the solve, so a visit costs three coalesced global loads, two velocity gathers and two mass gathers from
+ * shared memory and two predicated velocity stores; there is no scheduler, no atomics and no second warp.  Shared
+ * memory per world is the schedule tables, then -- over them -- the velocity and mass rows (10 KB at 736 manifolds),
+ * so residency is bound by registers and the dependent chains of twenty-odd worlds per SM interleave.  The next
+ * chunk's operands are in flight while the current one computes.
+ */
 __global__ void __launch_bounds__(PX_REPLAY_THREADS, PX_REPLAY_MINB) pxReplayKernel(const PxStepParams P) {
   extern __shared__ __align__(16) uint8_t smemRaw[];
   const PxBatchLayout &L = P.L;
@@ -2096,6 +2105,7 @@ __global__ void __launch_bounds__(PX_REPLAY_THREADS, PX_REPLAY_MINB) pxReplayKer
   const uint32_t lane = threadIdx.x;
   float4 *bodyV = (float4 *)(smemRaw + P.solveS.bodyV);
   float2 *bodyM = (float2 *)(smemRaw + P.solveS.bodyM);
+  uint16_t *segS = (uint16_t *)(smemRaw + P.solveS.sig); /* PX_SEG_SMEM entries behind the body rows */
   const uint32_t aBodyV = sAddr(bodyV), aBodyM = sAddr(bodyM);
   const float eps = L.epsilon;
   for (;;) {
@@ -2105,13 +2115,21 @@ __global__ void __launch_bounds__(PX_REPLAY_THREADS, PX_REPLAY_MINB) pxReplayKer
     if (world >= L.nWorlds) break;
     uint8_t *gmut = P.mut + (size_t)world * L.mutStride;
     const uint8_t *gimm = P.imm + (size_t)world * L.immStride;
-    const uint8_t *hand = P.hand + (size_t)world * P.H.stride;
+    uint8_t *hand = P.hand + (size_t)world * P.H.stride;
     float *gdyn = (float *)(gmut + L.offDyn);
     const uint32_t iterations = ((const PxWorldHeader *)(gmut + L.offHeader))->iterations & 255u;
-    const uint32_t *sc = (const uint32_t *)(hand + P.H.scalars);
-    const uint32_t M = min(sc[PX_HS_M], MM), II = sc[PX_HS_PERIOD], QN = sc[PX_HS_PHASES], depth = sc[PX_HS_DEPTH];
-    const uint32_t nVisits = sc[PX_HS_VISITS];
-    if (M && iterations && II && nVisits) { /* uniform: nothing to solve otherwise */
+    uint32_t *sc = (uint32_t *)(hand + P.H.scalars);
+    const uint32_t M = min(sc[PX_HS_M], MM), ring = sc[PX_HS_RING];
+    if (M && iterations) { /* uniform: nothing to solve otherwise */
+      unsigned long long *prof = P.prof ? P.prof + (size_t)world * PX_PROF_SLOTS : nullptr;
+      uint32_t II, QN, depth, nVisits;
+      buildSchedule(P, smemRaw, hand, M, ring, prof, II, QN, depth, nVisits);
+      __syncwarp(); /* the schedule tables are dead: the body rows take their place; the stream is in global memory */
+      /* the segment table is read at the head of every round, on the warp's critical path: keep it in shared memory */
+      if (II * QN + 1u <= PX_SEG_SMEM) {
+        const uint16_t *gseg = (const uint16_t *)(hand + P.H.seg);
+        for (uint32_t k = lane; k <= II * QN; k += PX_REPLAY_THREADS) segS[k] = gseg[k];
+      }
       const float *gc = (const float *)(gimm + L.offDynConst);
       for (uint32_t x = lane; x < D; x += PX_REPLAY_THREADS) {
         bodyV[x] = make_float4(gdyn[PX_DYN_VX * D + x], gdyn[PX_DYN_VY * D + x], gdyn[PX_DYN_AV * D + x], 0.0f);
@@ -2123,58 +2141,56 @@ __global__ void __launch_bounds__(PX_REPLAY_THREADS, PX_REPLAY_MINB) pxReplayKer
       }
       __syncwarp();
       long long t0 = 0;
-      unsigned long long *prof = P.prof ? P.prof + (size_t)world * PX_PROF_SLOTS : nullptr;
       if (prof && lane == 0) t0 = clock64();
 
-      const uint16_t *seg = (const uint16_t *)(hand + P.H.seg);
-      const float4 *pl0 = (const float4 *)(hand + P.H.stream), *pl1 = pl0 + PX_VCAP(MM), *pl2 = pl1 + PX_VCAP(MM);
+      /* Everything below is one warp's instruction stream and the kernel is issue-bound: the chunk iterator keeps
+       * its state in registers (row = slot * QN, the alive phase window [qlo, qhi1) changes only when the period
+       * wraps), the three operand planes are PX_PLANE entries apart so that one address serves all three loads. */
+      const uint16_t *seg = segS; /* the copy in shared memory, or (a table too long for it) the one in the hand-over record */
+      if (II * QN + 1u > PX_SEG_SMEM) seg = (const uint16_t *)(hand + P.H.seg);
+      const float4 *pl = (const float4 *)(hand + P.H.stream);
+      asm volatile("" : "+l"(seg), "+l"(pl)); /* opaque: kept in registers, not rebuilt from the parameters every chunk */
       const uint32_t nR = depth + (iterations - 1u) * II;
-      /* chunk iterator (warp-uniform): [beg, end) = the unprocessed visits of round R = Q * II + slot */
-      uint32_t R = 0, slot = 0, Q = 0, beg = 0, end = 0;
-      auto loadRound = [&]() {
-        const uint32_t qlo = Q + 1u > iterations ? Q + 1u - iterations : 0u, qhi = min(Q, QN - 1u);
-        if (qlo <= qhi) {
-          beg = __ldg(seg + slot * QN + qlo);
-          end = __ldg(seg + slot * QN + qhi + 1u);
-        } else {
-          beg = end = 0;
-        }
-      };
+      uint32_t R = 0, slot = 0, row = 0, Q = 0, qlo = 0, qhi1 = 1, beg = 0, end = 0;
+      beg = seg[0];
+      end = seg[1];
       auto nextChunk = [&](uint32_t &base, uint32_t &cnt) {
         while (beg >= end) {
           if (++R >= nR) {
             base = cnt = 0;
             return;
           }
+          row += QN;
           if (++slot == II) {
-            slot = 0;
+            slot = row = 0;
             Q++;
+            qlo = Q + 1u > iterations ? Q + 1u - iterations : 0u;
+            qhi1 = min(Q, QN - 1u) + 1u;
           }
-          loadRound();
+          if (qlo < qhi1) {
+            beg = seg[row + qlo];
+            end = seg[row + qhi1];
+          }
         }
         base = beg;
         cnt = min(32u, end - beg);
         beg += cnt;
       };
-      loadRound();
-      uint32_t b0, c0, chunks = 0, visits = 0;
-      nextChunk(b0, c0);
-      float4 r0, r1, r2;
-      {
-        const uint32_t idx = b0 + min(lane, c0 ? c0 - 1u : 0u);
-        r0 = ldgPinned(pl0 + idx);
-        r1 = ldgPinned(pl1 + idx);
-        r2 = ldgPinned(pl2 + idx);
-      }
-      while (c0) {
-        uint32_t b1, c1;
-        nextChunk(b1, c1);
+      uint32_t chunks = 0, visits = 0;
+      /* one chunk: start the NEXT chunk's three operand loads, then run this one.  Two register sets take turns
+       * (no copies: a copy at the end of the step would wait for the loads it had just issued). */
+      auto step = [&](const float4 &r0, const float4 &r1, const float4 &r2, const uint32_t cnt, float4 &n0, float4 &n1, float4 &n2,
+                      uint32_t &cntNext) {
+        uint32_t baseNext;
+        nextChunk(baseNext, cntNext);
         /* idle lanes repeat the chunk's last visit and store nothing; past the end: entry 0, discarded */
-        const uint32_t idx = b1 + min(lane, c1 ? c1 - 1u : 0u);
-        const float4 n0 = ldgPinned(pl0 + idx), n1 = ldgPinned(pl1 + idx), n2 = ldgPinned(pl2 + idx);
+        const float4 *at = pl + (baseNext + min(lane, cntNext ? cntNext - 1u : 0u));
+        n0 = ldgPinned(at);
+        n1 = ldgPinned(at + PX_PLANE);
+        n2 = ldgPinned(at + 2u * PX_PLANE);
         const uint32_t ids = __float_as_uint(r2.z);
         const uint32_t a16 = (ids & 0xffu) * 16u, b16 = ((ids >> 8) & 0x1ffu) * 16u;
-        const bool bdyn = ((ids >> 17) & 1u) != 0, active = lane < c0;
+        const bool bdyn = ((ids >> 17) & 1u) != 0, active = lane < cnt;
         float4 vA = lds128(aBodyV + a16), vB = lds128(aBodyV + b16);
         const float2 mA = lds64(aBodyM + (a16 >> 1)), mB = lds64(aBodyM + (b16 >> 1));
         contactImpulseCore(v2(r0.x, r0.y), v2(r0.z, r0.w), v2(r1.x, r1.y), r1.w, r2.x, r2.y, r1.z, mA.x, mA.y, mB.x, mB.y, bdyn, vA,
@@ -2182,12 +2198,23 @@ __global__ void __launch_bounds__(PX_REPLAY_THREADS, PX_REPLAY_MINB) pxReplayKer
         sts128If(aBodyV + a16, vA, active);
         sts128If(aBodyV + b16, vB, active && bdyn);
         __syncwarp();
-        visits += c0;
+        visits += cnt;
         chunks++;
-        r0 = n0;
-        r1 = n1;
-        r2 = n2;
-        c0 = c1;
+      };
+      uint32_t bA, cA, cB = 0;
+      nextChunk(bA, cA);
+      float4 a0, a1, a2, b0, b1, b2;
+      {
+        const float4 *at = pl + (bA + min(lane, cA ? cA - 1u : 0u));
+        a0 = ldgPinned(at);
+        a1 = ldgPinned(at + PX_PLANE);
+        a2 = ldgPinned(at + 2u * PX_PLANE);
+      }
+#pragma unroll 1
+      while (cA) {
+        step(a0, a1, a2, cA, b0, b1, b2, cB);
+        if (!cB) break;
+        step(b0, b1, b2, cB, a0, a1, a2, cA);
       }
       if (prof && lane == 0) {
         prof[4] += (unsigned long long)(clock64() - t0);
@@ -2199,12 +2226,12 @@ __global__ void __launch_bounds__(PX_REPLAY_THREADS, PX_REPLAY_MINB) pxReplayKer
         gdyn[PX_DYN_VY * D + x] = bv.y;
         gdyn[PX_DYN_AV * D + x] = bv.z;
       }
-      if (lane == 0 && visits != nVisits * iterations) {
+      if (lane == 0 && (visits != nVisits * iterations || (sc[PX_HS_READY] & 0x80000000u))) {
         PxWorldHeader *wh = (PxWorldHeader *)(gmut + L.offHeader);
         wh->statOverflow |= PX_OVERFLOW_INTERNAL;
       }
     }
-    __syncwarp(); /* the next world's load overwrites what the store above still reads */
+    __syncwarp(); /* the next world's tables overwrite what the store above still reads */
   }
 }
 
@@ -2509,10 +2536,10 @@ extern "C" void pxPlanHandover(const PxBatchLayout *L, const PxSmemPlan *S, PxHa
   H->stream = H->seg = 0;
   H->predA = H->predB = H->vrec = 0;
   if (S->rankOf) { /* static schedule */
-    H->stream = take(3 * PX_VCAP(MM) * 16);
+    H->stream = take(3 * PX_PLANE * 16);
     H->seg = take((PX_KCAP(MM) + 2) * 2);
     H->predA = take(MM * 2); H->predB = take(MM * 2);
-    H->vrec = take(3 * PX_VCAP(MM) * 16);
+    H->vrec = take(3 * PX_PLANE * 16);
   }
   H->stride = alignUp(o, 128);
 }
@@ -2526,10 +2553,14 @@ extern "C" void pxPlanSolveSmem(const PxBatchLayout *L, const PxSmemPlan *S, int
     o += alignUp(bytes, 16);
     return at;
   };
-  if (staticSolver) { /* pxReplayKernel: velocity and mass rows only */
+  if (staticSolver) { /* pxReplayKernel: the schedule tables, then -- in their place -- the velocity and mass rows */
     out->bodyV = take(NB * 16); out->bodyM = take(NB * 8);
+    out->sig = take(PX_SEG_SMEM * 2); /* the segment table's copy */
+    const uint32_t rows = o;
+    o = 0;
+    out->tlev = take(MM * 2); out->khist = take((PX_KCAP(MM) + 2) * 2); out->predA = take(MM * 4);
     out->qcap = S->qcap;
-    out->total = o;
+    out->total = o > rows ? o : rows;
     return;
   }
   out->bodyP = take(NB * 16); out->bodyV = take(NB * 16);
@@ -2553,45 +2584,6 @@ static cudaError_t configureSolve() {
   if (err != cudaSuccess) return err;
   if (dev >= 0 && dev < 64) done[dev] = true;
   return cudaSuccess;
-}
-
-extern "C" void pxPlanSchedSmem(const PxBatchLayout *L, PxSmemPlan *out) {
-  const uint32_t MM = L->maxManifolds;
-  memset(out, 0, sizeof(*out));
-  out->tlev = 0;
-  out->khist = alignUp(MM * 2, 16);
-  out->total = out->khist + alignUp((PX_KCAP(MM) + 2) * 2, 16);
-}
-
-static cudaError_t configureSched() {
-  static bool done[64] = {};
-  int dev = 0;
-  cudaError_t err = cudaGetDevice(&dev);
-  if (err != cudaSuccess) return err;
-  if (dev >= 0 && dev < 64 && done[dev]) return cudaSuccess;
-  int optin = 0;
-  err = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-  if (err != cudaSuccess) return err;
-  err = cudaFuncSetAttribute(pxSchedKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
-  if (err != cudaSuccess) return err;
-  err = cudaFuncSetAttribute(pxSchedKernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-  if (err != cudaSuccess) return err;
-  if (dev >= 0 && dev < 64) done[dev] = true;
-  return cudaSuccess;
-}
-
-extern "C" int pxLaunchSched(const PxStepParams *P, uint32_t grid, void *stream) {
-  if (grid == 0) return (int)cudaErrorInvalidValue;
-  cudaError_t err = configureSched();
-  if (err != cudaSuccess) return (int)err;
-  pxSchedKernel<<<grid, PX_SCHED_THREADS, P->schedS.total, (cudaStream_t)stream>>>(*P);
-  return (int)cudaGetLastError();
-}
-
-extern "C" int pxSchedOccupancy(const PxStepParams *P, int *ctasPerSm) {
-  cudaError_t err = configureSched();
-  if (err != cudaSuccess) return (int)err;
-  return (int)cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctasPerSm, pxSchedKernel, PX_SCHED_THREADS, P->schedS.total);
 }
 
 static cudaError_t configureReplay() {

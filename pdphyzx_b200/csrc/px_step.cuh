@@ -44,7 +44,7 @@ struct PxSmemPlan {
   uint32_t predA, predB; /* u16[MM] BY POOL RANK: predecessor of the manifold in its A / B body's ring: rank | closes the ring << 10 |
                             contacts of the predecessor << 11 | own contacts << 13 (0xffff: static B) */
   uint32_t rankOf;       /* u16[MM] pool rank by manifold slot */
-  /* pxSchedKernel only */
+  /* pxReplayKernel only (predA there: u32[MM], A word | B word << 16) */
   uint32_t tlev;         /* u16[MM] start round of the manifold's first contact inside one iteration, by rank */
   uint32_t khist;        /* u16[KCAP + 2] visits per (slot, phase) key, then their exclusive prefix = segment starts / cursors */
   uint32_t bodyM;        /* replay kernel only: float2[NB] {inverse mass, inverse inertia} */
@@ -55,6 +55,9 @@ struct PxSmemPlan {
 /* static schedule: contact visits per world <= 2 * maxManifolds; (slot, phase) keys <= depth + period <= 4 * maxManifolds + margin */
 #define PX_VCAP(MM) (2u * (MM))
 #define PX_KCAP(MM) (4u * (MM) + 16u)
+#define PX_SEG_SMEM 1024u /* segment-table entries pxReplayKernel keeps in shared memory (longer tables are read from global memory) */
+#define PX_PLANE 2048u /* entries between the operand planes of the visit records: >= PX_VCAP of the largest maxManifolds (1024), a
+                          constant so that one address register serves the three loads of a visit */
 #define PX_II_MARGIN 2u /* period tried first = longest body ring + this (profiles/sched_sim.py: on settled 252-body piles the least feasible period is ring + 0..5, ring + 2 on average; every extra round of period costs iterations - 1 replay rounds, a failed attempt costs a relaxation run to its cap) */
 
 /* A world's hand-over record in global memory (split pipeline): byte offsets of what the sweep
@@ -105,7 +108,6 @@ struct PxStepParams {
   uint8_t *hand; /* hand-over records, one per world, H.stride apart */
   PxHandLayout H;
   PxSmemPlan solveS; /* shared memory of pxSolveKernel (bodyP, bodyV, mids, nextw, sig, queue, misc, hdr) or pxReplayKernel (bodyV, bodyM) */
-  PxSmemPlan schedS; /* shared memory of pxSchedKernel (tlev, khist) */
 };
 
 
@@ -125,11 +127,8 @@ void pxPlanSolveSmem(const PxBatchLayout *L, const PxSmemPlan *S, int staticSolv
 int pxLaunchSolve(const PxStepParams *P, uint32_t grid, void *stream);
 int pxSolveOccupancy(const PxStepParams *P, int *ctasPerSm);
 #define PX_SOLVE_THREADS 64u  /* dynamic solver: scheduler warp + math warp */
-#define PX_REPLAY_THREADS 32u /* static solver: one warp replays the world's schedule */
-#define PX_SCHED_THREADS 32u  /* static solver: one warp derives the world's schedule */
-void pxPlanSchedSmem(const PxBatchLayout *L, PxSmemPlan *out);
-int pxLaunchSched(const PxStepParams *P, uint32_t grid, void *stream);
-int pxSchedOccupancy(const PxStepParams *P, int *ctasPerSm);
+#define PX_REPLAY_THREADS 32u /* static solver: one warp derives the world's schedule and replays it */
+
 
 /* control path: one command = one API call (px_batch.h "control path") */
 struct PxCommand {
