@@ -38,6 +38,7 @@
 #include <cuda_runtime.h>
 #include <float.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "px_step.cuh"
@@ -430,12 +431,10 @@ __device__ __forceinline__ uint32_t facingFace(const DBody &A, V2 dWorld) {
  * without contacts as soon as the LARGEST face separation of either polygon is >= 0; one face
  * whose separation -- evaluated with the reference's own arithmetic (faceSeparation) -- is
  * >= 0 therefore proves the same outcome without looking at the other faces.  The face tried
- * is the one pointing most towards the other body; pairs it cannot reject go on to the full
- * two-pass SAT. */
-__device__ __forceinline__ bool polygonsSeparatedQuick(const DBody &A, const DBody &B, float epsSq) {
-  const V2 d = B.pos - A.pos;
-  if (faceSeparation(A, B, facingFace(A, d), epsSq) >= 0.0f) return true;
-  return faceSeparation(B, A, facingFace(B, -d), epsSq) >= 0.0f;
+ * is the one pointing most towards the other body (separatedByFacingFace: the face of X that looks at Y; two lanes
+ * try the two polygons of a pair side by side); pairs neither can reject go on to the full two-pass SAT. */
+__device__ __forceinline__ bool separatedByFacingFace(const DBody &X, const DBody &Y, float epsSq) {
+  return faceSeparation(X, Y, facingFace(X, Y.pos - X.pos), epsSq) >= 0.0f;
 }
 
 /* pxClipSegmentToLine, px_collision.c:261-290 (IEEE division).  The reference appends, in this
@@ -842,7 +841,10 @@ __device__ __noinline__ void solverMath(const SolverCtx c) {
 
 /* ============================================================================ kernel ==== */
 template <int NT, int MODE>
-__global__ void __launch_bounds__(NT, NT == 128 ? PX_MINB128 : 3) pxStepKernel(const PxStepParams P) {
+#ifndef PX_SWEEP_MINB256
+#define PX_SWEEP_MINB256 3
+#endif
+__global__ void __launch_bounds__(NT, NT == 128 ? PX_MINB128 : (MODE == PX_MODE_SWEEP ? PX_SWEEP_MINB256 : 3)) pxStepKernel(const PxStepParams P) {
   constexpr int R = PX_DMAX / NT; /* body slots (and sorted positions) owned per thread */
   extern __shared__ __align__(16) uint8_t smemRaw[];
   const PxBatchLayout &L = P.L;
@@ -1248,15 +1250,19 @@ __global__ void __launch_bounds__(NT, NT == 128 ? PX_MINB128 : 3) pxStepKernel(c
       uint16_t *surv = (uint16_t *)s.sBox;
       /* pass 1: reject; a survivor leaves its size class (1: both polygons <= 4 vertices, 2: <= 6,
        * 3: larger) in validSlot[seq], which the sweep zeroed */
-      for (uint32_t base = 0; base < nPoly; base += NT) {
-        const uint32_t k = base + tid;
-        if (k >= nPoly) continue;
-        const uint32_t word = s.bins[nCircle + k];
-        if (word == 0xffffffffu) continue;
-        const DBody A = loadBody(s, BIN_A(word)), B = loadBody(s, BIN_B(word));
-        if (polygonsSeparatedQuick(A, B, epsSq)) continue;
-        const uint32_t big = max(A.nverts, B.nverts);
-        s.validSlot[BIN_SEQ(word)] = (uint16_t)(1u + (big > 4u ? 1u : 0u) + (big > 6u ? 1u : 0u));
+      for (uint32_t base = 0; base < nPoly; base += NT / 2u) {
+        /* two lanes per pair: the even one tries A's face that looks at B, the odd one B's face that looks at A */
+        const uint32_t k = base + (tid >> 1), q = tid & 1u;
+        const uint32_t word = k < nPoly ? s.bins[nCircle + k] : 0xffffffffu;
+        const bool valid = word != 0xffffffffu;
+        const uint32_t a = valid ? BIN_A(word) : 0u, b = valid ? BIN_B(word) : 0u;
+        const DBody X = loadBody(s, q ? b : a), Y = loadBody(s, q ? a : b);
+        bool separated = valid && separatedByFacingFace(X, Y, epsSq);
+        separated |= __shfl_xor_sync(0xffffffffu, separated, 1) != 0;
+        if (valid && !separated && q == 0) {
+          const uint32_t big = max(X.nverts, Y.nverts);
+          s.validSlot[BIN_SEQ(word)] = (uint16_t)(1u + (big > 4u ? 1u : 0u) + (big > 6u ? 1u : 0u));
+        }
       }
       __syncthreads();
       /* pass 2: survivors compacted class by class, so that the lanes of a warp of the SAT pass
@@ -1945,8 +1951,9 @@ __device__ __forceinline__ float2 lds64(uint32_t a) {
   return v;
 }
 
-/* Schedule of one world, by one warp (see above).  Shared memory: tlev u16[MM], khist u16[KCAP + 2], pred u32[MM]
- * (A word | B word << 16).  Leaves the visit stream and the segment table in the world's hand-over record. */
+/* Schedule of one world, by one warp (see above).  Shared memory: tlev u16[MM], khist u16[PX_KSM + 2]; the ring words
+ * are read from the hand-over record (coalesced, by rank).  Leaves the visit stream and the segment table in the
+ * world's hand-over record. */
 __device__ __forceinline__ void buildSchedule(const PxStepParams &P, uint8_t *smem, uint8_t *hand, const uint32_t M, const uint32_t ring,
                                               unsigned long long *prof, uint32_t &IIout, uint32_t &QNout, uint32_t &depthOut,
                                               uint32_t &visitsOut) {
@@ -1954,14 +1961,9 @@ __device__ __forceinline__ void buildSchedule(const PxStepParams &P, uint8_t *sm
   uint16_t *tlev = (uint16_t *)(smem + P.solveS.tlev);
   uint32_t *h32 = (uint32_t *)(smem + P.solveS.khist);
   uint16_t *h16 = (uint16_t *)h32;
-  uint32_t *pred = (uint32_t *)(smem + P.solveS.predA);
+  const uint16_t *gA = (const uint16_t *)(hand + P.H.predA), *gB = (const uint16_t *)(hand + P.H.predB);
   const uint32_t aT = sAddr(tlev);
   long long t0 = (prof && lane == 0) ? clock64() : 0;
-  {
-    const uint16_t *gA = (const uint16_t *)(hand + P.H.predA), *gB = (const uint16_t *)(hand + P.H.predB);
-#pragma unroll 4
-    for (uint32_t r = lane; r < M; r += 32u) pred[r] = (uint32_t)gA[r] | ((uint32_t)gB[r] << 16);
-  }
   uint32_t II = 1, passes = 0, depth = 0;
   bool converged = false, sequential = false;
   for (uint32_t attempt = 0; attempt < 5 && !converged; attempt++) {
@@ -1980,7 +1982,7 @@ __device__ __forceinline__ void buildSchedule(const PxStepParams &P, uint8_t *sm
         const bool valid = r < M;
         if (pass && !(__shfl_sync(0xffffffffu, myDeps, blk) & (movedPrev | movedNow))) continue;
         /* rank | closes the ring << 10 | predecessor's contacts << 11 | own contacts << 13; 0xffff: static B */
-        const uint32_t w = valid ? pred[r] : 0xffff0000u, pa = w & 0xffffu, pb = w >> 16;
+        const uint32_t pa = valid ? gA[r] : 0u, pb = valid ? gB[r] : 0xffffu;
         if (!pass) {
           const uint32_t deps = __reduce_or_sync(0xffffffffu, valid ? (1u << ((pa & 0x3ffu) >> 5)) | (pb == 0xffffu ? 0u : 1u << ((pb & 0x3ffu) >> 5)) : 0u);
           if (lane == blk) myDeps = deps;
@@ -2005,12 +2007,17 @@ __device__ __forceinline__ void buildSchedule(const PxStepParams &P, uint8_t *sm
       converged = movedNow == 0;
       movedPrev = movedNow;
     }
+    if (converged) {
+      /* depth of one iteration; own contact count: bits 13-14 of the A word */
+      depth = 0;
+      for (uint32_t r = lane; r < M; r += 32u) depth = max(depth, (uint32_t)tlev[r] + (((uint32_t)gA[r] >> 13) & 3u));
+      depth = max(__reduce_max_sync(0xffffffffu, depth), 1u);
+      if (sequential) II = depth;
+      /* keys = II * phases <= depth - 1 + II must fit the table; the sequential schedule's (= depth <= 2 * MM) always do */
+      if (II * ((depth - 1u) / II + 1u) > PX_KSM(MM)) converged = false;
+    }
   }
-  /* depth of one iteration; own contact count: bits 13-14 of the A word */
-  for (uint32_t r = lane; r < M; r += 32u) depth = max(depth, (uint32_t)tlev[r] + ((pred[r] >> 13) & 3u));
-  depth = max(__reduce_max_sync(0xffffffffu, depth), 1u);
-  if (sequential) II = depth;
-  const uint32_t QN = (depth - 1u) / II + 1u, nKeys = II * QN; /* <= depth - 1 + II < PX_KCAP */
+  const uint32_t QN = (depth - 1u) / II + 1u, nKeys = II * QN;
   if (prof && lane == 0) {
     const long long now = clock64();
     prof[15] += (unsigned long long)(now - t0);
@@ -2021,7 +2028,7 @@ __device__ __forceinline__ void buildSchedule(const PxStepParams &P, uint8_t *sm
   __syncwarp();
   for (uint32_t base = 0; base < 2u * M; base += 32u) {
     const uint32_t v = base + lane, r = v >> 1, ci = v & 1u;
-    if (r < M && ci < ((pred[r] >> 13) & 3u)) {
+    if (r < M && ci < (((uint32_t)gA[r] >> 13) & 3u)) {
       const uint32_t tau = (uint32_t)tlev[r] + ci, q = tau / II, key = (tau - q * II) * QN + q;
       atomicAdd(&h32[key >> 1], (key & 1u) ? 0x10000u : 1u);
     }
@@ -2058,7 +2065,7 @@ __device__ __forceinline__ void buildSchedule(const PxStepParams &P, uint8_t *sm
 #pragma unroll
     for (int u = 0; u < 2; u++) {
       const uint32_t v = base + 32u * u + lane, r = v >> 1, ci = v & 1u;
-      on[u] = r < M && ci < ((pred[min(r, M - 1u)] >> 13) & 3u);
+      on[u] = r < M && ci < (((uint32_t)gA[min(r, M - 1u)] >> 13) & 3u);
       if (on[u]) {
         a[u] = ldgStream(in0 + v); /* read once: first out of L2, which the visit stream should keep */
         b[u] = ldgStream(in1 + v);
@@ -2104,9 +2111,9 @@ __global__ void __launch_bounds__(PX_REPLAY_THREADS, PX_REPLAY_MINB) pxReplayKer
   const uint32_t D = L.maxDynamic, S = L.maxStatic, MM = L.maxManifolds;
   const uint32_t lane = threadIdx.x;
   float4 *bodyV = (float4 *)(smemRaw + P.solveS.bodyV);
-  float2 *bodyM = (float2 *)(smemRaw + P.solveS.bodyM);
+  float *bodyI = (float *)(smemRaw + P.solveS.bodyM); /* inverse inertia; the inverse mass rides in bodyV.w */
   uint16_t *segS = (uint16_t *)(smemRaw + P.solveS.sig); /* PX_SEG_SMEM entries behind the body rows */
-  const uint32_t aBodyV = sAddr(bodyV), aBodyM = sAddr(bodyM);
+  const uint32_t aBodyV = sAddr(bodyV), aBodyI = sAddr(bodyI);
   const float eps = L.epsilon;
   for (;;) {
     uint32_t world = 0;
@@ -2132,12 +2139,12 @@ __global__ void __launch_bounds__(PX_REPLAY_THREADS, PX_REPLAY_MINB) pxReplayKer
       }
       const float *gc = (const float *)(gimm + L.offDynConst);
       for (uint32_t x = lane; x < D; x += PX_REPLAY_THREADS) {
-        bodyV[x] = make_float4(gdyn[PX_DYN_VX * D + x], gdyn[PX_DYN_VY * D + x], gdyn[PX_DYN_AV * D + x], 0.0f);
-        bodyM[x] = make_float2(gc[PX_DYNC_IMASS * D + x], gc[PX_DYNC_IINERTIA * D + x]);
+        bodyV[x] = make_float4(gdyn[PX_DYN_VX * D + x], gdyn[PX_DYN_VY * D + x], gdyn[PX_DYN_AV * D + x], gc[PX_DYNC_IMASS * D + x]);
+        bodyI[x] = gc[PX_DYNC_IINERTIA * D + x];
       }
       for (uint32_t q = lane; q < S; q += PX_REPLAY_THREADS) {
         bodyV[D + q] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-        bodyM[D + q] = make_float2(0.0f, 0.0f);
+        bodyI[D + q] = 0.0f;
       }
       __syncwarp();
       long long t0 = 0;
@@ -2192,9 +2199,9 @@ __global__ void __launch_bounds__(PX_REPLAY_THREADS, PX_REPLAY_MINB) pxReplayKer
         const uint32_t a16 = (ids & 0xffu) * 16u, b16 = ((ids >> 8) & 0x1ffu) * 16u;
         const bool bdyn = ((ids >> 17) & 1u) != 0, active = lane < cnt;
         float4 vA = lds128(aBodyV + a16), vB = lds128(aBodyV + b16);
-        const float2 mA = lds64(aBodyM + (a16 >> 1)), mB = lds64(aBodyM + (b16 >> 1));
-        contactImpulseCore(v2(r0.x, r0.y), v2(r0.z, r0.w), v2(r1.x, r1.y), r1.w, r2.x, r2.y, r1.z, mA.x, mA.y, mB.x, mB.y, bdyn, vA,
-                           vB, eps);
+        const float iIA = __uint_as_float(lds32(aBodyI + (a16 >> 2))), iIB = __uint_as_float(lds32(aBodyI + (b16 >> 2)));
+        contactImpulseCore(v2(r0.x, r0.y), v2(r0.z, r0.w), v2(r1.x, r1.y), r1.w, r2.x, r2.y, r1.z, vA.w, iIA, vB.w, iIB, bdyn, vA, vB,
+                           eps);
         sts128If(aBodyV + a16, vA, active);
         sts128If(aBodyV + b16, vB, active && bdyn);
         __syncwarp();
@@ -2554,11 +2561,11 @@ extern "C" void pxPlanSolveSmem(const PxBatchLayout *L, const PxSmemPlan *S, int
     return at;
   };
   if (staticSolver) { /* pxReplayKernel: the schedule tables, then -- in their place -- the velocity and mass rows */
-    out->bodyV = take(NB * 16); out->bodyM = take(NB * 8);
+    out->bodyV = take(NB * 16); out->bodyM = take(NB * 4);
     out->sig = take(PX_SEG_SMEM * 2); /* the segment table's copy */
     const uint32_t rows = o;
     o = 0;
-    out->tlev = take(MM * 2); out->khist = take((PX_KCAP(MM) + 2) * 2); out->predA = take(MM * 4);
+    out->tlev = take(MM * 2); out->khist = take((PX_KSM(MM) + 2) * 2);
     out->qcap = S->qcap;
     out->total = o > rows ? o : rows;
     return;

@@ -55,10 +55,12 @@ struct PxSmemPlan {
 /* static schedule: contact visits per world <= 2 * maxManifolds; (slot, phase) keys <= depth + period <= 4 * maxManifolds + margin */
 #define PX_VCAP(MM) (2u * (MM))
 #define PX_KCAP(MM) (4u * (MM) + 16u)
-#define PX_SEG_SMEM 1024u /* segment-table entries pxReplayKernel keeps in shared memory (longer tables are read from global memory) */
+#define PX_KSM(MM) (2u * (MM) + 64u) /* (slot, phase) keys pxReplayKernel's counting sort has room for in shared memory; a period whose keys
+                                        do not fit is skipped (the sequential schedule's always fit) */
+#define PX_SEG_SMEM 512u /* segment-table entries pxReplayKernel keeps in shared memory (longer tables are read from global memory) */
 #define PX_PLANE 2048u /* entries between the operand planes of the visit records: >= PX_VCAP of the largest maxManifolds (1024), a
                           constant so that one address register serves the three loads of a visit */
-#define PX_II_MARGIN 2u /* period tried first = longest body ring + this (profiles/sched_sim.py: on settled 252-body piles the least feasible period is ring + 0..5, ring + 2 on average; every extra round of period costs iterations - 1 replay rounds, a failed attempt costs a relaxation run to its cap) */
+#define PX_II_MARGIN 3u /* period tried first = longest body ring + this (profiles/sched_sim.py: on settled 252-body piles the least feasible period is ring + 0..5, ring + 2 on average; every extra round of period costs iterations - 1 replay rounds, a failed attempt costs a relaxation run to its cap) */
 
 /* A world's hand-over record in global memory (split pipeline): byte offsets of what the sweep
  * kernel leaves for the solver kernel and for the phase F that follows it.  Laid out by
