@@ -110,6 +110,12 @@ __device__ __forceinline__ uint32_t ldsVolatile(uint32_t a) {
 __device__ __forceinline__ void stsVolatile(uint32_t a, uint32_t v) {
   asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
 }
+/* pulls a 128-byte line into L2 ahead of its use */
+__device__ __forceinline__ void prefetchL2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+/* lines [0, bytes / 128] of a region, spread over the CTA's (or warp's) threads */
+__device__ __forceinline__ void prefetchRegion(const uint8_t *base, uint32_t bytes, uint32_t tid, uint32_t nt) {
+  for (uint32_t off = tid * 128u; off < bytes; off += nt * 128u) prefetchL2(base + off);
+}
 /* a global load the compiler may not sink below later volatile asm statements */
 __device__ __forceinline__ float4 ldgPinned(const float4 *p) {
   float4 v;
@@ -2128,6 +2134,8 @@ __global__ void __launch_bounds__(PX_REPLAY_THREADS, PX_REPLAY_MINB) pxReplayKer
     uint32_t *sc = (uint32_t *)(hand + P.H.scalars);
     const uint32_t M = min(sc[PX_HS_M], MM), ring = sc[PX_HS_RING];
     if (M && iterations) { /* uniform: nothing to solve otherwise */
+      /* the visit operands by rank are read after the relaxation: start them on their way out of DRAM now */
+      for (uint32_t k = 0; k < 3u; k++) prefetchRegion(hand + P.H.vrec + k * PX_PLANE * 16u, 2u * M * 16u, lane, PX_REPLAY_THREADS);
       unsigned long long *prof = P.prof ? P.prof + (size_t)world * PX_PROF_SLOTS : nullptr;
       uint32_t II, QN, depth, nVisits;
       buildSchedule(P, smemRaw, hand, M, ring, prof, II, QN, depth, nVisits);

@@ -41,7 +41,7 @@ def to_bytes(value: str, unit: str) -> float:
 
 
 def kernel_key(name: str) -> str:
-    if "pxSolveKernel" in name:
+    if "pxSolveKernel" in name or "pxReplayKernel" in name:
         return "solve"
     m = re.search(r"pxStepKernel<[^>]*?,\s*(?:\(int\))?(\d)\s*>", name)
     if m:
