@@ -676,8 +676,17 @@ extern "C" int pxBatchStepHost(PxBatch *b, uint32_t kSubsteps, void *hostMut, ui
   if (flushCommands(b)) return -1;
   uint8_t *host = hostMut ? (uint8_t *)hostMut : b->hMut;
   const uint32_t W = b->L.nWorlds;
-  if (chunks == 0) chunks = 8;
+  if (chunks == 0) chunks = 4;
   if (chunks > W) chunks = W;
+  /* world ranges: the first and the last get half the worlds of an inner one -- nothing overlaps the first range's
+   * H2D copy or the last range's D2H copy, so those two are kept short */
+  const uint32_t units = chunks >= 3 ? 2u * (chunks - 1u) : chunks;
+  auto edge = [&](uint32_t c) -> uint32_t { /* first world of range c; c == chunks: W */
+    if (c == 0) return 0;
+    if (c >= chunks) return W;
+    const uint32_t u = chunks >= 3 ? 2u * c - 1u : c;
+    return (uint32_t)((uint64_t)W * u / units);
+  };
   if (!b->auxReady) {
     for (int i = 0; i < 2; i++) {
       CU(cudaStreamCreateWithFlags(&b->aux[i], cudaStreamNonBlocking));
@@ -691,7 +700,7 @@ extern "C" int pxBatchStepHost(PxBatch *b, uint32_t kSubsteps, void *hostMut, ui
   for (int i = 0; i < 2; i++) CU(cudaStreamWaitEvent(b->aux[i], b->evFork, 0));
   const size_t stride = b->L.mutStride;
   for (uint32_t c = 0; c < chunks; c++) {
-    const uint32_t first = (uint32_t)((uint64_t)W * c / chunks), last = (uint32_t)((uint64_t)W * (c + 1) / chunks);
+    const uint32_t first = edge(c), last = edge(c + 1);
     const uint32_t n = last - first;
     if (!n) continue;
     cudaStream_t st = b->aux[c & 1];
