@@ -85,6 +85,10 @@ def parse_args():
         args.mix, args.iterations, args.scaling = "mixed", 20, "strong"
     elif args.config == 5:
         args.worlds, args.control = 32768, True
+        # impulse-driven polygon stacks pile deeper than the settled bench scene: capacities above the library defaults,
+        # so that no world drops a manifold or a pair (worlds_overflowed must read 0)
+        args.max_manifolds = args.max_manifolds or 1024
+        args.max_pairs = args.max_pairs or 2304
     return args
 
 

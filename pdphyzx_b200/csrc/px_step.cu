@@ -1,15 +1,18 @@
 /*
- * px_step.cu -- the pdphyzx world substep as one fused sm_100a kernel.
+ * px_step.cu -- the pdphyzx world substep as hand-written sm_100a kernels.
  *
- * One CTA per world.  The CTA loads its world's SoA block from HBM with coalesced accesses,
- * keeps body state in shared memory (and the per-body state only its owner thread needs --
- * angle, force, torque, sleep time -- in registers) across K fused substeps
- * (K x pxWorldStepWithDt, reference src/px_world.c:410-420) and stores the mutable rows back.
- * The float records of the substep's manifolds live in an L2-resident scratch slot the CTA
- * claims on its SM (they were half of a world's shared-memory footprint): 37.6 KB of shared
- * memory per 252-body world, five resident worlds per SM.  No tensor cores: nothing here is a
- * dense contraction.  Compile with -fmad=false: every multiply-add must round twice, exactly
- * like the scalar CPU build.
+ * One CTA per world.  Two pipelines:
+ *   fused (small batches)   pxStepKernel<NT, FUSED>: the CTA loads its world's SoA block from HBM with coalesced
+ *                           accesses, keeps body state in shared memory (and what only a body's owner thread needs --
+ *                           angle, force, torque, sleep time -- in registers) across K fused substeps
+ *                           (K x pxWorldStepWithDt, reference src/px_world.c:410-420) and stores the mutable rows back;
+ *                           the solver is a dataflow execution on two specialised warps.
+ *   split (large batches)   per substep pxStepKernel<256, SWEEP> (phase F of the previous substep + phases A-D, hand-over
+ *                           record per world in global memory) and a solver kernel: pxReplayKernel (one warp per world
+ *                           derives a periodic schedule of the contact visits and replays it per iteration) or
+ *                           pxSolveKernel (the dataflow solver as a kernel of its own).
+ * No tensor cores: nothing here is a dense contraction.  Compile with -fmad=false: every multiply-add must round
+ * twice, exactly like the scalar CPU build.
  *
  * Phases of a substep and the reference code each one restates
  *   A  AABBs, stable order by aabb.min.x           px_body_array.c:81-102, px_circle.c:43-48
