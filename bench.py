@@ -642,6 +642,11 @@ def run_sharded(args):
         ms = max(ms, float(t.value))
     gpu_launches = g.launches() - launches0
     clocks = samplers[0].stop()
+    # the host buffers must hold the settled state the device holds (they still hold the uploaded one)
+    for s_ in range(g.n_shards):
+        h, first_w, n_w = g.shard(s_)
+        pxb._check(g.lib.pxBatchMutableD2H(h, None, 0, n_w), "pxBatchMutableD2H")
+    g.sync()
     for _ in range(2):
         g.step_host(args.fused, args.e2e_chunks)
         g.sync()

@@ -1940,7 +1940,7 @@ __global__ void __launch_bounds__(PX_SOLVE_THREADS, PX_SOLVE_MINB) pxSolveKernel
 #define PX_REPLAY_MINB 20
 #endif
 #ifndef PX_SCHED_PASSES
-#define PX_SCHED_PASSES 8u
+#define PX_SCHED_PASSES 7u
 #endif
 __device__ __forceinline__ uint32_t lds16(uint32_t a) {
   uint32_t v;
@@ -1975,8 +1975,17 @@ __device__ __forceinline__ void buildSchedule(const PxStepParams &P, uint8_t *sm
   long long t0 = (prof && lane == 0) ? clock64() : 0;
   uint32_t II = 1, passes = 0, depth = 0;
   bool converged = false, sequential = false;
+  /* The margin that worked for this world last substep is tried first (a pile's critical cycle changes slowly):
+   * a failed attempt costs a relaxation run to its pass cap, which the slowest world of a launch pays in full.
+   * hint word (persists in the hand-over record): margin | first-attempt successes in a row << 8; after 64 of those
+   * the margin is tightened by one round. */
+  uint32_t *hintWord = (uint32_t *)(hand + P.H.scalars) + PX_HS_HINT;
+  const uint32_t hint = *hintWord, margin0 = max(hint & 0xffu, PX_II_MARGIN);
+  uint32_t marginUsed = margin0, attemptUsed = 0;
   for (uint32_t attempt = 0; attempt < 5 && !converged; attempt++) {
-    II = min(attempt < 3 ? ring + (PX_II_MARGIN << attempt) : 2u * ring + 8u, 2u * MM + 8u);
+    marginUsed = margin0 + (attempt == 1 ? 2u : attempt == 2 ? 5u : 0u);
+    attemptUsed = attempt;
+    II = min(attempt < 3 ? ring + marginUsed : 2u * ring + 8u, 2u * MM + 8u);
     sequential = attempt == 4;
     const int closing = sequential ? 0x8000 : (int)II; /* dropped edges: a cost no start round can reach */
     for (uint32_t r = lane; r < M; r += 32u) tlev[r] = 0;
@@ -2025,6 +2034,19 @@ __device__ __forceinline__ void buildSchedule(const PxStepParams &P, uint8_t *sm
       /* keys = II * phases <= depth - 1 + II must fit the table; the sequential schedule's (= depth <= 2 * MM) always do */
       if (II * ((depth - 1u) / II + 1u) > PX_KSM(MM)) converged = false;
     }
+  }
+  if (lane == 0) {
+    uint32_t m = margin0, age = hint >> 8;
+    if (attemptUsed == 0) {
+      if (++age >= 64u) {
+        age = 0;
+        if (m > PX_II_MARGIN) m--;
+      }
+    } else {
+      m = min(attemptUsed < 3u ? marginUsed : margin0 + 6u, 24u);
+      age = 0;
+    }
+    *hintWord = m | (age << 8);
   }
   const uint32_t QN = (depth - 1u) / II + 1u, nKeys = II * QN;
   if (prof && lane == 0) {

@@ -79,7 +79,8 @@ struct PxHandLayout {
 };
 enum { PX_MODE_FUSED = 0, PX_MODE_SWEEP = 1 };
 enum { PX_SOLVER_DYNAMIC = 0, PX_SOLVER_STATIC = 1 };
-enum { PX_HS_M = 0, PX_HS_READY = 1, PX_HS_PERIOD = 2, PX_HS_PHASES = 3, PX_HS_DEPTH = 4, PX_HS_VISITS = 5, PX_HS_RING = 6 };
+enum { PX_HS_M = 0, PX_HS_READY = 1, PX_HS_PERIOD = 2, PX_HS_PHASES = 3, PX_HS_DEPTH = 4, PX_HS_VISITS = 5, PX_HS_RING = 6,
+       PX_HS_HINT = 7 /* written by pxReplayKernel only: the period margin that worked last substep */ };
 
 #define PX_PROF_SLOTS 16 /* 0-5 phases A-F, 6 solver rounds, 7 polygon pairs << 32 | after quick reject, 8-11 narrowphase stages,
                             12 static schedule (end of phase D), 13 relaxation votes << 32 | period, 14 sort + stream build cycles,
