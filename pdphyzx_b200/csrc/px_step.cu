@@ -2028,13 +2028,19 @@ __device__ __forceinline__ void buildSchedule(const PxStepParams &P, uint8_t *sm
     if (converged) {
       /* depth of one iteration; own contact count: bits 13-14 of the A word */
       depth = 0;
-      for (uint32_t r = lane; r < M; r += 32u) depth = max(depth, (uint32_t)tlev[r] + (((uint32_t)gA[r] >> 13) & 3u));
+      for (uint32_t r = lane; r < M; r += 32u) {
+        /* the manifold's contact count joins its start round (bits 14-15): the passes below read shared memory only */
+        const uint32_t cnt = ((uint32_t)gA[r] >> 13) & 3u, t = tlev[r];
+        depth = max(depth, t + cnt);
+        tlev[r] = (uint16_t)(t | (cnt << 14));
+      }
       depth = max(__reduce_max_sync(0xffffffffu, depth), 1u);
       if (sequential) II = depth;
       /* keys = II * phases <= depth - 1 + II must fit the table; the sequential schedule's (= depth <= 2 * MM) always do */
       if (II * ((depth - 1u) / II + 1u) > PX_KSM(MM)) converged = false;
     }
   }
+  __syncwarp();
   if (lane == 0) {
     uint32_t m = margin0, age = hint >> 8;
     if (attemptUsed == 0) {
@@ -2054,15 +2060,23 @@ __device__ __forceinline__ void buildSchedule(const PxStepParams &P, uint8_t *sm
     prof[15] += (unsigned long long)(now - t0);
     prof[13] += ((unsigned long long)passes << 32) + II;
   }
-  /* visits per key, two 16-bit counters per word */
+  /* visits per key, two 16-bit counters per word; every visit's key is kept for the scatter (0xffff: a manifold's
+   * absent second contact) */
+  uint16_t *keys = (uint16_t *)(smem + P.solveS.queue);
+  const uint32_t magic = 0xffffffffu / II + 1u; /* tau / II == umulhi(tau, magic) for tau * II < 2^32 */
   for (uint32_t i = lane; i < (nKeys + 3u) / 2u; i += 32u) h32[i] = 0;
   __syncwarp();
+#pragma unroll 2
   for (uint32_t base = 0; base < 2u * M; base += 32u) {
     const uint32_t v = base + lane, r = v >> 1, ci = v & 1u;
-    if (r < M && ci < (((uint32_t)gA[r] >> 13) & 3u)) {
-      const uint32_t tau = (uint32_t)tlev[r] + ci, q = tau / II, key = (tau - q * II) * QN + q;
+    uint32_t key = 0xffffu;
+    const uint32_t tl = r < M ? tlev[r] : 0u;
+    if (ci < (tl >> 14)) {
+      const uint32_t tau = (tl & 0x3fffu) + ci, q = __umulhi(tau, magic);
+      key = (tau - q * II) * QN + q;
       atomicAdd(&h32[key >> 1], (key & 1u) ? 0x10000u : 1u);
     }
+    if (r < M) keys[v] = (uint16_t)key;
   }
   __syncwarp();
   /* exclusive prefix over the keys, in place: segment starts, copied out (entry nKeys = the number of visits),
@@ -2092,12 +2106,12 @@ __device__ __forceinline__ void buildSchedule(const PxStepParams &P, uint8_t *sm
   float4 *out0 = (float4 *)(hand + P.H.stream), *out1 = out0 + PX_PLANE, *out2 = out1 + PX_PLANE;
   for (uint32_t base = 0; base < 2u * M; base += 64u) {
     float4 a[2], b[2], c[2];
-    bool on[2];
+    uint32_t key[2];
 #pragma unroll
     for (int u = 0; u < 2; u++) {
-      const uint32_t v = base + 32u * u + lane, r = v >> 1, ci = v & 1u;
-      on[u] = r < M && ci < (((uint32_t)gA[min(r, M - 1u)] >> 13) & 3u);
-      if (on[u]) {
+      const uint32_t v = base + 32u * u + lane;
+      key[u] = v < 2u * M ? keys[v] : 0xffffu;
+      if (key[u] != 0xffffu) {
         a[u] = ldgStream(in0 + v); /* read once: first out of L2, which the visit stream should keep */
         b[u] = ldgStream(in1 + v);
         c[u] = ldgStream(in2 + v);
@@ -2105,11 +2119,9 @@ __device__ __forceinline__ void buildSchedule(const PxStepParams &P, uint8_t *sm
     }
 #pragma unroll
     for (int u = 0; u < 2; u++) {
-      if (on[u]) {
-        const uint32_t v = base + 32u * u + lane, r = v >> 1, ci = v & 1u;
-        const uint32_t tau = (uint32_t)tlev[r] + ci, q = tau / II, key = (tau - q * II) * QN + q;
-        const uint32_t old = atomicAdd(&h32[key >> 1], (key & 1u) ? 0x10000u : 1u);
-        const uint32_t pos = (key & 1u) ? old >> 16 : old & 0xffffu;
+      if (key[u] != 0xffffu) {
+        const uint32_t old = atomicAdd(&h32[key[u] >> 1], (key[u] & 1u) ? 0x10000u : 1u);
+        const uint32_t pos = (key[u] & 1u) ? old >> 16 : old & 0xffffu;
         out0[pos] = a[u];
         out1[pos] = b[u];
         out2[pos] = c[u];
@@ -2598,7 +2610,7 @@ extern "C" void pxPlanSolveSmem(const PxBatchLayout *L, const PxSmemPlan *S, int
     out->sig = take(PX_SEG_SMEM * 2); /* the segment table's copy */
     const uint32_t rows = o;
     o = 0;
-    out->tlev = take(MM * 2); out->khist = take((PX_KSM(MM) + 2) * 2);
+    out->tlev = take(MM * 2); out->khist = take((PX_KSM(MM) + 2) * 2); out->queue = take(PX_VCAP(MM) * 2); /* `queue`: the visits' keys */
     out->qcap = S->qcap;
     out->total = o > rows ? o : rows;
     return;
