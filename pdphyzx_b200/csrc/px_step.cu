@@ -1995,12 +1995,16 @@ __device__ __forceinline__ void buildSchedule(const PxStepParams &P, uint8_t *sm
     uint32_t myDeps = 0, movedPrev = 0xffffffffu;
     for (uint32_t pass = 0; pass < (sequential ? 3u : PX_SCHED_PASSES) && !converged; pass++) {
       uint32_t movedNow = 0;
+      /* the ring words of the next block are on their way while this block is relaxed */
+      uint32_t paNext = lane < M ? gA[lane] : 0u, pbNext = lane < M ? gB[lane] : 0xffffu;
       for (uint32_t base = 0; base < M; base += 32u) {
         const uint32_t r = base + lane, blk = base >> 5;
         const bool valid = r < M;
-        if (pass && !(__shfl_sync(0xffffffffu, myDeps, blk) & (movedPrev | movedNow))) continue;
         /* rank | closes the ring << 10 | predecessor's contacts << 11 | own contacts << 13; 0xffff: static B */
-        const uint32_t pa = valid ? gA[r] : 0u, pb = valid ? gB[r] : 0xffffu;
+        const uint32_t pa = paNext, pb = pbNext;
+        paNext = r + 32u < M ? gA[r + 32u] : 0u;
+        pbNext = r + 32u < M ? gB[r + 32u] : 0xffffu;
+        if (pass && !(__shfl_sync(0xffffffffu, myDeps, blk) & (movedPrev | movedNow))) continue;
         if (!pass) {
           const uint32_t deps = __reduce_or_sync(0xffffffffu, valid ? (1u << ((pa & 0x3ffu) >> 5)) | (pb == 0xffffu ? 0u : 1u << ((pb & 0x3ffu) >> 5)) : 0u);
           if (lane == blk) myDeps = deps;
