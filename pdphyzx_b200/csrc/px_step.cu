@@ -2108,28 +2108,46 @@ __device__ __forceinline__ void buildSchedule(const PxStepParams &P, uint8_t *sm
   /* permute the visit operands from pool-rank order into schedule order, two blocks of 32 in flight */
   const float4 *in0 = (const float4 *)(hand + P.H.vrec), *in1 = in0 + PX_PLANE, *in2 = in1 + PX_PLANE;
   float4 *out0 = (float4 *)(hand + P.H.stream), *out1 = out0 + PX_PLANE, *out2 = out1 + PX_PLANE;
-  for (uint32_t base = 0; base < 2u * M; base += 64u) {
+  /* The operands come out of DRAM (the sweep kernel wrote them a launch ago): the loads of the next 64 visits are
+   * issued before the current 64 are scattered, two register sets taking turns. */
+  struct Vis {
     float4 a[2], b[2], c[2];
     uint32_t key[2];
+  };
+  auto fetch = [&](Vis &x, uint32_t base) {
 #pragma unroll
     for (int u = 0; u < 2; u++) {
       const uint32_t v = base + 32u * u + lane;
-      key[u] = v < 2u * M ? keys[v] : 0xffffu;
-      if (key[u] != 0xffffu) {
-        a[u] = ldgStream(in0 + v); /* read once: first out of L2, which the visit stream should keep */
-        b[u] = ldgStream(in1 + v);
-        c[u] = ldgStream(in2 + v);
+      x.key[u] = v < 2u * M ? keys[v] : 0xffffu;
+      if (x.key[u] != 0xffffu) {
+        x.a[u] = ldgStream(in0 + v); /* read once: first out of L2, which the visit stream should keep */
+        x.b[u] = ldgStream(in1 + v);
+        x.c[u] = ldgStream(in2 + v);
       }
     }
+  };
+  auto scatter = [&](const Vis &x) {
 #pragma unroll
     for (int u = 0; u < 2; u++) {
-      if (key[u] != 0xffffu) {
-        const uint32_t old = atomicAdd(&h32[key[u] >> 1], (key[u] & 1u) ? 0x10000u : 1u);
-        const uint32_t pos = (key[u] & 1u) ? old >> 16 : old & 0xffffu;
-        out0[pos] = a[u];
-        out1[pos] = b[u];
-        out2[pos] = c[u];
+      if (x.key[u] != 0xffffu) {
+        const uint32_t old = atomicAdd(&h32[x.key[u] >> 1], (x.key[u] & 1u) ? 0x10000u : 1u);
+        const uint32_t pos = (x.key[u] & 1u) ? old >> 16 : old & 0xffffu;
+        out0[pos] = x.a[u];
+        out1[pos] = x.b[u];
+        out2[pos] = x.c[u];
       }
+    }
+  };
+  {
+    Vis x, y;
+    fetch(x, 0);
+#pragma unroll 1
+    for (uint32_t base = 0; base < 2u * M; base += 128u) {
+      fetch(y, base + 64u);
+      scatter(x);
+      if (base + 64u >= 2u * M) break;
+      fetch(x, base + 128u);
+      scatter(y);
     }
   }
   if (prof && lane == 0) prof[14] += (unsigned long long)(clock64() - t0);
