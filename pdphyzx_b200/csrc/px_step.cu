@@ -911,6 +911,19 @@ __global__ void __launch_bounds__(NT, NT == 128 ? PX_MINB128 : (MODE == PX_MODE_
     copyRows<NT>((float *)s.order, (const float *)(gmut + L.offDynOrder), D / 4);
     copyRows<NT>((float *)s.hdr, (const float *)(gmut + L.offHeader), sizeof(PxWorldHeader) / 4);
     if (tid < 32 && tid != MI_WORLD) s.misc[tid] = 0;
+    if (MODE == PX_MODE_SWEEP && P.doFinish) {
+      /* split pipeline: the lists of the substep being finished come back from the world's hand-over record -- with
+       * the state loads above, in ONE round trip to DRAM (whole capacities: the manifold count is not awaited) */
+      const uint8_t *h = P.hand + (size_t)world * P.H.stride;
+      handCopy<NT>(s.mids, h + P.H.mids, MM * 4u);
+      handCopy<NT>(s.list, h + P.H.list, 2u * MM * 2u);
+      handCopy<NT>(s.listStart, h + P.H.listStart, (D + 1u) * 2u);
+      handCopy<NT>(s.cnt, h + P.H.cnt, D * 2u);
+      handCopy<NT>(s.cntB, h + P.H.cntB, D * 2u);
+      handCopy<NT>(s.posOf, h + P.H.posOf, D);
+      handCopy<NT>(s.restFlag, h + P.H.restFlag, D);
+      handCopy<NT>(s.wakeFlag, h + P.H.wakeFlag, D);
+    }
   }
   /* thread-private body state: slot x = tid + r * NT lives in this thread's registers */
   float rAngle[R], rFx[R], rFy[R], rTq[R], rSlp[R];
@@ -1668,20 +1681,6 @@ __global__ void __launch_bounds__(NT, NT == 128 ? PX_MINB128 : (MODE == PX_MODE_
     PROF_MARK(4)
 
     if (runFinish) {
-    if (sweepMode) {
-      /* the lists of the substep being finished come back from its hand-over record */
-      const uint32_t Mh = min(((const uint32_t *)(hand + P.H.scalars))[0], MM);
-      handCopy<NT>(s.mids, hand + P.H.mids, Mh * 4u);
-      handCopy<NT>(s.list, hand + P.H.list, 2u * Mh * 2u);
-      handCopy<NT>(s.listStart, hand + P.H.listStart, (D + 1u) * 2u);
-      handCopy<NT>(s.cnt, hand + P.H.cnt, D * 2u);
-      handCopy<NT>(s.cntB, hand + P.H.cntB, D * 2u);
-      handCopy<NT>(s.posOf, hand + P.H.posOf, D);
-      handCopy<NT>(s.restFlag, hand + P.H.restFlag, D);
-      handCopy<NT>(s.wakeFlag, hand + P.H.wakeFlag, D);
-      if (tid == 0) s.misc[MI_SLEEPING] = 0;
-      __syncthreads();
-    }
     /* ====================== phase F: integrate velocities, correct positions, sleep ==== */
     uint32_t sleepingLocal = 0;
 #pragma unroll
