@@ -179,8 +179,10 @@ PX_API void pxBatchFree(PxBatch *b);
 
 /* -------------------------------------------------------------------------------- stepping */
 
-/* K x pxWorldStepWithDt (src/px_world.c:410-420) for every world, one kernel launch, state
- * resident in shared memory across the K substeps.  Asynchronous on the batch's stream. */
+/* K x pxWorldStepWithDt (src/px_world.c:410-420) for every world.  Small batches: one kernel launch, state
+ * resident in shared memory across the K substeps.  Large batches: a sweep kernel and a solver kernel per
+ * substep, the two halves of the batch on two internal streams that fork from and join the batch's stream.
+ * Asynchronous on the batch's stream either way. */
 PX_API int pxBatchStep(PxBatch *b, uint32_t kSubsteps);
 
 /* One step with HOST buffers: the mutable blocks of every world are copied host -> HBM from

@@ -662,11 +662,40 @@ static int launchRange(PxBatch *b, uint32_t kSubsteps, uint32_t first, uint32_t 
   return 0;
 }
 
+/* the two helper streams (host-buffer steps pipeline their world ranges over them) */
+static int ensureAux(PxBatch *b) {
+  if (b->auxReady) return 0;
+  for (int i = 0; i < 2; i++) {
+    CU(cudaStreamCreateWithFlags(&b->aux[i], cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&b->evJoin[i], cudaEventDisableTiming));
+  }
+  CU(cudaEventCreateWithFlags(&b->evFork, cudaEventDisableTiming));
+  b->auxReady = true;
+  return 0;
+}
+
 extern "C" int pxBatchStep(PxBatch *b, uint32_t kSubsteps) {
   if (!b) return pxSetError(-1, "pxBatchStep: NULL batch");
   if (useDevice(b)) return -1;
   if (flushCommands(b)) return -1;
   if (kSubsteps == 0) return 0;
+  /* Split pipeline, large batches: the two halves of the batch are stepped on the two helper streams.  Each kernel of
+   * a half ends in a partial wave of resident CTAs (8 192 worlds are 2.8 waves of the solver kernel); with two
+   * independent chains of launches the other half's next kernel fills those SMs.  PX_OVERLAP=1 turns it off. */
+  static const char *ov = getenv("PX_OVERLAP");
+  const bool twoRanges = b->split && b->L.nWorlds >= 12u * (uint32_t)b->numSms && !(ov && atoi(ov) == 1);
+  if (twoRanges) {
+    if (ensureAux(b)) return -1;
+    CU(cudaEventRecord(b->evFork, b->stream));
+    const uint32_t W = b->L.nWorlds, half = W / 2u;
+    for (int i = 0; i < 2; i++) {
+      CU(cudaStreamWaitEvent(b->aux[i], b->evFork, 0));
+      if (launchRange(b, kSubsteps, i ? half : 0u, i ? W - half : half, b->aux[i], 0)) return -1;
+      CU(cudaEventRecord(b->evJoin[i], b->aux[i]));
+      CU(cudaStreamWaitEvent(b->stream, b->evJoin[i], 0));
+    }
+    return 0;
+  }
   return launchRange(b, kSubsteps, 0, b->L.nWorlds, b->stream, 0);
 }
 
@@ -687,14 +716,7 @@ extern "C" int pxBatchStepHost(PxBatch *b, uint32_t kSubsteps, void *hostMut, ui
     const uint32_t u = chunks >= 3 ? 2u * c - 1u : c;
     return (uint32_t)((uint64_t)W * u / units);
   };
-  if (!b->auxReady) {
-    for (int i = 0; i < 2; i++) {
-      CU(cudaStreamCreateWithFlags(&b->aux[i], cudaStreamNonBlocking));
-      CU(cudaEventCreateWithFlags(&b->evJoin[i], cudaEventDisableTiming));
-    }
-    CU(cudaEventCreateWithFlags(&b->evFork, cudaEventDisableTiming));
-    b->auxReady = true;
-  }
+  if (ensureAux(b)) return -1;
   /* fork: the helper streams start after everything already queued on the batch's stream */
   CU(cudaEventRecord(b->evFork, b->stream));
   for (int i = 0; i < 2; i++) CU(cudaStreamWaitEvent(b->aux[i], b->evFork, 0));
