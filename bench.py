@@ -55,7 +55,7 @@ def parse_args():
     ap.add_argument("--max-manifolds", type=int, default=0, help="per-world manifold capacity (0 = library default)")
     ap.add_argument("--max-pairs", type=int, default=0, help="per-world AABB-pass pair capacity (0 = library default)")
     ap.add_argument("--cpu-worlds", type=int, default=0, help="worlds in the CPU baseline sample (0 = 2 per core)")
-    ap.add_argument("--e2e-chunks", type=int, default=4, help="world ranges pipelined per host-buffer step")
+    ap.add_argument("--e2e-chunks", type=int, default=5, help="world ranges pipelined per host-buffer step")
     ap.add_argument("--control", action="store_true",
                     help="BASELINE config 5: polygon stacks, PDPHYZX_UNIT_MM, every step the host queues one applyImpulse per "
                          "world and a setGravity before stepping --fused substeps (compare --fused 1 with --fused 8)")

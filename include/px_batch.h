@@ -188,8 +188,9 @@ PX_API int pxBatchStep(PxBatch *b, uint32_t kSubsteps);
 /* One step with HOST buffers: the mutable blocks of every world are copied host -> HBM from
  * `hostMut` (layout and size of pxBatchHostMutable(); NULL = that staging buffer; pinned memory
  * for the copies to be asynchronous), stepped K substeps and copied back, in `chunks`
- * contiguous world ranges (0 = default) pipelined over two internal streams so that the PCIe
- * copies of one range run under the substeps of another.  Ordered after everything queued on
+ * contiguous world ranges (0 = default: five, the first and the last half as long as the inner ones)
+ * pipelined over three internal streams so that the PCIe copies of one range run under the substeps
+ * of another.  Ordered after everything queued on
  * the batch's stream; pxBatchSync (or later work on the stream) waits for all of it.  This is
  * what a px->world->step over N host-resident worlds costs end to end. */
 PX_API int pxBatchStepHost(PxBatch *b, uint32_t kSubsteps, void *hostMut, uint32_t chunks);

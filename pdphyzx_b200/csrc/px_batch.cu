@@ -19,7 +19,8 @@
 #include "px_internal.h"
 #include "px_step.cuh"
 
-#define PX_REGIONS 3u       /* scratch regions: the batch's stream and the two helper streams of pxBatchStepHost */
+#define PX_AUX 3           /* helper streams: world ranges of a step run side by side on them */
+#define PX_REGIONS 4u       /* scratch regions (fused pipeline): the batch's stream and the helper streams of pxBatchStepHost */
 #define PX_COUNTER_RING 1024u /* >= launches that can be in flight at once (a host-buffer step queues (2K + 1) x chunks) */
 
 struct PxBatch {
@@ -63,8 +64,8 @@ struct PxBatch {
   uint64_t launches;
   int ctasPerSm, numSms;
   /* pxBatchStepHost: two helper streams pipeline the chunks of a host-buffer step */
-  cudaStream_t aux[2];
-  cudaEvent_t evFork, evJoin[2];
+  cudaStream_t aux[PX_AUX];
+  cudaEvent_t evFork, evJoin[PX_AUX];
   bool auxReady;
   cudaEvent_t evTimer[2]; /* pxBatchTimerStart / pxBatchTimerStop */
   bool timerReady;
@@ -312,7 +313,7 @@ extern "C" void pxBatchFree(PxBatch *b) {
   cudaFree(b->dScratch);
   cudaFree(b->dHand);
   if (b->auxReady) {
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < PX_AUX; i++) {
       cudaStreamDestroy(b->aux[i]);
       cudaEventDestroy(b->evJoin[i]);
     }
@@ -665,7 +666,7 @@ static int launchRange(PxBatch *b, uint32_t kSubsteps, uint32_t first, uint32_t 
 /* the two helper streams (host-buffer steps pipeline their world ranges over them) */
 static int ensureAux(PxBatch *b) {
   if (b->auxReady) return 0;
-  for (int i = 0; i < 2; i++) {
+  for (int i = 0; i < PX_AUX; i++) {
     CU(cudaStreamCreateWithFlags(&b->aux[i], cudaStreamNonBlocking));
     CU(cudaEventCreateWithFlags(&b->evJoin[i], cudaEventDisableTiming));
   }
@@ -681,16 +682,17 @@ extern "C" int pxBatchStep(PxBatch *b, uint32_t kSubsteps) {
   if (kSubsteps == 0) return 0;
   /* Split pipeline, large batches: the two halves of the batch are stepped on the two helper streams.  Each kernel of
    * a half ends in a partial wave of resident CTAs (8 192 worlds are 2.8 waves of the solver kernel); with two
-   * independent chains of launches the other half's next kernel fills those SMs.  PX_OVERLAP=1 turns it off. */
+   * independent chains of launches the other half's next kernel fills those SMs.  PX_OVERLAP=<n>: n ranges (1 = off). */
   static const char *ov = getenv("PX_OVERLAP");
-  const bool twoRanges = b->split && b->L.nWorlds >= 12u * (uint32_t)b->numSms && !(ov && atoi(ov) == 1);
-  if (twoRanges) {
+  const uint32_t nRanges = (ov && atoi(ov) >= 1 && atoi(ov) <= PX_AUX) ? (uint32_t)atoi(ov) : 2u;
+  if (b->split && b->L.nWorlds >= 12u * (uint32_t)b->numSms && nRanges > 1) {
     if (ensureAux(b)) return -1;
     CU(cudaEventRecord(b->evFork, b->stream));
-    const uint32_t W = b->L.nWorlds, half = W / 2u;
-    for (int i = 0; i < 2; i++) {
+    const uint32_t W = b->L.nWorlds;
+    for (uint32_t i = 0; i < nRanges; i++) {
+      const uint32_t first = (uint32_t)((uint64_t)W * i / nRanges), last = (uint32_t)((uint64_t)W * (i + 1) / nRanges);
       CU(cudaStreamWaitEvent(b->aux[i], b->evFork, 0));
-      if (launchRange(b, kSubsteps, i ? half : 0u, i ? W - half : half, b->aux[i], 0)) return -1;
+      if (launchRange(b, kSubsteps, first, last - first, b->aux[i], 0)) return -1;
       CU(cudaEventRecord(b->evJoin[i], b->aux[i]));
       CU(cudaStreamWaitEvent(b->stream, b->evJoin[i], 0));
     }
@@ -705,7 +707,7 @@ extern "C" int pxBatchStepHost(PxBatch *b, uint32_t kSubsteps, void *hostMut, ui
   if (flushCommands(b)) return -1;
   uint8_t *host = hostMut ? (uint8_t *)hostMut : b->hMut;
   const uint32_t W = b->L.nWorlds;
-  if (chunks == 0) chunks = 4;
+  if (chunks == 0) chunks = 5;
   if (chunks > W) chunks = W;
   /* world ranges: the first and the last get half the worlds of an inner one -- nothing overlaps the first range's
    * H2D copy or the last range's D2H copy, so those two are kept short */
@@ -719,19 +721,21 @@ extern "C" int pxBatchStepHost(PxBatch *b, uint32_t kSubsteps, void *hostMut, ui
   if (ensureAux(b)) return -1;
   /* fork: the helper streams start after everything already queued on the batch's stream */
   CU(cudaEventRecord(b->evFork, b->stream));
-  for (int i = 0; i < 2; i++) CU(cudaStreamWaitEvent(b->aux[i], b->evFork, 0));
+  static const char *hs = getenv("PX_HOST_STREAMS"); /* tuning switch */
+  const uint32_t nStreams = (hs && atoi(hs) >= 1 && atoi(hs) <= PX_AUX) ? (uint32_t)atoi(hs) : (uint32_t)PX_AUX;
+  for (uint32_t i = 0; i < nStreams; i++) CU(cudaStreamWaitEvent(b->aux[i], b->evFork, 0));
   const size_t stride = b->L.mutStride;
   for (uint32_t c = 0; c < chunks; c++) {
     const uint32_t first = edge(c), last = edge(c + 1);
     const uint32_t n = last - first;
     if (!n) continue;
-    cudaStream_t st = b->aux[c & 1];
+    cudaStream_t st = b->aux[c % nStreams];
     CU(cudaMemcpyAsync(b->dMut + first * stride, host + first * stride, n * stride, cudaMemcpyHostToDevice, st));
-    if (kSubsteps && launchRange(b, kSubsteps, first, n, st, 1u + (c & 1u))) return -1;
+    if (kSubsteps && launchRange(b, kSubsteps, first, n, st, 1u + c % nStreams)) return -1;
     CU(cudaMemcpyAsync(host + first * stride, b->dMut + first * stride, n * stride, cudaMemcpyDeviceToHost, st));
   }
-  /* join: later work on the batch's stream (and pxBatchSync) waits for both helpers */
-  for (int i = 0; i < 2; i++) {
+  /* join: later work on the batch's stream (and pxBatchSync) waits for the helpers */
+  for (uint32_t i = 0; i < nStreams; i++) {
     CU(cudaEventRecord(b->evJoin[i], b->aux[i]));
     CU(cudaStreamWaitEvent(b->stream, b->evJoin[i], 0));
   }
