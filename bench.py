@@ -515,7 +515,9 @@ def run_ours(args):
             # costs -> issue-slot utilisation at the rate measured live above
             ks = facts["kernels"]
             dom = ks["sweep"] if pipe["split"] else ks["fused"]
-            out["roofline"]["traffic"] = dom["dram_bytes_per_launch"]
+            # the capture may hold launches over a part of the batch (large batches are stepped as two halves on two
+            # streams): scaled to the worlds of the launch that `launch_ms` and the algorithmic bytes refer to
+            out["roofline"]["traffic"] = dom["dram_bytes_per_launch"] * args.worlds / facts["worlds"]
             out["roofline"]["traffic_source"] = "profiles/" + facts["_file"]
             sm_hz = (clocks.get("sm_mhz") or 1965.0) * 1e6
             n_sms = info.get("num_sms", 148)
