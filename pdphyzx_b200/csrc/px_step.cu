@@ -2671,7 +2671,8 @@ static cudaError_t configureReplay() {
   err = cudaFuncSetAttribute(pxReplayKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
   if (err != cudaSuccess) return err;
   /* many small CTAs: ask for the largest shared-memory carve-out, or the default split caps residency */
-  err = cudaFuncSetAttribute(pxReplayKernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  static const char *cv = getenv("PX_REPLAY_CARVEOUT"); /* tuning switch: percent of the SM's L1/shared memory asked for as shared */
+  err = cudaFuncSetAttribute(pxReplayKernel, cudaFuncAttributePreferredSharedMemoryCarveout, cv ? atoi(cv) : (int)cudaSharedmemCarveoutMaxShared);
   if (err != cudaSuccess) return err;
   if (dev >= 0 && dev < 64) done[dev] = true;
   return cudaSuccess;
