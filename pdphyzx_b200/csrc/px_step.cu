@@ -2065,7 +2065,7 @@ __device__ __forceinline__ void buildSchedule(const PxStepParams &P, uint8_t *sm
   }
   /* visits per key, two 16-bit counters per word; every visit's key is kept for the scatter (0xffff: a manifold's
    * absent second contact) */
-  uint16_t *keys = (uint16_t *)(smem + P.solveS.queue);
+  uint16_t *keys = (uint16_t *)(smem + P.solveS.vkeys);
   const uint32_t magic = 0xffffffffu / II + 1u; /* tau / II == umulhi(tau, magic) for tau * II < 2^32 */
   for (uint32_t i = lane; i < (nKeys + 3u) / 2u; i += 32u) h32[i] = 0;
   __syncwarp();
@@ -2175,8 +2175,8 @@ __global__ void __launch_bounds__(PX_REPLAY_THREADS, PX_REPLAY_MINB) pxReplayKer
   const uint32_t D = L.maxDynamic, S = L.maxStatic, MM = L.maxManifolds;
   const uint32_t lane = threadIdx.x;
   float4 *bodyV = (float4 *)(smemRaw + P.solveS.bodyV);
-  float *bodyI = (float *)(smemRaw + P.solveS.bodyM); /* inverse inertia; the inverse mass rides in bodyV.w */
-  uint16_t *segS = (uint16_t *)(smemRaw + P.solveS.sig); /* PX_SEG_SMEM entries behind the body rows */
+  float *bodyI = (float *)(smemRaw + P.solveS.bodyI); /* inverse inertia; the inverse mass rides in bodyV.w */
+  uint16_t *segS = (uint16_t *)(smemRaw + P.solveS.segS); /* PX_SEG_SMEM entries behind the body rows */
   const uint32_t aBodyV = sAddr(bodyV), aBodyI = sAddr(bodyI);
   const float eps = L.epsilon;
   for (;;) {
@@ -2513,7 +2513,7 @@ extern "C" void pxPlanSmem(const PxBatchLayout *L, int vertsInSmem, int staticSo
   const uint32_t ry = o;
   S->nextw = take(2 * MM * 2); S->sig = take(MM * 4); S->queue = take((qcap + 4) * 4); /* + the dummy sink at [qcap] */
   const uint32_t ryEnd = o;
-  S->predA = S->predB = S->rankOf = S->tlev = S->khist = S->bodyM = 0;
+  S->predA = S->predB = S->rankOf = S->tlev = S->khist = S->vkeys = S->bodyI = S->segS = 0;
   if (staticSolver) { /* region Y': the rings in pool-rank space take the place of the dynamic solver's tables */
     o = ry;
     S->predA = take(MM * 2); S->predB = take(MM * 2); S->rankOf = take(MM * 2);
@@ -2627,11 +2627,10 @@ extern "C" void pxPlanSolveSmem(const PxBatchLayout *L, const PxSmemPlan *S, int
     return at;
   };
   if (staticSolver) { /* pxReplayKernel: the schedule tables, then -- in their place -- the velocity and mass rows */
-    out->bodyV = take(NB * 16); out->bodyM = take(NB * 4);
-    out->sig = take(PX_SEG_SMEM * 2); /* the segment table's copy */
+    out->bodyV = take(NB * 16); out->bodyI = take(NB * 4); out->segS = take(PX_SEG_SMEM * 2);
     const uint32_t rows = o;
     o = 0;
-    out->tlev = take(MM * 2); out->khist = take((PX_KSM(MM) + 2) * 2); out->queue = take(PX_VCAP(MM) * 2); /* `queue`: the visits' keys */
+    out->tlev = take(MM * 2); out->khist = take((PX_KSM(MM) + 2) * 2); out->vkeys = take(PX_VCAP(MM) * 2);
     out->qcap = S->qcap;
     out->total = o > rows ? o : rows;
     return;

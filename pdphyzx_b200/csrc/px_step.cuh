@@ -44,23 +44,29 @@ struct PxSmemPlan {
   uint32_t predA, predB; /* u16[MM] BY POOL RANK: predecessor of the manifold in its A / B body's ring: rank | closes the ring << 10 |
                             contacts of the predecessor << 11 | own contacts << 13 (0xffff: static B) */
   uint32_t rankOf;       /* u16[MM] pool rank by manifold slot */
-  /* pxReplayKernel only (predA there: u32[MM], A word | B word << 16) */
-  uint32_t tlev;         /* u16[MM] start round of the manifold's first contact inside one iteration, by rank */
-  uint32_t khist;        /* u16[KCAP + 2] visits per (slot, phase) key, then their exclusive prefix = segment starts / cursors */
-  uint32_t bodyM;        /* replay kernel only: float2[NB] {inverse mass, inverse inertia} */
+  /* pxReplayKernel's own plan (pxPlanSolveSmem, static solver).  While the schedule is built: */
+  uint32_t tlev;         /* u16[MM] by pool rank: start round of the manifold's first contact inside one iteration | contacts << 14 */
+  uint32_t khist;        /* u16[PX_KSM + 2] visits per (slot, phase) key, then their exclusive prefix = segment starts / scatter cursors */
+  uint32_t vkeys;        /* u16[2 * MM] key of every contact visit (0xffff: a manifold's absent second contact) */
+  /* ... and, in the same bytes, while it is replayed: bodyV above = float4[NB] {vel.x, vel.y, angularVelocity, inverse mass} */
+  uint32_t bodyI;        /* f32[NB] inverse inertia */
+  uint32_t segS;         /* u16[PX_SEG_SMEM] the segment table's copy */
   uint32_t total; /* bytes */
   uint32_t qcap;  /* ring capacity (power of two >= MM) */
   uint32_t vertsInSmem;
 };
 /* static schedule: contact visits per world <= 2 * maxManifolds; (slot, phase) keys <= depth + period <= 4 * maxManifolds + margin */
 #define PX_VCAP(MM) (2u * (MM))
-#define PX_KCAP(MM) (4u * (MM) + 16u)
+#define PX_KCAP(MM) (4u * (MM) + 16u) /* entries of the segment table in the hand-over record */
 #define PX_KSM(MM) (2u * (MM) + 64u) /* (slot, phase) keys pxReplayKernel's counting sort has room for in shared memory; a period whose keys
                                         do not fit is skipped (the sequential schedule's always fit) */
 #define PX_SEG_SMEM 512u /* segment-table entries pxReplayKernel keeps in shared memory (longer tables are read from global memory) */
 #define PX_PLANE 2048u /* entries between the operand planes of the visit records: >= PX_VCAP of the largest maxManifolds (1024), a
                           constant so that one address register serves the three loads of a visit */
-#define PX_II_MARGIN 3u /* period tried first = longest body ring + this (profiles/sched_sim.py: on settled 252-body piles the least feasible period is ring + 0..5, ring + 2 on average; every extra round of period costs iterations - 1 replay rounds, a failed attempt costs a relaxation run to its cap) */
+#define PX_II_MARGIN 3u /* smallest margin: the first period tried for a world is its longest body ring + max(this, the margin that
+                           worked last substep).  profiles/sched_sim.py: on settled 252-body piles the least feasible period is
+                           ring + 0..5, ring + 2 on average; every extra round of period costs iterations - 1 replay rounds, a
+                           failed attempt costs a relaxation run to its pass cap */
 
 /* A world's hand-over record in global memory (split pipeline): byte offsets of what the sweep
  * kernel leaves for the solver kernel and for the phase F that follows it.  Laid out by
@@ -68,7 +74,7 @@ struct PxSmemPlan {
 struct PxHandLayout {
   uint32_t mids, nextw, sig, queue;                              /* solver inputs */
   uint32_t list, listStart, cnt, cntB, posOf, restFlag, wakeFlag; /* phase F inputs */
-  uint32_t scalars;                                               /* u32[8]: manifolds, ready visits | period, phases, depth, contact visits, longest ring */
+  uint32_t scalars;                                               /* u32[8], see PX_HS_* */
   uint32_t records;                                               /* float4[3][maxManifolds] manifold records */
   /* static schedule: the contact visits of ONE iteration sorted by (round mod period, round div period), as three
    * float4 planes of PX_VCAP entries {n, ra | rb, rcpDenom, e | sf, df, ids, -}, and the segment starts by key */
@@ -79,8 +85,10 @@ struct PxHandLayout {
 };
 enum { PX_MODE_FUSED = 0, PX_MODE_SWEEP = 1 };
 enum { PX_SOLVER_DYNAMIC = 0, PX_SOLVER_STATIC = 1 };
-enum { PX_HS_M = 0, PX_HS_READY = 1, PX_HS_PERIOD = 2, PX_HS_PHASES = 3, PX_HS_DEPTH = 4, PX_HS_VISITS = 5, PX_HS_RING = 6,
-       PX_HS_HINT = 7 /* written by pxReplayKernel only: the period margin that worked last substep */ };
+/* hand-over scalars: manifolds kept | dataflow solver: visits ready at the start (bit 31: the replay kernel's "schedule
+ * did not converge", which cannot happen) | 2-5 unused | longest ring, in contact visits | written by pxReplayKernel
+ * only and kept from substep to substep: the period margin that worked last time */
+enum { PX_HS_M = 0, PX_HS_READY = 1, PX_HS_RING = 6, PX_HS_HINT = 7 };
 
 #define PX_PROF_SLOTS 16 /* 0-5 phases A-F, 6 solver rounds, 7 polygon pairs << 32 | after quick reject, 8-11 narrowphase stages,
                             12 static schedule (end of phase D), 13 relaxation votes << 32 | period, 14 sort + stream build cycles,
@@ -110,7 +118,7 @@ struct PxStepParams {
   uint32_t doFinish, doSweep, traceNow;
   uint8_t *hand; /* hand-over records, one per world, H.stride apart */
   PxHandLayout H;
-  PxSmemPlan solveS; /* shared memory of pxSolveKernel (bodyP, bodyV, mids, nextw, sig, queue, misc, hdr) or pxReplayKernel (bodyV, bodyM) */
+  PxSmemPlan solveS; /* shared memory of pxSolveKernel (bodyP, bodyV, mids, nextw, sig, queue, misc, hdr) or of pxReplayKernel */
 };
 
 

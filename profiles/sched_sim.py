@@ -9,6 +9,8 @@ manifold list of the last substep and measures, per world:
     max_m (T(m,k+1) - T(m,k)) a replayed (modulo) schedule would need,
   * the size of the ready set.
 Run: python profiles/sched_sim.py [--worlds 4] [--settle 1000] [--iterations 10] [--mix mixed]
+     python profiles/sched_sim.py --modulo     the periodic schedule pxReplayKernel derives: longest ring, least
+                                               feasible period, relaxation passes in rank order, replay chunks
 """
 from __future__ import annotations
 
@@ -128,7 +130,7 @@ def main():
               f"mean ready {np.mean(sz):.1f} (unlimited {np.mean(szi):.1f}) | both contacts per visit: {rm} rounds")
 
 
-if __name__ == "__main__" and "--static" not in sys.argv:
+if __name__ == "__main__" and "--static" not in sys.argv and "--modulo" not in sys.argv:
     main()
 
 
@@ -211,3 +213,88 @@ def main_static():
 
 if __name__ == "__main__" and "--static" in sys.argv:
     main_static()
+
+
+# ---------------------------------------------------------------- periodic (modulo) schedule: pxReplayKernel's
+def rings(idm):
+    """Per manifold: predecessor in its A body's ring and in its B body's ring (-1: static B), and whether that edge
+    closes the ring (carries the iteration boundary)."""
+    M = len(idm)
+    lists = {}
+    for m, (a, b, bd, cnt) in enumerate(idm):
+        lists.setdefault(int(a), []).append(m)
+        if bd:
+            lists.setdefault(int(b), []).append(m)
+    pA = np.zeros(M, np.int64); wA = np.zeros(M, np.int64)
+    pB = np.full(M, -1, np.int64); wB = np.zeros(M, np.int64)
+    for body, lst in lists.items():
+        for i, m in enumerate(lst):
+            p, w = lst[i - 1], (1 if i == 0 else 0)
+            if int(idm[m][0]) == body:
+                pA[m], wA[m] = p, w
+            else:
+                pB[m], wB[m] = p, w
+    return lists, pA, wA, pB, wB
+
+
+def relax_in_rank_order(idm, II, max_passes=40):
+    """Least start rounds t(m) with t(m) >= t(p) + contacts(p) - [closing edge] * II, relaxed in pool (rank) order as
+    the device does.  Returns (t, passes) or (None, passes) if the period is infeasible."""
+    M = len(idm)
+    d = idm[:, 3].astype(np.int64)
+    _, pA, wA, pB, wB = rings(idm)
+    t = np.zeros(M, np.int64)
+    for p in range(1, max_passes + 1):
+        moved = False
+        for m in range(M):
+            v = max(t[m], t[pA[m]] + d[pA[m]] - wA[m] * II)
+            if pB[m] >= 0:
+                v = max(v, t[pB[m]] + d[pB[m]] - wB[m] * II)
+            if v != t[m]:
+                t[m] = v
+                moved = True
+        if not moved:
+            return t, p
+        if t.max() > 4000:
+            break
+    return None, max_passes
+
+
+def replay_chunks(idm, t, II, iterations, cap=32):
+    d = idm[:, 3].astype(np.int64)
+    lv = np.concatenate([t, t[d > 1] + 1])
+    rounds = int(lv.max()) + (iterations - 1) * II + 1
+    counts = np.zeros(rounds, np.int64)
+    for k in range(iterations):
+        np.add.at(counts, lv + k * II, 1)
+    chunks = int(np.ceil(counts / cap).sum())
+    return rounds, chunks, float(counts.sum() / max(chunks, 1))
+
+
+def main_modulo():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--worlds", type=int, default=6)
+    ap.add_argument("--settle", type=int, default=1000)
+    ap.add_argument("--iterations", type=int, default=10)
+    ap.add_argument("--mix", default="mixed")
+    ap.add_argument("--modulo", action="store_true")
+    args = ap.parse_args()
+    for w, idm in enumerate(manifold_list(args)):
+        lists, *_ = rings(idm)
+        d = idm[:, 3].astype(np.int64)
+        ring = max(sum(d[m] for m in l) for l in lists.values())
+        dyn, _, _ = simulate(idm, args.iterations, 32)
+        least = next(II for II in range(max(ring, 1), ring + 200) if relax_in_rank_order(idm, II)[0] is not None)
+        line = f"world {w}: M={len(idm)} visits/it={int(d.sum())} longest ring={ring} dataflow rounds={dyn} | least period={least}"
+        for II in (least, ring + 3, ring + 5):
+            t, passes = relax_in_rank_order(idm, II)
+            if t is None:
+                line += f" | II={II}: infeasible"
+                continue
+            rounds, chunks, lanes = replay_chunks(idm, t, II, args.iterations)
+            line += f" | II={II}: passes {passes} depth {int(t.max()) + 1} rounds {rounds} chunks {chunks} lanes {lanes:.1f}"
+        print(line, flush=True)
+
+
+if __name__ == "__main__" and "--modulo" in sys.argv:
+    main_modulo()
