@@ -1408,6 +1408,16 @@ __global__ void __launch_bounds__(NT, NT == 128 ? PX_MINB128 : (MODE == PX_MODE_
           if (s.flags[b] & PX_FLAG_SLEEPING) s.wakeFlag[a] = 1;
         }
         if (bdyn) atomicAdd(&s.fillB[b], 1u); /* bodyB-role manifold count of b */
+        if (staticSched && g0.z > allowedPen) {
+          /* pxManifoldPositionalCorrection, px_manifold.c:217-255: the two moves depend on nothing the solver changes;
+           * phase F (in pxReplayKernel) adds them to the integrated positions body by body, in pool order */
+          const float excess = g0.z - allowedPen;
+          const float mag = fDiv(excess * 0.2f, pA.z + pB.z);
+          const V2 corr = normal * mag;
+          const V2 dA = -(corr * pA.z), dB = corr * pB.z;
+          ((float4 *)(smemRaw + P.S.cm))[ms] = make_float4(dA.x, dA.y, dB.x, dB.y);
+          s.mids[ms] = w | 0x80000000u; /* bit 31: the manifold corrects positions */
+        }
       }
     }
     __syncthreads();
@@ -1524,6 +1534,22 @@ __global__ void __launch_bounds__(NT, NT == 128 ? PX_MINB128 : (MODE == PX_MODE_
           ring += own;
         }
         if (ring) atomicMax(&s.misc[MI_RING], ring);
+        /* phase F's inputs for this body (pxReplayKernel): its positional-correction moves in pool order, and the
+         * sleep flags of its SORTED POSITION -- set by slot, tested by position: the reference's behaviour */
+        {
+          const float4 *cmS = (const float4 *)(smemRaw + P.S.cm);
+          float2 *cvec = (float2 *)(hand + P.H.cvec) + start;
+          uint32_t k = 0;
+          for (uint32_t i = 0; i < n; i++) {
+            const uint32_t ms = s.list[start + i];
+            if (s.mids[ms] >> 31) {
+              const float4 c = cmS[ms];
+              cvec[k++] = i >= nBx ? make_float2(c.x, c.y) : make_float2(c.z, c.w);
+            }
+          }
+          const uint32_t p = s.posOf[x];
+          ((uint32_t *)(hand + P.H.bodyF))[x] = start | (k << 16) | (s.wakeFlag[p] ? 0x40000000u : 0u) | (s.restFlag[p] ? 0x80000000u : 0u);
+        }
       } else {
       for (uint32_t i = 0; i < n; i++) {
         const uint32_t ms = s.list[start + i];
@@ -1588,14 +1614,13 @@ __global__ void __launch_bounds__(NT, NT == 128 ? PX_MINB128 : (MODE == PX_MODE_
       /* hand the substep over: what the solver kernel needs (dynamic: manifold ids, successor words, initial
        * signals, the first ready visits; static: the visit stream written above and its segment table) and what
        * phase F needs after it (the per-body lists) */
-      handCopy<NT>(hand + P.H.mids, s.mids, M * 4u);
       if (staticSched) {
         if (tid == 0) ((uint32_t *)(hand + P.H.scalars))[PX_HS_RING] = s.misc[MI_RING];
       } else {
-        handCopy<NT>(hand + P.H.nextw, s.nextw, M * 4u);
-        handCopy<NT>(hand + P.H.sig, s.sig, M * 4u);
-        handCopy<NT>(hand + P.H.queue, s.queue, min(s.misc[MI_QTAIL], P.S.qcap) * 4u);
-      }
+      handCopy<NT>(hand + P.H.mids, s.mids, M * 4u);
+      handCopy<NT>(hand + P.H.nextw, s.nextw, M * 4u);
+      handCopy<NT>(hand + P.H.sig, s.sig, M * 4u);
+      handCopy<NT>(hand + P.H.queue, s.queue, min(s.misc[MI_QTAIL], P.S.qcap) * 4u);
       handCopy<NT>(hand + P.H.list, s.list, 2u * M * 2u);
       handCopy<NT>(hand + P.H.listStart, s.listStart, (D + 1u) * 2u);
       handCopy<NT>(hand + P.H.cnt, s.cnt, D * 2u);
@@ -1603,6 +1628,7 @@ __global__ void __launch_bounds__(NT, NT == 128 ? PX_MINB128 : (MODE == PX_MODE_
       handCopy<NT>(hand + P.H.posOf, s.posOf, D);
       handCopy<NT>(hand + P.H.restFlag, s.restFlag, D);
       handCopy<NT>(hand + P.H.wakeFlag, s.wakeFlag, D);
+      }
       if (tid == 0) {
         uint32_t *sc = (uint32_t *)(hand + P.H.scalars);
         sc[0] = M;
@@ -2188,14 +2214,23 @@ __global__ void __launch_bounds__(PX_REPLAY_THREADS, PX_REPLAY_MINB) pxReplayKer
     const uint8_t *gimm = P.imm + (size_t)world * L.immStride;
     uint8_t *hand = P.hand + (size_t)world * P.H.stride;
     float *gdyn = (float *)(gmut + L.offDyn);
-    const uint32_t iterations = ((const PxWorldHeader *)(gmut + L.offHeader))->iterations & 255u;
+    PxWorldHeader *gh = (PxWorldHeader *)(gmut + L.offHeader);
+    const uint32_t iterations = gh->iterations & 255u;
+    const float dt = gh->dt, linSleepSq = gh->linearSleepThresholdSq, angSleep = gh->angularSleepThreshold;
+    const float timeToSleep = gh->timeToSleep;
     uint32_t *sc = (uint32_t *)(hand + P.H.scalars);
     const uint32_t M = min(sc[PX_HS_M], MM), ring = sc[PX_HS_RING];
-    if (M && iterations) { /* uniform: nothing to solve otherwise */
-      /* the visit operands by rank are read after the relaxation: start them on their way out of DRAM now */
+    const bool solving = M && iterations; /* uniform */
+    unsigned long long *prof = P.prof ? P.prof + (size_t)world * PX_PROF_SLOTS : nullptr;
+    /* what is read late is started on its way out of DRAM now: the visit operands by rank (after the relaxation), and
+     * phase F's rows, body words and correction moves (after the replay) */
+    if (solving)
       for (uint32_t k = 0; k < 3u; k++) prefetchRegion(hand + P.H.vrec + k * PX_PLANE * 16u, 2u * M * 16u, lane, PX_REPLAY_THREADS);
-      unsigned long long *prof = P.prof ? P.prof + (size_t)world * PX_PROF_SLOTS : nullptr;
-      uint32_t II, QN, depth, nVisits;
+    prefetchRegion(gmut + L.offDyn, PX_DYN_ROWS * D * 4u + D, lane, PX_REPLAY_THREADS);
+    prefetchRegion(hand + P.H.bodyF, D * 4u, lane, PX_REPLAY_THREADS);
+    prefetchRegion(hand + P.H.cvec, 2u * M * 8u, lane, PX_REPLAY_THREADS);
+    uint32_t II = 0, QN = 0, depth = 0, nVisits = 0;
+    if (solving) {
       buildSchedule(P, smemRaw, hand, M, ring, prof, II, QN, depth, nVisits);
       __syncwarp(); /* the schedule tables are dead: the body rows take their place; the stream is in global memory */
       /* the segment table is read at the head of every round, on the warp's critical path: keep it in shared memory */
@@ -2203,6 +2238,8 @@ __global__ void __launch_bounds__(PX_REPLAY_THREADS, PX_REPLAY_MINB) pxReplayKer
         const uint16_t *gseg = (const uint16_t *)(hand + P.H.seg);
         for (uint32_t k = lane; k <= II * QN; k += PX_REPLAY_THREADS) segS[k] = gseg[k];
       }
+    }
+    {
       const float *gc = (const float *)(gimm + L.offDynConst);
       for (uint32_t x = lane; x < D; x += PX_REPLAY_THREADS) {
         bodyV[x] = make_float4(gdyn[PX_DYN_VX * D + x], gdyn[PX_DYN_VY * D + x], gdyn[PX_DYN_AV * D + x], gc[PX_DYNC_IMASS * D + x]);
@@ -2213,8 +2250,10 @@ __global__ void __launch_bounds__(PX_REPLAY_THREADS, PX_REPLAY_MINB) pxReplayKer
         bodyI[D + q] = 0.0f;
       }
       __syncwarp();
-      long long t0 = 0;
-      if (prof && lane == 0) t0 = clock64();
+    }
+    long long t0 = 0;
+    if (prof && lane == 0) t0 = clock64();
+    if (solving) { /* phase E */
 
       /* Everything below is one warp's instruction stream and the kernel is issue-bound: the chunk iterator keeps
        * its state in registers (row = slot * QN, the alive phase window [qlo, qhi1) changes only when the period
@@ -2290,21 +2329,99 @@ __global__ void __launch_bounds__(PX_REPLAY_THREADS, PX_REPLAY_MINB) pxReplayKer
         step(b0, b1, b2, cB, a0, a1, a2, cA);
       }
       if (prof && lane == 0) {
-        prof[4] += (unsigned long long)(clock64() - t0);
+        const long long now = clock64();
+        prof[4] += (unsigned long long)(now - t0);
         prof[6] += chunks;
+        t0 = now;
       }
+      if (lane == 0 && (visits != nVisits * iterations || (sc[PX_HS_READY] & 0x80000000u))) gh->statOverflow |= PX_OVERFLOW_INTERNAL;
+    }
+
+    /* ---- phase F, one body per lane: integrate velocities (px_body.c:181-188), positional correction
+     * (px_world.c:288-292: the body's moves, precomputed by the sweep kernel, added in pool order), sleep update
+     * (px_world.c:179-219, flags of the body's sorted position), clear forces (px_world.c:302-311) */
+    {
+      const uint32_t *bodyF = (const uint32_t *)(hand + P.H.bodyF);
+      const float2 *cvec = (const float2 *)(hand + P.H.cvec);
+      uint8_t *gflags = gmut + L.offDynFlags;
+      uint32_t sleeping = 0;
       for (uint32_t x = lane; x < D; x += PX_REPLAY_THREADS) {
-        const float4 bv = bodyV[x];
+        uint32_t fl = gflags[x];
+        if (!(fl & 4u)) continue;
+        const uint32_t word = bodyF[x];
+        float posx = gdyn[PX_DYN_PX * D + x], posy = gdyn[PX_DYN_PY * D + x], angle = gdyn[PX_DYN_ANGLE * D + x];
+        float fx = gdyn[PX_DYN_FX * D + x], fy = gdyn[PX_DYN_FY * D + x], tq = gdyn[PX_DYN_TORQUE * D + x];
+        float slp = gdyn[PX_DYN_SLEEP * D + x];
+        float4 bv = bodyV[x];
+        if (!(fl & PX_FLAG_SLEEPING)) {
+          posx = posx + bv.x * dt;
+          posy = posy + bv.y * dt;
+          float radians = angle + bv.z * dt;
+          radians = fmodf(radians, D_2PI);
+          if (radians < 0) radians += D_2PI;
+          angle = radians;
+          const float c = fSin(P.sinTable, radians + D_PI * 0.5f), sn = fSin(P.sinTable, radians);
+          gdyn[PX_DYN_M00 * D + x] = c;
+          gdyn[PX_DYN_M01 * D + x] = -sn;
+          gdyn[PX_DYN_M10 * D + x] = sn;
+          gdyn[PX_DYN_M11 * D + x] = c;
+        }
+        {
+          const uint32_t start = word & 0xffffu, n = (word >> 16) & 0x3fffu;
+          for (uint32_t i = 0; i < n; i++) {
+            const float2 d = cvec[start + i];
+            posx = posx + d.x;
+            posy = posy + d.y;
+          }
+        }
+        if (word & 0x40000000u) { /* wake flag of the body's sorted position */
+          slp = 0.0f;
+          fl &= ~PX_FLAG_SLEEPING;
+        } else {
+          const bool below = (bv.x * bv.x + bv.y * bv.y <= linSleepSq) && (fabsf(bv.z) <= angSleep);
+          if (!below) {
+            slp = 0.0f;
+            fl &= ~PX_FLAG_SLEEPING;
+          } else if (!(fl & PX_FLAG_SLEEPING)) {
+            slp = slp + dt;
+            if (word & 0x80000000u) slp = slp + dt; /* rest flag of the body's sorted position */
+            if (slp >= timeToSleep) {
+              bv.x = 0.0f;
+              bv.y = 0.0f;
+              bv.z = 0.0f;
+              fx = 0.0f;
+              fy = 0.0f;
+              tq = 0.0f;
+              fl |= PX_FLAG_SLEEPING;
+            }
+          }
+        }
+        if (!(slp >= timeToSleep)) {
+          fx = 0.0f;
+          fy = 0.0f;
+          tq = 0.0f;
+        }
+        sleeping += (fl & PX_FLAG_SLEEPING) ? 1u : 0u;
+        gdyn[PX_DYN_PX * D + x] = posx;
+        gdyn[PX_DYN_PY * D + x] = posy;
         gdyn[PX_DYN_VX * D + x] = bv.x;
         gdyn[PX_DYN_VY * D + x] = bv.y;
         gdyn[PX_DYN_AV * D + x] = bv.z;
+        gdyn[PX_DYN_ANGLE * D + x] = angle;
+        gdyn[PX_DYN_FX * D + x] = fx;
+        gdyn[PX_DYN_FY * D + x] = fy;
+        gdyn[PX_DYN_TORQUE * D + x] = tq;
+        gdyn[PX_DYN_SLEEP * D + x] = slp;
+        gflags[x] = (uint8_t)fl;
       }
-      if (lane == 0 && (visits != nVisits * iterations || (sc[PX_HS_READY] & 0x80000000u))) {
-        PxWorldHeader *wh = (PxWorldHeader *)(gmut + L.offHeader);
-        wh->statOverflow |= PX_OVERFLOW_INTERNAL;
+      sleeping = __reduce_add_sync(0xffffffffu, sleeping);
+      if (lane == 0) {
+        gh->statSleeping = sleeping;
+        gh->substeps = gh->substeps + 1u;
       }
+      if (prof && lane == 0) prof[5] += (unsigned long long)(clock64() - t0);
     }
-    __syncwarp(); /* the next world's tables overwrite what the store above still reads */
+    __syncwarp(); /* the next world's tables overwrite the rows phase F has just read */
   }
 }
 
@@ -2513,10 +2630,12 @@ extern "C" void pxPlanSmem(const PxBatchLayout *L, int vertsInSmem, int staticSo
   const uint32_t ry = o;
   S->nextw = take(2 * MM * 2); S->sig = take(MM * 4); S->queue = take((qcap + 4) * 4); /* + the dummy sink at [qcap] */
   const uint32_t ryEnd = o;
+  S->cm = 0;
   S->predA = S->predB = S->rankOf = S->tlev = S->khist = S->vkeys = S->bodyI = S->segS = 0;
   if (staticSolver) { /* region Y': the rings in pool-rank space take the place of the dynamic solver's tables */
     o = ry;
     S->predA = take(MM * 2); S->predB = take(MM * 2); S->rankOf = take(MM * 2);
+    S->cm = take(MM * 16); /* written in phase C4, when bins / survivors / vertex pool under it are dead */
   }
   o = o > ryEnd ? o : ryEnd;
   o = o > rxEnd ? o : rxEnd;
@@ -2607,12 +2726,14 @@ extern "C" void pxPlanHandover(const PxBatchLayout *L, const PxSmemPlan *S, PxHa
   H->scalars = take(32);
   H->records = take(MM * 3 * 16);
   H->stream = H->seg = 0;
-  H->predA = H->predB = H->vrec = 0;
+  H->predA = H->predB = H->vrec = H->bodyF = H->cvec = 0;
   if (S->rankOf) { /* static schedule */
     H->stream = take(3 * PX_PLANE * 16);
     H->seg = take((PX_KCAP(MM) + 2) * 2);
     H->predA = take(MM * 2); H->predB = take(MM * 2);
     H->vrec = take(3 * PX_PLANE * 16);
+    H->bodyF = take(D * 4);
+    H->cvec = take(2 * MM * 8);
   }
   H->stride = alignUp(o, 128);
 }

@@ -44,6 +44,7 @@ struct PxSmemPlan {
   uint32_t predA, predB; /* u16[MM] BY POOL RANK: predecessor of the manifold in its A / B body's ring: rank | closes the ring << 10 |
                             contacts of the predecessor << 11 | own contacts << 13 (0xffff: static B) */
   uint32_t rankOf;       /* u16[MM] pool rank by manifold slot */
+  uint32_t cm;           /* float4[MM] positional-correction moves of a manifold {A's.x, A's.y, B's.x, B's.y} (phase C4 -> D) */
   /* pxReplayKernel's own plan (pxPlanSolveSmem, static solver).  While the schedule is built: */
   uint32_t tlev;         /* u16[MM] by pool rank: start round of the manifold's first contact inside one iteration | contacts << 14 */
   uint32_t khist;        /* u16[PX_KSM + 2] visits per (slot, phase) key, then their exclusive prefix = segment starts / scatter cursors */
@@ -81,6 +82,10 @@ struct PxHandLayout {
   uint32_t stream, seg;
   uint32_t predA, predB; /* u16[maxManifolds] rings by pool rank (PxSmemPlan.predA) */
   uint32_t vrec;         /* the visit operands by pool rank (entry 2 * rank + contact), same three planes as `stream` */
+  /* static solver: phase F runs in pxReplayKernel.  Per dynamic slot: first entry of its positional-correction moves in
+   * cvec | how many << 16 | its sorted position's wake flag << 30 | rest flag << 31 (px_world.c:179-219 tests them by position) */
+  uint32_t bodyF;        /* u32[maxDynamic] */
+  uint32_t cvec;         /* float2[2 * maxManifolds] the moves, per body in pool order (px_world.c:288-292) */
   uint32_t stride;
 };
 enum { PX_MODE_FUSED = 0, PX_MODE_SWEEP = 1 };
