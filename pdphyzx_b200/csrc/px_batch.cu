@@ -617,8 +617,7 @@ static void splitParams(PxBatch *b, uint32_t first, PxStepParams *P) {
 
 /* launch s of the split pipeline's sweep kernel: phase F of substep s - 1 (s > 0), phases A-D of substep s (s < K) */
 static int launchSweep(PxBatch *b, PxStepParams *P, uint32_t s, uint32_t kSubsteps, uint32_t grid, cudaStream_t stream) {
-  /* static solver: phase F runs in the solver kernel, every sweep launch is phases A-D of substep s */
-  P->doFinish = (!b->staticSched && s > 0) ? 1u : 0u;
+  P->doFinish = s > 0 ? 1u : 0u;
   P->doSweep = s < kSubsteps ? 1u : 0u;
   P->traceNow = (s + 1 == kSubsteps) ? 1u : 0u;
   P->worldCounter = b->dCounters + (b->launches % PX_COUNTER_RING);
@@ -658,7 +657,7 @@ static int launchRange(PxBatch *b, uint32_t kSubsteps, uint32_t first, uint32_t 
    * sweep(A-D) | solve(E) | sweep(F, A-D) | solve(E) | ... | sweep(F) */
   splitParams(b, first, &P);
   const uint32_t gridSweep = n < b->gridMax ? n : b->gridMax, gridSolve = n < b->gridSolve ? n : b->gridSolve;
-  const uint32_t nSweeps = b->staticSched ? kSubsteps : kSubsteps + 1u;
+  const uint32_t nSweeps = kSubsteps + 1u;
   for (uint32_t s = 0; s < nSweeps; s++) {
     if (launchSweep(b, &P, s, kSubsteps, gridSweep, stream)) return -1;
     if (s < kSubsteps && launchSolve(b, &P, gridSolve, stream)) return -1;
@@ -822,7 +821,7 @@ extern "C" int pxBatchStepTimedKernels(PxBatch *b, uint32_t kSubsteps, float ms[
   } else {
     splitParams(b, 0, &P);
     const uint32_t gridSweep = W < b->gridMax ? W : b->gridMax, gridSolve = W < b->gridSolve ? W : b->gridSolve;
-    const uint32_t nSweeps = b->staticSched ? kSubsteps : kSubsteps + 1u;
+    const uint32_t nSweeps = kSubsteps + 1u;
     for (uint32_t s = 0; s < nSweeps; s++) {
       if (launchSweep(b, &P, s, kSubsteps, gridSweep, b->stream) || mark(0)) return -1;
       if (s < kSubsteps && (launchSolve(b, &P, gridSolve, b->stream) || mark(2))) return -1;

@@ -911,8 +911,8 @@ __global__ void __launch_bounds__(NT, NT == 128 ? PX_MINB128 : (MODE == PX_MODE_
     copyRows<NT>((float *)s.order, (const float *)(gmut + L.offDynOrder), D / 4);
     copyRows<NT>((float *)s.hdr, (const float *)(gmut + L.offHeader), sizeof(PxWorldHeader) / 4);
     if (tid < 32 && tid != MI_WORLD) s.misc[tid] = 0;
-    if (MODE == PX_MODE_SWEEP && P.doFinish) {
-      /* split pipeline: the lists of the substep being finished come back from the world's hand-over record -- with
+    if (MODE == PX_MODE_SWEEP && P.doFinish && P.solver != PX_SOLVER_STATIC) {
+      /* split pipeline, dataflow solver: the lists of the substep being finished come back from the world's hand-over record -- with
        * the state loads above, in ONE round trip to DRAM (whole capacities: the manifold count is not awaited) */
       const uint8_t *h = P.hand + (size_t)world * P.H.stride;
       handCopy<NT>(s.mids, h + P.H.mids, MM * 4u);
@@ -936,6 +936,15 @@ __global__ void __launch_bounds__(NT, NT == 128 ? PX_MINB128 : (MODE == PX_MODE_
     rFy[r] = in ? gdynC[PX_DYN_FY * D + x] : 0.0f;
     rTq[r] = in ? gdynC[PX_DYN_TORQUE * D + x] : 0.0f;
     rSlp[r] = in ? gdynC[PX_DYN_SLEEP * D + x] : 0.0f;
+  }
+  /* static solver, phase F of the substep just solved: the body's word (its correction moves in H.cvec, the sleep flags
+   * of its sorted position), loaded with the state */
+  uint32_t rWord[R];
+#pragma unroll
+  for (int r = 0; r < R; r++) {
+    const uint32_t x = tid + r * NT;
+    rWord[r] = (MODE == PX_MODE_SWEEP && P.solver == PX_SOLVER_STATIC && P.doFinish && x < D)
+                   ? ((const uint32_t *)(P.hand + (size_t)world * P.H.stride + P.H.bodyF))[x] : 0u;
   }
   __syncthreads();
 
@@ -1713,7 +1722,7 @@ __global__ void __launch_bounds__(NT, NT == 128 ? PX_MINB128 : (MODE == PX_MODE_
     for (int r = 0; r < R; r++) {
       const uint32_t x = tid + r * NT;
       if (x >= D || !(s.flags[x] & 4u)) continue;
-      const uint32_t p = s.posOf[x];
+      const uint32_t p = staticSched ? 0u : s.posOf[x];
       uint32_t fl = s.flags[x];
       float4 bp = s.bodyP[x];
       float4 bv = s.bodyV[x];
@@ -1730,7 +1739,15 @@ __global__ void __launch_bounds__(NT, NT == 128 ? PX_MINB128 : (MODE == PX_MODE_
         s.bodyR[x] = make_float4(c, -sn, sn, c);
       }
       /* pxCorrectPositions, px_world.c:288-292: this body's terms, in pool order */
-      {
+      if (staticSched) { /* precomputed by the previous launch's phase D: they depend on nothing the solver changes */
+        const float2 *cvec = (const float2 *)(hand + P.H.cvec);
+        const uint32_t start = rWord[r] & 0xffffu, n = (rWord[r] >> 16) & 0x3fffu;
+        for (uint32_t i = 0; i < n; i++) {
+          const float2 d = cvec[start + i];
+          posx = posx + d.x;
+          posy = posy + d.y;
+        }
+      } else {
         const uint32_t start = s.listStart[x], n = s.cnt[x], nBx = s.cntB[x];
         for (uint32_t i = 0; i < n; i++) {
           const uint32_t ms = s.list[start + i];
@@ -1759,7 +1776,9 @@ __global__ void __launch_bounds__(NT, NT == 128 ? PX_MINB128 : (MODE == PX_MODE_
       /* body pass of pxUpdateSleepStates, px_world.c:179-219: the flags are TESTED by sorted
        * position p although they were set by slot -- the reference's behaviour */
       float slp = rSlp[r];
-      if (s.wakeFlag[p]) {
+      const bool wake = staticSched ? (rWord[r] & 0x40000000u) != 0 : s.wakeFlag[p] != 0;
+      const bool rest = staticSched ? (rWord[r] & 0x80000000u) != 0 : s.restFlag[p] != 0;
+      if (wake) {
         slp = 0.0f;
         fl &= ~PX_FLAG_SLEEPING;
       } else {
@@ -1769,7 +1788,7 @@ __global__ void __launch_bounds__(NT, NT == 128 ? PX_MINB128 : (MODE == PX_MODE_
           fl &= ~PX_FLAG_SLEEPING;
         } else if (!(fl & PX_FLAG_SLEEPING)) {
           slp = slp + dt;
-          if (s.restFlag[p]) slp = slp + dt;
+          if (rest) slp = slp + dt;
           if (slp >= timeToSleep) {
             bv.x = 0.0f;
             bv.y = 0.0f;
@@ -2216,19 +2235,13 @@ __global__ void __launch_bounds__(PX_REPLAY_THREADS, PX_REPLAY_MINB) pxReplayKer
     float *gdyn = (float *)(gmut + L.offDyn);
     PxWorldHeader *gh = (PxWorldHeader *)(gmut + L.offHeader);
     const uint32_t iterations = gh->iterations & 255u;
-    const float dt = gh->dt, linSleepSq = gh->linearSleepThresholdSq, angSleep = gh->angularSleepThreshold;
-    const float timeToSleep = gh->timeToSleep;
     uint32_t *sc = (uint32_t *)(hand + P.H.scalars);
     const uint32_t M = min(sc[PX_HS_M], MM), ring = sc[PX_HS_RING];
     const bool solving = M && iterations; /* uniform */
     unsigned long long *prof = P.prof ? P.prof + (size_t)world * PX_PROF_SLOTS : nullptr;
-    /* what is read late is started on its way out of DRAM now: the visit operands by rank (after the relaxation), and
-     * phase F's rows, body words and correction moves (after the replay) */
+    /* what is read late is started on its way out of DRAM now: the visit operands by rank (after the relaxation) */
     if (solving)
       for (uint32_t k = 0; k < 3u; k++) prefetchRegion(hand + P.H.vrec + k * PX_PLANE * 16u, 2u * M * 16u, lane, PX_REPLAY_THREADS);
-    prefetchRegion(gmut + L.offDyn, PX_DYN_ROWS * D * 4u + D, lane, PX_REPLAY_THREADS);
-    prefetchRegion(hand + P.H.bodyF, D * 4u, lane, PX_REPLAY_THREADS);
-    prefetchRegion(hand + P.H.cvec, 2u * M * 8u, lane, PX_REPLAY_THREADS);
     uint32_t II = 0, QN = 0, depth = 0, nVisits = 0;
     if (solving) {
       buildSchedule(P, smemRaw, hand, M, ring, prof, II, QN, depth, nVisits);
@@ -2239,7 +2252,7 @@ __global__ void __launch_bounds__(PX_REPLAY_THREADS, PX_REPLAY_MINB) pxReplayKer
         for (uint32_t k = lane; k <= II * QN; k += PX_REPLAY_THREADS) segS[k] = gseg[k];
       }
     }
-    {
+    if (solving) {
       const float *gc = (const float *)(gimm + L.offDynConst);
       for (uint32_t x = lane; x < D; x += PX_REPLAY_THREADS) {
         bodyV[x] = make_float4(gdyn[PX_DYN_VX * D + x], gdyn[PX_DYN_VY * D + x], gdyn[PX_DYN_AV * D + x], gc[PX_DYNC_IMASS * D + x]);
@@ -2337,91 +2350,15 @@ __global__ void __launch_bounds__(PX_REPLAY_THREADS, PX_REPLAY_MINB) pxReplayKer
       if (lane == 0 && (visits != nVisits * iterations || (sc[PX_HS_READY] & 0x80000000u))) gh->statOverflow |= PX_OVERFLOW_INTERNAL;
     }
 
-    /* ---- phase F, one body per lane: integrate velocities (px_body.c:181-188), positional correction
-     * (px_world.c:288-292: the body's moves, precomputed by the sweep kernel, added in pool order), sleep update
-     * (px_world.c:179-219, flags of the body's sorted position), clear forces (px_world.c:302-311) */
-    {
-      const uint32_t *bodyF = (const uint32_t *)(hand + P.H.bodyF);
-      const float2 *cvec = (const float2 *)(hand + P.H.cvec);
-      uint8_t *gflags = gmut + L.offDynFlags;
-      uint32_t sleeping = 0;
+    if (solving) {
       for (uint32_t x = lane; x < D; x += PX_REPLAY_THREADS) {
-        uint32_t fl = gflags[x];
-        if (!(fl & 4u)) continue;
-        const uint32_t word = bodyF[x];
-        float posx = gdyn[PX_DYN_PX * D + x], posy = gdyn[PX_DYN_PY * D + x], angle = gdyn[PX_DYN_ANGLE * D + x];
-        float fx = gdyn[PX_DYN_FX * D + x], fy = gdyn[PX_DYN_FY * D + x], tq = gdyn[PX_DYN_TORQUE * D + x];
-        float slp = gdyn[PX_DYN_SLEEP * D + x];
-        float4 bv = bodyV[x];
-        if (!(fl & PX_FLAG_SLEEPING)) {
-          posx = posx + bv.x * dt;
-          posy = posy + bv.y * dt;
-          float radians = angle + bv.z * dt;
-          radians = fmodf(radians, D_2PI);
-          if (radians < 0) radians += D_2PI;
-          angle = radians;
-          const float c = fSin(P.sinTable, radians + D_PI * 0.5f), sn = fSin(P.sinTable, radians);
-          gdyn[PX_DYN_M00 * D + x] = c;
-          gdyn[PX_DYN_M01 * D + x] = -sn;
-          gdyn[PX_DYN_M10 * D + x] = sn;
-          gdyn[PX_DYN_M11 * D + x] = c;
-        }
-        {
-          const uint32_t start = word & 0xffffu, n = (word >> 16) & 0x3fffu;
-          for (uint32_t i = 0; i < n; i++) {
-            const float2 d = cvec[start + i];
-            posx = posx + d.x;
-            posy = posy + d.y;
-          }
-        }
-        if (word & 0x40000000u) { /* wake flag of the body's sorted position */
-          slp = 0.0f;
-          fl &= ~PX_FLAG_SLEEPING;
-        } else {
-          const bool below = (bv.x * bv.x + bv.y * bv.y <= linSleepSq) && (fabsf(bv.z) <= angSleep);
-          if (!below) {
-            slp = 0.0f;
-            fl &= ~PX_FLAG_SLEEPING;
-          } else if (!(fl & PX_FLAG_SLEEPING)) {
-            slp = slp + dt;
-            if (word & 0x80000000u) slp = slp + dt; /* rest flag of the body's sorted position */
-            if (slp >= timeToSleep) {
-              bv.x = 0.0f;
-              bv.y = 0.0f;
-              bv.z = 0.0f;
-              fx = 0.0f;
-              fy = 0.0f;
-              tq = 0.0f;
-              fl |= PX_FLAG_SLEEPING;
-            }
-          }
-        }
-        if (!(slp >= timeToSleep)) {
-          fx = 0.0f;
-          fy = 0.0f;
-          tq = 0.0f;
-        }
-        sleeping += (fl & PX_FLAG_SLEEPING) ? 1u : 0u;
-        gdyn[PX_DYN_PX * D + x] = posx;
-        gdyn[PX_DYN_PY * D + x] = posy;
+        const float4 bv = bodyV[x];
         gdyn[PX_DYN_VX * D + x] = bv.x;
         gdyn[PX_DYN_VY * D + x] = bv.y;
         gdyn[PX_DYN_AV * D + x] = bv.z;
-        gdyn[PX_DYN_ANGLE * D + x] = angle;
-        gdyn[PX_DYN_FX * D + x] = fx;
-        gdyn[PX_DYN_FY * D + x] = fy;
-        gdyn[PX_DYN_TORQUE * D + x] = tq;
-        gdyn[PX_DYN_SLEEP * D + x] = slp;
-        gflags[x] = (uint8_t)fl;
       }
-      sleeping = __reduce_add_sync(0xffffffffu, sleeping);
-      if (lane == 0) {
-        gh->statSleeping = sleeping;
-        gh->substeps = gh->substeps + 1u;
-      }
-      if (prof && lane == 0) prof[5] += (unsigned long long)(clock64() - t0);
     }
-    __syncwarp(); /* the next world's tables overwrite the rows phase F has just read */
+    __syncwarp(); /* the next world's tables overwrite what the store above still reads */
   }
 }
 
