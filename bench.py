@@ -497,7 +497,7 @@ def run_ours(args):
             },
             "clocks": clocks, "gpu_launches": int(gpu_launches),
             "kernels": {"sweep_ms_per_launch": sweep_ms, "sweep_launches_per_step": kt["sweep_launches"] // 3,
-                        "sched_ms_per_launch": sched_ms, "sched_launches_per_step": kt["sched_launches"] // 3,
+                        "finish_ms_per_launch": sched_ms, "finish_launches_per_step": kt["sched_launches"] // 3,
                         "solve_ms_per_launch": solve_ms, "solve_launches_per_step": kt["solve_launches"] // 3,
                         "timed_with": "CUDA events around every launch (pxBatchStepTimedKernels), 3 steps"},
             "roofline": {"bound": "hbm", "kernel": "pxStepKernel (sweep)" if pipe["split"] else "pxStepKernel (fused)",

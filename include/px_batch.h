@@ -201,8 +201,8 @@ PX_API int pxBatchStepHost(PxBatch *b, uint32_t kSubsteps, void *hostMut, uint32
 PX_API int pxBatchTimerStart(PxBatch *b);
 PX_API int pxBatchTimerStop(PxBatch *b, float *ms);
 /* One step with EVERY kernel launch bracketed by CUDA events; blocks.  ms[c] / n[c]: summed device time and number of
- * the launches of class c -- 0 the sweep kernel (or the one fused launch), 1 reserved (always 0), 2 the solver
- * kernel (dataflow, or schedule + replay).  The roofline numbers of bench.py come from here. */
+ * the launches of class c -- 0 the sweep kernel (or the one fused launch), 1 the finish kernel (phase F of the
+ * step's last substep; static solver only), 2 the solver kernel (dataflow, or schedule + replay).  The roofline numbers of bench.py come from here. */
 PX_API int pxBatchStepTimedKernels(PxBatch *b, uint32_t kSubsteps, float ms[3], uint32_t n[3]);
 /* which pipeline the batch runs: *split = 0 for the fused kernel, 1 for sweep + dataflow-solver kernels per substep,
  * 2 for sweep + schedule-and-replay kernels per substep (large batches); resident CTAs per SM of the solver

@@ -637,6 +637,14 @@ static int launchSolve(PxBatch *b, PxStepParams *P, uint32_t grid, cudaStream_t 
   return 0;
 }
 
+/* static solver: phase F of a step's last substep */
+static int launchFinish(PxBatch *b, PxStepParams *P, cudaStream_t stream) {
+  int rc = pxLaunchFinish(P, stream);
+  if (rc != 0) return pxSetError(-rc - 1000, "finish kernel launch: %s", cudaGetErrorString((cudaError_t)rc));
+  b->launches++;
+  return 0;
+}
+
 /* K substeps for worlds [first, first + n) on `stream`; launches that may overlap in time use
  * different scratch regions */
 static int launchRange(PxBatch *b, uint32_t kSubsteps, uint32_t first, uint32_t n, cudaStream_t stream, uint32_t region) {
@@ -653,15 +661,17 @@ static int launchRange(PxBatch *b, uint32_t kSubsteps, uint32_t first, uint32_t 
     b->launches++;
     return 0;
   }
-  /* split pipeline.  Static solver: sweep(A-D) | solve(E, F) per substep.  Dataflow solver:
-   * sweep(A-D) | solve(E) | sweep(F, A-D) | solve(E) | ... | sweep(F) */
+  /* split pipeline: sweep(A-D) | solve(E) | sweep(F, A-D) | solve(E) | ... | F */
   splitParams(b, first, &P);
   const uint32_t gridSweep = n < b->gridMax ? n : b->gridMax, gridSolve = n < b->gridSolve ? n : b->gridSolve;
-  const uint32_t nSweeps = kSubsteps + 1u;
+  /* the last substep's phase F: static solver -- the streaming finish kernel; dataflow solver -- a sweep launch that
+   * only finishes */
+  const uint32_t nSweeps = b->staticSched ? kSubsteps : kSubsteps + 1u;
   for (uint32_t s = 0; s < nSweeps; s++) {
     if (launchSweep(b, &P, s, kSubsteps, gridSweep, stream)) return -1;
     if (s < kSubsteps && launchSolve(b, &P, gridSolve, stream)) return -1;
   }
+  if (b->staticSched && launchFinish(b, &P, stream)) return -1;
   return 0;
 }
 
@@ -790,7 +800,7 @@ extern "C" int pxBatchTimerStop(PxBatch *b, float *ms) {
 
 /* One step with every kernel launch bracketed by CUDA events: device time per kernel class.
  * ms[c] / n[c] = summed durations and number of the launches of class c: 0 sweep (or the one fused launch),
- * 1 reserved (a kernel between the two; none at present), 2 solver (dataflow or schedule + replay).  Blocks. */
+ * 1 finish kernel (the last substep's phase F, static solver only), 2 solver (dataflow or schedule + replay).  Blocks. */
 extern "C" int pxBatchStepTimedKernels(PxBatch *b, uint32_t kSubsteps, float ms[3], uint32_t n[3]) {
   if (!b || !ms || !n) return pxSetError(-1, "pxBatchStepTimedKernels: NULL argument");
   if (useDevice(b)) return -1;
@@ -821,11 +831,12 @@ extern "C" int pxBatchStepTimedKernels(PxBatch *b, uint32_t kSubsteps, float ms[
   } else {
     splitParams(b, 0, &P);
     const uint32_t gridSweep = W < b->gridMax ? W : b->gridMax, gridSolve = W < b->gridSolve ? W : b->gridSolve;
-    const uint32_t nSweeps = kSubsteps + 1u;
+    const uint32_t nSweeps = b->staticSched ? kSubsteps : kSubsteps + 1u;
     for (uint32_t s = 0; s < nSweeps; s++) {
       if (launchSweep(b, &P, s, kSubsteps, gridSweep, b->stream) || mark(0)) return -1;
       if (s < kSubsteps && (launchSolve(b, &P, gridSolve, b->stream) || mark(2))) return -1;
     }
+    if (b->staticSched && (launchFinish(b, &P, b->stream) || mark(1))) return -1;
   }
   CU(cudaEventSynchronize(ev.back()));
   for (size_t k = 1; k < ev.size(); k++) {

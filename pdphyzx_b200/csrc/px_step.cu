@@ -2362,6 +2362,107 @@ __global__ void __launch_bounds__(PX_REPLAY_THREADS, PX_REPLAY_MINB) pxReplayKer
   }
 }
 
+/* ======================================================================= finish kernel ==== */
+/*
+ * Split pipeline with the static solver, phase F of the LAST substep of a step (the others are finished at the head of
+ * the next sweep launch): one thread per body, one CTA per world.  Integrate velocities (px_body.c:181-188), positional
+ * correction (px_world.c:288-292: the body's moves, precomputed by the sweep kernel, added in pool order), sleep update
+ * (px_world.c:179-219, with the flags of the body's sorted position), clear forces (px_world.c:302-311) -- the same
+ * expressions as phase F of pxStepKernel.  Pure streaming: every row is read and written once, coalesced.
+ */
+__global__ void __launch_bounds__(PX_DMAX) pxFinishKernel(const PxStepParams P) {
+  const PxBatchLayout &L = P.L;
+  const uint32_t D = L.maxDynamic, x = threadIdx.x, world = blockIdx.x;
+  uint8_t *gmut = P.mut + (size_t)world * L.mutStride;
+  const uint8_t *hand = P.hand + (size_t)world * P.H.stride;
+  PxWorldHeader *gh = (PxWorldHeader *)(gmut + L.offHeader);
+  float *gdyn = (float *)(gmut + L.offDyn);
+  uint8_t *gflags = gmut + L.offDynFlags;
+  const float dt = gh->dt, linSleepSq = gh->linearSleepThresholdSq, angSleep = gh->angularSleepThreshold;
+  const float timeToSleep = gh->timeToSleep;
+  uint32_t asleep = 0;
+  uint32_t fl = x < D ? gflags[x] : 0u;
+  if (fl & 4u) {
+    const uint32_t word = ((const uint32_t *)(hand + P.H.bodyF))[x];
+    const float2 *cvec = (const float2 *)(hand + P.H.cvec);
+    float posx = gdyn[PX_DYN_PX * D + x], posy = gdyn[PX_DYN_PY * D + x], angle = gdyn[PX_DYN_ANGLE * D + x];
+    float fx = gdyn[PX_DYN_FX * D + x], fy = gdyn[PX_DYN_FY * D + x], tq = gdyn[PX_DYN_TORQUE * D + x];
+    float slp = gdyn[PX_DYN_SLEEP * D + x];
+    float bvx = gdyn[PX_DYN_VX * D + x], bvy = gdyn[PX_DYN_VY * D + x], bvz = gdyn[PX_DYN_AV * D + x];
+    if (!(fl & PX_FLAG_SLEEPING)) {
+      posx = posx + bvx * dt;
+      posy = posy + bvy * dt;
+      float radians = angle + bvz * dt;
+      radians = fmodf(radians, D_2PI);
+      if (radians < 0) radians += D_2PI;
+      angle = radians;
+      const float c = fSin(P.sinTable, radians + D_PI * 0.5f), sn = fSin(P.sinTable, radians);
+      gdyn[PX_DYN_M00 * D + x] = c;
+      gdyn[PX_DYN_M01 * D + x] = -sn;
+      gdyn[PX_DYN_M10 * D + x] = sn;
+      gdyn[PX_DYN_M11 * D + x] = c;
+    }
+    {
+      const uint32_t start = word & 0xffffu, n = (word >> 16) & 0x3fffu;
+      for (uint32_t i = 0; i < n; i++) {
+        const float2 d = cvec[start + i];
+        posx = posx + d.x;
+        posy = posy + d.y;
+      }
+    }
+    if (word & 0x40000000u) { /* wake flag of the body's sorted position */
+      slp = 0.0f;
+      fl &= ~PX_FLAG_SLEEPING;
+    } else {
+      const bool below = (bvx * bvx + bvy * bvy <= linSleepSq) && (fabsf(bvz) <= angSleep);
+      if (!below) {
+        slp = 0.0f;
+        fl &= ~PX_FLAG_SLEEPING;
+      } else if (!(fl & PX_FLAG_SLEEPING)) {
+        slp = slp + dt;
+        if (word & 0x80000000u) slp = slp + dt; /* rest flag of the body's sorted position */
+        if (slp >= timeToSleep) {
+          bvx = 0.0f;
+          bvy = 0.0f;
+          bvz = 0.0f;
+          fx = 0.0f;
+          fy = 0.0f;
+          tq = 0.0f;
+          fl |= PX_FLAG_SLEEPING;
+        }
+      }
+    }
+    if (!(slp >= timeToSleep)) {
+      fx = 0.0f;
+      fy = 0.0f;
+      tq = 0.0f;
+    }
+    asleep = (fl & PX_FLAG_SLEEPING) ? 1u : 0u;
+    gdyn[PX_DYN_PX * D + x] = posx;
+    gdyn[PX_DYN_PY * D + x] = posy;
+    gdyn[PX_DYN_VX * D + x] = bvx;
+    gdyn[PX_DYN_VY * D + x] = bvy;
+    gdyn[PX_DYN_AV * D + x] = bvz;
+    gdyn[PX_DYN_ANGLE * D + x] = angle;
+    gdyn[PX_DYN_FX * D + x] = fx;
+    gdyn[PX_DYN_FY * D + x] = fy;
+    gdyn[PX_DYN_TORQUE * D + x] = tq;
+    gdyn[PX_DYN_SLEEP * D + x] = slp;
+    gflags[x] = (uint8_t)fl;
+  }
+  const uint32_t total = __syncthreads_count(asleep != 0u);
+  if (x == 0) {
+    gh->statSleeping = total;
+    gh->substeps = gh->substeps + 1u;
+  }
+}
+
+extern "C" int pxLaunchFinish(const PxStepParams *P, void *stream) {
+  if (P->L.nWorlds == 0) return (int)cudaErrorInvalidValue;
+  pxFinishKernel<<<P->L.nWorlds, PX_DMAX, 0, (cudaStream_t)stream>>>(*P);
+  return (int)cudaGetLastError();
+}
+
 /* ------------------------------------------------------------------- control commands */
 /* One thread per world applies that world's queued API calls in submission order, merged
  * with the batch-wide (PX_ALL_WORLDS) calls by sequence number. */

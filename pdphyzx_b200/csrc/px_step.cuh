@@ -141,6 +141,8 @@ int pxStepOccupancy(const PxStepParams *P, uint32_t threads, int *ctasPerSm);
 void pxPlanHandover(const PxBatchLayout *L, const PxSmemPlan *S, PxHandLayout *H);
 void pxPlanSolveSmem(const PxBatchLayout *L, const PxSmemPlan *S, int staticSolver, PxSmemPlan *out);
 int pxLaunchSolve(const PxStepParams *P, uint32_t grid, void *stream);
+/* static solver: phase F of a step's last substep as a streaming kernel of its own, one CTA per world */
+int pxLaunchFinish(const PxStepParams *P, void *stream);
 int pxSolveOccupancy(const PxStepParams *P, int *ctasPerSm);
 #define PX_SOLVE_THREADS 64u  /* dynamic solver: scheduler warp + math warp */
 #define PX_REPLAY_THREADS 32u /* static solver: one warp derives the world's schedule and replays it */
