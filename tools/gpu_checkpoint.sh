@@ -14,12 +14,13 @@ PX_SOLVER=dynamic timeout 1500 python -m pytest tests -m gpu -x -q > $out/${tag}
 python bench.py --steps 20 --warmup 3 > $out/${tag}_bench_line.json 2> $out/${tag}_bench.err; tail -c 300 $out/${tag}_bench.err
 python bench.py --impl reference --steps 20 --warmup 3 > $out/${tag}_bench_reference_line.json 2> $out/${tag}_bench_reference.err
 python bench.py --steps 10 --warmup 3 --profile --no-cpu --no-e2e > $out/${tag}_phase_breakdown.json 2> $out/${tag}_phase.err
-# launch list: skip the settle + warm-up launches.  Large batches are stepped as two halves on two streams: 2 x (6 sweep +
-# 5 solver) = 22 launches per step of 5 substeps, 4 040 for the 1 000 settle substeps, 88 for warm-up: the timed region
-# starts at launch 4 128.  Every launch then covers HALF the batch: summarize with --worlds 4096.
+# launch list: skip the settle + warm-up launches.  Large batches are stepped as two halves on two streams: 2 x (5 sweep +
+# 5 solver + 1 finish) = 22 launches per step of 5 substeps, 4 040 for the 1 000 settle substeps, 88 for warm-up: the timed
+# region starts at launch 4 128 (a half's chain: sweep, solve, sweep, solve, ..., finish; launch 4 130 is a sweep that also
+# finishes the previous substep).  Every launch then covers HALF the batch: summarize with --worlds 4096.
 python bench.py --steps 2 --warmup 3 --no-cpu --no-e2e > $out/${tag}_plain.json 2> $out/${tag}_plain.err &&
-  ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"px(Step|Solve|Replay)" -s 4130 -c 44 --csv \
+  ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"px(Step|Solve|Replay|Finish)" -s 4130 -c 44 --csv \
       --log-file $out/${tag}_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu --no-e2e > $out/${tag}_ncu_launches.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:"px(Step|Solve|Replay)" -s 4130 -c 2 -o $out/${tag}_full -f \
+ncu --set full --clock-control none --import-source on -k regex:"px(Step|Solve|Replay|Finish)" -s 4130 -c 2 -o $out/${tag}_full -f \
     python bench.py --steps 2 --warmup 3 --no-cpu --no-e2e > $out/${tag}_ncu_full.log 2>&1
 echo checkpoint done
