@@ -233,10 +233,11 @@ extern "C" PxBatch *pxBatchCreate(uint32_t nWorlds, const PxBatchDesc *desc) {
     b->ctasPerSm = occ;
     const uint64_t capacity = (uint64_t)occ * (uint64_t)b->numSms;
     b->gridMax = (uint32_t)(capacity < nWorlds ? capacity : nWorlds);
-    if (!b->split) {
+    if (!b->split || b->staticSched) {
       const size_t scratchBytes = (size_t)PX_REGIONS * b->gridMax * b->L.maxManifolds * 3 * sizeof(float4);
       if ((e = cudaMalloc(&b->dScratch, scratchBytes)) != cudaSuccess) return fail("cudaMalloc(scratch)", e);
-    } else {
+    }
+    if (b->split) {
       pxPlanHandover(&b->L, &b->plan, &b->hand);
       pxPlanSolveSmem(&b->L, &b->plan, b->staticSched ? 1 : 0, &b->solvePlan);
       P.solveS = b->solvePlan;
@@ -609,7 +610,7 @@ static void baseParams(PxBatch *b, uint32_t kSubsteps, uint32_t first, uint32_t 
 static void splitParams(PxBatch *b, uint32_t first, PxStepParams *P) {
   P->mode = PX_MODE_SWEEP;
   P->solver = b->staticSched ? PX_SOLVER_STATIC : PX_SOLVER_DYNAMIC;
-  P->scratch = nullptr;
+  if (!b->staticSched) P->scratch = nullptr; /* static solver: the sweep kernel's manifold records live in the launch's scratch region */
   P->hand = b->dHand + (size_t)first * b->hand.stride;
   P->H = b->hand;
   P->solveS = b->solvePlan;
@@ -704,7 +705,7 @@ extern "C" int pxBatchStep(PxBatch *b, uint32_t kSubsteps) {
     for (uint32_t i = 0; i < nRanges; i++) {
       const uint32_t first = (uint32_t)((uint64_t)W * i / nRanges), last = (uint32_t)((uint64_t)W * (i + 1) / nRanges);
       CU(cudaStreamWaitEvent(b->aux[i], b->evFork, 0));
-      if (launchRange(b, kSubsteps, first, last - first, b->aux[i], 0)) return -1;
+      if (launchRange(b, kSubsteps, first, last - first, b->aux[i], 1u + i)) return -1;
       CU(cudaEventRecord(b->evJoin[i], b->aux[i]));
       CU(cudaStreamWaitEvent(b->stream, b->evJoin[i], 0));
     }
@@ -829,6 +830,7 @@ extern "C" int pxBatchStepTimedKernels(PxBatch *b, uint32_t kSubsteps, float ms[
     if (launchRange(b, kSubsteps, 0, W, b->stream, 0)) return -1;
     if (mark(0)) return -1;
   } else {
+    P.scratch = b->dScratch; /* region 0 */
     splitParams(b, 0, &P);
     const uint32_t gridSweep = W < b->gridMax ? W : b->gridMax, gridSolve = W < b->gridSolve ? W : b->gridSolve;
     const uint32_t nSweeps = b->staticSched ? kSubsteps : kSubsteps + 1u;

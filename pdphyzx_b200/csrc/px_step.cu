@@ -985,7 +985,10 @@ __global__ void __launch_bounds__(NT, NT == 128 ? PX_MINB128 : (MODE == PX_MODE_
   const bool staticSched = sweepMode && P.solver == PX_SOLVER_STATIC;
   uint8_t *hand = sweepMode ? P.hand + (size_t)world * P.H.stride : nullptr;
   if (sweepMode) {
-    s.man = (float4 *)(hand + P.H.records);
+    /* dataflow solver: the manifold records cross to the solver kernel and back to phase F in the hand-over record;
+     * static solver: nothing outside this launch reads them (the visit operands and correction moves are derived from
+     * them in phase D), so they stay in the CTA's L2-resident scratch slot like the fused kernel's */
+    s.man = staticSched ? P.scratch + (size_t)blockIdx.x * MM * 3u : (float4 *)(hand + P.H.records);
     statPairs = s.hdr->statPairs;
     statManifolds = s.hdr->statManifolds;
   }
@@ -2762,7 +2765,7 @@ extern "C" void pxPlanHandover(const PxBatchLayout *L, const PxSmemPlan *S, PxHa
   H->list = take(2 * MM * 2); H->listStart = take((D + 1) * 2); H->cnt = take(D * 2); H->cntB = take(D * 2);
   H->posOf = take(D); H->restFlag = take(D); H->wakeFlag = take(D);
   H->scalars = take(32);
-  H->records = take(MM * 3 * 16);
+  H->records = S->rankOf ? 0 : take(MM * 3 * 16); /* static solver: the records never leave the sweep launch (scratch slot) */
   H->stream = H->seg = 0;
   H->predA = H->predB = H->vrec = H->bodyF = H->cvec = 0;
   if (S->rankOf) { /* static schedule */
