@@ -110,9 +110,6 @@ __device__ __forceinline__ uint32_t ldsVolatile(uint32_t a) {
   asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
   return v;
 }
-__device__ __forceinline__ void stsVolatile(uint32_t a, uint32_t v) {
-  asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
-}
 /* pulls a 128-byte line into L2 ahead of its use */
 __device__ __forceinline__ void prefetchL2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 /* lines [0, bytes / 128] of a region, spread over the CTA's (or warp's) threads */
@@ -138,11 +135,6 @@ __device__ __forceinline__ uint32_t atomAddSIf(uint32_t a, uint32_t v, bool p) {
                : "+r"(old)
                : "r"(a), "r"(v), "r"((uint32_t)p)
                : "memory");
-  return old;
-}
-__device__ __forceinline__ uint32_t atomAddS(uint32_t a, uint32_t v) {
-  uint32_t old;
-  asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(a), "r"(v) : "memory");
   return old;
 }
 
@@ -1999,11 +1991,6 @@ __device__ __forceinline__ void sts16(uint32_t a, uint32_t v) { asm volatile("st
 __device__ __forceinline__ float4 ldgStream(const float4 *p) {
   float4 v;
   asm volatile("ld.global.cs.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
-  return v;
-}
-__device__ __forceinline__ float2 lds64(uint32_t a) {
-  float2 v;
-  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
   return v;
 }
 
