@@ -504,9 +504,10 @@ def run_ours(args):
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": sweep_ms,
-                         "note": "HBM is the nominal bound of this path (SURVEY 8d) but not the binding one: the L1 / "
-                                 "shared-memory data pipe (random float4 gathers of the solver, bank conflicts) and "
-                                 "non-FMA fp32 issue are; see roofline_lsu, roofline_issue, DESIGN.md and profiles/"},
+                         "note": "HBM is the nominal bound of this path (SURVEY 8d) but not the binding one: non-FMA "
+                                 "fp32 issue slots at 19.6 of 32 lanes (sweep kernel) and the per-world dependent chain "
+                                 "of the order-preserving solver (visit stream out of L2) are; see roofline_issue, "
+                                 "roofline_lsu, DESIGN.md 3.5 and profiles/"},
         }
         facts = kernel_facts(args)
         if facts and pipe["split"] == ("sweep" in facts.get("kernels", {})):
