@@ -45,6 +45,7 @@
 #include <string.h>
 
 #include "px_step.cuh"
+#include <type_traits>
 
 #define PX_FLAG_SLEEPING 8u /* PX_BODY_FLAG_SLEEPING, px_body.h:67 */
 #define PX_OVERFLOW_INTERNAL 0x80000000u
@@ -2256,56 +2257,72 @@ __global__ void __launch_bounds__(PX_REPLAY_THREADS, PX_REPLAY_MINB) pxReplayKer
     }
     long long t0 = 0;
     if (prof && lane == 0) t0 = clock64();
-    if (solving) { /* phase E */
+    /* phase E; `segInSmem` (a std::bool_constant) says where the segment table is: the copy in shared memory, or -- a
+     * table too long for it -- the one in the hand-over record.  Two instantiations, so that the common one reads the
+     * table with 32-bit shared-memory addresses instead of generic loads. */
+    auto replay = [&](auto segInSmem) {
+      constexpr bool SEG_SMEM = decltype(segInSmem)::value;
 
       /* Everything below is one warp's instruction stream and the kernel is issue-bound: the chunk iterator keeps
        * its state in registers (row = slot * QN, the alive phase window [qlo, qhi1) changes only when the period
        * wraps), the three operand planes are PX_PLANE entries apart so that one address serves all three loads. */
-      const uint16_t *seg = segS; /* the copy in shared memory, or (a table too long for it) the one in the hand-over record */
-      if (II * QN + 1u > PX_SEG_SMEM) seg = (const uint16_t *)(hand + P.H.seg);
+      const uint16_t *gseg = (const uint16_t *)(hand + P.H.seg);
       const float4 *pl = (const float4 *)(hand + P.H.stream);
-      asm volatile("" : "+l"(seg), "+l"(pl)); /* opaque: kept in registers, not rebuilt from the parameters every chunk */
+      asm volatile("" : "+l"(gseg), "+l"(pl)); /* opaque: kept in registers, not rebuilt from the parameters every chunk */
+      uint32_t aSeg = sAddr(segS);
+      asm volatile("" : "+r"(aSeg));
+      auto segAt = [&](uint32_t i) -> uint32_t {
+        if constexpr (SEG_SMEM) {
+          uint32_t v;
+          asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(aSeg + 2u * i));
+          return v;
+        } else {
+          return gseg[i];
+        }
+      };
       const uint32_t nR = depth + (iterations - 1u) * II;
       uint32_t R = 0, slot = 0, row = 0, Q = 0, qlo = 0, qhi1 = 1, beg = 0, end = 0;
-      beg = seg[0];
-      end = seg[1];
-      auto nextChunk = [&](uint32_t &base, uint32_t &cnt) {
+      beg = segAt(0);
+      end = segAt(1);
+      /* a chunk is [base, min(base + 32, lim)) of the stream; lim == 0: the schedule is exhausted.  The alive window
+       * slides by increments when the period wraps (Q -> Q + 1: qlo = max(0, Q + 1 - iterations) and
+       * qhi1 = min(Q, QN - 1) + 1): no min / max on the iterator's path, which runs on the uniform datapath. */
+      auto nextChunk = [&](uint32_t &base, uint32_t &lim) {
         while (beg >= end) {
           if (++R >= nR) {
-            base = cnt = 0;
+            base = lim = 0;
             return;
           }
           row += QN;
           if (++slot == II) {
             slot = row = 0;
+            if (Q + 1u >= iterations) qlo++;
+            if (Q + 1u < QN) qhi1++;
             Q++;
-            qlo = Q + 1u > iterations ? Q + 1u - iterations : 0u;
-            qhi1 = min(Q, QN - 1u) + 1u;
           }
           if (qlo < qhi1) {
-            beg = seg[row + qlo];
-            end = seg[row + qhi1];
+            beg = segAt(row + qlo);
+            end = segAt(row + qhi1);
           }
         }
         base = beg;
-        cnt = min(32u, end - beg);
-        beg += cnt;
+        lim = end;
+        beg += 32u;
       };
-      uint32_t chunks = 0, visits = 0;
+      uint32_t chunks = 0, visits = 0; /* visits: per lane, summed at the end */
       /* one chunk: start the NEXT chunk's three operand loads, then run this one.  Two register sets take turns
        * (no copies: a copy at the end of the step would wait for the loads it had just issued). */
-      auto step = [&](const float4 &r0, const float4 &r1, const float4 &r2, const uint32_t cnt, float4 &n0, float4 &n1, float4 &n2,
-                      uint32_t &cntNext) {
-        uint32_t baseNext;
-        nextChunk(baseNext, cntNext);
-        /* idle lanes repeat the chunk's last visit and store nothing; past the end: entry 0, discarded */
-        const float4 *at = pl + (baseNext + min(lane, cntNext ? cntNext - 1u : 0u));
+      auto step = [&](const float4 &r0, const float4 &r1, const float4 &r2, const uint32_t base, const uint32_t lim, float4 &n0,
+                      float4 &n1, float4 &n2, uint32_t &baseNext, uint32_t &limNext) {
+        nextChunk(baseNext, limNext);
+        /* idle lanes repeat the chunk's last visit and store nothing; past the end (limNext == 0): entry `lane`, discarded */
+        const float4 *at = pl + min(baseNext + lane, limNext - 1u);
         n0 = ldgPinned(at);
         n1 = ldgPinned(at + PX_PLANE);
         n2 = ldgPinned(at + 2u * PX_PLANE);
         const uint32_t ids = __float_as_uint(r2.z);
         const uint32_t a16 = (ids & 0xffu) * 16u, b16 = ((ids >> 8) & 0x1ffu) * 16u;
-        const bool bdyn = ((ids >> 17) & 1u) != 0, active = lane < cnt;
+        const bool bdyn = ((ids >> 17) & 1u) != 0, active = base + lane < lim;
         float4 vA = lds128(aBodyV + a16), vB = lds128(aBodyV + b16);
         const float iIA = __uint_as_float(lds32(aBodyI + (a16 >> 2))), iIB = __uint_as_float(lds32(aBodyI + (b16 >> 2)));
         contactImpulseCore(v2(r0.x, r0.y), v2(r0.z, r0.w), v2(r1.x, r1.y), r1.w, r2.x, r2.y, r1.z, vA.w, iIA, vB.w, iIB, bdyn, vA, vB,
@@ -2313,24 +2330,25 @@ __global__ void __launch_bounds__(PX_REPLAY_THREADS, PX_REPLAY_MINB) pxReplayKer
         sts128If(aBodyV + a16, vA, active);
         sts128If(aBodyV + b16, vB, active && bdyn);
         __syncwarp();
-        visits += cnt;
+        visits += active ? 1u : 0u;
         chunks++;
       };
-      uint32_t bA, cA, cB = 0;
-      nextChunk(bA, cA);
+      uint32_t bA, lA, bB = 0, lB = 0;
+      nextChunk(bA, lA);
       float4 a0, a1, a2, b0, b1, b2;
       {
-        const float4 *at = pl + (bA + min(lane, cA ? cA - 1u : 0u));
+        const float4 *at = pl + min(bA + lane, lA - 1u);
         a0 = ldgPinned(at);
         a1 = ldgPinned(at + PX_PLANE);
         a2 = ldgPinned(at + 2u * PX_PLANE);
       }
 #pragma unroll 1
-      while (cA) {
-        step(a0, a1, a2, cA, b0, b1, b2, cB);
-        if (!cB) break;
-        step(b0, b1, b2, cB, a0, a1, a2, cA);
+      while (lA) {
+        step(a0, a1, a2, bA, lA, b0, b1, b2, bB, lB);
+        if (!lB) break;
+        step(b0, b1, b2, bB, lB, a0, a1, a2, bA, lA);
       }
+      visits = __reduce_add_sync(0xffffffffu, visits);
       if (prof && lane == 0) {
         const long long now = clock64();
         prof[4] += (unsigned long long)(now - t0);
@@ -2338,6 +2356,10 @@ __global__ void __launch_bounds__(PX_REPLAY_THREADS, PX_REPLAY_MINB) pxReplayKer
         t0 = now;
       }
       if (lane == 0 && (visits != nVisits * iterations || (sc[PX_HS_READY] & 0x80000000u))) gh->statOverflow |= PX_OVERFLOW_INTERNAL;
+    };
+    if (solving) {
+      if (II * QN + 1u <= PX_SEG_SMEM) replay(std::true_type{});
+      else replay(std::false_type{});
     }
 
     if (solving) {
