@@ -1597,7 +1597,8 @@ __global__ void __launch_bounds__(NT, NT == 128 ? PX_MINB128 : (MODE == PX_MODE_
     if constexpr (sweepMode) {
       if (staticSched && iterations) {
         /* static schedule: the rings in pool-rank space and, by rank, the frozen operands of every contact visit
-         * {n, ra | rb, rcpDenom, e | sf, df, ids} (entry 2 * rank + contact); pxReplayKernel orders them */
+         * {n, ra | rb, rcpDenom, e | sf, df, ids, inverse inertia of A} (entry 2 * rank + contact); pxReplayKernel
+         * orders them */
         float4 *pl0 = (float4 *)(hand + P.H.vrec), *pl1 = pl0 + PX_PLANE, *pl2 = pl1 + PX_PLANE;
         for (uint32_t v = tid; v < 2u * M; v += NT) {
           const uint32_t m = v >> 1, ci = v & 1u, w = s.mids[m];
@@ -1609,7 +1610,7 @@ __global__ void __launch_bounds__(NT, NT == 128 ? PX_MINB128 : (MODE == PX_MODE_
             const V2 ra = cpt - v2(pA.x, pA.y), rb = cpt - v2(pB.x, pB.y); /* px_manifold.c:112-113 */
             pl0[at] = make_float4(mA.x, mA.y, ra.x, ra.y);
             pl1[at] = make_float4(rb.x, rb.y, ci ? mC.w : mC.z, mA.z);
-            pl2[at] = make_float4(mA.w, mB.x, __uint_as_float(a | (b << 8) | (MID_BDYN(w) << 17)), 0.0f);
+            pl2[at] = make_float4(mA.w, mB.x, __uint_as_float(a | (b << 8) | (MID_BDYN(w) << 17)), pA.w);
           }
         }
         handCopy<NT>(hand + P.H.predA, s.predA, M * 2u);
@@ -2324,8 +2325,9 @@ __global__ void __launch_bounds__(PX_REPLAY_THREADS, PX_REPLAY_MINB) pxReplayKer
         const uint32_t a16 = (ids & 0xffu) * 16u, b16 = ((ids >> 8) & 0x1ffu) * 16u;
         const bool bdyn = ((ids >> 17) & 1u) != 0, active = base + lane < lim;
         float4 vA = lds128(aBodyV + a16), vB = lds128(aBodyV + b16);
-        const float iIA = __uint_as_float(lds32(aBodyI + (a16 >> 2))), iIB = __uint_as_float(lds32(aBodyI + (b16 >> 2)));
-        contactImpulseCore(v2(r0.x, r0.y), v2(r0.z, r0.w), v2(r1.x, r1.y), r1.w, r2.x, r2.y, r1.z, vA.w, iIA, vB.w, iIB, bdyn, vA, vB,
+        /* A's inverse inertia fills the record's twelfth word: one gather (three or four shared-memory wavefronts) less */
+        const float iIB = __uint_as_float(lds32(aBodyI + (b16 >> 2)));
+        contactImpulseCore(v2(r0.x, r0.y), v2(r0.z, r0.w), v2(r1.x, r1.y), r1.w, r2.x, r2.y, r1.z, vA.w, r2.w, vB.w, iIB, bdyn, vA, vB,
                            eps);
         sts128If(aBodyV + a16, vA, active);
         sts128If(aBodyV + b16, vB, active && bdyn);
