@@ -6,6 +6,7 @@ from __future__ import annotations
 
 import importlib.util
 import os
+import random
 import sys
 
 import numpy as np
@@ -81,3 +82,64 @@ def test_too_short_a_period_is_detected():
     ring = max(int(sum(d[m] for m in lst)) for lst in lists.values())
     t, _ = ss.relax_in_rank_order(idm, ring - 1, max_passes=7)
     assert t is None  # shorter than a ring: never converges, the device moves on to the next period after 7 passes
+
+
+# ---- the replay kernel's chunk iterator (pxReplayKernel, px_step.cu: nextChunk) --------------------------------------
+#
+# Visits are sorted by key = (round mod II) * QN + (round div II); round R of the replay is slot R mod II, period index
+# Q = R div II, and the visits alive in it are the phases q with 0 <= Q - q < iterations: ONE contiguous segment
+# seg[row + qlo] .. seg[row + qhi1] of the sorted order (row = slot * QN).  The kernel slides the window [qlo, qhi1) by
+# increments when the period wraps instead of evaluating max / min; this is the same arithmetic on the host.
+
+def _iterator_chunks(seg, II, QN, depth, iterations):
+    n_rounds = depth + (iterations - 1) * II
+    out = []
+    R = slot = row = Q = 0
+    qlo, qhi1 = 0, 1
+    beg, end = seg[0], seg[1]
+    while True:
+        while beg >= end:
+            R += 1
+            if R >= n_rounds:
+                return out
+            row += QN
+            slot += 1
+            if slot == II:
+                slot = row = 0
+                if Q + 1 >= iterations:
+                    qlo += 1
+                if Q + 1 < QN:
+                    qhi1 += 1
+                Q += 1
+                assert qlo == max(0, Q + 1 - iterations) and qhi1 == min(Q, QN - 1) + 1
+            if qlo < qhi1:
+                beg, end = seg[row + qlo], seg[row + qhi1]
+        out.append((beg, min(beg + 32, end)))  # a chunk: [base, min(base + 32, limit))
+        beg += 32
+
+
+def test_replay_iterator_visits_every_contact_once_per_iteration():
+    rng = random.Random(7)
+    for _ in range(3000):
+        II, QN, iterations = rng.randint(1, 9), rng.randint(1, 6), rng.randint(1, 7)
+        depth = rng.randint((QN - 1) * II + 1, QN * II)
+        count = [0] * (II * QN)
+        for slot in range(II):
+            for q in range(QN):
+                if slot + II * q < depth:
+                    count[slot * QN + q] = rng.choice([0, 0, 1, 2, 33, 70])
+        last = depth - 1
+        count[(last % II) * QN + last // II] = max(1, count[(last % II) * QN + last // II])
+        seg = [0]
+        for c in count:
+            seg.append(seg[-1] + c)
+        seen = [0] * seg[-1]
+        order = []
+        for base, lim in _iterator_chunks(seg, II, QN, depth, iterations):
+            assert 0 < lim - base <= 32
+            for v in range(base, lim):
+                seen[v] += 1
+            order.append(base)
+        assert all(s == iterations for s in seen)
+        # the phases alive in a round share its chunks: never more chunks than one per (key, iteration) and 32 visits
+        assert -(-seg[-1] * iterations // 32) <= len(order) <= sum(-(-c // 32) for c in count) * iterations
